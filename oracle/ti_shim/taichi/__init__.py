@@ -1,0 +1,726 @@
+"""Minimal serial emulator of the Taichi 1.2.2 API surface used by Rabmelon/tiSPHi.
+
+TEST INFRASTRUCTURE ONLY (lives under oracle/).  It exists so that the reference's *own, unmodified*
+Python sources under /root/reference/eng can be imported and executed in this container (Taichi itself is
+not installable here: no wheel, no network, Python 3.12 > taichi 1.2.2's 3.10 ceiling).  The product path
+never imports this module.  It is used by ``oracle/gen_golden.py`` to produce the fixtures committed under
+``tests/golden/``.
+
+Semantics emulated (SURVEY.md Appendix D lists them; each is isolated in one function here):
+  * every top-level ``for`` of a ``@ti.kernel`` runs serially in program order -> this is the reference's
+    ``ti.init(arch=ti.cpu, cpu_max_num_threads=1)`` mode (run_simulation.py:22), the only configuration in
+    which the reference is deterministic;
+  * ``ti.template()`` arguments are by-reference (``ret += ...`` inside a task updates the caller's variable);
+  * ``ti.atomic_add/sub/max/min`` return the old value and update the target in place;
+  * ``cast(int)`` truncates toward zero; float ``%`` is ``a - floor(a/b)*b``;
+  * default float is f64 (run_simulation.py:23 ``default_fp=ti.f64``), default int is a Python int;
+  * ``Matrix.inverse()/determinant`` are the closed forms for n <= 3; ``a * b`` on matrices is element-wise;
+    ``@`` is the matrix product; vectors are n x 1 matrices; ``.norm()`` = sqrt(sum of squares);
+  * out-of-range reads of a dense field return 0 (zero-initialised padding) and are counted in
+    ``OOB_READS``;
+  * ``ti.algorithms.PrefixSumExecutor(n).run(f)`` = in-place inclusive scan.
+
+Implementation note: ``@ti.kernel`` / ``@ti.func`` re-compile the decorated function through a small AST pass
+(by-reference accumulators, atomics on subscripts, float modulo).  Everything else executes as plain Python.
+"""
+import ast
+import inspect
+import math as _math
+import textwrap
+import itertools
+
+import numpy as _np
+
+__version__ = (1, 2, 2)
+OOB_READS = [0]
+
+
+# ----------------------------------------------------------------------------------------------------------
+# dtypes / misc markers
+# ----------------------------------------------------------------------------------------------------------
+class _DType:
+    def __init__(self, name, py):
+        self.name, self.py = name, py
+
+    def __repr__(self):
+        return self.name
+
+
+f64 = _DType("f64", float)
+f32 = _DType("f32", float)
+i32 = _DType("i32", int)
+cpu = "cpu"
+gpu = "gpu"
+
+
+def _py_of(dt):
+    if dt is int or dt is i32:
+        return int
+    return float
+
+
+def init(**kwargs):
+    return None
+
+
+def data_oriented(cls):
+    return cls
+
+
+class _Template:
+    pass
+
+
+def template():
+    return _Template
+
+
+def static(x):
+    return x
+
+
+def loop_config(**kw):
+    return None
+
+
+def random(dt=float):
+    raise NotImplementedError("ti.random is not on the emulated path")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Matrix / Vector (vectors are n x 1 matrices)
+# ----------------------------------------------------------------------------------------------------------
+def _isnum(x):
+    return isinstance(x, (int, float, _np.floating, _np.integer, bool))
+
+
+class Matrix:
+    __slots__ = ("n", "m", "d")
+
+    def __init__(self, arr=None, dt=None, _raw=None):
+        if _raw is not None:
+            self.n, self.m, self.d = _raw
+            return
+        if isinstance(arr, Matrix):
+            self.n, self.m, self.d = arr.n, arr.m, list(arr.d)
+            return
+        a = _np.asarray(arr)
+        if a.ndim == 1:
+            self.n, self.m = a.shape[0], 1
+        else:
+            self.n, self.m = a.shape
+        conv = int if a.dtype.kind in "iub" else float
+        self.d = [conv(v) for v in a.reshape(-1)]
+
+    # constructors -------------------------------------------------------------------------------------
+    @staticmethod
+    def zero(dt, n, m=1):
+        z = _py_of(dt)(0)
+        return Matrix(_raw=(n, m, [z] * (n * m)))
+
+    @staticmethod
+    def identity(dt, n):
+        d = [0.0] * (n * n)
+        for i in range(n):
+            d[i * n + i] = 1.0
+        return Matrix(_raw=(n, n, d))
+
+    def copy(self):
+        return Matrix(_raw=(self.n, self.m, list(self.d)))
+
+    # element access -----------------------------------------------------------------------------------
+    def _idx(self, key):
+        if isinstance(key, tuple):
+            i, j = key
+            return int(i) * self.m + int(j)
+        if self.m == 1 or self.n == 1:
+            return int(key)
+        raise IndexError("single index on a 2-D matrix")
+
+    def __getitem__(self, key):
+        return self.d[self._idx(key)]
+
+    def __setitem__(self, key, v):
+        if isinstance(v, (_np.floating, _np.integer)):
+            v = v.item()
+        self.d[self._idx(key)] = v
+
+    __array_ufunc__ = None   # numpy scalars must defer to the reflected operators below
+
+    def __len__(self):
+        return self.n * self.m if (self.m == 1 or self.n == 1) else self.n
+
+    def __iter__(self):
+        return iter(self.d)
+
+    x = property(lambda s: s.d[0])
+    y = property(lambda s: s.d[1])
+    z = property(lambda s: s.d[2])
+
+    # arithmetic ---------------------------------------------------------------------------------------
+    def _bin(self, o, f):
+        if isinstance(o, Matrix):
+            assert (self.n, self.m) == (o.n, o.m), "shape mismatch in element-wise op"
+            return Matrix(_raw=(self.n, self.m, [f(a, b) for a, b in zip(self.d, o.d)]))
+        return Matrix(_raw=(self.n, self.m, [f(a, o) for a in self.d]))
+
+    def _rbin(self, o, f):
+        return Matrix(_raw=(self.n, self.m, [f(o, a) for a in self.d]))
+
+    def __add__(self, o):
+        return self._bin(o, lambda a, b: a + b)
+
+    def __radd__(self, o):
+        return self._rbin(o, lambda a, b: a + b)
+
+    def __sub__(self, o):
+        return self._bin(o, lambda a, b: a - b)
+
+    def __rsub__(self, o):
+        return self._rbin(o, lambda a, b: a - b)
+
+    def __mul__(self, o):
+        return self._bin(o, lambda a, b: a * b)
+
+    def __rmul__(self, o):
+        return self._rbin(o, lambda a, b: a * b)
+
+    def __truediv__(self, o):
+        return self._bin(o, lambda a, b: a / b)
+
+    def __rtruediv__(self, o):
+        return self._rbin(o, lambda a, b: a / b)
+
+    def __neg__(self):
+        return Matrix(_raw=(self.n, self.m, [-a for a in self.d]))
+
+    def __abs__(self):
+        return Matrix(_raw=(self.n, self.m, [abs(a) for a in self.d]))
+
+    def __lt__(self, o):
+        return self._bin(o, lambda a, b: a < b)
+
+    def __matmul__(self, o):
+        assert isinstance(o, Matrix) and self.m == o.n, "matmul shape mismatch"
+        n, k, m = self.n, self.m, o.m
+        out = [0.0] * (n * m)
+        for i in range(n):
+            for j in range(m):
+                s = 0.0
+                for t in range(k):
+                    s += self.d[i * k + t] * o.d[t * m + j]
+                out[i * m + j] = s
+        return Matrix(_raw=(n, m, out))
+
+    def transpose(self):
+        n, m = self.n, self.m
+        return Matrix(_raw=(m, n, [self.d[i * m + j] for j in range(m) for i in range(n)]))
+
+    def trace(self):
+        return sum(self.d[i * self.m + i] for i in range(min(self.n, self.m)))
+
+    def sum(self):
+        s = 0.0
+        for a in self.d:
+            s += a
+        return s
+
+    def norm(self):
+        s = 0.0
+        for a in self.d:
+            s += a * a
+        return _math.sqrt(s)
+
+    def dot(self, o):
+        s = 0.0
+        for a, b in zip(self.d, o.d):
+            s += a * b
+        return s
+
+    def cast(self, dt):
+        c = _py_of(dt)
+        return Matrix(_raw=(self.n, self.m, [c(a) for a in self.d]))  # int() truncates toward zero
+
+    def determinant(self):
+        d = self.d
+        if self.n == 2:
+            return d[0] * d[3] - d[1] * d[2]
+        if self.n == 3:
+            return (d[0] * (d[4] * d[8] - d[5] * d[7]) - d[1] * (d[3] * d[8] - d[5] * d[6])
+                    + d[2] * (d[3] * d[7] - d[4] * d[6]))
+        raise NotImplementedError
+
+    def inverse(self):
+        d = self.d
+        if self.n == 2:
+            inv = 1.0 / self.determinant()
+            return Matrix(_raw=(2, 2, [d[3] * inv, -d[1] * inv, -d[2] * inv, d[0] * inv]))
+        if self.n == 3:
+            inv = 1.0 / self.determinant()
+            c = [
+                (d[4] * d[8] - d[5] * d[7]), -(d[1] * d[8] - d[2] * d[7]), (d[1] * d[5] - d[2] * d[4]),
+                -(d[3] * d[8] - d[5] * d[6]), (d[0] * d[8] - d[2] * d[6]), -(d[0] * d[5] - d[2] * d[3]),
+                (d[3] * d[7] - d[4] * d[6]), -(d[0] * d[7] - d[1] * d[6]), (d[0] * d[4] - d[1] * d[3]),
+            ]
+            return Matrix(_raw=(3, 3, [v * inv for v in c]))
+        raise NotImplementedError
+
+    def to_list(self):
+        if self.m == 1:
+            return list(self.d)
+        return [[self.d[i * self.m + j] for j in range(self.m)] for i in range(self.n)]
+
+    def __repr__(self):
+        return f"Matrix({self.to_list()})"
+
+
+def Vector(arr, dt=None):
+    return Matrix(arr, dt)
+
+
+Vector.zero = lambda dt, n: Matrix.zero(dt, n, 1)
+
+
+class _VecType:
+    def __init__(self, n, dt):
+        self.n, self.dt = n, dt
+
+    def __call__(self, *args):
+        c = _py_of(self.dt)
+        if len(args) == 1 and _isnum(args[0]):
+            return Matrix(_raw=(self.n, 1, [c(args[0])] * self.n))
+        if len(args) == 1:
+            m = Matrix(args[0])
+            assert m.n * m.m == self.n
+            return Matrix(_raw=(self.n, 1, [c(v) for v in m.d]))
+        flat = []
+        for a in args:
+            flat.extend(a.d if isinstance(a, Matrix) else [a])
+        assert len(flat) == self.n, "vector constructor arity"
+        return Matrix(_raw=(self.n, 1, [c(v) for v in flat]))
+
+    def field(self, shape):
+        return _MatField(self.n, 1, shape)
+
+
+class _MatType:
+    def __init__(self, n, m, dt):
+        self.n, self.m, self.dt = n, m, dt
+
+    def __call__(self, *args):
+        c = _py_of(self.dt)
+        if len(args) == 1 and _isnum(args[0]):
+            return Matrix(_raw=(self.n, self.m, [c(args[0])] * (self.n * self.m)))
+        if len(args) == 1:
+            m = Matrix(args[0])
+        else:
+            m = Matrix([list(a) for a in args])
+        assert (m.n, m.m) == (self.n, self.m)
+        return Matrix(_raw=(self.n, self.m, [c(v) for v in m.d]))
+
+    def field(self, shape):
+        return _MatField(self.n, self.m, shape)
+
+
+class types:
+    @staticmethod
+    def vector(n, dt):
+        return _VecType(n, dt)
+
+    @staticmethod
+    def matrix(n, m, dt):
+        return _MatType(n, m, dt)
+
+    @staticmethod
+    def ndarray(*a, **k):
+        return None
+
+
+class math:
+    pi = _math.pi
+
+    @staticmethod
+    def eye(n):
+        return Matrix.identity(float, n)
+
+    @staticmethod
+    def determinant(m):
+        return m.determinant()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# scalar functions
+# ----------------------------------------------------------------------------------------------------------
+def sqrt(x):
+    return _math.sqrt(x)
+
+
+def pow(x, y):  # noqa: A001
+    return _math.pow(x, y)
+
+
+def sin(x):
+    return _math.sin(x)
+
+
+def tan(x):
+    return _math.tan(x)
+
+
+def ceil(x):
+    return float(_math.ceil(x))
+
+
+def floor(x):
+    return float(_math.floor(x))
+
+
+def abs(x):  # noqa: A001
+    return x.__abs__()
+
+
+def max(a, b):  # noqa: A001
+    return a if a >= b else b
+
+
+def min(a, b):  # noqa: A001
+    return a if a <= b else b
+
+
+def cast(x, dt):
+    if isinstance(x, Matrix):
+        return x.cast(dt)
+    return _py_of(dt)(x)
+
+
+def _mod(a, b):
+    """Taichi float/int ``%``: a - floor(a / b) * b."""
+    if isinstance(a, int) and isinstance(b, int):
+        return a % b
+    return a - _math.floor(a / b) * b
+
+
+def polar_decompose(A):
+    raise NotImplementedError("rigid bodies are outside the emulated path")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# fields
+# ----------------------------------------------------------------------------------------------------------
+def _nelem(shape):
+    if shape == () or shape is None:
+        return 1
+    if isinstance(shape, (int, _np.integer)):
+        return int(shape)
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n
+
+
+class _ScalarField:
+    def __init__(self, dt, shape):
+        self.py = _py_of(dt)
+        self.zero_d = (shape == ())
+        self.n = _nelem(shape)
+        self.shape = () if self.zero_d else (self.n,)
+        self.d = [self.py(0)] * self.n
+
+    def __getitem__(self, i):
+        if i is None:
+            return self.d[0]
+        i = int(i)
+        if i < 0 or i >= self.n:
+            OOB_READS[0] += 1
+            return self.py(0)
+        return self.d[i]
+
+    def __setitem__(self, i, v):
+        if i is None:
+            self.d[0] = self.py(v)
+            return
+        i = int(i)
+        if i < 0 or i >= self.n:
+            raise IndexError(f"out-of-range field write at {i} (size {self.n})")
+        self.d[i] = self.py(v)
+
+    def fill(self, v):
+        self.d = [self.py(v)] * self.n
+
+    def to_numpy(self):
+        return _np.array(self.d)
+
+
+class _MatField:
+    def __init__(self, n, m, shape):
+        self.nn = _nelem(shape)
+        self.shape = (self.nn,)
+        self.d = [Matrix.zero(float, n, m) for _ in range(self.nn)]
+
+    def __getitem__(self, i):
+        return self.d[0 if i is None else int(i)]
+
+    def __setitem__(self, i, v):
+        self.d[0 if i is None else int(i)] = Matrix(v)
+
+
+def field(dt, shape):
+    return _ScalarField(dt, shape)
+
+
+class _Elem:
+    """Proxy for ``struct_field[i]``; attribute reads return the live member, writes copy the value in."""
+    __slots__ = ("_f", "_i")
+
+    def __init__(self, f, i):
+        object.__setattr__(self, "_f", f)
+        object.__setattr__(self, "_i", i)
+
+    def __getattr__(self, name):
+        return object.__getattribute__(self, "_f").cols[name][object.__getattribute__(self, "_i")]
+
+    def __setattr__(self, name, v):
+        f = object.__getattribute__(self, "_f")
+        kind = f.kinds[name]
+        if kind is None:
+            f.cols[name][self._i] = Matrix(v)   # copy (Taichi assigns by value)
+        else:
+            f.cols[name][self._i] = kind(v)
+
+
+class _Member:
+    def __init__(self, f, name):
+        self.f, self.name = f, name
+
+    def __getitem__(self, i):
+        return self.f.cols[self.name][int(i)]
+
+
+class _StructField:
+    def __init__(self, stype, shape):
+        self.stype = stype
+        self.n = _nelem(shape)
+        self.shape = (self.n,)
+        self.cols, self.kinds = {}, {}
+        for name, t in stype.members.items():
+            if isinstance(t, _VecType):
+                self.cols[name] = [Matrix.zero(t.dt, t.n, 1) for _ in range(self.n)]
+                self.kinds[name] = None
+            elif isinstance(t, _MatType):
+                self.cols[name] = [Matrix.zero(t.dt, t.n, t.m) for _ in range(self.n)]
+                self.kinds[name] = None
+            else:
+                py = _py_of(t)
+                self.cols[name] = [py(0)] * self.n
+                self.kinds[name] = py
+        self.elem_cls = stype.elem_cls
+
+    def __getitem__(self, i):
+        return self.elem_cls(self, 0 if i is None else int(i))
+
+    def __setitem__(self, i, other):
+        i = 0 if i is None else int(i)
+        of, oi = object.__getattribute__(other, "_f"), object.__getattribute__(other, "_i")
+        for name, kind in self.kinds.items():
+            v = of.cols[name][oi]
+            self.cols[name][i] = v.copy() if kind is None else v
+
+    def __getattr__(self, name):
+        cols = self.__dict__.get("cols", {})
+        if name in cols:
+            return _Member(self, name)
+        raise AttributeError(name)
+
+
+class _StructType:
+    def __init__(self, cls):
+        self.members = dict(cls.__annotations__)
+        methods = {k: v for k, v in cls.__dict__.items() if callable(v)}
+        self.elem_cls = type(cls.__name__ + "Elem", (_Elem,), dict(methods, __slots__=()))
+
+    def field(self, shape):
+        return _StructField(self, shape)
+
+
+def dataclass(cls):
+    return _StructType(cls)
+
+
+def struct_class(cls):
+    return cls
+
+
+# ----------------------------------------------------------------------------------------------------------
+# loops
+# ----------------------------------------------------------------------------------------------------------
+class _NdRange:
+    def __init__(self, ranges):
+        self.ranges = [r if isinstance(r, tuple) else (0, r) for r in ranges]
+
+
+def ndrange(*ranges):
+    return _NdRange(ranges)
+
+
+def grouped(x):
+    if isinstance(x, _NdRange):
+        for idx in itertools.product(*[range(a, b) for a, b in x.ranges]):   # first axis slowest
+            yield Matrix(_raw=(len(idx), 1, list(idx)))
+    elif isinstance(x, (_StructField, _ScalarField)):
+        yield from range(x.n)
+    else:
+        raise TypeError("ti.grouped on unsupported object")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# by-reference helpers used by the AST pass
+# ----------------------------------------------------------------------------------------------------------
+class _Box:
+    __slots__ = ("v",)
+
+    def __init__(self, v):
+        self.v = v
+
+    def add(self, e):
+        self.v = self.v + e
+
+
+def _atomic(container, index, v, op):
+    old = container[index]
+    if op == "add":
+        container[index] = old + v
+    elif op == "sub":
+        container[index] = old - v
+    elif op == "max":
+        container[index] = max(old, v)
+    elif op == "min":
+        container[index] = min(old, v)
+    return old
+
+
+def atomic_add(*a):
+    raise RuntimeError("ti.atomic_* must be rewritten by the AST pass")
+
+
+atomic_sub = atomic_max = atomic_min = atomic_add
+
+
+class algorithms:
+    class PrefixSumExecutor:
+        def __init__(self, length):
+            self.length = length
+
+        def run(self, f):
+            s = 0
+            d = f.d
+            for i in range(len(d)):
+                s += d[i]
+                d[i] = s
+
+
+# ----------------------------------------------------------------------------------------------------------
+# AST pass for @ti.kernel / @ti.func
+# ----------------------------------------------------------------------------------------------------------
+def _is_ti_attr(node, names):
+    return (isinstance(node, ast.Attribute) and isinstance(node.value, ast.Name) and node.value.id == "ti"
+            and node.attr in names)
+
+
+class _Rewrite(ast.NodeTransformer):
+    def __init__(self):
+        self.tmpl = set()
+        self.counter = 0
+
+    def visit_FunctionDef(self, node):
+        node.decorator_list = []
+        for a in node.args.args:
+            an = a.annotation
+            if isinstance(an, ast.Call) and _is_ti_attr(an.func, {"template"}):
+                self.tmpl.add(a.arg)
+        node.returns = None
+        self.generic_visit(node)
+        return node
+
+    def visit_AugAssign(self, node):
+        self.generic_visit(node)
+        if isinstance(node.target, ast.Name) and node.target.id in self.tmpl and isinstance(node.op, ast.Add):
+            call = ast.Call(func=ast.Attribute(value=ast.Name(id=node.target.id, ctx=ast.Load()), attr="add",
+                                               ctx=ast.Load()), args=[node.value], keywords=[])
+            return ast.copy_location(ast.Expr(value=call), node)
+        return node
+
+    def visit_BinOp(self, node):
+        self.generic_visit(node)
+        if isinstance(node.op, ast.Mod):
+            call = ast.Call(func=ast.Attribute(value=ast.Name(id="ti", ctx=ast.Load()), attr="_mod", ctx=ast.Load()),
+                            args=[node.left, node.right], keywords=[])
+            return ast.copy_location(call, node)
+        return node
+
+    def visit_Call(self, node):
+        self.generic_visit(node)
+        if _is_ti_attr(node.func, {"atomic_add", "atomic_sub", "atomic_max", "atomic_min"}):
+            tgt = node.args[0]
+            if isinstance(tgt, ast.Subscript):
+                op = node.func.attr.split("_")[1]
+                call = ast.Call(func=ast.Attribute(value=ast.Name(id="ti", ctx=ast.Load()), attr="_atomic",
+                                                   ctx=ast.Load()),
+                                args=[tgt.value, tgt.slice, node.args[1], ast.Constant(value=op)], keywords=[])
+                return ast.copy_location(call, node)
+        return node
+
+    def visit_Expr(self, node):
+        v = node.value
+        # statement-level atomic on a local name:  ti.atomic_max(ymax, e)  ->  ymax = ti.max(ymax, e)
+        if isinstance(v, ast.Call) and _is_ti_attr(v.func, {"atomic_max", "atomic_min", "atomic_add", "atomic_sub"}) \
+                and isinstance(v.args[0], ast.Name):
+            self.generic_visit(node)
+            name = v.args[0].id
+            op = v.func.attr.split("_")[1]
+            if op in ("max", "min"):
+                val = ast.Call(func=ast.Attribute(value=ast.Name(id="ti", ctx=ast.Load()), attr=op, ctx=ast.Load()),
+                               args=[ast.Name(id=name, ctx=ast.Load()), v.args[1]], keywords=[])
+            else:
+                val = ast.BinOp(left=ast.Name(id=name, ctx=ast.Load()),
+                                op=ast.Add() if op == "add" else ast.Sub(), right=v.args[1])
+            return ast.copy_location(ast.Assign(targets=[ast.Name(id=name, ctx=ast.Store())], value=val), node)
+        # by-reference accumulator:  X.for_all_neighbors(i, task, acc)
+        if isinstance(v, ast.Call) and isinstance(v.func, ast.Attribute) and v.func.attr == "for_all_neighbors" \
+                and len(v.args) == 3 and isinstance(v.args[2], ast.Name) and v.args[2].id not in self.tmpl:
+            self.generic_visit(node)
+            acc = v.args[2].id
+            self.counter += 1
+            box = f"__box{self.counter}"
+            pre = ast.Assign(targets=[ast.Name(id=box, ctx=ast.Store())],
+                             value=ast.Call(func=ast.Attribute(value=ast.Name(id="ti", ctx=ast.Load()), attr="_Box",
+                                                               ctx=ast.Load()),
+                                            args=[ast.Name(id=acc, ctx=ast.Load())], keywords=[]))
+            v.args[2] = ast.Name(id=box, ctx=ast.Load())
+            post = ast.Assign(targets=[ast.Name(id=acc, ctx=ast.Store())],
+                              value=ast.Attribute(value=ast.Name(id=box, ctx=ast.Load()), attr="v", ctx=ast.Load()))
+            return [ast.copy_location(pre, node), node, ast.copy_location(post, node)]
+        self.generic_visit(node)
+        return node
+
+
+def _recompile(fn):
+    src = textwrap.dedent(inspect.getsource(fn))
+    tree = ast.parse(src)
+    tree = _Rewrite().visit(tree)
+    ast.fix_missing_locations(tree)
+    fname = inspect.getsourcefile(fn) or "<ti_shim>"
+    code = compile(tree, fname + ":ti_shim", "exec")
+    ns = {}
+    g = fn.__globals__
+    exec(code, g, ns)
+    new = ns[fn.__name__]
+    new.__ti_shim__ = True
+    return new
+
+
+def kernel(fn):
+    return _recompile(fn)
+
+
+def func(fn):
+    return _recompile(fn)
