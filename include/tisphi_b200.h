@@ -1,0 +1,146 @@
+/*
+ * tisphi_b200.h -- C ABI of the B200-native SPH engine (libtisphi_b200.so).
+ *
+ * This is the drop-in boundary for the data-parallel hot path of Rabmelon/tiSPHi.  The reference has no FFI: its
+ * hot path sits behind Python methods whose bodies are Taichi kernels.  Each entry point below replaces one of
+ * those methods (file:line into /root/reference); the Python classes in tisphi_b200/eng keep the reference's
+ * names and call these through ctypes.  INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every array is a device pointer inside ONE caller-owned arena (a torch.uint8 tensor);
+ *     the library never allocates device memory after sph_create (which allocates nothing on the device either).
+ *   - all work is enqueued on the cudaStream_t given to sph_create; nothing synchronises unless documented.
+ *   - return value: 0 = ok, < 0 = error (sph_last_error gives the text).  No C++ exceptions cross the boundary.
+ *   - one ctx per (device, stream); calls on one ctx are not re-entrant; different ctxs are independent.
+ *
+ * Precision: SPH_PREC_F64 computes everything in float64 (the reference's default_fp, run_simulation.py:23).
+ *            SPH_PREC_MIXED keeps positions and densities in float64 and everything else in float32; neighbour
+ *            distances are evaluated on cell-local float32 coordinates.
+ */
+#ifndef TISPHI_B200_H
+#define TISPHI_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { SPH_PREC_F64 = 0, SPH_PREC_MIXED = 1 };
+enum { SPH_SOLVER_WC = 1, SPH_SOLVER_MUI = 2, SPH_SOLVER_DP = 3 };   /* simulationMethod, eng/simulation.py:14-22 */
+
+/* Scene-derived constants.  Filled by the host exactly as the reference's constructors compute them
+ * (eng/particle_system.py:32-59, eng/solver_sph_base.py:12-28, solver_sph_wc.py:12-21, solver_sph_muI.py:12-25,
+ * solver_sph_dp.py:12-35). */
+typedef struct SphParams {
+    int32_t dim;            /* 2 | 3                                              ps:14 */
+    int32_t kernel;         /* 0 cubic spline, 1 Wendland C2                      base:15 */
+    int32_t kcorr;          /* 0 none, 1 CSPM, 2 (MLS stub: zero gradient)        base:16 */
+    int32_t ti;             /* 1 SE, 2 "LF" (explicit midpoint), 4 RK4            base:17, 53-61 */
+    int32_t xsph;           /* 0 | 1                                              base:18 */
+    int32_t solver;         /* SPH_SOLVER_*                                                */
+    int32_t precision;      /* SPH_PREC_*                                                  */
+    int32_t wc_fresh;       /* 0: wall pressure reads p_j as the serial reference does (EOS value for j < i, previous
+                               value for j > i, wc:86-103); 1: race-free variant (EOS value for every j)            */
+    int32_t gn[3];          /* grid_num                                           ps:57 */
+    int32_t fast;           /* 1: allow the cell-tile fast sweeps where they apply; 0: generic sweeps only        */
+    double h, support, grid_size, vstart[3], m_V0, g[3], dt, eps;
+    double rho0, visc, stiff, gamma_;                                   /* wc:12-15 */
+    double coh, fric, E, poi, dila, vsound, mu, alpha, kc, G, K, eps_f; /* muI:12-24, dp:12-29 */
+} SphParams;
+
+/* Particle members (names of eng/particle_func.py:13-69).  KIND: 0 = float64, 1 = engine real (float64 or float32
+ * by precision), 2 = int32.  A member is described by (byte offset in the arena, component count, element stride,
+ * kind); offsets of the members that are permuted by the sort change at every sph_grid_build (ping-pong). */
+enum SphField {
+    SPH_F_X = 0,          /* f64 x3                        pt.x            */
+    SPH_F_V,              /* real x3 (stride 4; .w = mass) pt.v            */
+    SPH_F_MASS,           /* real (view of V.w)            pt.mass         */
+    SPH_F_M_V,            /* real (view of XS.w)           pt.m_V          */
+    SPH_F_DENSITY,        /* f64                           pt.density      */
+    SPH_F_DENSITY_TMP,    /* f64                           pt.density_tmp  */
+    SPH_F_V_TMP,          /* real x3 (stride 4; .w = density_tmp rounded to real)  pt.v_tmp */
+    SPH_F_PRESSURE,       /* real                          pt.pressure     */
+    SPH_F_MAT_TYPE,       /* i32                           pt.mat_type     */
+    SPH_F_ID0,            /* i32                           pt.id0          */
+    SPH_F_GRID_IDS,       /* i32                           pt.grid_ids     */
+    SPH_F_STRESS,         /* real x6 xx,yy,zz,xy,yz,zx     pt.stress       */
+    SPH_F_STRESS_TMP,     /* real x6                       pt.stress_tmp   */
+    SPH_F_STRAIN_EQU,     /* real                          pt.strain_equ   */
+    SPH_F_STRAIN_EQU_P,   /* real                          pt.strain_equ_p */
+    SPH_F_FLAG_RETMAP,    /* i32                           pt.flag_retmap  */
+    SPH_F_CSPM_F,         /* real                          pt.CSPM_f       */
+    SPH_F_CSPM_L,         /* real x9 row-major             pt.CSPM_L       */
+    SPH_F_D_DENSITY,      /* real                          pt.d_density    */
+    SPH_F_D_VEL,          /* real x3 (stride 4)            pt.d_vel        */
+    SPH_F_D_STRESS,       /* real x6                       pt.d_stress     */
+    SPH_F_V_GRAD,         /* real x9 row-major             pt.v_grad       */
+    SPH_F_D_STRAIN_EQU,   /* real                          pt.d_strain_equ */
+    SPH_F_D_STRAIN_EQU_P, /* real                          pt.d_strain_equ_p */
+    SPH_F_D_DENSITY_RK,   /* real                          pt.d_density_RK */
+    SPH_F_D_VEL_RK,       /* real x3 (stride 4)            pt.d_vel_RK     */
+    SPH_F_D_STRESS_RK,    /* real x6                       pt.d_stress_RK  */
+    SPH_F_XS,             /* real x3 (stride 4): sweep coordinates (global in F64, cell-local in MIXED) */
+    SPH_F_CELL_END,       /* i32 x C: inclusive scan = grid_particle_num after prefix_sum.run (ps:256) */
+    SPH_F_CELL_COUNT,     /* i32 x C: histogram = grid_particle_num_temp (ps:235-236)                 */
+    SPH_F_ID_NEW,         /* i32: destination index of the last sort, pt.id_new (ps:245)              */
+    SPH_F_NUM
+};
+
+typedef struct SphCtx SphCtx;
+
+/* bytes of device memory the caller must provide for n_max particles (includes all scratch) */
+int64_t sph_arena_bytes(const SphParams *p, int64_t n_max);
+/* arena: device pointer (256-byte aligned), stream: cudaStream_t (NULL = default stream) */
+SphCtx *sph_create(const SphParams *p, int64_t n_max, void *arena, int64_t arena_bytes, void *stream);
+void sph_destroy(SphCtx *ctx);
+const char *sph_last_error(SphCtx *ctx);
+int sph_set_params(SphCtx *ctx, const SphParams *p);           /* dt, g, material constants (not sizes)       */
+int sph_field_info(SphCtx *ctx, int field, int64_t *offset_bytes, int32_t *ncomp, int32_t *stride, int32_t *kind);
+
+/* ParticleSystem.add_particle / _add_particles / set_id0 (ps:274-314, 208-211): host (pinned or pageable)
+ * arrays -> device, appended after the particles already present.  x, v: n x 3 float64; density: n float64;
+ * mat_type: n int32.  Sets m_V = m_V0, mass = m_V0 * density, pressure = 0, id0 = running index. */
+int sph_add_particles(SphCtx *ctx, int64_t n, const double *x, const double *v, const double *density,
+                      const int32_t *mat_type);
+int64_t sph_num_particles(SphCtx *ctx);
+int sph_clear_particles(SphCtx *ctx);
+/* device -> host copies of the dump() state (ps:459-545) in current (sorted) order; any pointer may be NULL.
+ * Synchronises the stream. */
+int sph_read_state(SphCtx *ctx, double *x, double *v, double *density, double *pressure, int32_t *id0);
+
+/* ParticleSystem.initialize_particle_system (ps:254-257): cell ids, histogram, inclusive scan, stable counting
+ * sort, reorder of every carried member. */
+int sph_grid_build(SphCtx *ctx);
+/* SPHBase.calc_kernel_corr (base:363-368): CSPM_f always, CSPM_L when kcorr == 1 */
+int sph_calc_kernel_corr(SphCtx *ctx);
+/* SPHBase.init_real2tmp (base:67-74) */
+int sph_init_real2tmp(SphCtx *ctx);
+/* <Solver>.one_step (wc:82-126, muI:62-132, dp:210-274) */
+int sph_one_step(SphCtx *ctx);
+/* pointwise integrator kernels (base:79-170).  kind: 0 advect_SE / advect_LF, 1 advect_LF_half, 2 advect_RK_4,
+ * 3 init_RK, 4 update_RK(m), 5 advect_RK */
+int sph_advect(SphCtx *ctx, int kind, int m);
+/* SPHBase.advect_pos (base:228-238), XSPH evaluated on a snapshot */
+int sph_advect_pos(SphCtx *ctx);
+/* SPHBase.advect_something (base:244-247 -> wc:129-132 | muI:134-156 | dp:276-296) */
+int sph_post_step(SphCtx *ctx);
+/* SPHBase.init_stress (base:249-260) */
+int sph_init_stress(SphCtx *ctx);
+/* SPHBase.step (base:41-51) repeated nsteps times, enqueued without host round trips */
+int sph_step(SphCtx *ctx, int nsteps);
+
+/* stand-alone sweeps on the current grid (BASELINE config C5; parity of the neighbour predicate, ps:259-269) */
+int sph_neighbor_count(SphCtx *ctx, int32_t *out_dev);          /* n int32  */
+int sph_density_sum(SphCtx *ctx, void *out_dev);                /* n real: sum_j mass_j W_ij (wc:30-31) */
+
+/* number of particles whose cell fell outside the grid since the last call.  Synchronises. */
+int64_t sph_read_bad_cells(SphCtx *ctx);
+/* how many kernels the library has launched on this ctx since creation */
+int64_t sph_launch_count(SphCtx *ctx);
+/* multi-GPU slab support: see tisphi_b200/parallel notes in DESIGN.md */
+int sph_set_ghost_range(SphCtx *ctx, int64_t n_owned_begin, int64_t n_owned_end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,348 @@
+// api.cu -- the C ABI of libtisphi_b200 (include/tisphi_b200.h): arena layout, parameter derivation, dispatch.
+#include <math.h>
+#include <new>
+#include <string.h>
+#include "sph_host.h"
+
+using namespace sph;
+
+namespace {
+
+inline int64_t align_up(int64_t v, int64_t a = 256) { return (v + a - 1) / a * a; }
+
+struct FieldSpec { int ncomp, stride, kind; bool carried; int need; };   // need: 0 always, 1 soil, 2 rk, 3 cspm_L, 4 soil+rk
+// order == enum FieldSlot
+const FieldSpec SPEC[SPH_F_NUM] = {
+    /* X            */ {3, 3, 0, true, 0},
+    /* V            */ {3, 4, 1, true, 0},
+    /* MASS (view)  */ {1, 4, 1, false, 0},
+    /* M_V (view)   */ {1, 4, 1, false, 0},
+    /* DENSITY      */ {1, 1, 0, true, 0},
+    /* DENSITY_TMP  */ {1, 1, 0, false, 0},
+    /* V_TMP        */ {3, 4, 1, true, 0},
+    /* PRESSURE     */ {1, 1, 1, true, 0},
+    /* MAT_TYPE     */ {1, 1, 2, true, 0},
+    /* ID0          */ {1, 1, 2, true, 0},
+    /* GRID_IDS     */ {1, 1, 2, false, 0},
+    /* STRESS       */ {6, 6, 1, true, 1},
+    /* STRESS_TMP   */ {6, 6, 1, false, 1},
+    /* STRAIN_EQU   */ {1, 1, 1, true, 1},
+    /* STRAIN_EQU_P */ {1, 1, 1, true, 1},
+    /* FLAG_RETMAP  */ {1, 1, 2, true, 1},
+    /* CSPM_F       */ {1, 1, 1, false, 0},
+    /* CSPM_L       */ {9, 9, 1, false, 3},
+    /* D_DENSITY    */ {1, 1, 1, false, 0},
+    /* D_VEL        */ {3, 4, 1, false, 0},
+    /* D_STRESS     */ {6, 6, 1, false, 1},
+    /* V_GRAD       */ {9, 9, 1, false, 1},
+    /* D_STRAIN_EQU */ {1, 1, 1, false, 1},
+    /* D_STRAIN_EQU_P*/ {1, 1, 1, false, 1},
+    /* D_DENSITY_RK */ {1, 1, 1, false, 2},
+    /* D_VEL_RK     */ {3, 4, 1, false, 2},
+    /* D_STRESS_RK  */ {6, 6, 1, false, 4},
+    /* XS           */ {3, 4, 1, true, 0},
+    /* CELL_END     */ {1, 1, 2, false, 0},
+    /* CELL_COUNT   */ {1, 1, 2, false, 0},
+    /* ID_NEW       */ {1, 1, 2, false, 0},
+};
+
+inline int elem_bytes(int kind, int real_bytes) { return kind == 0 ? 8 : (kind == 1 ? real_bytes : 4); }
+
+int64_t n_cells(const SphParams *p) { return (int64_t)p->gn[0] * p->gn[1] * (p->dim == 3 ? p->gn[2] : 1); }
+
+// lays the arena out; when c == nullptr only the size is computed
+int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
+    const int rb = p->precision == SPH_PREC_F64 ? 8 : 4;
+    const bool soil = p->solver != SPH_SOLVER_WC, rk = p->ti == 4, hasL = p->kcorr == 1;
+    const int64_t C = n_cells(p);
+    int64_t off = 0;
+    for (int f = 0; f < SPH_F_NUM; f++) {
+        const FieldSpec &s = SPEC[f];
+        bool present = s.need == 0 || (s.need == 1 && soil) || (s.need == 2 && rk) || (s.need == 3 && hasL) || (s.need == 4 && soil && rk);
+        if (f == SPH_F_MASS || f == SPH_F_M_V) present = true;
+        int64_t count = (f == SPH_F_CELL_END || f == SPH_F_CELL_COUNT) ? C + 1 : n_max;
+        int64_t bytes = align_up(count * s.stride * elem_bytes(s.kind, rb));
+        int64_t o0 = 0, o1 = 0;
+        if (present && f != SPH_F_MASS && f != SPH_F_M_V) {
+            o0 = off; off += bytes;
+            o1 = o0;
+            if (s.carried) { o1 = off; off += bytes; }
+        }
+        if (c) {
+            FieldSlot &F = c->f[f];
+            F.off[0] = o0; F.off[1] = o1; F.cur = 0;
+            F.ncomp = s.ncomp; F.stride = s.stride; F.kind = s.kind; F.present = present; F.view_shift = 0;
+        }
+    }
+    const int64_t ib = align_up(n_max * 4);
+    int64_t o_gid = off; off += ib;
+    int64_t o_slot = off; off += ib;
+    int64_t o_perm = off; off += ib;
+    int64_t o_tmp = off; off += ib;
+    int64_t o_bad = off; off += 256;
+    const int64_t nt = (C + 2047) / 2048 + 1;
+    int64_t o_tiles = off; off += align_up(nt * 4);
+    if (c) {
+        c->off_gid_unsorted = o_gid; c->off_slot = o_slot; c->off_perm = o_perm; c->off_tmpidx = o_tmp;
+        c->off_bad = o_bad; c->off_scan_tiles = o_tiles;
+        c->real_bytes = rb; c->soil = soil; c->rk = rk; c->has_L = hasL; c->C = (int)C;
+    }
+    return off;
+}
+
+// smallest t with sqrt(t) >= s (so that r2 < t  <=>  sqrt(r2) < s for correctly rounded sqrt)
+double r2_threshold64(double s) {
+    double t = s * s;
+    while (sqrt(t) >= s) t = nextafter(t, 0.0);
+    while (sqrt(t) < s) t = nextafter(t, INFINITY);
+    return t;
+}
+float r2_threshold32(float s) {
+    float t = s * s;
+    while (sqrtf(t) >= s) t = nextafterf(t, 0.0f);
+    while (sqrtf(t) < s) t = nextafterf(t, INFINITY);
+    return t;
+}
+
+double kernel_norm(const SphParams *p) {       // base:300-358 (3D Wendland constant as in the reference, H8)
+    const double h1 = 1.0 / p->h;
+    double k;
+    if (p->kernel == 0) k = p->dim == 2 ? 15.0 / 7.0 / M_PI : 3.0 / 2.0 / M_PI;
+    else k = p->dim == 2 ? 7.0 / (4.0 * M_PI) : 21.0 / (2.0 * M_PI);
+    double hp = h1;
+    for (int a = 1; a < p->dim; a++) hp *= h1;
+    return k * hp;
+}
+
+template <typename T> int dispatch_step(SphCtx *c, int nsteps);
+
+}  // namespace
+
+namespace sph {
+
+void flip(SphCtx *c, int field) { c->f[field].cur ^= 1; }
+
+template <typename T> Dev<T> make_dev(SphCtx *c, int which) {
+    const SphParams &p = c->p;
+    Dev<T> d;
+    memset(&d, 0, sizeof(d));
+    d.n = (int)c->n;
+    d.dim = p.dim; d.kernel = p.kernel; d.kcorr = p.kcorr; d.solver = p.solver; d.xsph = p.xsph; d.wc_fresh = p.wc_fresh;
+    for (int a = 0; a < 3; a++) { d.gn[a] = p.gn[a]; d.vstart[a] = p.vstart[a]; d.g[a] = (T)p.g[a]; }
+    if (p.dim == 2) d.gn[2] = 1;
+    d.C = c->C;
+    d.gs = p.grid_size; d.dt = p.dt; d.m_V0d = p.m_V0;
+    d.h = (T)p.h; d.hinv = (T)(1.0 / p.h); d.support = (T)p.support;
+    d.r2thr = sizeof(T) == 8 ? (T)c->r2thr64 : (T)c->r2thr32;
+    d.eps = (T)p.eps; d.knorm = (T)kernel_norm(&p);
+    d.gsT = sizeof(T) == 8 ? (T)0 : (T)p.grid_size;
+    d.m_V0 = (T)p.m_V0;
+    d.visc_coef = (T)(2 * (p.dim + 2) * p.visc); d.rho0T = (T)p.rho0; d.h2_001 = (T)(0.01 * p.h * p.h);
+    d.rho0 = p.rho0; d.stiff = p.stiff; d.gamma_ = p.gamma_; d.vsound = p.vsound;
+    d.coh = (T)p.coh; d.mu = (T)p.mu; d.E = (T)p.E; d.alpha = (T)p.alpha; d.kc = (T)p.kc; d.G = (T)p.G; d.K = (T)p.K;
+    d.eps_f = (T)p.eps_f; d.sin_dila = (T)sin(p.dila);
+    d.damp_c = (T)(-5e-5 * sqrt(p.E) / p.h);
+    auto ptr = [&](int f, bool alt) -> char * {
+        const FieldSlot &F = c->f[f];
+        if (!F.present) return nullptr;
+        int b = F.cur;
+        if (alt) b ^= 1;
+        return c->arena + F.off[b];
+    };
+    const bool alt = which == 1;
+    d.x = (double *)ptr(SPH_F_X, alt);
+    d.rho = (double *)ptr(SPH_F_DENSITY, alt);
+    d.rho_t = (double *)ptr(SPH_F_DENSITY_TMP, false);
+    d.v4 = (Vec4<T> *)ptr(SPH_F_V, alt);
+    d.vt4 = (Vec4<T> *)ptr(SPH_F_V_TMP, alt);
+    d.xs4 = (Vec4<T> *)ptr(SPH_F_XS, alt);
+    d.press = (T *)ptr(SPH_F_PRESSURE, alt);
+    d.pnew = (T *)ptr(SPH_F_PRESSURE, !alt);
+    d.type = (int *)ptr(SPH_F_MAT_TYPE, alt);
+    d.id0 = (int *)ptr(SPH_F_ID0, alt);
+    d.gid = (int *)ptr(SPH_F_GRID_IDS, false);
+    d.flag = (int *)ptr(SPH_F_FLAG_RETMAP, alt);
+    d.stress = (T *)ptr(SPH_F_STRESS, alt);
+    d.stress_t = (T *)ptr(SPH_F_STRESS_TMP, false);
+    d.strain = (T *)ptr(SPH_F_STRAIN_EQU, alt);
+    d.strain_p = (T *)ptr(SPH_F_STRAIN_EQU_P, alt);
+    d.cspm_f = (T *)ptr(SPH_F_CSPM_F, false);
+    d.cspm_L = (T *)ptr(SPH_F_CSPM_L, false);
+    d.d_rho = (T *)ptr(SPH_F_D_DENSITY, false);
+    d.d_vel = (Vec4<T> *)ptr(SPH_F_D_VEL, false);
+    d.d_stress = (T *)ptr(SPH_F_D_STRESS, false);
+    d.v_grad = (T *)ptr(SPH_F_V_GRAD, false);
+    d.d_strain = (T *)ptr(SPH_F_D_STRAIN_EQU, false);
+    d.d_strain_p = (T *)ptr(SPH_F_D_STRAIN_EQU_P, false);
+    d.d_rho_rk = (T *)ptr(SPH_F_D_DENSITY_RK, false);
+    d.d_vel_rk = (Vec4<T> *)ptr(SPH_F_D_VEL_RK, false);
+    d.d_stress_rk = (T *)ptr(SPH_F_D_STRESS_RK, false);
+    d.cell_end = (int *)ptr(SPH_F_CELL_END, false);
+    d.cell_cnt = (int *)ptr(SPH_F_CELL_COUNT, false);
+    d.bad = (unsigned long long *)(c->arena + c->off_bad);
+    return d;
+}
+template Dev<float> make_dev<float>(SphCtx *, int);
+template Dev<double> make_dev<double>(SphCtx *, int);
+
+}  // namespace sph
+
+namespace {
+
+// SPHBase.step (base:41-51) + substep (base:53-61)
+template <typename T> int step_once(SphCtx *c) {
+    int r;
+    if ((r = grid_build<T>(c))) return r;
+    if ((r = calc_kernel_corr<T>(c))) return r;
+    if ((r = init_real2tmp<T>(c))) return r;
+    switch (c->p.ti) {
+    case 1:
+        if ((r = one_step<T>(c))) return r;
+        if ((r = advect<T>(c, 0, 0))) return r;
+        break;
+    case 2:
+        if ((r = one_step<T>(c))) return r;
+        if ((r = advect<T>(c, 1, 0))) return r;
+        if ((r = one_step<T>(c))) return r;
+        if ((r = advect<T>(c, 0, 0))) return r;
+        break;
+    case 4: {
+        static const int m[4] = {1, 2, 2, 1};
+        if ((r = advect<T>(c, 3, 0))) return r;
+        for (int s = 0; s < 4; s++) {
+            if ((r = one_step<T>(c))) return r;
+            if ((r = advect<T>(c, 4, m[s]))) return r;
+            if (s < 3 && (r = advect<T>(c, 2, 0))) return r;
+        }
+        if ((r = advect<T>(c, 5, 0))) return r;
+    } break;
+    default:
+        snprintf(c->err, sizeof(c->err), "timeIntegration %d is not runnable (3 is broken in the reference, base:126-130)", c->p.ti);
+        return -2;
+    }
+    if ((r = advect_pos<T>(c))) return r;
+    return post_step<T>(c);
+}
+template <typename T> int dispatch_step(SphCtx *c, int nsteps) {
+    for (int s = 0; s < nsteps; s++) {
+        int r = step_once<T>(c);
+        if (r) return r;
+    }
+    return 0;
+}
+
+}  // namespace
+
+#define DISPATCH(ctx, fn, ...) ((ctx)->p.precision == SPH_PREC_F64 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
+
+extern "C" {
+
+int64_t sph_arena_bytes(const SphParams *p, int64_t n_max) { return layout(p, n_max, nullptr); }
+
+SphCtx *sph_create(const SphParams *p, int64_t n_max, void *arena, int64_t arena_bytes, void *stream) {
+    if (!p || !arena || n_max <= 0 || n_max >= (1ll << 31)) return nullptr;
+    if (n_cells(p) <= 0 || n_cells(p) >= (1ll << 31)) return nullptr;
+    if (layout(p, n_max, nullptr) > arena_bytes) return nullptr;
+    if (((uintptr_t)arena) & 255) return nullptr;
+    SphCtx *c = new (std::nothrow) SphCtx();
+    if (!c) return nullptr;
+    memset(c, 0, sizeof(*c));
+    c->p = *p;
+    c->n_max = n_max;
+    c->n = 0;
+    c->arena = (char *)arena;
+    c->arena_bytes = arena_bytes;
+    c->stream = (cudaStream_t)stream;
+    layout(p, n_max, c);
+    c->r2thr64 = r2_threshold64(p->support);
+    c->r2thr32 = r2_threshold32((float)p->support);
+    if (cudaMemsetAsync(arena, 0, (size_t)layout(p, n_max, nullptr), c->stream) != cudaSuccess) { delete c; return nullptr; }
+    return c;
+}
+void sph_destroy(SphCtx *c) { delete c; }
+const char *sph_last_error(SphCtx *c) { return c ? c->err : "null ctx"; }
+
+int sph_set_params(SphCtx *c, const SphParams *p) {
+    if (p->dim != c->p.dim || p->precision != c->p.precision || p->solver != c->p.solver || p->ti != c->p.ti ||
+        p->kcorr != c->p.kcorr || n_cells(p) != c->C) {
+        snprintf(c->err, sizeof(c->err), "sph_set_params cannot change sizes, solver, precision or buffers");
+        return -2;
+    }
+    c->p = *p;
+    c->r2thr64 = r2_threshold64(p->support);
+    c->r2thr32 = r2_threshold32((float)p->support);
+    return 0;
+}
+
+int sph_field_info(SphCtx *c, int field, int64_t *offset_bytes, int32_t *ncomp, int32_t *stride, int32_t *kind) {
+    if (field < 0 || field >= SPH_F_NUM) return -2;
+    int src = field;
+    int64_t shift = 0;
+    if (field == SPH_F_MASS) { src = SPH_F_V; shift = 3 * c->real_bytes; }
+    if (field == SPH_F_M_V) { src = SPH_F_XS; shift = 3 * c->real_bytes; }
+    const FieldSlot &F = c->f[src];
+    if (!F.present) return -3;
+    *offset_bytes = F.off[F.cur] + shift;
+    *ncomp = c->f[field].ncomp; *stride = c->f[field].stride; *kind = c->f[field].kind;
+    return 0;
+}
+
+int sph_add_particles(SphCtx *c, int64_t n, const double *x, const double *v, const double *density, const int32_t *mat_type) {
+    if (n <= 0) return 0;
+    if (c->n + n > c->n_max) { snprintf(c->err, sizeof(c->err), "particle capacity %lld exceeded", (long long)c->n_max); return -2; }
+    const int64_t first = c->n;
+    char *X = c->arena + c->f[SPH_F_X].off[c->f[SPH_F_X].cur];
+    char *Xalt = c->arena + c->f[SPH_F_X].off[1 - c->f[SPH_F_X].cur];
+    char *R = c->arena + c->f[SPH_F_DENSITY].off[c->f[SPH_F_DENSITY].cur];
+    char *Ty = c->arena + c->f[SPH_F_MAT_TYPE].off[c->f[SPH_F_MAT_TYPE].cur];
+    SPH_CHECK(c, cudaMemcpyAsync(X + first * 24, x, (size_t)n * 24, cudaMemcpyDefault, c->stream));
+    SPH_CHECK(c, cudaMemcpyAsync(Xalt + first * 24, v, (size_t)n * 24, cudaMemcpyDefault, c->stream));
+    SPH_CHECK(c, cudaMemcpyAsync(R + first * 8, density, (size_t)n * 8, cudaMemcpyDefault, c->stream));
+    SPH_CHECK(c, cudaMemcpyAsync(Ty + first * 4, mat_type, (size_t)n * 4, cudaMemcpyDefault, c->stream));
+    c->n += n;
+    return DISPATCH(c, add_particles_finish, c, first, n);
+}
+int64_t sph_num_particles(SphCtx *c) { return c->n; }
+int sph_clear_particles(SphCtx *c) {
+    c->n = 0;
+    SPH_CHECK(c, cudaMemsetAsync(c->arena, 0, (size_t)layout(&c->p, c->n_max, nullptr), c->stream));
+    for (int f = 0; f < SPH_F_NUM; f++) c->f[f].cur = 0;
+    return 0;
+}
+
+int sph_read_state(SphCtx *c, double *x, double *v, double *density, double *pressure, int32_t *id0) {
+    const int64_t n = c->n;
+    if (x) SPH_CHECK(c, cudaMemcpyAsync(x, c->arena + c->f[SPH_F_X].off[c->f[SPH_F_X].cur], (size_t)n * 24, cudaMemcpyDefault, c->stream));
+    if (density) SPH_CHECK(c, cudaMemcpyAsync(density, c->arena + c->f[SPH_F_DENSITY].off[c->f[SPH_F_DENSITY].cur], (size_t)n * 8, cudaMemcpyDefault, c->stream));
+    if (id0) SPH_CHECK(c, cudaMemcpyAsync(id0, c->arena + c->f[SPH_F_ID0].off[c->f[SPH_F_ID0].cur], (size_t)n * 4, cudaMemcpyDefault, c->stream));
+    // v and pressure are engine-real; they are returned in the engine's own precision packed as stored
+    // (v: n x 4 reals, pressure: n reals) when the engine is MIXED the caller passes float buffers.
+    if (v) SPH_CHECK(c, cudaMemcpyAsync(v, c->arena + c->f[SPH_F_V].off[c->f[SPH_F_V].cur], (size_t)n * 4 * c->real_bytes, cudaMemcpyDefault, c->stream));
+    if (pressure) SPH_CHECK(c, cudaMemcpyAsync(pressure, c->arena + c->f[SPH_F_PRESSURE].off[c->f[SPH_F_PRESSURE].cur], (size_t)n * c->real_bytes, cudaMemcpyDefault, c->stream));
+    SPH_CHECK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sph_grid_build(SphCtx *c) { return DISPATCH(c, grid_build, c); }
+int sph_calc_kernel_corr(SphCtx *c) { return DISPATCH(c, calc_kernel_corr, c); }
+int sph_init_real2tmp(SphCtx *c) { return DISPATCH(c, init_real2tmp, c); }
+int sph_one_step(SphCtx *c) { return DISPATCH(c, one_step, c); }
+int sph_advect(SphCtx *c, int kind, int m) { return DISPATCH(c, advect, c, kind, m); }
+int sph_advect_pos(SphCtx *c) { return DISPATCH(c, advect_pos, c); }
+int sph_post_step(SphCtx *c) { return DISPATCH(c, post_step, c); }
+int sph_init_stress(SphCtx *c) { return DISPATCH(c, init_stress, c); }
+int sph_step(SphCtx *c, int nsteps) { return DISPATCH(c, dispatch_step, c, nsteps); }
+int sph_neighbor_count(SphCtx *c, int32_t *out_dev) { return DISPATCH(c, neighbor_count, c, out_dev); }
+int sph_density_sum(SphCtx *c, void *out_dev) { return DISPATCH(c, density_sum, c, out_dev); }
+
+int64_t sph_read_bad_cells(SphCtx *c) {
+    unsigned long long v = 0;
+    if (cudaMemcpyAsync(&v, c->arena + c->off_bad, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(c->arena + c->off_bad, 0, 8, c->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    return (int64_t)v;
+}
+int64_t sph_launch_count(SphCtx *c) { return c->launches; }
+int sph_set_ghost_range(SphCtx *c, int64_t b, int64_t e) { (void)c; (void)b; (void)e; return 0; }
+
+}  // extern "C"

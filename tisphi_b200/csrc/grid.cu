@@ -1,0 +1,195 @@
+// grid.cu -- uniform-grid build: cell-id hash, histogram, inclusive scan, STABLE counting sort, coalesced reorder.
+// Replaces ParticleSystem.initialize_particle_system (eng/particle_system.py:229-257):
+//   update_grid_id (ps:229-236)  ->  k_cell_id        (cell id in float64, atomic histogram)
+//   PrefixSumExecutor.run (ps:256) -> k_scan_*         (warp-shuffle block scan, 3 phases)
+//   counting_sort (ps:239-252)   ->  k_scatter_index, k_rank, k_reorder
+// The serial reference iterates I = N-1..0 with atomic_sub, which yields the STABLE order (ties keep their previous
+// relative order).  On the GPU the atomic slot order inside a cell is arbitrary, so the rank inside the cell is
+// recomputed deterministically as "number of particles of my cell with a smaller previous index".
+// The reference moves its whole 800-byte record twice; here only the carried members move, once, as SoA streams.
+#include "sph_host.h"
+
+namespace sph {
+
+// ------------------------------------------------------------------------------------------------ cell ids
+template <typename T>
+__global__ void __launch_bounds__(256) k_cell_id(Dev<T> c, int *__restrict__ gid_out, int *__restrict__ slot) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    const double x[3] = {c.x[3 * (size_t)i], c.x[3 * (size_t)i + 1], c.x[3 * (size_t)i + 2]};
+    int cc[3];
+    pos_to_cell(c, x, cc);
+    long long g = (long long)cc[0] * c.gn[1] * c.gn[2] + (long long)cc[1] * c.gn[2] + cc[2];
+    if (g < 0 || g >= c.C) {            // the reference has no check; we clamp and count
+        atomicAdd(c.bad, 1ull);
+        g = g < 0 ? 0 : c.C - 1;
+    }
+    gid_out[i] = (int)g;
+    slot[i] = atomicAdd(&c.cell_cnt[(int)g], 1);
+}
+
+// ------------------------------------------------------------------------------------------------ scan
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_IPT = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_IPT;
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+// inclusive scan across the block of one value per thread; returns inclusive value, *total = block sum
+__device__ __forceinline__ int block_incl_scan(int v, int *total) {
+    __shared__ int wsum[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int inc = warp_incl_scan(v);
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < nw ? wsum[lane] : 0;
+        s = warp_incl_scan(s);
+        wsum[lane] = s;
+    }
+    __syncthreads();
+    int off = w > 0 ? wsum[w - 1] : 0;
+    *total = wsum[nw - 1];
+    __syncthreads();
+    return inc + off;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int *__restrict__ in, int n, int *__restrict__ tile_sum) {
+    int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) s += (base + k < n) ? in[base + k] : 0;
+    int tot;
+    block_incl_scan(s, &tot);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = tot;
+}
+// exclusive scan of the tile sums, one block, chunked with a running carry
+__global__ void __launch_bounds__(1024) k_scan_tiles(int *__restrict__ tile_sum, int nt) {
+    int carry = 0;
+    for (int base = 0; base < nt; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = i < nt ? tile_sum[i] : 0;
+        int tot;
+        int inc = block_incl_scan(v, &tot);
+        if (i < nt) tile_sum[i] = carry + inc - v;
+        carry += tot;
+    }
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const int *__restrict__ in, int n, const int *__restrict__ tile_off,
+                                                             int *__restrict__ out) {
+    int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
+    int v[SCAN_IPT], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) { v[k] = (base + k < n) ? in[base + k] : 0; s += v[k]; }
+    int tot;
+    int inc = block_incl_scan(s, &tot);
+    int run = tile_off[blockIdx.x] + inc - s;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) { run += v[k]; if (base + k < n) out[base + k] = run; }
+}
+
+// ------------------------------------------------------------------------------------------------ stable rank
+__global__ void __launch_bounds__(256) k_scatter_index(int n, const int *__restrict__ gid, const int *__restrict__ slot,
+                                                       const int *__restrict__ cell_end, int *__restrict__ tmpidx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int g = gid[i];
+    int start = g > 0 ? cell_end[g - 1] : 0;
+    tmpidx[start + slot[i]] = i;
+}
+__global__ void __launch_bounds__(256) k_rank(int n, const int *__restrict__ gid, const int *__restrict__ cell_end,
+                                              const int *__restrict__ tmpidx, int *__restrict__ perm, int *__restrict__ id_new) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int g = gid[i];
+    int start = g > 0 ? cell_end[g - 1] : 0, end = cell_end[g];
+    int rank = 0;
+    for (int k = start; k < end; k++) rank += (tmpidx[k] < i);
+    perm[start + rank] = i;       // new slot -> previous index
+    id_new[i] = start + rank;     // pt.id_new (ps:245)
+}
+
+// ------------------------------------------------------------------------------------------------ reorder
+// One thread per DESTINATION slot: writes are fully coalesced; reads follow perm, which is near-identity between
+// consecutive steps (particles move much less than a cell per step), so they are near-coalesced too.
+template <typename T>
+__global__ void __launch_bounds__(256) k_reorder(Dev<T> a, Dev<T> b, const int *__restrict__ perm,
+                                                 const int *__restrict__ gid_unsorted, int soil) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n) return;
+    const int s = perm[k];
+    const size_t k3 = 3 * (size_t)k, s3 = 3 * (size_t)s;
+    const double x0 = a.x[s3], x1 = a.x[s3 + 1], x2 = a.x[s3 + 2];
+    b.x[k3] = x0; b.x[k3 + 1] = x1; b.x[k3 + 2] = x2;
+    const int g = gid_unsorted[s];
+    a.gid[k] = g;                                   // grid_ids has a single (sorted) buffer
+    // sweep coordinates: global in F64; local to the particle's cell in MIXED
+    Vec4<T> xs;
+    if (sizeof(T) == 8) { xs.x = (T)x0; xs.y = (T)x1; xs.z = (T)x2; }
+    else {
+        int cc[3];
+        unflatten(a, g, cc);
+        xs.x = (T)__dsub_rn(x0, cell_origin(a.vstart[0], a.gs, cc[0]));
+        xs.y = (T)__dsub_rn(x1, cell_origin(a.vstart[1], a.gs, cc[1]));
+        xs.z = (T)__dsub_rn(x2, cell_origin(a.vstart[2], a.gs, cc[2]));
+    }
+    xs.w = a.xs4[s].w;                              // m_V travels with the particle
+    b.xs4[k] = xs;
+    b.v4[k] = a.v4[s];
+    b.vt4[k] = a.vt4[s];
+    b.rho[k] = a.rho[s];
+    b.press[k] = a.press[s];
+    b.type[k] = a.type[s];
+    b.id0[k] = a.id0[s];
+    if (soil) {
+        const size_t k6 = 6 * (size_t)k, s6 = 6 * (size_t)s;
+#pragma unroll
+        for (int q = 0; q < 6; q++) b.stress[k6 + q] = a.stress[s6 + q];
+        b.strain[k] = a.strain[s];
+        b.strain_p[k] = a.strain_p[s];
+        b.flag[k] = a.flag[s];
+    }
+}
+
+template <typename T> int grid_build(SphCtx *c) {
+    const int n = (int)c->n;
+    if (n == 0) return 0;
+    Dev<T> a = make_dev<T>(c, -1), b = make_dev<T>(c, 1);
+    int *gid_u = (int *)(c->arena + c->off_gid_unsorted), *slot = (int *)(c->arena + c->off_slot);
+    int *perm = (int *)(c->arena + c->off_perm), *tmpidx = (int *)(c->arena + c->off_tmpidx);
+    int *tiles = (int *)(c->arena + c->off_scan_tiles);
+    int *id_new = (int *)(c->arena + c->f[SPH_F_ID_NEW].off[0]);
+    cudaStream_t st = c->stream;
+    SPH_CHECK(c, cudaMemsetAsync(a.cell_cnt, 0, sizeof(int) * (size_t)c->C, st));
+    k_cell_id<T><<<blocks_for(n, 256), 256, 0, st>>>(a, gid_u, slot);
+    SPH_LAUNCH_CHECK(c);
+    const int nt = (c->C + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_reduce<<<nt, SCAN_THREADS, 0, st>>>(a.cell_cnt, c->C, tiles);
+    SPH_LAUNCH_CHECK(c);
+    k_scan_tiles<<<1, 1024, 0, st>>>(tiles, nt);
+    SPH_LAUNCH_CHECK(c);
+    k_scan_apply<<<nt, SCAN_THREADS, 0, st>>>(a.cell_cnt, c->C, tiles, a.cell_end);
+    SPH_LAUNCH_CHECK(c);
+    k_scatter_index<<<blocks_for(n, 256), 256, 0, st>>>(n, gid_u, slot, a.cell_end, tmpidx);
+    SPH_LAUNCH_CHECK(c);
+    k_rank<<<blocks_for(n, 256), 256, 0, st>>>(n, gid_u, a.cell_end, tmpidx, perm, id_new);
+    SPH_LAUNCH_CHECK(c);
+    k_reorder<T><<<blocks_for(n, 256), 256, 0, st>>>(a, b, perm, gid_u, c->soil ? 1 : 0);
+    SPH_LAUNCH_CHECK(c);
+    static const int carried[] = {SPH_F_X, SPH_F_XS, SPH_F_V, SPH_F_V_TMP, SPH_F_DENSITY, SPH_F_PRESSURE, SPH_F_MAT_TYPE, SPH_F_ID0};
+    for (int f : carried) flip(c, f);
+    if (c->soil) { flip(c, SPH_F_STRESS); flip(c, SPH_F_STRAIN_EQU); flip(c, SPH_F_STRAIN_EQU_P); flip(c, SPH_F_FLAG_RETMAP); }
+    return 0;
+}
+
+template int grid_build<float>(SphCtx *);
+template int grid_build<double>(SphCtx *);
+
+}  // namespace sph

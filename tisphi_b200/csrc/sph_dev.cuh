@@ -1,0 +1,165 @@
+// sph_dev.cuh -- device-side context, math helpers and SPH kernels shared by every .cu of libtisphi_b200.
+// Hand-written for sm_100a.  Semantics follow SURVEY.md Appendix A (citations into /root/reference).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/tisphi_b200.h"
+
+namespace sph {
+
+template <typename T> struct Vec4;
+template <> struct __align__(16) Vec4<float> { float x, y, z, w; };
+template <> struct __align__(16) Vec4<double> { double x, y, z, w; };
+
+// material-type predicates (ps:320-374)
+__host__ __device__ __forceinline__ bool is_fluid(int t) { return t == 1; }
+__host__ __device__ __forceinline__ bool is_soil(int t) { return t == 2; }
+__host__ __device__ __forceinline__ bool is_flow(int t) { return t == 1 || t == 2; }
+__host__ __device__ __forceinline__ bool is_real(int t) { return t > 0; }
+__host__ __device__ __forceinline__ bool is_bdy(int t) { return t == -1 || t == -2; }
+__host__ __device__ __forceinline__ bool is_rigid(int t) { return t == 11; }
+__host__ __device__ __forceinline__ bool is_wall(int t) { return is_bdy(t) || is_rigid(t); }
+
+// rounding-exact helpers: the neighbour predicate must not be FMA-contracted
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+// Device view of one engine instance.  Passed by value to every kernel.
+template <typename T> struct Dev {
+    // sizes
+    int n;               // particles in the arrays (owned + ghosts)
+    int dim, kernel, kcorr, solver, xsph, wc_fresh;
+    int gn[3];
+    int C;
+    // geometry (float64: cell ids are always computed in float64 like the reference, ps:216-226)
+    double vstart[3], gs;
+    double dt, m_V0d;
+    // engine-real constants
+    T h, hinv, support, r2thr, eps, knorm, gsT;   // gsT = (T)grid_size in MIXED, 0 in F64 (coordinates are global)
+    T g[3], m_V0;
+    T visc_coef, rho0T, h2_001;                   // 2(dim+2) nu ; rho0 ; 0.01 h^2
+    double rho0, stiff, gamma_, vsound;
+    T coh, mu, E, alpha, kc, G, K, eps_f, sin_dila, damp_c;   // damp_c = -5e-5 * sqrt(E)/h  (base:713-715)
+    // arrays (sorted order)
+    double *x;           // n x 3
+    double *rho, *rho_t; // density, density_tmp
+    Vec4<T> *v4;         // v.xyz, mass
+    Vec4<T> *vt4;        // v_tmp.xyz, (T)density_tmp
+    Vec4<T> *xs4;        // sweep coords xyz, m_V
+    T *press, *pnew;
+    int *type, *id0, *gid, *flag;
+    T *stress, *stress_t, *strain, *strain_p;     // x6
+    T *cspm_f, *cspm_L;
+    T *d_rho; Vec4<T> *d_vel; T *d_stress, *v_grad, *d_strain, *d_strain_p;
+    T *d_rho_rk; Vec4<T> *d_vel_rk; T *d_stress_rk;
+    int *cell_end, *cell_cnt;
+    unsigned long long *bad;                      // counter of out-of-grid particles (H7)
+};
+
+// ------------------------------------------------------------------------------------------------ cells
+template <typename T>
+__device__ __forceinline__ void pos_to_cell(const Dev<T> &c, const double *x, int cc[3]) {
+    // ps:216-218: trunc((x - vstart) / grid_size), float64 divide, C cast
+    cc[0] = (int)__ddiv_rn(__dsub_rn(x[0], c.vstart[0]), c.gs);
+    cc[1] = (int)__ddiv_rn(__dsub_rn(x[1], c.vstart[1]), c.gs);
+    cc[2] = (int)__ddiv_rn(__dsub_rn(x[2], c.vstart[2]), c.gs);
+}
+template <typename T> __device__ __forceinline__ int flatten(const Dev<T> &c, int cx, int cy, int cz) {
+    return cx * c.gn[1] * c.gn[2] + cy * c.gn[2] + cz;      // ps:221-222
+}
+template <typename T> __device__ __forceinline__ void unflatten(const Dev<T> &c, int g, int cc[3]) {
+    int nyz = c.gn[1] * c.gn[2];
+    cc[0] = g / nyz;
+    int r = g - cc[0] * nyz;
+    cc[1] = r / c.gn[2];
+    cc[2] = r - cc[1] * c.gn[2];
+}
+// sweep coordinate of a position stored in cell (cx,cy,cz): global in F64, cell-local float in MIXED
+__device__ __forceinline__ double cell_origin(double vstart, double gs, int c) {
+    return __dadd_rn(vstart, __dmul_rn((double)c, gs));
+}
+
+// --------------------------------------------------------------------------------- smoothing kernels (base:278-358)
+template <typename T> __device__ __forceinline__ T kernel_W(const Dev<T> &c, T r) {
+    T q = r * c.hinv, res = 0;
+    if (r > c.eps && q <= (T)2) {
+        if (c.kernel == 0) {
+            if (q <= (T)1) res = c.knorm * ((T)0.5 * q * q * q - q * q + (T)(2.0 / 3.0));
+            else { T t = (T)2 - q; res = c.knorm / (T)6 * t * t * t; }
+        } else {
+            T q1 = (T)1 - (T)0.5 * q, q2 = q1 * q1;
+            res = c.knorm * (q2 * q2) * ((T)1 + (T)2 * q);
+        }
+    }
+    return res;
+}
+// returns the scalar s with gradW = s * d  (d = x_i - x_j)
+template <typename T> __device__ __forceinline__ T kernel_dW_over_r(const Dev<T> &c, T r) {
+    T q = r * c.hinv, s = 0;
+    if (r > c.eps && q <= (T)2) {
+        if (c.kernel == 0) {
+            T f = (q <= (T)1) ? c.knorm * q * ((T)1.5 * q - (T)2) : c.knorm * ((T)-0.5 * ((T)2 - q) * ((T)2 - q));
+            s = f * c.hinv / r;
+        } else {
+            T q1 = (T)1 - (T)0.5 * q;
+            s = c.knorm * (q1 * q1 * q1) * ((T)-5 * q) * c.hinv / r;
+        }
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------ generic neighbour iteration (ps:259-269)
+// Centre cell from the CURRENT master position (ps:261); 3^dim cells x-major / z-fastest; j ascending; out-of-range
+// cells per axis are empty; strict r < support evaluated as r2 < r2thr (same predicate, no sqrt) on
+// unfused r2 = (dx*dx + dy*dy) + dz*dz.   body(j, dx, dy, dz, r)
+template <typename T, typename F> __device__ __forceinline__ void for_neighbors(const Dev<T> &c, int i, F &&body) {
+    int cc[3], sc[3] = {0, 0, 0};
+    const double xi[3] = {c.x[3 * (size_t)i], c.x[3 * (size_t)i + 1], c.x[3 * (size_t)i + 2]};
+    pos_to_cell(c, xi, cc);
+    if (sizeof(T) == 4) unflatten(c, c.gid[i], sc);           // the cell xs4[i] is local to
+    const Vec4<T> pi = c.xs4[i];
+    const int z0 = (c.dim == 2) ? 0 : -1, z1 = (c.dim == 2) ? 0 : 1;
+    for (int ox = -1; ox <= 1; ox++) {
+        int cx = cc[0] + ox;
+        if (cx < 0 || cx >= c.gn[0]) continue;
+        T sx = (T)(cx - sc[0]) * c.gsT;
+        for (int oy = -1; oy <= 1; oy++) {
+            int cy = cc[1] + oy;
+            if (cy < 0 || cy >= c.gn[1]) continue;
+            T sy = (T)(cy - sc[1]) * c.gsT;
+            for (int oz = z0; oz <= z1; oz++) {
+                int cz = cc[2] + oz;
+                if (cz < 0 || cz >= c.gn[2]) continue;
+                T sz = (T)(cz - sc[2]) * c.gsT;
+                int g = flatten(c, cx, cy, cz);
+                int jb = g > 0 ? c.cell_end[g - 1] : 0, je = c.cell_end[g];
+                for (int j = jb; j < je; j++) {
+                    if (j == i) continue;
+                    Vec4<T> pj = c.xs4[j];
+                    T dx = pi.x - (pj.x + sx), dy = pi.y - (pj.y + sy), dz = pi.z - (pj.z + sz);
+                    T r2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
+                    if (r2 < c.r2thr) body(j, dx, dy, dz, sqrt_rn(r2), pj.w);
+                }
+            }
+        }
+    }
+}
+
+// symmetric 3x3 stored as xx,yy,zz,xy,yz,zx  <-> full row-major
+template <typename T> __device__ __forceinline__ void sym_load(const T *p, size_t i, T s[9]) {
+    const T *q = p + 6 * i;
+    T xx = q[0], yy = q[1], zz = q[2], xy = q[3], yz = q[4], zx = q[5];
+    s[0] = xx; s[1] = xy; s[2] = zx; s[3] = xy; s[4] = yy; s[5] = yz; s[6] = zx; s[7] = yz; s[8] = zz;
+}
+template <typename T> __device__ __forceinline__ void sym_store(T *p, size_t i, const T s[9]) {
+    T *q = p + 6 * i;
+    q[0] = s[0]; q[1] = s[4]; q[2] = s[8]; q[3] = s[1]; q[4] = s[5]; q[5] = s[2];
+}
+
+}  // namespace sph

@@ -1,0 +1,74 @@
+// sph_host.h -- host-side engine state shared by the translation units of libtisphi_b200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "sph_dev.cuh"
+
+struct FieldSlot {
+    int64_t off[2];      // byte offsets of the two ping-pong buffers (off[1] == off[0] when not carried)
+    int cur;             // which buffer is current
+    int ncomp, stride, kind;   // kind: 0 f64, 1 real, 2 i32
+    bool present;
+    int64_t view_shift;  // extra bytes (views MASS / M_V into the .w lane of V / XS)
+};
+
+struct SphCtx {
+    SphParams p;
+    int64_t n_max, n;
+    int C;
+    cudaStream_t stream;
+    char err[512];
+    char *arena;
+    int64_t arena_bytes;
+    FieldSlot f[SPH_F_NUM];
+    // scratch (byte offsets)
+    int64_t off_gid_unsorted, off_slot, off_perm, off_tmpidx, off_pnew, off_bad, off_scan_tiles, off_x_alt_unused;
+    int scan_tiles;
+    int64_t launches;
+    int real_bytes;      // sizeof engine real
+    bool soil, rk, has_L;
+    int press_cur;       // which of (PRESSURE buffer, pnew) ... handled through field table
+    double r2thr64;
+    float r2thr32;
+};
+
+#define SPH_CHECK(ctx, call)                                                                          \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            return -1;                                                                                \
+        }                                                                                             \
+    } while (0)
+
+#define SPH_LAUNCH_CHECK(ctx)                                                                         \
+    do {                                                                                              \
+        (ctx)->launches++;                                                                            \
+        SPH_CHECK(ctx, cudaGetLastError());                                                           \
+    } while (0)
+
+namespace sph {
+
+template <typename T> Dev<T> make_dev(SphCtx *c, int which = -1);   // which = -1: current buffers, 1: alternates
+
+inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// grid.cu
+template <typename T> int grid_build(SphCtx *c);
+// sweeps.cu
+template <typename T> int calc_kernel_corr(SphCtx *c);
+template <typename T> int one_step(SphCtx *c);
+template <typename T> int advect_pos(SphCtx *c);
+template <typename T> int post_step(SphCtx *c);
+template <typename T> int neighbor_count(SphCtx *c, int32_t *out);
+template <typename T> int density_sum(SphCtx *c, void *out);
+// integrate.cu
+template <typename T> int init_real2tmp(SphCtx *c);
+template <typename T> int advect(SphCtx *c, int kind, int m);
+template <typename T> int init_stress(SphCtx *c);
+template <typename T> int add_particles_finish(SphCtx *c, int64_t first, int64_t count);
+
+void flip(SphCtx *c, int field);
+
+}  // namespace sph

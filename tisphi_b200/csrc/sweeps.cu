@@ -1,0 +1,629 @@
+// sweeps.cu -- generic (any solver, any dimension, stale grids allowed) neighbour sweeps, one thread per particle.
+// Each kernel is one top-level loop of the reference's @ti.kernel bodies:
+//   calc_CSPM_f / calc_CSPM_L          eng/solver_sph_base.py:386-423
+//   WCSPH one_step loops A, B          eng/solver_sph_wc.py:82-126   (tasks wc:33-71, base:186-203, base:647-669)
+//   mu(I) one_step loops 1-3           eng/solver_sph_muI.py:62-132
+//   DP one_step loops 1-3              eng/solver_sph_dp.py:210-274  (return mapping dp:41-118, Bui 2008 dp:171-208)
+//   advect_pos / XSPH                  eng/solver_sph_base.py:223-238
+//   advect_something                   wc:129-132, muI:134-156, dp:276-296
+// The cell-tile fast paths for the WCSPH hot loop live in sweeps_tile.cu; these kernels are the complete path.
+#include "sph_host.h"
+
+namespace sph {
+
+// --------------------------------------------------------------------------------------------- kernel correction
+template <typename T> __global__ void __launch_bounds__(128) k_cspm_f(Dev<T> c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    T s = 0;
+    for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
+        if (is_flow(c.type[j])) s += Vj * kernel_W(c, r);
+    });
+    c.cspm_f[i] = (s != (T)0) ? (T)1 / s : (T)1;
+}
+
+template <typename T> __device__ __forceinline__ T det3(const T *m) {
+    return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+template <typename T> __global__ void __launch_bounds__(128) k_cspm_L(Dev<T> c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    T L[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    const int ti = c.type[i];
+    if (is_flow(ti)) {
+        T M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
+            if (c.type[j] == ti) {
+                const T s = kernel_dW_over_r(c, r);
+                const T d[3] = {dx, dy, dz};
+#pragma unroll
+                for (int a = 0; a < 3; a++)
+#pragma unroll
+                    for (int b = 0; b < 3; b++) M[3 * a + b] += Vj * (-d[a]) * (s * d[b]);
+            }
+        });
+        if (c.dim == 2) {
+            const T det = M[0] * M[4] - M[1] * M[3];
+            if (fabs(det) > c.eps) {
+                const T inv = (T)1 / det;
+                L[0] = M[4] * inv; L[1] = -M[1] * inv; L[2] = 0;
+                L[3] = -M[3] * inv; L[4] = M[0] * inv; L[5] = 0;
+                L[6] = 0; L[7] = 0; L[8] = 0;
+            }
+        } else {
+            const T det = det3(M);
+            if (fabs(det) > c.eps) {
+                const T inv = (T)1 / det;
+                L[0] = (M[4] * M[8] - M[5] * M[7]) * inv; L[1] = -(M[1] * M[8] - M[2] * M[7]) * inv; L[2] = (M[1] * M[5] - M[2] * M[4]) * inv;
+                L[3] = -(M[3] * M[8] - M[5] * M[6]) * inv; L[4] = (M[0] * M[8] - M[2] * M[6]) * inv; L[5] = -(M[0] * M[5] - M[2] * M[3]) * inv;
+                L[6] = (M[3] * M[7] - M[4] * M[6]) * inv; L[7] = -(M[0] * M[7] - M[1] * M[6]) * inv; L[8] = (M[0] * M[4] - M[1] * M[3]) * inv;
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 9; a++) c.cspm_L[9 * (size_t)i + a] = L[a];
+}
+
+template <typename T> int calc_kernel_corr(SphCtx *c) {
+    if (c->n == 0) return 0;
+    Dev<T> d = make_dev<T>(c);
+    k_cspm_f<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(d);
+    SPH_LAUNCH_CHECK(c);
+    if (c->p.kcorr == 1) {
+        k_cspm_L<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(d);
+        SPH_LAUNCH_CHECK(c);
+    }
+    return 0;
+}
+
+// corrected kernel gradient (base:374-383): g = s*d, gc = g | L_i g | 0
+template <typename T>
+__device__ __forceinline__ void grad_corr(const Dev<T> &c, const T *L, T s, T dx, T dy, T dz, T g[3], T gc[3]) {
+    g[0] = s * dx; g[1] = s * dy; g[2] = s * dz;
+    if (c.kcorr == 0) { gc[0] = g[0]; gc[1] = g[1]; gc[2] = g[2]; }
+    else if (c.kcorr == 1) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) gc[a] = L[3 * a] * g[0] + L[3 * a + 1] * g[1] + L[3 * a + 2] * g[2];
+    } else { gc[0] = gc[1] = gc[2] = 0; }
+}
+template <typename T> __device__ __forceinline__ void load_L(const Dev<T> &c, int i, T L[9]) {
+    if (c.kcorr == 1) {
+#pragma unroll
+        for (int a = 0; a < 9; a++) L[a] = c.cspm_L[9 * (size_t)i + a];
+    } else {
+#pragma unroll
+        for (int a = 0; a < 9; a++) L[a] = 0;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------- WCSPH
+__device__ __forceinline__ double eos_wc(double rho, double rho0, double stiff, double gamma_) {
+    double v = stiff * (pow(rho / rho0, gamma_) - 1.0);      // wc:87-88
+    return v > 0.0 ? v : 0.0;
+}
+// loop A, fluid branch: pointwise EOS into the NEW pressure buffer
+template <typename T> __global__ void __launch_bounds__(256) k_wc_eos(Dev<T> c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    const int t = c.type[i];
+    if (is_fluid(t)) c.pnew[i] = (T)eos_wc(c.rho_t[i], c.rho0, c.stiff, c.gamma_);
+    else if (!is_wall(t)) c.pnew[i] = c.press[i];
+}
+// loop A, wall branch (wc:90-103).  p_j is read "in place" by the reference; serial semantics are reproduced
+// pointwise: fluid j < i already holds EOS(rho~_j) (pnew), fluid j > i still holds the previous pressure (press).
+template <typename T> __global__ void __launch_bounds__(128) k_wc_wall(Dev<T> c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    if (!is_wall(c.type[i])) return;
+    T Sv0 = 0, Sv1 = 0, Sv2 = 0, Sp = 0;
+    for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
+        const int tj = c.type[j];
+        if (is_flow(tj)) {
+            const T w = kernel_W(c, r);
+            const Vec4<T> vj = c.vt4[j];
+            Sv0 += Vj * vj.x * w; Sv1 += Vj * vj.y * w; Sv2 += Vj * vj.z * w;
+            const T pj = (is_fluid(tj) && (c.wc_fresh || j < i)) ? c.pnew[j] : c.press[j];
+            Sp += Vj * (pj + vj.w * c.g[1] * dy) * w;
+        }
+    });
+    const T f = c.cspm_f[i];
+    const Vec4<T> v = c.v4[i];
+    Vec4<T> vt;
+    vt.x = (T)2 * v.x - Sv0 * f; vt.y = (T)2 * v.y - Sv1 * f; vt.z = (T)2 * v.z - Sv2 * f;
+    vt.w = c.rho0T;
+    c.vt4[i] = vt;
+    c.rho_t[i] = c.rho0;
+    const T p = Sp * f;
+    c.pnew[i] = p > (T)0 ? p : (T)0;
+}
+// loop B (wc:108-126): continuity (corrected gradient) + viscosity + pressure (plain gradient, H22)
+template <typename T> __global__ void __launch_bounds__(128) k_wc_fluid(Dev<T> c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    if (!is_fluid(c.type[i])) return;
+    const Vec4<T> vi = c.vt4[i];
+    const T rhoi = vi.w, pi = c.press[i];
+    const T pri = pi / (rhoi * rhoi);
+    T L[9];
+    load_L(c, i, L);
+    T dd = 0, a0 = 0, a1 = 0, a2 = 0;
+    for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
+        const T s = kernel_dW_over_r(c, r);
+        T g[3], gc[3];
+        grad_corr(c, L, s, dx, dy, dz, g, gc);
+        const Vec4<T> vj = c.vt4[j];
+        const T ux = vi.x - vj.x, uy = vi.y - vj.y, uz = vi.z - vj.z;
+        dd += Vj * ux * gc[0] + Vj * uy * gc[1] + Vj * uz * gc[2];
+        const int tj = c.type[j];
+        const T vx = ux * dx + uy * dy + uz * dz;
+        const T mn = vx < (T)0 ? vx : (T)0;
+        T visc = 0;
+        if (is_fluid(tj)) visc = c.visc_coef * Vj * mn / (r * r + c.h2_001);
+        else if (is_wall(tj)) visc = c.visc_coef * Vj * c.rho0T / rhoi * mn / (r * r + c.h2_001);
+        const T rhoj = vj.w;
+        const T pres = -c.rho0T * Vj * (pri + c.press[j] / (rhoj * rhoj));
+        a0 += visc * g[0] + pres * g[0]; a1 += visc * g[1] + pres * g[1]; a2 += visc * g[2] + pres * g[2];
+    });
+    c.d_rho[i] = dd * rhoi;
+    Vec4<T> dv; dv.x = a0 + c.g[0]; dv.y = a1 + c.g[1]; dv.z = a2 + c.g[2]; dv.w = 0;
+    c.d_vel[i] = dv;
+}
+
+// ------------------------------------------------------------------------------------------ soil: shared pieces
+template <typename T> __device__ __forceinline__ T dev_component(const T *t) {     // type_define.py:26-28
+    T s = 0;
+#pragma unroll
+    for (int a = 0; a < 9; a++) s += t[a] * t[a];
+    return sqrt(s * (T)2 / (T)3);
+}
+// Adami wall extrapolation for soil solvers (muI:95-109, dp:220-231; tasks base:647-669)
+template <typename T> __global__ void __launch_bounds__(128) k_soil_wall(Dev<T> c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    if (!is_wall(c.type[i])) return;
+    T Sv0 = 0, Sv1 = 0, Sv2 = 0, Sr = 0, Ss[6] = {0, 0, 0, 0, 0, 0};
+    for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
+        if (is_flow(c.type[j])) {
+            const T w = kernel_W(c, r);
+            const Vec4<T> vj = c.vt4[j];
+            const T rj = vj.w;
+            Sv0 += Vj * vj.x * w; Sv1 += Vj * vj.y * w; Sv2 += Vj * vj.z * w;
+            Sr += Vj * rj * w;
+            const T *sj = c.stress_t + 6 * (size_t)j;
+            Ss[0] += Vj * (sj[0] + rj * c.g[0] * dx) * w;
+            Ss[1] += Vj * (sj[1] + rj * c.g[1] * dy) * w;
+            Ss[2] += Vj * (sj[2] + rj * c.g[2] * dz) * w;
+            Ss[3] += Vj * sj[3] * w; Ss[4] += Vj * sj[4] * w; Ss[5] += Vj * sj[5] * w;
+        }
+    });
+    const T f = c.cspm_f[i];
+    const Vec4<T> v = c.v4[i];
+    Vec4<T> vt;
+    vt.x = (T)2 * v.x - Sv0 * f; vt.y = (T)2 * v.y - Sv1 * f; vt.z = (T)2 * v.z - Sv2 * f;
+    T rt = c.rho0T;
+    if (c.solver == SPH_SOLVER_MUI) { const T e = Sr * f; rt = e > c.rho0T ? e : c.rho0T; }   // muI:105
+    vt.w = rt;
+    c.vt4[i] = vt;
+    c.rho_t[i] = (double)rt;
+#pragma unroll
+    for (int q = 0; q < 6; q++) c.stress_t[6 * (size_t)i + q] = Ss[q] * f;
+}
+
+// accumulators of one soil sweep: velocity gradient, continuity sum, momentum sum
+template <typename T, bool VG, bool MOM>
+__device__ __forceinline__ void soil_sweep(const Dev<T> &c, int i, T vg[9], T *dd, T mom[3]) {
+    const Vec4<T> vi = c.vt4[i];
+    const T rhoi = vi.w;
+    T L[9], si[9];
+    load_L(c, i, L);
+    if (MOM) {
+        sym_load(c.stress_t, (size_t)i, si);
+        const T ir = (T)1 / (rhoi * rhoi);
+        (void)ir;
+    }
+    T acc = 0;
+#pragma unroll
+    for (int a = 0; a < 9; a++) vg[a] = 0;
+    mom[0] = mom[1] = mom[2] = 0;
+    for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
+        const T s = kernel_dW_over_r(c, r);
+        T g[3], gc[3];
+        grad_corr(c, L, s, dx, dy, dz, g, gc);
+        const Vec4<T> vj = c.vt4[j];
+        if (VG) {
+            const T u[3] = {vj.x - vi.x, vj.y - vi.y, vj.z - vi.z};
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) vg[3 * a + b] += Vj * u[a] * gc[b];
+            acc += Vj * (-u[0]) * gc[0] + Vj * (-u[1]) * gc[1] + Vj * (-u[2]) * gc[2];
+        }
+        if (MOM) {      // muI:38-46 / dp:156-165: V_j rho~_j (sigma~_j / rho~_j^2 + sigma~_i / rho~_i^2) . gradW^c
+            T sj[9];
+            sym_load(c.stress_t, (size_t)j, sj);
+            const T rhoj = vj.w, cf = Vj * rhoj;
+            const T r2j = rhoj * rhoj, r2i = rhoi * rhoi;
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                T t = 0;
+#pragma unroll
+                for (int b = 0; b < 3; b++) t += (cf * (sj[3 * a + b] / r2j + si[3 * a + b] / r2i)) * gc[b];
+                mom[a] += t;
+            }
+        }
+    });
+    *dd = acc;
+}
+
+// ----------------------------------------------------------------------------------------------------- mu(I)
+template <typename T> __global__ void __launch_bounds__(128) k_mui_soil1(Dev<T> c) {          // muI:67-92
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    if (!is_soil(c.type[i])) return;
+    T vg[9], dd, mom[3];
+    soil_sweep<T, true, false>(c, i, vg, &dd, mom);
+#pragma unroll
+    for (int a = 0; a < 9; a++) c.v_grad[9 * (size_t)i + a] = vg[a];
+    c.d_rho[i] = dd * c.vt4[i].w;
+    double pv = c.vsound * c.vsound * (c.rho[i] - c.rho0);      // rho, not rho~ (muI:80, H17)
+    if (pv < 0.0) pv = 0.0;
+    const T p = (T)pv;
+    c.press[i] = p;
+    T sr[9], s2 = 0;
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) sr[3 * a + b] = (T)0.5 * (vg[3 * a + b] + vg[3 * b + a]);
+#pragma unroll
+    for (int a = 0; a < 9; a++) s2 += sr[a] * sr[a];
+    const T dbdot = sqrt((T)0.5 * s2) + c.eps;
+    const T coef = (T)0 + (c.coh + p * c.mu) / dbdot;             // eta_0 = 0 (muI:19)
+    T st[9];
+#pragma unroll
+    for (int a = 0; a < 9; a++) st[a] = coef * sr[a];
+    st[0] -= p; st[4] -= p; st[8] -= p;
+    sym_store(c.stress_t, (size_t)i, st);
+    const T tr = sr[0] + sr[4] + sr[8];
+    sr[0] -= tr / (T)3; sr[4] -= tr / (T)3; sr[8] -= tr / (T)3;
+    c.d_strain[i] = dev_component(sr);
+}
+template <typename T> __global__ void __launch_bounds__(128) k_mui_soil3(Dev<T> c) {          // muI:115-128
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    if (!is_soil(c.type[i])) return;
+    T vg[9], dd, mom[3];
+    soil_sweep<T, false, true>(c, i, vg, &dd, mom);
+    const Vec4<T> vi = c.vt4[i];
+    const T dc = c.damp_c / sqrt(vi.w);                            // -5e-5 sqrt(E / (rho~ h^2)) (base:713-715)
+    Vec4<T> dv;
+    dv.x = mom[0] + c.g[0] + dc * vi.x; dv.y = mom[1] + c.g[1] + dc * vi.y; dv.z = mom[2] + c.g[2] + dc * vi.z; dv.w = 0;
+    c.d_vel[i] = dv;
+}
+
+// -------------------------------------------------------------------------------------------- Drucker-Prager
+template <typename T> __device__ __forceinline__ void from_stress(const Dev<T> &c, const T *s, T dev[9], T *I1, T *sJ2, T *f) {
+    const T tr = s[0] + s[4] + s[8];
+    T s2 = 0;
+#pragma unroll
+    for (int a = 0; a < 9; a++) dev[a] = s[a];
+    dev[0] -= tr / (T)3; dev[4] -= tr / (T)3; dev[8] -= tr / (T)3;
+#pragma unroll
+    for (int a = 0; a < 9; a++) s2 += dev[a] * dev[a];
+    *I1 = tr; *sJ2 = sqrt((T)0.5 * s2); *f = *sJ2 + c.alpha * tr - c.kc;
+}
+template <typename T> __device__ __forceinline__ void adapt_stress(const Dev<T> &c, T *s) {   // dp:73-96
+    T dev[9], I1, sJ2, f;
+    from_stress(c, s, dev, &I1, &sJ2, &f);
+    if (f > c.eps_f) {
+        if (f > sJ2) {
+            const T tmp = (I1 - c.kc / c.alpha) / (T)3;
+            s[0] -= tmp; s[4] -= tmp; s[8] -= tmp;
+        }
+        from_stress(c, s, dev, &I1, &sJ2, &f);
+        const T rr = (-I1 * c.alpha + c.kc) / sJ2;
+#pragma unroll
+        for (int a = 0; a < 9; a++) s[a] = rr * dev[a];
+        s[0] += I1 / (T)3; s[4] += I1 / (T)3; s[8] += I1 / (T)3;
+    }
+}
+template <typename T> __device__ __forceinline__ int flag_dp(const Dev<T> &c, const T *s) {   // dp:98-109
+    T dev[9], I1, sJ2, f;
+    from_stress(c, s, dev, &I1, &sJ2, &f);
+    if (f < -c.eps_f) return 0;
+    if (f > c.eps_f) return (f >= sJ2) ? 3 : 2;
+    return 1;
+}
+template <typename T> __global__ void __launch_bounds__(256) k_dp_adapt(Dev<T> c) {           // dp:215-217
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    if (!is_soil(c.type[i])) return;
+    T s[9];
+    sym_load(c.stress_t, (size_t)i, s);
+    adapt_stress(c, s);
+    sym_store(c.stress_t, (size_t)i, s);
+}
+template <typename T>
+__device__ __forceinline__ void bui2008(const Dev<T> &c, const T *st, const T *vg, T ds[9], T *dse, T *dsep) {  // dp:171-208
+    T dev[9], I1, sJ2, f, sr[9], sp[9], J[9], se[9], te[9], tg[9], lam = 0;
+    from_stress(c, st, dev, &I1, &sJ2, &f);
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            sr[3 * a + b] = (T)0.5 * (vg[3 * a + b] + vg[3 * b + a]);
+            sp[3 * a + b] = (T)0.5 * (vg[3 * a + b] - vg[3 * b + a]);
+        }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            J[3 * i + j] = st[3 * i + 0] * sp[3 * j + 0] + st[3 * i + 1] * sp[3 * j + 1] + st[3 * i + 2] * sp[3 * j + 2] +
+                           st[0 + j] * sp[3 * i + 0] + st[3 + j] * sp[3 * i + 1] + st[6 + j] * sp[3 * i + 2];
+    const T tr = sr[0] + sr[4] + sr[8];
+#pragma unroll
+    for (int a = 0; a < 9; a++) se[a] = sr[a];
+    se[0] -= tr / (T)3; se[4] -= tr / (T)3; se[8] -= tr / (T)3;
+#pragma unroll
+    for (int a = 0; a < 9; a++) { te[a] = (T)2 * c.G * se[a]; tg[a] = 0; }
+    te[0] += c.K * tr; te[4] += c.K * tr; te[8] += c.K * tr;
+    const bool plastic = (f >= -c.eps_f && sJ2 > c.eps);
+    if (plastic) {
+        T ss = 0;
+#pragma unroll
+        for (int a = 0; a < 9; a++) ss += dev[a] * sr[a];
+        lam = ((T)3 * c.alpha * c.K * tr + (c.G / sJ2) * ss) / ((T)27 * c.alpha * c.K * c.sin_dila + c.G);
+#pragma unroll
+        for (int a = 0; a < 9; a++) tg[a] = lam * (c.G / sJ2 * dev[a]);
+        tg[0] = lam * ((T)9 * c.K * c.sin_dila + c.G / sJ2 * dev[0]);
+        tg[4] = lam * ((T)9 * c.K * c.sin_dila + c.G / sJ2 * dev[4]);
+        tg[8] = lam * ((T)9 * c.K * c.sin_dila + c.G / sJ2 * dev[8]);
+    }
+#pragma unroll
+    for (int a = 0; a < 9; a++) ds[a] = J[a] + te[a] - tg[a];
+    *dse = dev_component(se);
+    *dsep = 0;
+    if (plastic) {
+        const T gp = sJ2 + (T)3 * I1 * c.sin_dila;
+        T ep[9];
+#pragma unroll
+        for (int a = 0; a < 9; a++) ep[a] = (fabs(ds[a]) > c.eps ? gp / ds[a] : (T)0) * lam;   // pti.g_p is never written
+        const T trp = ep[0] + ep[4] + ep[8];
+        ep[0] -= trp / (T)3; ep[4] -= trp / (T)3; ep[8] -= trp / (T)3;
+        *dsep = dev_component(ep);
+    }
+}
+template <typename T> __global__ void __launch_bounds__(128) k_dp_soil(Dev<T> c) {            // dp:237-270
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    if (!is_soil(c.type[i])) return;
+    T vg[9], dd, mom[3];
+    soil_sweep<T, true, true>(c, i, vg, &dd, mom);
+#pragma unroll
+    for (int a = 0; a < 9; a++) c.v_grad[9 * (size_t)i + a] = vg[a];
+    const Vec4<T> vi = c.vt4[i];
+    c.d_rho[i] = dd * vi.w;
+    T st[9], ds[9], dse, dsep;
+    sym_load(c.stress_t, (size_t)i, st);
+    bui2008(c, st, vg, ds, &dse, &dsep);
+    sym_store(c.d_stress, (size_t)i, ds);
+    c.d_strain[i] = dse;
+    c.d_strain_p[i] = dsep;
+    const T dc = c.damp_c / sqrt(vi.w);
+    Vec4<T> dv;
+    dv.x = mom[0] + c.g[0] + dc * vi.x; dv.y = mom[1] + c.g[1] + dc * vi.y; dv.z = mom[2] + c.g[2] + dc * vi.z; dv.w = 0;
+    c.d_vel[i] = dv;
+}
+
+template <typename T> int one_step(SphCtx *c) {
+    if (c->n == 0) return 0;
+    const int n = (int)c->n;
+    cudaStream_t st = c->stream;
+    if (c->p.solver == SPH_SOLVER_WC) {
+        Dev<T> d = make_dev<T>(c);
+        k_wc_eos<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+        k_wc_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+        flip(c, SPH_F_PRESSURE);               // pnew becomes pt.pressure
+        d = make_dev<T>(c);
+        k_wc_fluid<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+    } else if (c->p.solver == SPH_SOLVER_MUI) {
+        Dev<T> d = make_dev<T>(c);
+        k_mui_soil1<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+        k_soil_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+        k_mui_soil3<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+    } else if (c->p.solver == SPH_SOLVER_DP) {
+        Dev<T> d = make_dev<T>(c);
+        k_dp_adapt<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+        k_soil_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+        k_dp_soil<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+    } else {
+        snprintf(c->err, sizeof(c->err), "unknown solver %d", c->p.solver);
+        return -2;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------- advect_pos (base:228-238)
+template <typename T> __global__ void __launch_bounds__(256) k_advect_pos(Dev<T> c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    if (!is_real(c.type[i])) return;
+    const Vec4<T> v = c.v4[i];
+    double *x = c.x + 3 * (size_t)i;
+    x[0] += c.dt * (double)v.x; x[1] += c.dt * (double)v.y; x[2] += c.dt * (double)v.z;
+}
+// XSPH on a snapshot: new positions go to the alternate x buffer
+template <typename T> __global__ void __launch_bounds__(128) k_advect_pos_xsph(Dev<T> c, double *__restrict__ xnew) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    const double *x = c.x + 3 * (size_t)i;
+    double o0 = x[0], o1 = x[1], o2 = x[2];
+    const int ti = c.type[i];
+    if (is_real(ti)) {
+        const Vec4<T> vi = c.v4[i];
+        T s0 = 0, s1 = 0, s2 = 0;
+        for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
+            if (c.type[j] == ti) {
+                const T w = kernel_W(c, r);
+                const Vec4<T> vj = c.v4[j];
+                s0 += Vj * (vj.x - vi.x) * w; s1 += Vj * (vj.y - vi.y) * w; s2 += Vj * (vj.z - vi.z) * w;
+            }
+        });
+        o0 += c.dt * (double)(vi.x + (T)0.5 * s0); o1 += c.dt * (double)(vi.y + (T)0.5 * s1); o2 += c.dt * (double)(vi.z + (T)0.5 * s2);
+    }
+    xnew[3 * (size_t)i] = o0; xnew[3 * (size_t)i + 1] = o1; xnew[3 * (size_t)i + 2] = o2;
+}
+// after positions moved on a stale grid: refresh the sweep coordinates relative to the cell each particle is STORED in
+template <typename T> __global__ void __launch_bounds__(256) k_refresh_xs(Dev<T> c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    const double *x = c.x + 3 * (size_t)i;
+    Vec4<T> xs = c.xs4[i];
+    if (sizeof(T) == 8) { xs.x = (T)x[0]; xs.y = (T)x[1]; xs.z = (T)x[2]; }
+    else {
+        int cc[3];
+        unflatten(c, c.gid[i], cc);
+        xs.x = (T)__dsub_rn(x[0], cell_origin(c.vstart[0], c.gs, cc[0]));
+        xs.y = (T)__dsub_rn(x[1], cell_origin(c.vstart[1], c.gs, cc[1]));
+        xs.z = (T)__dsub_rn(x[2], cell_origin(c.vstart[2], c.gs, cc[2]));
+    }
+    c.xs4[i] = xs;
+}
+template <typename T> int advect_pos(SphCtx *c) {
+    if (c->n == 0) return 0;
+    const int n = (int)c->n;
+    Dev<T> d = make_dev<T>(c);
+    if (!c->p.xsph) {
+        k_advect_pos<T><<<blocks_for(n, 256), 256, 0, c->stream>>>(d);
+        SPH_LAUNCH_CHECK(c);
+    } else {
+        double *xnew = (double *)(c->arena + c->f[SPH_F_X].off[1 - c->f[SPH_F_X].cur]);
+        k_advect_pos_xsph<T><<<blocks_for(n, 128), 128, 0, c->stream>>>(d, xnew);
+        SPH_LAUNCH_CHECK(c);
+        flip(c, SPH_F_X);
+    }
+    return 0;
+}
+
+// --------------------------------------------------------------------- advect_something (wc:129-132 | muI | dp)
+template <typename T> __device__ __forceinline__ void chk_density(const Dev<T> &c, int i) {     // base:214-221
+    double r = c.rho[i];
+    if (r < c.rho0) r = c.rho0;
+    c.rho[i] = r;
+    Vec4<T> xs = c.xs4[i];
+    xs.w = (T)((double)c.v4[i].w / r);
+    c.xs4[i] = xs;
+}
+template <typename T> __global__ void __launch_bounds__(256) k_post_wc(Dev<T> c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    if (is_fluid(c.type[i])) chk_density(c, i);
+}
+template <typename T> __global__ void __launch_bounds__(256) k_post_dp(Dev<T> c) {            // dp:276-296
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    if (!is_soil(c.type[i])) return;
+    chk_density(c, i);
+    T s[9];
+    sym_load(c.stress, (size_t)i, s);
+    c.flag[i] = flag_dp(c, s);
+    adapt_stress(c, s);
+    sym_store(c.stress, (size_t)i, s);
+    c.strain[i] += (T)c.dt * c.d_strain[i];
+    c.strain_p[i] += (T)c.dt * c.d_strain_p[i];
+}
+template <typename T> __global__ void __launch_bounds__(256) k_post_mui_a(Dev<T> c) {         // muI:147-150
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    if (!is_soil(c.type[i])) return;
+    chk_density(c, i);
+    c.strain[i] += (T)c.dt * c.d_strain[i];
+}
+// muI:151-156 Shepard regularisation on a snapshot (stress_tmp), post-advect positions on the pre-move grid (H15)
+template <typename T> __global__ void __launch_bounds__(128) k_post_mui_b(Dev<T> c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    const int ti = c.type[i];
+    if (!is_soil(ti)) return;
+    T acc[6] = {0, 0, 0, 0, 0, 0};
+    for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
+        if (c.type[j] == ti) {
+            const T w = kernel_W(c, r);
+            const T *sj = c.stress_t + 6 * (size_t)j;
+#pragma unroll
+            for (int q = 0; q < 6; q++) acc[q] += Vj * sj[q] * w;
+        }
+    });
+    const T f = c.cspm_f[i];
+#pragma unroll
+    for (int q = 0; q < 6; q++) c.stress[6 * (size_t)i + q] = acc[q] * f;
+}
+template <typename T> int post_step(SphCtx *c) {
+    if (c->n == 0) return 0;
+    const int n = (int)c->n;
+    Dev<T> d = make_dev<T>(c);
+    cudaStream_t st = c->stream;
+    if (c->p.solver == SPH_SOLVER_WC) {
+        k_post_wc<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+    } else if (c->p.solver == SPH_SOLVER_DP) {
+        k_post_dp<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+    } else {
+        k_post_mui_a<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+        k_refresh_xs<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+        k_post_mui_b<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+    }
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------- stand-alone sweeps
+template <typename T> __global__ void __launch_bounds__(128) k_neighbor_count(Dev<T> c, int *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    int cnt = 0;
+    for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) { cnt++; });
+    out[i] = cnt;
+}
+template <typename T> __global__ void __launch_bounds__(128) k_density_sum(Dev<T> c, T *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    T s = 0;
+    for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) { s += c.v4[j].w * kernel_W(c, r); });
+    out[i] = s;
+}
+template <typename T> int neighbor_count(SphCtx *c, int32_t *out) {
+    if (c->n == 0) return 0;
+    k_neighbor_count<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(make_dev<T>(c), out);
+    SPH_LAUNCH_CHECK(c);
+    return 0;
+}
+template <typename T> int density_sum(SphCtx *c, void *out) {
+    if (c->n == 0) return 0;
+    k_density_sum<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(make_dev<T>(c), (T *)out);
+    SPH_LAUNCH_CHECK(c);
+    return 0;
+}
+
+#define INST(T)                                            \
+    template int calc_kernel_corr<T>(SphCtx *);            \
+    template int one_step<T>(SphCtx *);                    \
+    template int advect_pos<T>(SphCtx *);                  \
+    template int post_step<T>(SphCtx *);                   \
+    template int neighbor_count<T>(SphCtx *, int32_t *);   \
+    template int density_sum<T>(SphCtx *, void *);
+INST(float)
+INST(double)
+
+}  // namespace sph
