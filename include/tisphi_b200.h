@@ -137,6 +137,14 @@ int sph_density_sum(SphCtx *ctx, void *out_dev);                /* n real: sum_j
 int64_t sph_read_bad_cells(SphCtx *ctx);
 /* how many kernels the library has launched on this ctx since creation */
 int64_t sph_launch_count(SphCtx *ctx);
+/* sizeof(SphParams) as compiled, so that bindings can verify their mirror of the struct */
+int64_t sph_params_size(void);
+/* per-kernel-class device timing with CUDA events on the engine's stream (used by bench.py for the roofline line).
+ * ms_by_kernel / launches_by_kernel: arrays of sph_profile_num_kernels() entries; reading synchronises and resets. */
+int sph_profile_enable(SphCtx *ctx, int on);
+int sph_profile_num_kernels(void);
+const char *sph_profile_name(int id);
+int sph_profile_read(SphCtx *ctx, double *ms_by_kernel, int64_t *launches_by_kernel);
 /* multi-GPU slab support: see tisphi_b200/parallel notes in DESIGN.md */
 int sph_set_ghost_range(SphCtx *ctx, int64_t n_owned_begin, int64_t n_owned_end);
 

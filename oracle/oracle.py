@@ -70,7 +70,8 @@ def lib():
         L.orc_grid_build.restype = C.c_int64
         L.orc_step.argtypes = [C.c_void_p]
         L.orc_step.restype = C.c_int64
-        for fn in ("orc_neighbor_count", "orc_neighbor_count_f32", "orc_density_sum", "orc_density_sum_f32pos"):
+        for fn in ("orc_neighbor_count", "orc_neighbor_count_f32", "orc_neighbor_count_f32local", "orc_density_sum",
+                   "orc_density_sum_f32pos"):
             getattr(L, fn).argtypes = [C.c_void_p, C.c_void_p]
             getattr(L, fn).restype = None
         L.orc_r2_threshold_f32.argtypes = [C.c_float]
@@ -248,9 +249,11 @@ class Oracle:
     def step(self):
         return self.L.orc_step(self.h)
 
-    def neighbor_count(self, f32=False):
+    def neighbor_count(self, f32=False, f32global=False):
+        """f32: the MIXED engine's predicate (cell-local float32 coordinates); f32global: globally rounded float32."""
         out = np.zeros(self.n, dtype=np.int32)
-        (self.L.orc_neighbor_count_f32 if f32 else self.L.orc_neighbor_count)(self.h, out.ctypes.data_as(C.c_void_p))
+        fn = self.L.orc_neighbor_count_f32 if f32global else (self.L.orc_neighbor_count_f32local if f32 else self.L.orc_neighbor_count)
+        fn(self.h, out.ctypes.data_as(C.c_void_p))
         return out
 
     def density_sum(self, f32pos=False):

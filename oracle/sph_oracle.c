@@ -766,6 +766,58 @@ void orc_neighbor_count_f32(Orc *o, int32_t *out) {
         out[i] = c;
     }
 }
+
+/* float32 predicate of the MIXED engine: coordinates local to the cell each particle is stored in (grid_ids),
+ * xs = (float)(x - (vstart + cell*gs)) with unfused float64 ops, neighbour coordinates shifted by
+ * (float)(cell_j - cell_i) * (float)gs, r2 = fl(fl(dx*dx + dy*dy) + dz*dz), sqrtf(r2) < (float)support. */
+static inline void unflatten(const OrcParams *p, int64_t g, int c[3]) {
+    int64_t nyz = (int64_t)p->gn[1] * p->gn[2];
+    c[0] = (int)(g / nyz);
+    int64_t r = g - c[0] * nyz;
+    c[1] = (int)(r / p->gn[2]);
+    c[2] = (int)(r - (int64_t)c[1] * p->gn[2]);
+}
+static inline void local_xs(const Orc *o, int64_t i, const int sc[3], float xs[3]) {
+    const OrcParams *p = &o->p;
+    for (int a = 0; a < 3; a++) {
+        double org = p->vstart[a] + (double)sc[a] * p->grid_size;
+        xs[a] = (float)(X(o, i)[a] - org);
+    }
+}
+void orc_neighbor_count_f32local(Orc *o, int32_t *out) {
+    const OrcParams *p = &o->p;
+    const float sup = (float)p->support, gsf = (float)p->grid_size;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < o->n; i++) {
+        int cc[3], sc[3];
+        pos_to_index(p, X(o, i), cc);
+        unflatten(p, o->ia[I_GRID_IDS][i], sc);
+        float xi[3];
+        local_xs(o, i, sc, xi);
+        int32_t c = 0;
+        for (int ox = -1; ox <= 1; ox++) for (int oy = -1; oy <= 1; oy++) for (int oz = -1; oz <= 1; oz++) {
+            if (p->dim == 2 && oz != 0) continue;
+            int cl[3] = {cc[0] + ox, cc[1] + oy, cc[2] + oz};
+            if (cl[0] < 0 || cl[0] >= p->gn[0] || cl[1] < 0 || cl[1] >= p->gn[1] || cl[2] < 0 || cl[2] >= p->gn[2]) continue;
+            float sh[3];
+            for (int a = 0; a < 3; a++) sh[a] = (float)(cl[a] - sc[a]) * gsf;
+            int64_t g = flatten(p, cl), jb = g > 0 ? o->cell_end[g - 1] : 0, je = o->cell_end[g];
+            for (int64_t j = jb; j < je; j++) {
+                if (j == i) continue;
+                int sj[3];
+                float xj[3];
+                unflatten(p, o->ia[I_GRID_IDS][j], sj);
+                local_xs(o, j, sj, xj);
+                float tx = xj[0] + sh[0], ty = xj[1] + sh[1], tz = xj[2] + sh[2];
+                float dx = xi[0] - tx, dy = xi[1] - ty, dz = xi[2] - tz;
+                float r2 = dx * dx + dy * dy;
+                r2 = r2 + dz * dz;
+                if (sqrtf(r2) < sup) c++;
+            }
+        }
+        out[i] = c;
+    }
+}
 /* C5: rho_i = sum_j mass_j W_ij (wc:30-31 calc_density_task; self excluded like every for_all_neighbors sum) */
 void orc_density_sum(Orc *o, double *out) {
     const OrcParams *p = &o->p;

@@ -34,3 +34,33 @@ def sym6_to_9(s6):
     """(n,6) xx,yy,zz,xy,yz,zx -> (n,9) row-major full tensor."""
     xx, yy, zz, xy, yz, zx = [s6[:, k] for k in range(6)]
     return np.stack([xx, xy, zx, xy, yy, yz, zx, yz, zz], axis=1)
+
+
+def make_sim(scene, precision="f64", device="cuda:0", **extra):
+    """Simulation built through the reference-shaped API of tisphi_b200.eng from an in-memory scene dict."""
+    import copy
+    from tisphi_b200.eng.simulation import Simulation, SimConfiger
+    sc = copy.deepcopy(scene)
+    sc["Configuration"]["precision"] = precision
+    sc["Configuration"].update(extra)
+    return Simulation(SimConfiger(config=sc), device=device)
+
+
+def engine_fields(sim):
+    """Every comparable particle member as float64/int64 numpy arrays in current order (tensors as (n, 9))."""
+    pt, ps = sim.ps.pt, sim.ps
+    out = {}
+    for k in ("x", "v", "density", "m_V", "mass", "pressure", "d_density", "d_vel", "density_tmp", "v_tmp", "CSPM_f"):
+        out[k] = getattr(pt, k).detach().cpu().double().numpy()
+    for k in ("id0", "grid_ids", "mat_type"):
+        out[k] = getattr(pt, k).detach().cpu().long().numpy()
+    if sim.solver_type != 1:
+        for k in ("stress", "d_stress", "stress_tmp"):
+            out[k] = sym6_to_9(ps.sym6(k).detach().cpu().double().numpy())
+        out["v_grad"] = pt.v_grad.detach().cpu().double().numpy().reshape(-1, 9)
+        for k in ("strain_equ", "strain_equ_p", "d_strain_equ", "d_strain_equ_p"):
+            out[k] = getattr(pt, k).detach().cpu().double().numpy()
+        out["flag_retmap"] = pt.flag_retmap.detach().cpu().long().numpy()
+    if sim.ps.params.kcorr == 1:
+        out["CSPM_L"] = pt.CSPM_L.detach().cpu().double().numpy().reshape(-1, 9)
+    return out

@@ -1,0 +1,233 @@
+"""GPU parity tests: the CUDA engine (through the reference-shaped Python API and the C ABI) against
+  (a) the golden fixtures produced by executing the reference's own sources (oracle/gen_golden.py), and
+  (b) the CPU oracle (oracle/sph_oracle.c) on the same inputs.
+Integer work (cell ids, sorted order, cell offsets, neighbour counts) must be bit-exact; floating-point fields in
+float64 mode agree to summation-order noise; mixed float32 mode within 1e-5 relative after one step.
+"""
+import numpy as np
+import pytest
+
+from helpers import Golden, relmax, sym6_to_9, make_sim, engine_fields
+
+pytestmark = pytest.mark.gpu
+
+WC_CASES = ["wc2d_small_lf", "wc2d_small_se_cubic", "wc2d_small_rk4_cspm", "wc3d_tiny_lf", "c1_test1_wc_lf"]
+SOIL_CASES = ["mui2d_small_lf", "dp2d_small_rk4_cspm", "dp2d_small_lf", "c2_test2_mui_lf", "c3_test2_dp_rk4_cspm"]
+ALL_CASES = WC_CASES + SOIL_CASES
+
+F64_TOL = 1e-9
+# strain_equ_p integrates lambda*g_p/d_stress[a][b] (dp:111-118, 203-206): ill-conditioned by the reference's formula
+FIELD_TOL = {"strain_equ_p": 5e-2, "d_strain_equ_p": 5e-2}
+# fields the serial reference computes with in-place reads that a parallel engine evaluates on a snapshot:
+# XSPH positions (base:231-238) and the mu(I) regularised stress (muI:151-156, output-only field, H25)
+RACY = {"mui": {"stress"}, "xsph": {"x"}}
+STATE = ["x", "v", "density", "m_V", "pressure", "d_density", "d_vel", "density_tmp", "v_tmp", "CSPM_f"]
+SOIL_STATE = ["stress", "d_stress", "v_grad", "strain_equ", "strain_equ_p", "stress_tmp"]
+
+
+def _grid_checks(sim, g, s, exact_counts=True):
+    ps = sim.ps
+    ps.initialize_particle_system()
+    sim.solver.calc_kernel_corr()
+    assert np.array_equal(ps.pt.grid_ids.cpu().numpy(), g.grid(s, "grid_ids")), f"cell ids differ at step {s}"
+    assert np.array_equal(ps.pt.id0.cpu().numpy(), g.grid(s, "id0")), f"sorted order differs at step {s}"
+    assert np.array_equal(ps.grid_particle_num.cpu().numpy(), g.grid(s, "grid_particle_num")), f"cell offsets differ at step {s}"
+    if exact_counts:
+        assert np.array_equal(ps.neighbor_count().cpu().numpy(), g.grid(s, "neighbor_count")), f"neighbour counts differ at step {s}"
+    return ps
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_f64_matches_reference_fixtures(name):
+    """float64 engine vs the reference run: bit-exact integers at every snapshot, floats to 1e-9."""
+    g = Golden(name)
+    sim = make_sim(g.scene, precision="f64")
+    assert sim.ps.particle_num[None] == g.meta["n"]
+    assert sim.solver.dt[None] == g.meta["dt"]
+    cfg = g.scene["Configuration"]
+    racy = set()
+    if cfg["simulationMethod"] == 2:
+        racy |= RACY["mui"]
+    if cfg["xsph"]:
+        racy |= RACY["xsph"]
+    last = max(g.steps) if ("small_lf" in name and not cfg["xsph"]) or "tiny" in name else min(max(g.steps), 10)
+    # with XSPH the serial reference moves particles in place: positions drift from the snapshot evaluation by
+    # O(dt * |v| * 1e-4) per step, so only the first snapshots are compared tightly
+    if cfg["xsph"]:
+        last = 1
+    for s in range(1, last + 1):
+        if s in g.steps:
+            ps = _grid_checks(sim, g, s)
+            assert relmax(ps.pt.CSPM_f.cpu().numpy(), g.grid(s, "CSPM_f")) < F64_TOL
+            if cfg["kernelCorrection"] == 1:
+                assert relmax(ps.pt.CSPM_L.cpu().numpy().reshape(-1, 9), g.grid(s, "CSPM_L")) < F64_TOL
+        sim.solver.step()
+        if s in g.steps:
+            got = engine_fields(sim)
+            assert np.array_equal(got["id0"], g.end(s, "id0"))
+            if cfg["simulationMethod"] == 3:
+                assert np.array_equal(got["flag_retmap"], g.end(s, "flag_retmap"))
+            fields = STATE + (SOIL_STATE if cfg["simulationMethod"] != 1 else [])
+            for f in fields:
+                if f in racy:
+                    continue
+                err = relmax(got[f], g.end(s, f))
+                assert err < FIELD_TOL.get(f, F64_TOL), f"{name}: step {s} field {f}: rel err {err:.3e}"
+    assert sim.ps.engine.L.sph_read_bad_cells(sim.ps.engine.h) == 0
+
+
+@pytest.mark.parametrize("name", ["mui2d_small_lf", "dp2d_small_lf", "dp2d_small_rk4_cspm", "wc2d_small_lf"])
+def test_f64_matches_oracle_jacobi_long(name):
+    """float64 engine vs the oracle in snapshot ('jacobi') mode over the whole horizon of the fixture, all fields."""
+    from oracle import oracle as orc
+    g = Golden(name)
+    sim = make_sim(g.scene, precision="f64")
+    o = orc.Oracle.from_scene(g.scene, serial=0)
+    nsteps = min(max(g.steps), 30)
+    for s in range(1, nsteps + 1):
+        sim.solver.step()
+        assert o.step() == 0
+        if s in (1, 2, 5, 10, nsteps):
+            got = engine_fields(sim)
+            assert np.array_equal(got["id0"], o.id0)
+            assert np.array_equal(got["grid_ids"], o.grid_ids)
+            fields = STATE + (SOIL_STATE if g.scene["Configuration"]["simulationMethod"] != 1 else [])
+            for f in fields:
+                err = relmax(got[f], getattr(o, f))
+                # errors grow with step count through threshold branches (DP) - stated tolerance 1e-7 at 30 steps
+                tol = FIELD_TOL.get(f, 1e-9 if s <= 2 else 1e-7)
+                assert err < tol, f"{name}: step {s} field {f}: rel err {err:.3e}"
+
+
+@pytest.mark.parametrize("name", ["wc2d_small_lf", "wc3d_tiny_lf"])
+def test_native_step_loop_equals_python_orchestration(name):
+    """sph_step (whole step enqueued natively) must be bit-identical to SPHBase.step() driven from Python."""
+    g = Golden(name)
+    a = make_sim(g.scene, precision="f64")
+    b = make_sim(g.scene, precision="f64")
+    for _ in range(3):
+        a.solver.step()
+    b.solver.run_steps(3)
+    fa, fb = engine_fields(a), engine_fields(b)
+    for k in ("id0", "x", "v", "density", "pressure", "d_vel"):
+        assert np.array_equal(fa[k], fb[k]), k
+
+
+# -------------------------------------------------------------------------------------------- mixed precision
+MIXED_TOL_1 = 1e-5     # north_star: density, pressure, acceleration, stress within 1e-5 relative after one step
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_mixed_one_step_within_1e5(name):
+    g = Golden(name)
+    sim = make_sim(g.scene, precision="f32")
+    cfg = g.scene["Configuration"]
+    _grid_checks(sim, g, 1, exact_counts=False)      # cell ids / order / offsets are float64 work in both modes
+    sim.solver.step()
+    got = engine_fields(sim)
+    assert np.array_equal(got["id0"], g.end(1, "id0"))
+    fields = ["density", "pressure", "d_vel", "v", "d_density", "x"]
+    if cfg["simulationMethod"] == 3:
+        fields += ["stress", "d_stress"]
+    if cfg["simulationMethod"] == 2:
+        fields += ["stress_tmp"]
+    for f in fields:
+        err = relmax(got[f], g.end(1, f))
+        assert err < MIXED_TOL_1, f"{name}: field {f}: rel err {err:.3e}"
+
+
+def test_mixed_neighbor_counts_bit_exact_vs_oracle():
+    """The float32 predicate (cell-local coordinates) restated in the oracle gives identical counts."""
+    from oracle import oracle as orc
+    for name in ("c1_test1_wc_lf", "wc3d_tiny_lf"):
+        g = Golden(name)
+        sim = make_sim(g.scene, precision="f32")
+        o = orc.Oracle.from_scene(g.scene, serial=0)
+        for s in range(3):
+            sim.ps.initialize_particle_system()
+            o.grid_build()
+            assert np.array_equal(sim.ps.neighbor_count().cpu().numpy(), o.neighbor_count(f32=True)), (name, s)
+            sim.solver.step()
+            o.x[:] = sim.ps.pt.x.cpu().numpy()      # same positions on both sides
+
+
+def test_mixed_100_step_horizon_wc():
+    """Stated tolerance over a 100-step horizon (2D dambreak, 'LF'): rho 1e-6, v 1e-3, p 2e-2 (max-norm relative)
+    against the reference fixture.  Pressure is the Tait EOS of a density known to ~1e-7, amplified by gamma*k/p."""
+    g = Golden("wc2d_small_lf")
+    sim = make_sim(g.scene, precision="f32")
+    sim.solver.run_steps(100)
+    got = engine_fields(sim)
+    assert np.array_equal(got["id0"], g.end(100, "id0"))
+    assert relmax(got["density"], g.end(100, "density")) < 1e-6
+    assert relmax(got["x"], g.end(100, "x")) < 1e-6
+    assert relmax(got["v"], g.end(100, "v")) < 1e-3
+    assert relmax(got["pressure"], g.end(100, "pressure")) < 2e-2
+
+
+def test_f64_100_step_horizon_wc():
+    g = Golden("wc2d_small_lf")
+    sim = make_sim(g.scene, precision="f64")
+    sim.solver.run_steps(100)
+    got = engine_fields(sim)
+    assert np.array_equal(got["id0"], g.end(100, "id0"))
+    for f in ("density", "x", "v", "pressure", "d_vel"):
+        assert relmax(got[f], g.end(100, f)) < 1e-8, f
+
+
+# -------------------------------------------------------------------------------------------- properties at size
+def _box_scene(n_side, is2d=False):
+    d = 0.01
+    L = n_side * d
+    return {
+        "Configuration": dict(is2D=is2d, domainStart=[0.0, 0.0, 0.0], domainEnd=[2 * L, 1.5 * L, L if not is2d else 0.5],
+                              gravitation=[0.0, -9.81, 0.0], particleRadius=d / 2, kappa=2.0, kh=1.5, simulationMethod=1,
+                              timeStepSizeMin=1e-6, boundary=2, kernel=1, kernelCorrection=0, timeIntegration=2,
+                              xsph=False, colorTitle=0, colorGroup=0, showBdyPts=True),
+        "Materials": [dict(matId=0, matType=1, density0=1000.0, viscosity=0.01, stiffness=50000.0, exponent=7.0,
+                           color=[50, 100, 200])],
+        "Blocks": [dict(objectId=0, materialId=0, translation=[0.0, 0.0, 0.0], size=[L, L, L if not is2d else 0.5],
+                        velocity=[0.0, 0.0, 0.0], rotationAxis=[0, 0, 1], rotationAngle=0)],
+    }
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_large_3d_sort_properties(prec):
+    """~1M fluid particles: sortedness, permutation, histogram/offset consistency, idempotence of the grid build,
+    symmetry of the neighbour relation (sum of counts is even) and agreement of the two precisions' step."""
+    import torch
+    sim = make_sim(_box_scene(100), precision=prec)
+    ps = sim.ps
+    n = ps.particle_num[None]
+    assert n > 1_000_000
+    sim.solver.run_steps(2)
+    ps.initialize_particle_system()
+    gid = ps.pt.grid_ids
+    assert bool((gid[1:] >= gid[:-1]).all()), "cell ids not sorted"
+    id0 = ps.pt.id0.long()
+    assert bool((torch.sort(id0).values == torch.arange(n, device=id0.device)).all()), "id0 is not a permutation"
+    cell_end = ps.grid_particle_num.long()
+    hist = torch.bincount(gid.long(), minlength=ps.grid_num_total)
+    assert bool((torch.cumsum(hist, 0) == cell_end).all())
+    assert bool((ps.grid_particle_num_temp.long() == hist).all())
+    # stability: inside a cell the previous relative order is kept -> a second build is the identity
+    before = id0.clone()
+    ps.initialize_particle_system()
+    assert bool((ps.pt.id0.long() == before).all())
+    cnt = ps.neighbor_count().long()
+    assert int(cnt.sum()) % 2 == 0
+    assert int(cnt.max()) < 400
+    assert sim.ps.engine.L.sph_read_bad_cells(sim.ps.engine.h) == 0
+    assert bool(torch.isfinite(ps.pt.v).all()) and bool(torch.isfinite(ps.pt.density).all())
+
+
+def test_density_sum_matches_oracle_small_3d():
+    from oracle import oracle as orc
+    g = Golden("wc3d_tiny_lf")
+    for prec, tol in (("f64", 1e-12), ("f32", 2e-6)):
+        sim = make_sim(g.scene, precision=prec)
+        o = orc.Oracle.from_scene(g.scene, serial=0)
+        sim.ps.initialize_particle_system()
+        o.grid_build()
+        got = sim.ps.density_sum().cpu().numpy()
+        assert relmax(got, o.density_sum()) < tol, prec

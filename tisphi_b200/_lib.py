@@ -22,7 +22,8 @@ SYMBOLS = ["sph_arena_bytes", "sph_create", "sph_destroy", "sph_last_error", "sp
            "sph_add_particles", "sph_num_particles", "sph_clear_particles", "sph_read_state", "sph_grid_build",
            "sph_calc_kernel_corr", "sph_init_real2tmp", "sph_one_step", "sph_advect", "sph_advect_pos", "sph_post_step",
            "sph_init_stress", "sph_step", "sph_neighbor_count", "sph_density_sum", "sph_read_bad_cells",
-           "sph_launch_count", "sph_set_ghost_range"]
+           "sph_launch_count", "sph_set_ghost_range", "sph_profile_enable", "sph_profile_num_kernels",
+           "sph_profile_name", "sph_profile_read", "sph_params_size"]
 
 
 class SphParams(C.Structure):
@@ -71,6 +72,13 @@ def load():
     L.sph_read_bad_cells.restype, L.sph_read_bad_cells.argtypes = i64, [vp]
     L.sph_launch_count.restype, L.sph_launch_count.argtypes = i64, [vp]
     L.sph_set_ghost_range.restype, L.sph_set_ghost_range.argtypes = C.c_int, [vp, i64, i64]
+    L.sph_profile_enable.restype, L.sph_profile_enable.argtypes = C.c_int, [vp, C.c_int]
+    L.sph_profile_num_kernels.restype, L.sph_profile_num_kernels.argtypes = C.c_int, []
+    L.sph_profile_name.restype, L.sph_profile_name.argtypes = C.c_char_p, [C.c_int]
+    L.sph_profile_read.restype, L.sph_profile_read.argtypes = C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i64)]
+    L.sph_params_size.restype, L.sph_params_size.argtypes = i64, []
+    if L.sph_params_size() != C.sizeof(SphParams):
+        raise SphError('SphParams layout mismatch between tisphi_b200/_lib.py and include/tisphi_b200.h')
     _lib = L
     return L
 
@@ -143,6 +151,16 @@ class Engine:
         if nc.value == 1:
             return flat.as_strided((count,), (stride.value,))
         return flat.as_strided((count, nc.value), (stride.value, 1))
+
+    def profile(self, on=True):
+        self.check(self.L.sph_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """{kernel class: (total ms, launches)} since the last read (CUDA events on the engine's stream)."""
+        k = self.L.sph_profile_num_kernels()
+        ms, cnt = (C.c_double * k)(), (C.c_int64 * k)()
+        self.check(self.L.sph_profile_read(self.h, ms, cnt))
+        return {self.L.sph_profile_name(i).decode(): (ms[i], cnt[i]) for i in range(k) if cnt[i] > 0}
 
     def add_particles(self, x, v, density, mat_type):
         import numpy as np

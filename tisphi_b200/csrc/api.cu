@@ -118,6 +118,36 @@ template <typename T> int dispatch_step(SphCtx *c, int nsteps);
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------- profiling
+#include <vector>
+namespace {
+struct ProfState {
+    std::vector<cudaEvent_t> pool;         // event pairs (begin, end)
+    std::vector<int> ids;                  // kernel id of each recorded pair
+    size_t used = 0;
+};
+const char *KNAMES[K_NUM] = {"cell_id", "scan", "scatter_index", "rank", "reorder", "cspm_f", "cspm_L", "wc_eos", "wc_wall",
+                             "wc_fluid", "mui_soil1", "soil_wall", "mui_soil3", "dp_adapt", "dp_soil", "advect_pos", "post",
+                             "post_sweep", "neighbor_count", "density_sum", "other", "init_real2tmp", "advect", "tile_mask",
+                             "tile_fluid", "tile_wall", "halo"};
+}
+void sph_prof_begin(SphCtx *c, int id) {
+    ProfState *ps = (ProfState *)c->prof_state;
+    if (ps->used + 2 > ps->pool.size()) {
+        for (int k = 0; k < 2; k++) { cudaEvent_t e; cudaEventCreate(&e); ps->pool.push_back(e); }
+    }
+    ps->ids.push_back(id);
+    cudaEventRecord(ps->pool[ps->used], c->stream);
+    c->prof_open = 1;
+}
+void sph_prof_end(SphCtx *c) {
+    if (!c->prof_open) return;
+    ProfState *ps = (ProfState *)c->prof_state;
+    cudaEventRecord(ps->pool[ps->used + 1], c->stream);
+    ps->used += 2;
+    c->prof_open = 0;
+}
+
 namespace sph {
 
 void flip(SphCtx *c, int field) { c->f[field].cur ^= 1; }
@@ -259,7 +289,15 @@ SphCtx *sph_create(const SphParams *p, int64_t n_max, void *arena, int64_t arena
     if (cudaMemsetAsync(arena, 0, (size_t)layout(p, n_max, nullptr), c->stream) != cudaSuccess) { delete c; return nullptr; }
     return c;
 }
-void sph_destroy(SphCtx *c) { delete c; }
+void sph_destroy(SphCtx *c) {
+    if (!c) return;
+    if (c->prof_state) {
+        ProfState *ps = (ProfState *)c->prof_state;
+        for (cudaEvent_t e : ps->pool) cudaEventDestroy(e);
+        delete ps;
+    }
+    delete c;
+}
 const char *sph_last_error(SphCtx *c) { return c ? c->err : "null ctx"; }
 
 int sph_set_params(SphCtx *c, const SphParams *p) {
@@ -343,6 +381,31 @@ int64_t sph_read_bad_cells(SphCtx *c) {
     return (int64_t)v;
 }
 int64_t sph_launch_count(SphCtx *c) { return c->launches; }
+int64_t sph_params_size(void) { return (int64_t)sizeof(SphParams); }
+
+int sph_profile_enable(SphCtx *c, int on) {
+    if (!c->prof_state) c->prof_state = new ProfState();
+    c->prof_on = on != 0;
+    return 0;
+}
+int sph_profile_num_kernels(void) { return K_NUM; }
+const char *sph_profile_name(int id) { return (id >= 0 && id < K_NUM) ? KNAMES[id] : ""; }
+int sph_profile_read(SphCtx *c, double *ms_by_kernel, int64_t *launches_by_kernel) {
+    for (int k = 0; k < K_NUM; k++) { ms_by_kernel[k] = 0.0; launches_by_kernel[k] = 0; }
+    ProfState *ps = (ProfState *)c->prof_state;
+    if (!ps) return 0;
+    SPH_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (size_t k = 0; k < ps->ids.size() && k < ps->used / 2; k++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ps->pool[2 * k], ps->pool[2 * k + 1]) == cudaSuccess) {
+            ms_by_kernel[ps->ids[k]] += ms;
+            launches_by_kernel[ps->ids[k]]++;
+        }
+    }
+    ps->ids.clear();
+    ps->used = 0;
+    return 0;
+}
 int sph_set_ghost_range(SphCtx *c, int64_t b, int64_t e) { (void)c; (void)b; (void)e; return 0; }
 
 }  // extern "C"

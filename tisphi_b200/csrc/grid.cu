@@ -168,19 +168,26 @@ template <typename T> int grid_build(SphCtx *c) {
     int *id_new = (int *)(c->arena + c->f[SPH_F_ID_NEW].off[0]);
     cudaStream_t st = c->stream;
     SPH_CHECK(c, cudaMemsetAsync(a.cell_cnt, 0, sizeof(int) * (size_t)c->C, st));
+    SPH_PROF(c, K_CELL_ID);
     k_cell_id<T><<<blocks_for(n, 256), 256, 0, st>>>(a, gid_u, slot);
     SPH_LAUNCH_CHECK(c);
     const int nt = (c->C + SCAN_TILE - 1) / SCAN_TILE;
+    SPH_PROF(c, K_SCAN);
     k_scan_reduce<<<nt, SCAN_THREADS, 0, st>>>(a.cell_cnt, c->C, tiles);
     SPH_LAUNCH_CHECK(c);
+    SPH_PROF(c, K_SCAN);
     k_scan_tiles<<<1, 1024, 0, st>>>(tiles, nt);
     SPH_LAUNCH_CHECK(c);
+    SPH_PROF(c, K_SCAN);
     k_scan_apply<<<nt, SCAN_THREADS, 0, st>>>(a.cell_cnt, c->C, tiles, a.cell_end);
     SPH_LAUNCH_CHECK(c);
+    SPH_PROF(c, K_SCATTER);
     k_scatter_index<<<blocks_for(n, 256), 256, 0, st>>>(n, gid_u, slot, a.cell_end, tmpidx);
     SPH_LAUNCH_CHECK(c);
+    SPH_PROF(c, K_RANK);
     k_rank<<<blocks_for(n, 256), 256, 0, st>>>(n, gid_u, a.cell_end, tmpidx, perm, id_new);
     SPH_LAUNCH_CHECK(c);
+    SPH_PROF(c, K_REORDER);
     k_reorder<T><<<blocks_for(n, 256), 256, 0, st>>>(a, b, perm, gid_u, c->soil ? 1 : 0);
     SPH_LAUNCH_CHECK(c);
     static const int carried[] = {SPH_F_X, SPH_F_XS, SPH_F_V, SPH_F_V_TMP, SPH_F_DENSITY, SPH_F_PRESSURE, SPH_F_MAT_TYPE, SPH_F_ID0};

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256) k_add_finish(Dev<T> c, const double *__re
 template <typename T> int add_particles_finish(SphCtx *c, int64_t first, int64_t count) {
     Dev<T> d = make_dev<T>(c);
     const double *vstage = (const double *)(c->arena + c->f[SPH_F_X].off[1 - c->f[SPH_F_X].cur]);
+    SPH_PROF(c, K_OTHER);
     k_add_finish<T><<<blocks_for(count, 256), 256, 0, c->stream>>>(d, vstage, (int)first, (int)count);
     SPH_LAUNCH_CHECK(c);
     return 0;
@@ -51,6 +52,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_init_real2tmp(Dev
 }
 template <typename T> int init_real2tmp(SphCtx *c) {
     if (c->n == 0) return 0;
+    SPH_PROF(c, K_INIT_TMP);
     k_init_real2tmp<T><<<blocks_for(c->n, 256), 256, 0, c->stream>>>(make_dev<T>(c));
     SPH_LAUNCH_CHECK(c);
     return 0;
@@ -132,6 +134,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_advect(Dev<T> c, 
 template <typename T> int advect(SphCtx *c, int kind, int m) {
     if (c->n == 0) return 0;
     if (kind >= 3 && !c->rk) { snprintf(c->err, sizeof(c->err), "RK buffers exist only when timeIntegration == 4"); return -2; }
+    SPH_PROF(c, K_ADVECT);
     k_advect<T><<<blocks_for(c->n, 256), 256, 0, c->stream>>>(make_dev<T>(c), kind, (T)m);
     SPH_LAUNCH_CHECK(c);
     return 0;
@@ -165,8 +168,10 @@ template <typename T> int init_stress(SphCtx *c) {
     Dev<T> d = make_dev<T>(c);
     unsigned long long *ymax = (unsigned long long *)(c->arena + c->off_bad + 8);
     SPH_CHECK(c, cudaMemsetAsync(ymax, 0, 8, c->stream));
+    SPH_PROF(c, K_OTHER);
     k_ymax<T><<<blocks_for(c->n, 256), 256, 0, c->stream>>>(d, ymax);
     SPH_LAUNCH_CHECK(c);
+    SPH_PROF(c, K_OTHER);
     k_init_stress<T><<<blocks_for(c->n, 256), 256, 0, c->stream>>>(d, ymax, 1.0 - sin(c->p.fric), c->p.g[1]);
     SPH_LAUNCH_CHECK(c);
     return 0;

@@ -30,6 +30,10 @@ struct SphCtx {
     bool soil, rk, has_L;
     int press_cur;       // which of (PRESSURE buffer, pnew) ... handled through field table
     double r2thr64;
+    bool prof_on;
+    int prof_open;
+    int64_t launches_by_kernel[32];
+    void *prof_state;
     float r2thr32;
 };
 
@@ -42,9 +46,24 @@ struct SphCtx {
         }                                                                                             \
     } while (0)
 
+// per-kernel-class device timing (CUDA events on the launch stream), enabled with sph_profile_enable
+enum SphKernelId { K_CELL_ID = 0, K_SCAN, K_SCATTER, K_RANK, K_REORDER, K_CSPM_F, K_CSPM_L, K_WC_EOS, K_WC_WALL, K_WC_FLUID,
+                   K_MUI_SOIL1, K_SOIL_WALL, K_MUI_SOIL3, K_DP_ADAPT, K_DP_SOIL, K_ADVECT_POS, K_POST, K_POST_SWEEP,
+                   K_NEIGHBOR_COUNT, K_DENSITY_SUM, K_OTHER, K_INIT_TMP, K_ADVECT, K_TILE_MASK, K_TILE_FLUID, K_TILE_WALL,
+                   K_HALO, K_NUM };
+void sph_prof_begin(SphCtx *c, int id);
+void sph_prof_end(SphCtx *c);
+
+#define SPH_PROF(ctx, id)                                                                             \
+    do {                                                                                              \
+        if ((ctx)->prof_on) sph_prof_begin(ctx, id);                                                  \
+        (ctx)->launches_by_kernel[id]++;                                                              \
+    } while (0)
+
 #define SPH_LAUNCH_CHECK(ctx)                                                                         \
     do {                                                                                              \
         (ctx)->launches++;                                                                            \
+        if ((ctx)->prof_on) sph_prof_end(ctx);                                                        \
         SPH_CHECK(ctx, cudaGetLastError());                                                           \
     } while (0)
 

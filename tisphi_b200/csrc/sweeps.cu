@@ -67,9 +67,11 @@ template <typename T> __global__ void __launch_bounds__(128) k_cspm_L(Dev<T> c) 
 template <typename T> int calc_kernel_corr(SphCtx *c) {
     if (c->n == 0) return 0;
     Dev<T> d = make_dev<T>(c);
+    SPH_PROF(c, K_CSPM_F);
     k_cspm_f<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(d);
     SPH_LAUNCH_CHECK(c);
     if (c->p.kcorr == 1) {
+        SPH_PROF(c, K_CSPM_L);
         k_cspm_L<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(d);
         SPH_LAUNCH_CHECK(c);
     }
@@ -420,28 +422,37 @@ template <typename T> int one_step(SphCtx *c) {
     cudaStream_t st = c->stream;
     if (c->p.solver == SPH_SOLVER_WC) {
         Dev<T> d = make_dev<T>(c);
+        SPH_PROF(c, K_WC_EOS);
         k_wc_eos<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
+        SPH_PROF(c, K_WC_WALL);
         k_wc_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
         flip(c, SPH_F_PRESSURE);               // pnew becomes pt.pressure
         d = make_dev<T>(c);
+        SPH_PROF(c, K_WC_FLUID);
         k_wc_fluid<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
     } else if (c->p.solver == SPH_SOLVER_MUI) {
         Dev<T> d = make_dev<T>(c);
+        SPH_PROF(c, K_MUI_SOIL1);
         k_mui_soil1<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
+        SPH_PROF(c, K_SOIL_WALL);
         k_soil_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
+        SPH_PROF(c, K_MUI_SOIL3);
         k_mui_soil3<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
     } else if (c->p.solver == SPH_SOLVER_DP) {
         Dev<T> d = make_dev<T>(c);
+        SPH_PROF(c, K_DP_ADAPT);
         k_dp_adapt<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
+        SPH_PROF(c, K_SOIL_WALL);
         k_soil_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
+        SPH_PROF(c, K_DP_SOIL);
         k_dp_soil<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
     } else {
@@ -502,10 +513,12 @@ template <typename T> int advect_pos(SphCtx *c) {
     const int n = (int)c->n;
     Dev<T> d = make_dev<T>(c);
     if (!c->p.xsph) {
+        SPH_PROF(c, K_ADVECT_POS);
         k_advect_pos<T><<<blocks_for(n, 256), 256, 0, c->stream>>>(d);
         SPH_LAUNCH_CHECK(c);
     } else {
         double *xnew = (double *)(c->arena + c->f[SPH_F_X].off[1 - c->f[SPH_F_X].cur]);
+        SPH_PROF(c, K_ADVECT_POS);
         k_advect_pos_xsph<T><<<blocks_for(n, 128), 128, 0, c->stream>>>(d, xnew);
         SPH_LAUNCH_CHECK(c);
         flip(c, SPH_F_X);
@@ -572,16 +585,21 @@ template <typename T> int post_step(SphCtx *c) {
     Dev<T> d = make_dev<T>(c);
     cudaStream_t st = c->stream;
     if (c->p.solver == SPH_SOLVER_WC) {
+        SPH_PROF(c, K_POST);
         k_post_wc<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
     } else if (c->p.solver == SPH_SOLVER_DP) {
+        SPH_PROF(c, K_POST);
         k_post_dp<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
     } else {
+        SPH_PROF(c, K_POST);
         k_post_mui_a<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
+        SPH_PROF(c, K_POST);
         k_refresh_xs<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
+        SPH_PROF(c, K_POST_SWEEP);
         k_post_mui_b<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
     }
@@ -605,12 +623,14 @@ template <typename T> __global__ void __launch_bounds__(128) k_density_sum(Dev<T
 }
 template <typename T> int neighbor_count(SphCtx *c, int32_t *out) {
     if (c->n == 0) return 0;
+    SPH_PROF(c, K_NEIGHBOR_COUNT);
     k_neighbor_count<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(make_dev<T>(c), out);
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
 template <typename T> int density_sum(SphCtx *c, void *out) {
     if (c->n == 0) return 0;
+    SPH_PROF(c, K_DENSITY_SUM);
     k_density_sum<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(make_dev<T>(c), (T *)out);
     SPH_LAUNCH_CHECK(c);
     return 0;
