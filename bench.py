@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of the tiSPHi hot path on B200 (BASELINE.json metric), one JSON line on stdout.
+
+Workload (config.workload): BASELINE config C4, the 3D WCSPH dambreak (Wendland C2, dummy walls, "LF" integrator)
+with 10 240 000 fluid + 2 719 788 dummy = 12 959 788 particles on 269 x 136 x 56 cells; one "step" = one
+SPHBase.step() = grid build + kernel correction + 2 x one_step + integrator + advect_pos + post-step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA engine (MIXED precision: fp32 sweeps,
+                                                                  fp64 positions/densities)
+  python bench.py --impl reference ...                           the CPU restatement of the reference (oracle/, float64,
+                                                                  OpenMP on all host cores) on a bounded sample of
+                                                                  the same workload (Taichi itself is not installable here)
+value        device-timed (CUDA events), state resident in HBM.
+e2e          the same metric through the C ABI with HOST buffers: every step uploads the particle state from pinned
+             host memory (sph_add_particles), runs sph_step(1) and reads the state back (sph_read_state).
+roofline     dominant kernel class, algorithmic bytes / CUDA-event time measured inside the timed region.
+cpu_baseline the oracle timed on this box's host cores on a bounded sample (rank 0, N = 1 only).
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC, UNIT = "particle-updates/s", "particle-updates/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi style clock / throttle-reason samples during the timed region (pynvml)."""
+
+    def __init__(self, index=0, period=0.1):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.period = period
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            log("clock sampling unavailable:", e)
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.nv:
+            self.t.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU baseline
+def cpu_reference(scale, steps, warmup=0):
+    """Oracle (float64 restatement of the reference, OpenMP) on the C4 scene coarsened by `scale`."""
+    from oracle import oracle as orc
+    from tisphi_b200 import scenes
+    scene = scenes.dambreak3d(scale=scale, precision="f64")
+    o = orc.Oracle.from_scene(scene, serial=0)
+    for _ in range(warmup):
+        o.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        assert o.step() == 0
+    dt = time.perf_counter() - t0
+    cores = os.cpu_count()
+    return {"value": o.n * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"C4 scene coarsened x{1 / scale:g} (N={o.n}), {steps} steps, float64, OpenMP {cores} threads, "
+                      f"{dt:.1f} s; restated CPU baseline (Taichi not installable in this image)"}, o.n, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, n, dt = cpu_reference(args.cpu_scale, max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / max(1, args.steps) * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "C4 3D WCSPH dambreak (Wendland C2, dummy walls, LF), bounded sample: " + base["sample"]},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- algorithmic bytes
+def algorithmic_bytes(kernel, n, n_fluid, n_wall, cells):
+    """Algorithmic bytes per launch of a kernel class (DESIGN.md section 'Kernels and their roofline')."""
+    table = {
+        # read {x,y,z,V | v~x,v~y,v~z,rho~ | type | p} = 36 B of every particle, write {d_rho, d_vel} = 16 B per fluid
+        "wc_fluid": 36 * n + 16 * n_fluid, "tile_fluid": 36 * n + 16 * n_fluid,
+        # read the same 36 B of every particle (+4 B previous pressure), write {v~, rho~, p} = 20 B per wall particle
+        "wc_wall": 40 * n + 20 * n_wall, "tile_wall": 40 * n + 20 * n_wall,
+        # read {x,y,z,V} + type = 20 B, write f = 4 B
+        "cspm_f": 24 * n, "tile_mask": 24 * n,
+        # read perm 4 + key 4 + carried payload, write payload + key: x 24, xs 16, v 16, v~ 16, rho 8, p 4, type 4, id0 4
+        "reorder": 8 * n + 2 * 92 * n + 4 * n,
+        "cell_id": 24 * n + 8 * n, "rank": 12 * n, "scatter_index": 12 * n, "scan": 12 * cells,
+        "advect": 56 * n_fluid, "init_real2tmp": 52 * n_fluid, "wc_eos": 16 * n, "advect_pos": 64 * n_fluid, "post": 40 * n_fluid,
+    }
+    return table.get(kernel)
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from tisphi_b200.parallel import run_bench_multi
+        return run_bench_multi(args, rank, local, world)
+    torch.cuda.set_device(local)
+    from tisphi_b200 import scenes
+    from tisphi_b200.eng.simulation import Simulation, SimConfiger
+
+    scene = scenes.dambreak3d(scale=args.scale, precision=args.precision)
+    t0 = time.time()
+    sim = Simulation(SimConfiger(config=scene), device=f"cuda:{local}")
+    ps, solver, eng = sim.ps, sim.solver, sim.ps.engine
+    n = ps.particle_num[None]
+    typ = ps.pt.mat_type
+    n_fluid = int((typ == 1).sum())
+    n_wall = n - n_fluid
+    log(f"scene built: N={n} (fluid {n_fluid}, wall {n_wall}), cells={ps.grid_num_total}, dt={solver.dt[None]!r}, {time.time() - t0:.1f}s")
+
+    # host copy of the initial state for the end-to-end leg (pinned)
+    pin = lambda t: t.detach().cpu().contiguous().pin_memory()
+    h_x, h_rho, h_typ = pin(ps.pt.x), pin(ps.pt.density), pin(ps.pt.mat_type)
+    h_v = pin(ps.pt.v.double())
+
+    solver.run_steps(args.warmup)
+    torch.cuda.synchronize()
+    launches0 = eng.L.sph_launch_count(eng.h)
+    eng.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record(eng.stream)
+        solver.run_steps(args.steps)
+        e1.record(eng.stream)
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    prof = eng.profile_read()
+    eng.profile(False)
+    launches = eng.L.sph_launch_count(eng.h) - launches0
+    bad = eng.L.sph_read_bad_cells(eng.h)
+    value = n * args.steps / (ms * 1e-3)
+    assert bool(torch.isfinite(ps.pt.v).all()), "non-finite velocities after the timed region"
+
+    # roofline of the dominant kernel class
+    peak, peak_kind = measured_peaks()
+    dom = max(prof.items(), key=lambda kv: kv[1][0])
+    dom_name, (dom_ms, dom_cnt) = dom
+    ab = algorithmic_bytes(dom_name, n, n_fluid, n_wall, ps.grid_num_total)
+    achieved = ab / (dom_ms / dom_cnt * 1e-3) / 1e9 if ab else None
+    kernel_share = {k: round(v[0] / ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    kernel_ms = {k: round(v[0] / v[1], 4) for k, v in prof.items()}
+    kernel_gbs = {}
+    for k, v in prof.items():
+        b = algorithmic_bytes(k, n, n_fluid, n_wall, ps.grid_num_total)
+        if b:
+            kernel_gbs[k] = round(b / (v[0] / v[1] * 1e-3) / 1e9, 1)
+    step_bytes = 208 * n + 104 * n_wall + 12 * ps.grid_num_total          # SURVEY 8(d) formula, per step
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None, "traffic": None, "peak_kind": peak_kind,
+                "note": "neighbour sweeps are fp32-issue bound, not HBM bound (SURVEY 8d); frac is the HBM view of the "
+                        "dominant kernel; per-kernel figures in kernel_gbs",
+                "kernel_share_of_step": kernel_share, "kernel_ms": kernel_ms, "kernel_gbs": kernel_gbs,
+                "whole_step_algorithmic_gbs": step_bytes * args.steps / (ms * 1e-3) / 1e9}
+
+    # end-to-end through the C ABI with host buffers
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    out_x = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    out_v = torch.empty((n, 4), dtype=eng.real).pin_memory()
+    out_rho = torch.empty(n, dtype=torch.float64).pin_memory()
+    out_p = torch.empty(n, dtype=eng.real).pin_memory()
+    out_id = torch.empty(n, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        eng.call("sph_clear_particles")
+        eng.call("sph_add_particles", n, h_x.data_ptr(), h_v.data_ptr(), h_rho.data_ptr(), h_typ.data_ptr())
+        eng.call("sph_step", 1)
+        eng.call("sph_read_state", out_x.data_ptr(), out_v.data_ptr(), out_rho.data_ptr(), out_p.data_ptr(), out_id.data_ptr())
+
+    e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = n * (24 + 24 + 8 + 4)
+    d2h = n * (24 + 4 * out_v.element_size() + 8 + out_p.element_size() + 4)
+    e2e = {"value": n * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3}
+
+    cpu = None
+    if not args.no_cpu:
+        cpu, _, _ = cpu_reference(args.cpu_scale, args.cpu_steps)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if args.precision != "f64" else "f64", "data": "synthetic",
+            "config": {"workload": f"C4 3D WCSPH dambreak (Wendland C2, dummy walls, LF): N={n} ({n_fluid} fluid + {n_wall} wall), "
+                                   f"cells={ps.grid_num_total}, dt={solver.dt[None]!r}, scale={args.scale}",
+                       "precision": "mixed: fp32 sweeps, fp64 positions+densities" if args.precision != "f64" else "f64",
+                       "l2": "state (>= 2 GB) larger than L2, no flush needed", "bad_cells": int(bad)},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "real_particle_updates_per_s": n_fluid * args.steps / (ms * 1e-3)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="lattice refinement of the C4 scene (1 = 12.96 M particles)")
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-scale", type=float, default=0.25, help="coarsening of the CPU-baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,15 @@ __device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
 __device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
 
+// squared distance of the neighbour predicate.  float64: unfused (dx*dx + dy*dy) + dz*dz, the expression the reference
+// evaluates (ps:268 norm()).  float32 (MIXED): fma(dz,dz, fma(dy,dy, dx*dx)), restated verbatim with fmaf() in the oracle.
+__device__ __forceinline__ double dist2(double dx, double dy, double dz) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+__device__ __forceinline__ float dist2(float dx, float dy, float dz) {
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
 // Device view of one engine instance.  Passed by value to every kernel.
 template <typename T> struct Dev {
     // sizes
@@ -116,8 +125,8 @@ template <typename T> __device__ __forceinline__ T kernel_dW_over_r(const Dev<T>
 
 // ------------------------------------------------------------------ generic neighbour iteration (ps:259-269)
 // Centre cell from the CURRENT master position (ps:261); 3^dim cells x-major / z-fastest; j ascending; out-of-range
-// cells per axis are empty; strict r < support evaluated as r2 < r2thr (same predicate, no sqrt) on
-// unfused r2 = (dx*dx + dy*dy) + dz*dz.   body(j, dx, dy, dz, r)
+// cells per axis are empty; strict r < support evaluated as r2 < r2thr (same predicate, no sqrt);
+// d = (x_i - x_j) - cell shift, which is exactly antisymmetric in (i, j) in both precisions.   body(j, dx, dy, dz, r, V_j)
 template <typename T, typename F> __device__ __forceinline__ void for_neighbors(const Dev<T> &c, int i, F &&body) {
     int cc[3], sc[3] = {0, 0, 0};
     const double xi[3] = {c.x[3 * (size_t)i], c.x[3 * (size_t)i + 1], c.x[3 * (size_t)i + 2]};
@@ -142,8 +151,8 @@ template <typename T, typename F> __device__ __forceinline__ void for_neighbors(
                 for (int j = jb; j < je; j++) {
                     if (j == i) continue;
                     Vec4<T> pj = c.xs4[j];
-                    T dx = pi.x - (pj.x + sx), dy = pi.y - (pj.y + sy), dz = pi.z - (pj.z + sz);
-                    T r2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
+                    T dx = (pi.x - pj.x) - sx, dy = (pi.y - pj.y) - sy, dz = (pi.z - pj.z) - sz;
+                    T r2 = dist2(dx, dy, dz);
                     if (r2 < c.r2thr) body(j, dx, dy, dz, sqrt_rn(r2), pj.w);
                 }
             }
