@@ -769,7 +769,7 @@ void orc_neighbor_count_f32(Orc *o, int32_t *out) {
 
 /* float32 predicate of the MIXED engine: coordinates local to the cell each particle is stored in (grid_ids),
  * xs = (float)(x - (vstart + cell*gs)) with unfused float64 ops, neighbour coordinates shifted by
- * d = (xs_i - xs_j) - (float)(cell_j - cell_i) * (float)gs, r2 = fma(dz,dz, fma(dy,dy, fl(dx*dx))),
+ * d = (xs_i - (float)(cell_j - cell_i) * (float)gs) - xs_j, r2 = fma(dz,dz, fma(dy,dy, fl(dx*dx))),
  * sqrtf(r2) < (float)support. */
 static inline void unflatten(const OrcParams *p, int64_t g, int c[3]) {
     int64_t nyz = (int64_t)p->gn[1] * p->gn[2];
@@ -809,8 +809,8 @@ void orc_neighbor_count_f32local(Orc *o, int32_t *out) {
                 float xj[3];
                 unflatten(p, o->ia[I_GRID_IDS][j], sj);
                 local_xs(o, j, sj, xj);
-                float ex = xi[0] - xj[0], ey = xi[1] - xj[1], ez = xi[2] - xj[2];
-                float dx = ex - sh[0], dy = ey - sh[1], dz = ez - sh[2];
+                float ex = xi[0] - sh[0], ey = xi[1] - sh[1], ez = xi[2] - sh[2];
+                float dx = ex - xj[0], dy = ey - xj[1], dz = ez - xj[2];
                 float xx = dx * dx;
                 float r2 = fmaf(dz, dz, fmaf(dy, dy, xx));
                 if (sqrtf(r2) < sup) c++;

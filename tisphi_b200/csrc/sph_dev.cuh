@@ -126,7 +126,7 @@ template <typename T> __device__ __forceinline__ T kernel_dW_over_r(const Dev<T>
 // ------------------------------------------------------------------ generic neighbour iteration (ps:259-269)
 // Centre cell from the CURRENT master position (ps:261); 3^dim cells x-major / z-fastest; j ascending; out-of-range
 // cells per axis are empty; strict r < support evaluated as r2 < r2thr (same predicate, no sqrt);
-// d = (x_i - x_j) - cell shift, which is exactly antisymmetric in (i, j) in both precisions.   body(j, dx, dy, dz, r, V_j)
+// d = (x_i - cell shift) - x_j: the own coordinate is moved into the frame of the neighbour's cell once per cell.   body(j, dx, dy, dz, r, V_j)
 template <typename T, typename F> __device__ __forceinline__ void for_neighbors(const Dev<T> &c, int i, F &&body) {
     int cc[3], sc[3] = {0, 0, 0};
     const double xi[3] = {c.x[3 * (size_t)i], c.x[3 * (size_t)i + 1], c.x[3 * (size_t)i + 2]};
@@ -151,7 +151,7 @@ template <typename T, typename F> __device__ __forceinline__ void for_neighbors(
                 for (int j = jb; j < je; j++) {
                     if (j == i) continue;
                     Vec4<T> pj = c.xs4[j];
-                    T dx = (pi.x - pj.x) - sx, dy = (pi.y - pj.y) - sy, dz = (pi.z - pj.z) - sz;
+                    T dx = (pi.x - sx) - pj.x, dy = (pi.y - sy) - pj.y, dz = (pi.z - sz) - pj.z;
                     T r2 = dist2(dx, dy, dz);
                     if (r2 < c.r2thr) body(j, dx, dy, dz, sqrt_rn(r2), pj.w);
                 }
