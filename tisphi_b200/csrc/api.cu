@@ -82,7 +82,21 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
     int64_t o_bad = off; off += 256;
     const int64_t nt = (C + 2047) / 2048 + 1;
     int64_t o_tiles = off; off += align_up(nt * 4);
+    // cell-tile fast path scratch: MIXED precision WCSPH without CSPM_L
+    const bool fast = p->fast && p->precision == SPH_PREC_MIXED && p->solver == SPH_SOLVER_WC && p->kcorr == 0;
+    const int mask_words = p->dim == 3 ? 27 : 9;
+    int64_t o_ps4 = 0, o_pk4 = 0, o_mask = 0, o_nflow = 0, o_cflag = 0, o_nflag = 0;
+    if (fast) {
+        o_ps4 = off; off += align_up(n_max * 16);
+        o_pk4 = off; off += align_up(n_max * 16);
+        o_mask = off; off += align_up(n_max * 4 * mask_words);
+        o_nflow = off; off += align_up(n_max);
+        o_cflag = off; off += align_up(C + 1);
+        o_nflag = off; off += 256;
+    }
     if (c) {
+        c->off_ps4 = o_ps4; c->off_pk4 = o_pk4; c->off_mask = o_mask; c->off_nflow = o_nflow; c->off_cellflag = o_cflag;
+        c->off_nflag = o_nflag; c->fast = fast; c->mask_words = mask_words;
         c->off_gid_unsorted = o_gid; c->off_slot = o_slot; c->off_perm = o_perm; c->off_tmpidx = o_tmp;
         c->off_bad = o_bad; c->off_scan_tiles = o_tiles;
         c->real_bytes = rb; c->soil = soil; c->rk = rk; c->has_L = hasL; c->C = (int)C;
@@ -210,6 +224,14 @@ template <typename T> Dev<T> make_dev(SphCtx *c, int which) {
     d.cell_end = (int *)ptr(SPH_F_CELL_END, false);
     d.cell_cnt = (int *)ptr(SPH_F_CELL_COUNT, false);
     d.bad = (unsigned long long *)(c->arena + c->off_bad);
+    if (c->fast) {
+        d.ps4 = (Vec4<T> *)(c->arena + c->off_ps4);
+        d.pk4 = (Vec4<T> *)(c->arena + c->off_pk4);
+        d.mask = (unsigned *)(c->arena + c->off_mask);
+        d.nflow = (unsigned char *)(c->arena + c->off_nflow);
+        d.cellflag = (unsigned char *)(c->arena + c->off_cellflag);
+        d.nflag = (int *)(c->arena + c->off_nflag);
+    }
     return d;
 }
 template Dev<float> make_dev<float>(SphCtx *, int);
@@ -302,7 +324,7 @@ const char *sph_last_error(SphCtx *c) { return c ? c->err : "null ctx"; }
 
 int sph_set_params(SphCtx *c, const SphParams *p) {
     if (p->dim != c->p.dim || p->precision != c->p.precision || p->solver != c->p.solver || p->ti != c->p.ti ||
-        p->kcorr != c->p.kcorr || n_cells(p) != c->C) {
+        p->kcorr != c->p.kcorr || n_cells(p) != c->C || p->fast != c->p.fast) {
         snprintf(c->err, sizeof(c->err), "sph_set_params cannot change sizes, solver, precision or buffers");
         return -2;
     }

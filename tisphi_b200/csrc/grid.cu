@@ -142,11 +142,13 @@ __global__ void __launch_bounds__(256) k_reorder(Dev<T> a, Dev<T> b, const int *
     }
     xs.w = a.xs4[s].w;                              // m_V travels with the particle
     b.xs4[k] = xs;
+    const int ty = a.type[s];
+    if (a.ps4) { Vec4<T> ps = xs; ps.w = is_flow(ty) ? xs.w : -xs.w; a.ps4[k] = ps; }
     b.v4[k] = a.v4[s];
     b.vt4[k] = a.vt4[s];
     b.rho[k] = a.rho[s];
     b.press[k] = a.press[s];
-    b.type[k] = a.type[s];
+    b.type[k] = ty;
     b.id0[k] = a.id0[s];
     if (soil) {
         const size_t k6 = 6 * (size_t)k, s6 = 6 * (size_t)s;

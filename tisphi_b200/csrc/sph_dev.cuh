@@ -69,6 +69,14 @@ template <typename T> struct Dev {
     T *d_rho_rk; Vec4<T> *d_vel_rk; T *d_stress_rk;
     int *cell_end, *cell_cnt;
     unsigned long long *bad;                      // counter of out-of-grid particles (H7)
+    // cell-tile fast path (sweeps_tile.cu); null when the fast path is not allocated
+    Vec4<T> *ps4;        // sweep coords xyz, +m_V for flow particles / -m_V otherwise (tile payload A)
+    Vec4<T> *pk4;        // v_tmp.xyz, pressure / density_tmp^2                        (tile payload B of the fluid pass)
+    unsigned *mask;      // neighbour bit masks, word-major: mask[word * n + i], word = neighbour cell (x-major, z fastest)
+    unsigned char *nflow;     // min(number of flow neighbours, 255) per particle
+    unsigned char *cellflag;  // 1: this centre cell cannot use the tile path (a cell of its stencil holds > 32 particles ...)
+    int *nflag;               // number of flagged cells (device counter)
+    int flagged_only;         // generic kernels: process only particles of flagged cells
 };
 
 // ------------------------------------------------------------------------------------------------ cells

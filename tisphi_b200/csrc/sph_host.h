@@ -24,6 +24,9 @@ struct SphCtx {
     FieldSlot f[SPH_F_NUM];
     // scratch (byte offsets)
     int64_t off_gid_unsorted, off_slot, off_perm, off_tmpidx, off_pnew, off_bad, off_scan_tiles, off_x_alt_unused;
+    int64_t off_ps4, off_pk4, off_mask, off_nflow, off_cellflag, off_nflag;
+    bool fast;           // cell-tile fast path allocated (MIXED precision, WCSPH, no CSPM_L)
+    int mask_words;
     int scan_tiles;
     int64_t launches;
     int real_bytes;      // sizeof engine real
@@ -82,6 +85,10 @@ template <typename T> int advect_pos(SphCtx *c);
 template <typename T> int post_step(SphCtx *c);
 template <typename T> int neighbor_count(SphCtx *c, int32_t *out);
 template <typename T> int density_sum(SphCtx *c, void *out);
+// sweeps_tile.cu (float only)
+int tile_mask(SphCtx *c);
+int tile_wc_prep_and_wall(SphCtx *c);
+int tile_wc_fluid(SphCtx *c);
 // integrate.cu
 template <typename T> int init_real2tmp(SphCtx *c);
 template <typename T> int advect(SphCtx *c, int kind, int m);

@@ -12,9 +12,17 @@
 namespace sph {
 
 // --------------------------------------------------------------------------------------------- kernel correction
+// flagged-only mode: the cell-tile kernels handled every particle except those of flagged cells
+template <typename T> __device__ __forceinline__ bool skip_unflagged(const Dev<T> &c, int i) {
+    if (!c.flagged_only) return false;
+    if (*c.nflag == 0) return true;
+    return c.cellflag[c.gid[i]] == 0;
+}
+
 template <typename T> __global__ void __launch_bounds__(128) k_cspm_f(Dev<T> c) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n) return;
+    if (skip_unflagged(c, i)) return;
     T s = 0;
     for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
         if (is_flow(c.type[j])) s += Vj * kernel_W(c, r);
@@ -67,6 +75,11 @@ template <typename T> __global__ void __launch_bounds__(128) k_cspm_L(Dev<T> c) 
 template <typename T> int calc_kernel_corr(SphCtx *c) {
     if (c->n == 0) return 0;
     Dev<T> d = make_dev<T>(c);
+    if (c->fast) {                       // tile path: masks + CSPM_f; the generic kernel completes flagged cells
+        int r = tile_mask(c);
+        if (r) return r;
+        d.flagged_only = 1;
+    }
     SPH_PROF(c, K_CSPM_F);
     k_cspm_f<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(d);
     SPH_LAUNCH_CHECK(c);
@@ -117,6 +130,7 @@ template <typename T> __global__ void __launch_bounds__(128) k_wc_wall(Dev<T> c)
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n) return;
     if (!is_wall(c.type[i])) return;
+    if (skip_unflagged(c, i)) return;
     T Sv0 = 0, Sv1 = 0, Sv2 = 0, Sp = 0;
     for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
         const int tj = c.type[j];
@@ -136,13 +150,16 @@ template <typename T> __global__ void __launch_bounds__(128) k_wc_wall(Dev<T> c)
     c.vt4[i] = vt;
     c.rho_t[i] = c.rho0;
     const T p = Sp * f;
-    c.pnew[i] = p > (T)0 ? p : (T)0;
+    const T pc = p > (T)0 ? p : (T)0;
+    c.pnew[i] = pc;
+    if (c.pk4) { Vec4<T> pk = vt; pk.w = pc / (c.rho0T * c.rho0T); c.pk4[i] = pk; }
 }
 // loop B (wc:108-126): continuity (corrected gradient) + viscosity + pressure (plain gradient, H22)
 template <typename T> __global__ void __launch_bounds__(128) k_wc_fluid(Dev<T> c) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n) return;
     if (!is_fluid(c.type[i])) return;
+    if (skip_unflagged(c, i)) return;
     const Vec4<T> vi = c.vt4[i];
     const T rhoi = vi.w, pi = c.press[i];
     const T pri = pi / (rhoi * rhoi);
@@ -420,7 +437,22 @@ template <typename T> int one_step(SphCtx *c) {
     if (c->n == 0) return 0;
     const int n = (int)c->n;
     cudaStream_t st = c->stream;
-    if (c->p.solver == SPH_SOLVER_WC) {
+    if (c->p.solver == SPH_SOLVER_WC && c->fast) {
+        int r = tile_wc_prep_and_wall(c);
+        if (r) return r;
+        Dev<T> d = make_dev<T>(c);
+        d.flagged_only = 1;
+        SPH_PROF(c, K_WC_WALL);
+        k_wc_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+        flip(c, SPH_F_PRESSURE);
+        if ((r = tile_wc_fluid(c))) return r;
+        d = make_dev<T>(c);
+        d.flagged_only = 1;
+        SPH_PROF(c, K_WC_FLUID);
+        k_wc_fluid<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
+    } else if (c->p.solver == SPH_SOLVER_WC) {
         Dev<T> d = make_dev<T>(c);
         SPH_PROF(c, K_WC_EOS);
         k_wc_eos<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
