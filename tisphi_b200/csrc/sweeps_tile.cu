@@ -23,20 +23,22 @@ namespace sph {
 
 constexpr int ZB = 4;                 // cells (warps) per block along the fastest axis
 constexpr int BT = ZB * 32;           // threads per block
-constexpr int TILE_CAP = 1664;        // particles per block tile (3D rest lattice: 9 * 6 * 27 = 1458)
+constexpr int TILE_CAP = 1536;        // particles per block tile (3D rest lattice: 9 * 6 * 27 = 1458)
 constexpr int NRMAX = 9;
 constexpr int CBW = ZB + 3;           // cell boundaries per run
 
 typedef Vec4<float> F4;
 typedef Dev<float> DevF;
 
-struct TileShared {
-    F4 A[TILE_CAP];                   // ps4 spans
-    F4 B[TILE_CAP];                   // second payload (vt4 or pk4) spans
+// NPAY payload arrays of TILE_CAP float4 (+8 entries of slack: the chunked test loop may read past a cell's end)
+template <int NPAY> struct TileShared {
+    F4 P[NPAY][TILE_CAP + 8];
     unsigned long long bar;           // mbarrier
     int cb[NRMAX * CBW];              // tile index of the first particle of each (run, cell)
     int gdelta[NRMAX];                // global index = tile index + gdelta[run]
-    int total, overflow, any;
+    int total, overflow;
+    F4 ctab[ZB * 27];                 // per (warp, neighbour cell): shift xyz, tile index of the cell's first particle (int bits)
+    int cgd[ZB * 27];                 // per (warp, neighbour cell): global index - tile index
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -76,18 +78,39 @@ __host__ __device__ inline TileGeom make_geom(int dim, const int gn[3]) {
     g.nseg = (g.nF + ZB - 1) / ZB;
     return g;
 }
-// shift of neighbour cell (run r, fast offset dzi in 0..2) relative to the centre cell, in units of the cell edge
+// shift of neighbour cell (run r, fast offset dzi in 0..2) relative to the centre cell
 __device__ __forceinline__ void cell_shift(const DevF &c, const TileGeom &g, int r, int dzi, float &sx, float &sy, float &sz) {
-    if (g.nR == 9) { sx = (float)(r / 3 - 1) * c.gsT; sy = (float)(r % 3 - 1) * c.gsT; sz = (float)(dzi - 1) * c.gsT; }
-    else { sx = (float)(r - 1) * c.gsT; sy = (float)(dzi - 1) * c.gsT; sz = 0.f; }
+    if (g.nR == 9) {
+        const int rx = r / 3;
+        sx = (float)(rx - 1) * c.gsT; sy = (float)(r - 3 * rx - 1) * c.gsT; sz = (float)(dzi - 1) * c.gsT;
+    } else { sx = (float)(r - 1) * c.gsT; sy = (float)(dzi - 1) * c.gsT; sz = 0.f; }
+}
+
+// per-warp table of the stencil cells, so that advancing to the next cell costs one shared load
+template <int NPAY>
+__device__ __forceinline__ void build_ctab(const DevF &c, const TileGeom &g, TileShared<NPAY> &sh, int w, int lane) {
+    const int NW = g.nR * 3;
+    if (lane < NW) {
+        const int r = lane / 3, dzi = lane - 3 * r;
+        F4 t;
+        if (g.nR == 9) {
+            const int rx = r / 3;
+            t.x = (float)(rx - 1) * c.gsT; t.y = (float)(r - 3 * rx - 1) * c.gsT; t.z = (float)(dzi - 1) * c.gsT;
+        } else { t.x = (float)(r - 1) * c.gsT; t.y = (float)(dzi - 1) * c.gsT; t.z = 0.f; }
+        t.w = __int_as_float(sh.cb[r * CBW + w + dzi]);
+        sh.ctab[w * 27 + lane] = t;
+        sh.cgd[w * 27 + lane] = sh.gdelta[r];
+    }
+    __syncwarp();
 }
 
 __device__ __forceinline__ int cell_start(const int *cell_end, int g) { return g > 0 ? cell_end[g - 1] : 0; }
 
-// Computes spans and cell boundaries, issues the TMA copies (payload A always, payload B when srcB != null) and
-// waits for them.  Returns false (uniformly) when the tile does not fit.  col/f0 identify the block's cells.
-__device__ __forceinline__ bool tile_setup(const DevF &c, const TileGeom &g, TileShared &sh, int col, int f0,
-                                           const F4 *srcA, const F4 *srcB) {
+// Computes spans and cell boundaries, issues the TMA copies of NPAY payload arrays and waits for them.
+// Returns false (uniformly) when the tile does not fit.
+template <int NPAY>
+__device__ __forceinline__ bool tile_setup(const DevF &c, const TileGeom &g, TileShared<NPAY> &sh, int col, int f0,
+                                           const F4 *src0, const F4 *src1) {
     const int tid = threadIdx.x;
     const int f_lo = max(f0 - 1, 0), f_hi = min(f0 + ZB, g.nF - 1);
     if (tid < 32) {
@@ -131,11 +154,11 @@ __device__ __forceinline__ bool tile_setup(const DevF &c, const TileGeom &g, Til
         }
         __syncwarp();
         if (total <= TILE_CAP) {
-            if (tid == 0) mbar_expect_tx(&sh.bar, (unsigned)(total * 16 * (srcB ? 2 : 1)));
+            if (tid == 0) mbar_expect_tx(&sh.bar, (unsigned)(total * 16 * NPAY));
             __syncwarp();
             if (tid < g.nR && len > 0) {
-                tma_load_1d(&sh.A[roff], srcA + S, (unsigned)(len * 16), &sh.bar);
-                if (srcB) tma_load_1d(&sh.B[roff], srcB + S, (unsigned)(len * 16), &sh.bar);
+                tma_load_1d(&sh.P[0][roff], src0 + S, (unsigned)(len * 16), &sh.bar);
+                if (NPAY > 1) tma_load_1d(&sh.P[NPAY - 1][roff], src1 + S, (unsigned)(len * 16), &sh.bar);
             }
         }
     }
@@ -145,28 +168,54 @@ __device__ __forceinline__ bool tile_setup(const DevF &c, const TileGeom &g, Til
     return true;
 }
 
-// float32 forms of the smoothing kernels (base:278-358) without divisions: W(r) and s with gradW = s * d
-__device__ __forceinline__ float tile_W(const DevF &c, float r) {
-    return kernel_W(c, r);
+// ------------------------------------------------------------------------------------------------ float32 kernels
+// Division-free float32 forms of base:278-358 on the squared distance (MUFU.RSQ instead of IEEE sqrt/div).
+// Guards: r > 1e-8 and q <= 2 as in the reference.  KERNEL: 0 cubic spline, 1 Wendland C2.
+struct KernConst { float hinv, eps2, knorm, c_grad; };   // c_grad = -5 knorm / h^2 (Wendland) | knorm / h^2 (cubic)
+__device__ __forceinline__ KernConst kern_const(const DevF &c) {
+    KernConst k;
+    k.hinv = c.hinv; k.eps2 = c.eps * c.eps; k.knorm = c.knorm;
+    k.c_grad = (c.kernel == 0 ? 1.f : -5.f) * c.knorm * c.hinv * c.hinv;
+    return k;
 }
-__device__ __forceinline__ float tile_dW(const DevF &c, float r) {
-    return kernel_dW_over_r(c, r);
+template <int KERNEL> __device__ __forceinline__ float fastW(const KernConst &k, float r2) {
+    const float rinv = rsqrtf(r2), q = r2 * rinv * k.hinv;
+    float w;
+    if (KERNEL == 1) { const float q1 = fmaf(-0.5f, q, 1.f), q2 = q1 * q1; w = k.knorm * (q2 * q2) * fmaf(2.f, q, 1.f); }
+    else {
+        const float t = 2.f - q;
+        w = q <= 1.f ? k.knorm * (q * q * fmaf(0.5f, q, -1.f) + (float)(2.0 / 3.0)) : k.knorm * (1.f / 6.f) * t * t * t;
+    }
+    return (r2 > k.eps2 && q <= 2.f) ? w : 0.f;
+}
+// s with gradW = s * d
+template <int KERNEL> __device__ __forceinline__ float fastdW(const KernConst &k, float r2) {
+    const float rinv = rsqrtf(r2), q = r2 * rinv * k.hinv;
+    float s;
+    if (KERNEL == 1) { const float q1 = fmaf(-0.5f, q, 1.f); s = k.c_grad * (q1 * q1 * q1); }
+    else {
+        const float t = 2.f - q;
+        s = q <= 1.f ? k.c_grad * fmaf(1.5f, q, -2.f) : -0.5f * k.c_grad * t * t * (rinv / k.hinv);
+    }
+    return (r2 > k.eps2 && q <= 2.f) ? s : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------ pass 0: masks
 // One launch per step, right after the grid build: neighbour masks, flow-neighbour counts and the Shepard factor
 // CSPM_f (base:386-398) of every particle.
+template <int KERNEL>
 __global__ void __launch_bounds__(BT) k_tile_mask(DevF c, TileGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileShared &sh = *reinterpret_cast<TileShared *>(smem_raw);
+    TileShared<1> &sh = *reinterpret_cast<TileShared<1> *>(smem_raw);
+    unsigned *smask = reinterpret_cast<unsigned *>(smem_raw + sizeof(TileShared<1>));   // [NW][BT]
     const int col = blockIdx.x / g.nseg, seg = blockIdx.x - col * g.nseg;
-    const int f0 = seg * ZB, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f0 = seg * ZB, w = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int f = f0 + w;
     const int gcell = col * g.nF + f;
     int is = 0, nc = 0;
     if (f < g.nF) { is = cell_start(c.cell_end, gcell); nc = c.cell_end[gcell] - is; }
     if (!__syncthreads_or(nc > 0)) return;                         // empty segment
-    const bool ok = tile_setup(c, g, sh, col, f0, c.ps4, nullptr);
+    const bool ok = tile_setup<1>(c, g, sh, col, f0, c.ps4, nullptr);
     if (nc == 0) return;
     // can this cell be represented?  (uniform per warp)
     bool flagged = !ok || nc > 32;
@@ -182,39 +231,76 @@ __global__ void __launch_bounds__(BT) k_tile_mask(DevF c, TileGeom g) {
         if (lane == 0) { c.cellflag[gcell] = 1; atomicAdd(c.nflag, 1); }
         return;
     }
-    if (lane >= nc) return;
+    const bool mine = lane < nc;
     const int i = is + lane;
+    const F4 *A = sh.P[0];
     const int rc = g.nR / 2;                                       // centre run
-    const F4 pi = sh.A[sh.cb[rc * CBW + w + 1] + lane];
-    float ssum = 0.f;
-    int nflow = 0;
+    const F4 pi = A[sh.cb[rc * CBW + w + 1] + (mine ? lane : 0)];
+    const float thr = c.r2thr;
+    unsigned nz = 0;                                               // which stencil cells hold at least one neighbour
+    // ---- predicate: every lane tests every candidate of the 3^dim stencil (broadcast reads, 8-way ILP)
     for (int cc = 0; cc < NW; cc++) {
         const int r = cc / 3, dzi = cc - 3 * r;
         const int a = sh.cb[r * CBW + w + dzi], nb = sh.cb[r * CBW + w + dzi + 1] - a;
         float sx, sy, sz;
         cell_shift(c, g, r, dzi, sx, sy, sz);
         const float ex = pi.x - sx, ey = pi.y - sy, ez = pi.z - sz;
-        unsigned m = 0, bit = 1;
-        for (int t = 0; t < nb; t++, bit <<= 1) {
-            const F4 pj = sh.A[a + t];                            // broadcast read
-            const float dx = ex - pj.x, dy = ey - pj.y, dz = ez - pj.z;
-            if (dist2(dx, dy, dz) < c.r2thr) m |= bit;
+        unsigned m = 0;
+        for (int t0 = 0; t0 < nb; t0 += 8) {
+            unsigned cm = 0;
+            F4 pj[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) pj[u] = A[a + t0 + u];     // may run past the cell: masked below
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const float dx = ex - pj[u].x, dy = ey - pj[u].y, dz = ez - pj[u].z;
+                if (dist2(dx, dy, dz) < thr) cm |= 1u << u;
+            }
+            m |= cm << t0;
         }
+        m &= nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
         if (cc == NW / 2) m &= ~(1u << lane);                      // i != j
-        c.mask[(size_t)cc * c.n + i] = m;
-        while (m) {                                                // Shepard sum over flow neighbours, j ascending
+        if (!mine) m = 0;
+        smask[cc * BT + tid] = m;
+        if (m) nz |= 1u << cc;
+        if (mine) c.mask[(size_t)cc * c.n + i] = m;
+    }
+    // ---- Shepard sum over flow neighbours in stencil order (cells x-major, j ascending): warp-uniform rounds
+    const KernConst kc = kern_const(c);
+    build_ctab<1>(c, g, sh, w, lane);
+    const F4 *ct = sh.ctab + w * 27;
+    float ssum = 0.f, ex = 0.f, ey = 0.f, ez = 0.f;
+    int nflow = 0, a = 0;
+    unsigned m = 0;
+    bool alive = mine;
+    while (true) {
+        if (alive && m == 0) {                                      // jump to the next non-empty stencil cell
+            if (nz == 0) alive = false;
+            else {
+                const int cc = __ffs(nz) - 1;
+                nz &= nz - 1;
+                m = smask[cc * BT + tid];
+                const F4 t = ct[cc];
+                a = __float_as_int(t.w);
+                ex = pi.x - t.x; ey = pi.y - t.y; ez = pi.z - t.z;
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) break;
+        if (alive) {
             const int t = __ffs(m) - 1;
             m &= m - 1;
-            const F4 pj = sh.A[a + t];
+            const F4 pj = A[a + t];
             if (pj.w > 0.f) {
                 const float dx = ex - pj.x, dy = ey - pj.y, dz = ez - pj.z;
-                ssum += pj.w * tile_W(c, sqrt_rn(dist2(dx, dy, dz)));
+                ssum += pj.w * fastW<KERNEL>(kc, dist2(dx, dy, dz));
                 nflow++;
             }
         }
     }
-    c.cspm_f[i] = (ssum != 0.f) ? 1.f / ssum : 1.f;
-    c.nflow[i] = (unsigned char)min(nflow, 255);
+    if (mine) {
+        c.cspm_f[i] = (ssum != 0.f) ? 1.f / ssum : 1.f;
+        c.nflow[i] = (unsigned char)min(nflow, 255);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ prep (pointwise)
@@ -242,12 +328,30 @@ __global__ void __launch_bounds__(256) k_tile_prep(DevF c) {
 }
 
 // ------------------------------------------------------------------------------------------------ pass A: walls
+// loads the NW mask words of this thread's particle into shared memory (coalesced, all in flight at once) and
+// returns the bitmap of non-empty stencil cells
+__device__ __forceinline__ unsigned load_masks(const DevF &c, unsigned *smask, int NW, int i, bool work) {
+    unsigned nz = 0;
+    if (work) {
+        const unsigned *mp = c.mask + i;
+#pragma unroll 9
+        for (int cc = 0; cc < NW; cc++) {
+            const unsigned m = mp[(size_t)cc * c.n];
+            smask[cc * BT + threadIdx.x] = m;
+            if (m) nz |= 1u << cc;
+        }
+    }
+    return nz;
+}
+
 // wc:90-103 for dummy-wall particles: v~ = 2v - f sum V v~ W, rho~ = rho0, p = max(f sum V (p_j + rho~_j g_y dy) W, 0).
+template <int KERNEL>
 __global__ void __launch_bounds__(BT) k_tile_wall(DevF c, TileGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileShared &sh = *reinterpret_cast<TileShared *>(smem_raw);
+    TileShared<2> &sh = *reinterpret_cast<TileShared<2> *>(smem_raw);
+    unsigned *smask = reinterpret_cast<unsigned *>(smem_raw + sizeof(TileShared<2>));   // [NW][BT]
     const int col = blockIdx.x / g.nseg, seg = blockIdx.x - col * g.nseg;
-    const int f0 = seg * ZB, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f0 = seg * ZB, w = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int f = f0 + w;
     const int gcell = col * g.nF + f;
     int is = 0, nc = 0;
@@ -269,35 +373,52 @@ __global__ void __launch_bounds__(BT) k_tile_wall(DevF c, TileGeom g) {
         }
     }
     if (!__syncthreads_or(work)) return;
-    if (!tile_setup(c, g, sh, col, f0, c.ps4, c.vt4)) return;      // cannot happen for unflagged cells
-    if (!work) return;
-    const int rc = g.nR / 2, NW = g.nR * 3;
-    const F4 pi = sh.A[sh.cb[rc * CBW + w + 1] + lane];
-    float Sv0 = 0.f, Sv1 = 0.f, Sv2 = 0.f, Sp = 0.f;
-    for (int cc = 0; cc < NW; cc++) {
-        unsigned m = c.mask[(size_t)cc * c.n + i];
-        if (!m) continue;
-        const int r = cc / 3, dzi = cc - 3 * r;
-        const int a = sh.cb[r * CBW + w + dzi];
-        const int gd = sh.gdelta[r];
-        float sx, sy, sz;
-        cell_shift(c, g, r, dzi, sx, sy, sz);
-        const float ex = pi.x - sx, ey = pi.y - sy, ez = pi.z - sz;
-        while (m) {
+    const int NW = g.nR * 3;
+    unsigned nz = load_masks(c, smask, NW, i, work);
+    if (!tile_setup<2>(c, g, sh, col, f0, c.ps4, c.vt4)) return;   // cannot happen for unflagged cells
+    build_ctab<2>(c, g, sh, w, lane);
+    const F4 *A = sh.P[0], *B = sh.P[1];
+    const F4 *ct = sh.ctab + w * 27;
+    const int *cg = sh.cgd + w * 27;
+    const int rc = g.nR / 2;
+    const F4 pi = A[sh.cb[rc * CBW + w + 1] + (work ? lane : 0)];
+    const KernConst kc = kern_const(c);
+    const float gy = c.g[1];
+    float Sv0 = 0.f, Sv1 = 0.f, Sv2 = 0.f, Sp = 0.f, ex = 0.f, ey = 0.f, ez = 0.f;
+    int a = 0, gd = 0;
+    unsigned m = 0;
+    bool alive = work;
+    while (true) {
+        if (alive && m == 0) {
+            if (nz == 0) alive = false;
+            else {
+                const int cc = __ffs(nz) - 1;
+                nz &= nz - 1;
+                m = smask[cc * BT + tid];
+                const F4 t = ct[cc];
+                a = __float_as_int(t.w);
+                gd = cg[cc];
+                ex = pi.x - t.x; ey = pi.y - t.y; ez = pi.z - t.z;
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) break;
+        if (alive) {
             const int t = __ffs(m) - 1;
             m &= m - 1;
-            const F4 pj = sh.A[a + t];
+            const F4 pj = A[a + t];
             if (pj.w > 0.f) {
                 const float dx = ex - pj.x, dy = ey - pj.y, dz = ez - pj.z;
-                const float wgt = tile_W(c, sqrt_rn(dist2(dx, dy, dz)));
-                const F4 vj = sh.B[a + t];
+                const float wgt = fastW<KERNEL>(kc, dist2(dx, dy, dz));
+                const F4 vj = B[a + t];
                 const int j = a + t + gd;
-                Sv0 += pj.w * vj.x * wgt; Sv1 += pj.w * vj.y * wgt; Sv2 += pj.w * vj.z * wgt;
+                const float vw = pj.w * wgt;
+                Sv0 = fmaf(vw, vj.x, Sv0); Sv1 = fmaf(vw, vj.y, Sv1); Sv2 = fmaf(vw, vj.z, Sv2);
                 const float pjv = (c.wc_fresh || j < i) ? c.pnew[j] : c.press[j];
-                Sp += pj.w * (pjv + vj.w * c.g[1] * dy) * wgt;
+                Sp = fmaf(vw, fmaf(vj.w * gy, dy, pjv), Sp);
             }
         }
     }
+    if (!work) return;
     const float fi = c.cspm_f[i];
     const F4 v = c.v4[i];
     F4 vt;
@@ -313,10 +434,29 @@ __global__ void __launch_bounds__(BT) k_tile_wall(DevF c, TileGeom g) {
 
 // ------------------------------------------------------------------------------------------------ pass B: fluid
 // wc:108-126 for fluid particles: continuity + viscosity + pressure in one visit of the set bits.
+//   d_rho_i = rho~_i sum_j V_j (v~_i - v~_j) . gradW_ij
+//   d_v_i   = g + sum_j [ 2(dim+2) nu V_j min(v_ij . x_ij, 0) / (r^2 + 0.01 h^2) {1 | rho0 / rho~_i} - rho0 V_j (p_i/rho~_i^2 + p_j/rho~_j^2) ] gradW_ij
+struct FluidI { float ex, ey, ez, vx, vy, vz, pr, visc_f, visc_w, h2, nrho0; };
+// one pair: returns V_j s (v_ij . x_ij) through ddc and the coefficient cf with  d_v += cf * d
+template <int KERNEL>
+__device__ __forceinline__ void fluid_pair(const KernConst &kc, const FluidI &I, const F4 pj, const F4 qj, float valid,
+                                           float &ddc, float &cf, float &dx, float &dy, float &dz) {
+    dx = I.ex - pj.x; dy = I.ey - pj.y; dz = I.ez - pj.z;
+    const float r2 = dist2(dx, dy, dz);
+    const float s = fastdW<KERNEL>(kc, r2);
+    const float ux = I.vx - qj.x, uy = I.vy - qj.y, uz = I.vz - qj.z;
+    const float vx = fmaf(uz, dz, fmaf(uy, dy, ux * dx));          // v_ij . x_ij
+    const float Vs = fabsf(pj.w) * s * valid;
+    ddc = Vs * vx;
+    const float visc = (pj.w < 0.f ? I.visc_w : I.visc_f) * fminf(vx, 0.f) * __fdividef(1.f, r2 + I.h2);
+    cf = Vs * fmaf(I.nrho0, I.pr + qj.w, visc);
+}
+
+template <int KERNEL>
 __global__ void __launch_bounds__(BT) k_tile_fluid(DevF c, TileGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileShared &sh = *reinterpret_cast<TileShared *>(smem_raw);
-    unsigned *smask = reinterpret_cast<unsigned *>(smem_raw + sizeof(TileShared));   // [NW][BT]
+    TileShared<2> &sh = *reinterpret_cast<TileShared<2> *>(smem_raw);
+    unsigned *smask = reinterpret_cast<unsigned *>(smem_raw + sizeof(TileShared<2>));   // [NW][BT]
     const int col = blockIdx.x / g.nseg, seg = blockIdx.x - col * g.nseg;
     const int f0 = seg * ZB, w = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int f = f0 + w;
@@ -328,99 +468,113 @@ __global__ void __launch_bounds__(BT) k_tile_fluid(DevF c, TileGeom g) {
     const bool work = lane < nc && c.type[i] == 1;
     if (!__syncthreads_or(work)) return;
     const int NW = g.nR * 3;
-    if (work) {
-        for (int cc = 0; cc < NW; cc++) smask[cc * BT + tid] = c.mask[(size_t)cc * c.n + i];
-    }
-    if (!tile_setup(c, g, sh, col, f0, c.ps4, c.pk4)) return;
-    if (!work) return;
+    unsigned nz = load_masks(c, smask, NW, i, work);
+    if (!tile_setup<2>(c, g, sh, col, f0, c.ps4, c.pk4)) return;
+    build_ctab<2>(c, g, sh, w, lane);
+    const F4 *A = sh.P[0], *B = sh.P[1];
+    const F4 *ct = sh.ctab + w * 27;
     const int rc = g.nR / 2;
-    const int ci = sh.cb[rc * CBW + w + 1] + lane;
-    const F4 pi = sh.A[ci], qi = sh.B[ci];                         // qi = v~_i, p_i / rho~_i^2
-    const float rhoi = c.vt4[i].w;
-    const float wallfac = c.rho0T / rhoi;                           // wc:43-44 factor for wall neighbours
+    const int ci = sh.cb[rc * CBW + w + 1] + (work ? lane : 0);
+    const F4 pi = A[ci], qi = B[ci];                               // qi = v~_i, p_i / rho~_i^2
+    const float rhoi = work ? c.vt4[i].w : 1.f;
+    const KernConst kc = kern_const(c);
+    FluidI I;
+    I.vx = qi.x; I.vy = qi.y; I.vz = qi.z; I.pr = qi.w;
+    I.visc_f = c.visc_coef; I.visc_w = c.visc_coef * c.rho0T / rhoi;   // wc:41-44
+    I.h2 = c.h2_001; I.nrho0 = -c.rho0T;
+    I.ex = I.ey = I.ez = 0.f;
     float dd = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    int cc = -1, a = 0;
+    int a = 0;
     unsigned m = 0;
-    float ex = 0.f, ey = 0.f, ez = 0.f;
+    bool alive = work;
     while (true) {
-        while (m == 0) {                                            // advance to the next non-empty neighbour cell
-            if (++cc >= NW) break;
-            m = smask[cc * BT + tid];
-            if (m) {
-                const int r = cc / 3, dzi = cc - 3 * r;
-                a = sh.cb[r * CBW + w + dzi];
-                float sx, sy, sz;
-                cell_shift(c, g, r, dzi, sx, sy, sz);
-                ex = pi.x - sx; ey = pi.y - sy; ez = pi.z - sz;
+        if (alive && m == 0) {                                      // jump to the next non-empty stencil cell
+            if (nz == 0) alive = false;
+            else {
+                const int cc = __ffs(nz) - 1;
+                nz &= nz - 1;
+                m = smask[cc * BT + tid];
+                const F4 t = ct[cc];
+                a = __float_as_int(t.w);
+                I.ex = pi.x - t.x; I.ey = pi.y - t.y; I.ez = pi.z - t.z;
             }
         }
-        if (cc >= NW) break;
-        const int t = __ffs(m) - 1;
-        m &= m - 1;
-        const F4 pj = sh.A[a + t], qj = sh.B[a + t];
-        const float dx = ex - pj.x, dy = ey - pj.y, dz = ez - pj.z;
-        const float r2 = dist2(dx, dy, dz);
-        const float s = tile_dW(c, sqrt_rn(r2));
-        const float Vj = fabsf(pj.w);
-        const float ux = qi.x - qj.x, uy = qi.y - qj.y, uz = qi.z - qj.z;
-        const float gx = s * dx, gy = s * dy, gz = s * dz;
-        dd += Vj * ux * gx + Vj * uy * gy + Vj * uz * gz;
-        const float vx = ux * dx + uy * dy + uz * dz;
-        const float mn = vx < 0.f ? vx : 0.f;
-        float visc = c.visc_coef * Vj;
-        if (pj.w < 0.f) visc = visc * c.rho0T / rhoi;
-        visc = visc * mn / (r2 + c.h2_001);
-        (void)wallfac;
-        const float pres = -c.rho0T * Vj * (qi.w + qj.w);
-        a0 += visc * gx + pres * gx; a1 += visc * gy + pres * gy; a2 += visc * gz + pres * gz;
+        if (!__any_sync(0xffffffffu, alive)) break;                 // warp-uniform round: lanes reconverge here
+        if (alive) {                                                // two neighbours of the same cell per round (ILP)
+            const int t1 = __ffs(m) - 1;
+            m &= m - 1;
+            const bool two = m != 0;
+            const int t2 = two ? __ffs(m) - 1 : t1;
+            m &= m - 1;                                             // no-op when m == 0
+            const F4 pj1 = A[a + t1], qj1 = B[a + t1], pj2 = A[a + t2], qj2 = B[a + t2];
+            float d1, c1, x1, y1, z1, d2, c2, x2, y2, z2;
+            fluid_pair<KERNEL>(kc, I, pj1, qj1, 1.f, d1, c1, x1, y1, z1);
+            fluid_pair<KERNEL>(kc, I, pj2, qj2, two ? 1.f : 0.f, d2, c2, x2, y2, z2);
+            dd += d1; a0 = fmaf(c1, x1, a0); a1 = fmaf(c1, y1, a1); a2 = fmaf(c1, z1, a2);
+            dd += d2; a0 = fmaf(c2, x2, a0); a1 = fmaf(c2, y2, a1); a2 = fmaf(c2, z2, a2);
+        }
     }
+    if (!work) return;
     c.d_rho[i] = dd * rhoi;
     F4 dv; dv.x = a0 + c.g[0]; dv.y = a1 + c.g[1]; dv.z = a2 + c.g[2]; dv.w = 0.f;
     c.d_vel[i] = dv;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-static size_t tile_smem(bool with_mask, int NW) { return sizeof(TileShared) + (with_mask ? (size_t)NW * BT * 4 : 0); }
+static size_t smem_mask(int NW) { return sizeof(TileShared<1>) + (size_t)NW * BT * 4; }
+static size_t smem_pass(int NW = 27) { return sizeof(TileShared<2>) + (size_t)NW * BT * 4; }
+
+template <int KERNEL> static int set_attrs(SphCtx *c) {
+    SPH_CHECK(c, cudaFuncSetAttribute(k_tile_mask<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mask(27)));
+    SPH_CHECK(c, cudaFuncSetAttribute(k_tile_wall<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pass()));
+    SPH_CHECK(c, cudaFuncSetAttribute(k_tile_fluid<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pass()));
+    return 0;
+}
+static int ensure_attrs(SphCtx *c) {
+    static bool done = false;
+    if (done) return 0;
+    int r = set_attrs<0>(c);
+    if (!r) r = set_attrs<1>(c);
+    done = r == 0;
+    return r;
+}
 
 int tile_mask(SphCtx *c) {
     DevF d = make_dev<float>(c);
     const TileGeom g = make_geom(c->p.dim, d.gn);
-    const int ncol = g.nslow0 * g.nslow1;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SPH_CHECK(c, cudaFuncSetAttribute(k_tile_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(false, 27)));
-        SPH_CHECK(c, cudaFuncSetAttribute(k_tile_wall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(false, 27)));
-        SPH_CHECK(c, cudaFuncSetAttribute(k_tile_fluid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(true, 27)));
-        attr_done = true;
-    }
+    const int nblk = g.nslow0 * g.nslow1 * g.nseg;
+    int r = ensure_attrs(c);
+    if (r) return r;
     SPH_CHECK(c, cudaMemsetAsync(d.cellflag, 0, (size_t)c->C, c->stream));
     SPH_CHECK(c, cudaMemsetAsync(d.nflag, 0, 4, c->stream));
     SPH_PROF(c, K_TILE_MASK);
-    k_tile_mask<<<ncol * g.nseg, BT, tile_smem(false, g.nR * 3), c->stream>>>(d, g);
+    if (c->p.kernel == 0) k_tile_mask<0><<<nblk, BT, smem_mask(g.nR * 3), c->stream>>>(d, g);
+    else k_tile_mask<1><<<nblk, BT, smem_mask(g.nR * 3), c->stream>>>(d, g);
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
 
 // WCSPH one_step (wc:82-126) on the tile path; flagged cells are completed by the generic kernels (flagged_only).
-
 int tile_wc_prep_and_wall(SphCtx *c) {
     DevF d = make_dev<float>(c);
     const TileGeom g = make_geom(c->p.dim, d.gn);
-    const int ncol = g.nslow0 * g.nslow1, n = (int)c->n;
+    const int nblk = g.nslow0 * g.nslow1 * g.nseg, n = (int)c->n;
     SPH_PROF(c, K_WC_EOS);
     k_tile_prep<<<blocks_for(n, 256), 256, 0, c->stream>>>(d);
     SPH_LAUNCH_CHECK(c);
     SPH_PROF(c, K_TILE_WALL);
-    k_tile_wall<<<ncol * g.nseg, BT, tile_smem(false, g.nR * 3), c->stream>>>(d, g);
+    if (c->p.kernel == 0) k_tile_wall<0><<<nblk, BT, smem_pass(g.nR * 3), c->stream>>>(d, g);
+    else k_tile_wall<1><<<nblk, BT, smem_pass(g.nR * 3), c->stream>>>(d, g);
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
 int tile_wc_fluid(SphCtx *c) {
     DevF d = make_dev<float>(c);
     const TileGeom g = make_geom(c->p.dim, d.gn);
-    const int ncol = g.nslow0 * g.nslow1;
+    const int nblk = g.nslow0 * g.nslow1 * g.nseg;
     SPH_PROF(c, K_TILE_FLUID);
-    k_tile_fluid<<<ncol * g.nseg, BT, tile_smem(true, g.nR * 3), c->stream>>>(d, g);
+    if (c->p.kernel == 0) k_tile_fluid<0><<<nblk, BT, smem_pass(g.nR * 3), c->stream>>>(d, g);
+    else k_tile_fluid<1><<<nblk, BT, smem_pass(g.nR * 3), c->stream>>>(d, g);
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
