@@ -85,16 +85,19 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
     // cell-tile fast path scratch: MIXED precision WCSPH without CSPM_L
     const bool fast = p->fast && p->precision == SPH_PREC_MIXED && p->solver == SPH_SOLVER_WC && p->kcorr == 0;
     const int mask_words = p->dim == 3 ? 27 : 9;
+    int64_t o_pw4 = 0;
     int64_t o_ps4 = 0, o_pk4 = 0, o_mask = 0, o_nflow = 0, o_cflag = 0, o_nflag = 0;
     if (fast) {
         o_ps4 = off; off += align_up(n_max * 16);
         o_pk4 = off; off += align_up(n_max * 16);
+        o_pw4 = off; off += align_up(n_max * 16);
         o_mask = off; off += align_up(n_max * 4 * mask_words);
         o_nflow = off; off += align_up(n_max);
         o_cflag = off; off += align_up(C + 1);
         o_nflag = off; off += 256;
     }
     if (c) {
+        c->off_pw4 = o_pw4;
         c->off_ps4 = o_ps4; c->off_pk4 = o_pk4; c->off_mask = o_mask; c->off_nflow = o_nflow; c->off_cellflag = o_cflag;
         c->off_nflag = o_nflag; c->fast = fast; c->mask_words = mask_words;
         c->off_gid_unsorted = o_gid; c->off_slot = o_slot; c->off_perm = o_perm; c->off_tmpidx = o_tmp;
@@ -227,6 +230,7 @@ template <typename T> Dev<T> make_dev(SphCtx *c, int which) {
     if (c->fast) {
         d.ps4 = (Vec4<T> *)(c->arena + c->off_ps4);
         d.pk4 = (Vec4<T> *)(c->arena + c->off_pk4);
+        d.pw4 = (Vec4<T> *)(c->arena + c->off_pw4);
         d.mask = (unsigned *)(c->arena + c->off_mask);
         d.nflow = (unsigned char *)(c->arena + c->off_nflow);
         d.cellflag = (unsigned char *)(c->arena + c->off_cellflag);

@@ -72,6 +72,7 @@ template <typename T> struct Dev {
     // cell-tile fast path (sweeps_tile.cu); null when the fast path is not allocated
     Vec4<T> *ps4;        // sweep coords xyz, +m_V for flow particles / -m_V otherwise (tile payload A)
     Vec4<T> *pk4;        // v_tmp.xyz, pressure / density_tmp^2                        (tile payload B of the fluid pass)
+    Vec4<T> *pw4;        // EOS pressure, previous pressure, 0, 0                       (tile payload C of the wall pass)
     unsigned *mask;      // neighbour bit masks, word-major: mask[word * n + i], word = neighbour cell (x-major, z fastest)
     unsigned char *nflow;     // min(number of flow neighbours, 255) per particle
     unsigned char *cellflag;  // 1: this centre cell cannot use the tile path (a cell of its stencil holds > 32 particles ...)

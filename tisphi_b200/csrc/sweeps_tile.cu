@@ -110,7 +110,7 @@ __device__ __forceinline__ int cell_start(const int *cell_end, int g) { return g
 // Returns false (uniformly) when the tile does not fit.
 template <int NPAY>
 __device__ __forceinline__ bool tile_setup(const DevF &c, const TileGeom &g, TileShared<NPAY> &sh, int col, int f0,
-                                           const F4 *src0, const F4 *src1) {
+                                           const F4 *src0, const F4 *src1, const F4 *src2 = nullptr) {
     const int tid = threadIdx.x;
     const int f_lo = max(f0 - 1, 0), f_hi = min(f0 + ZB, g.nF - 1);
     if (tid < 32) {
@@ -158,7 +158,8 @@ __device__ __forceinline__ bool tile_setup(const DevF &c, const TileGeom &g, Til
             __syncwarp();
             if (tid < g.nR && len > 0) {
                 tma_load_1d(&sh.P[0][roff], src0 + S, (unsigned)(len * 16), &sh.bar);
-                if (NPAY > 1) tma_load_1d(&sh.P[NPAY - 1][roff], src1 + S, (unsigned)(len * 16), &sh.bar);
+                if (NPAY > 1) tma_load_1d(&sh.P[1][roff], src1 + S, (unsigned)(len * 16), &sh.bar);
+                if (NPAY > 2) tma_load_1d(&sh.P[NPAY - 1][roff], src2 + S, (unsigned)(len * 16), &sh.bar);
             }
         }
     }
@@ -198,6 +199,36 @@ template <int KERNEL> __device__ __forceinline__ float fastdW(const KernConst &k
         s = q <= 1.f ? k.c_grad * fmaf(1.5f, q, -2.f) : -0.5f * k.c_grad * t * t * (rinv / k.hinv);
     }
     return (r2 > k.eps2 && q <= 2.f) ? s : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------ bit iteration
+// Per-lane cursor over the set bits of the neighbour masks in stencil order.  A round takes up to four neighbours:
+// two from the current cell, then (after an optional jump to the next non-empty cell) two more.  Slots that find no
+// bit are marked invalid and contribute exactly zero, so the summation order (cells x-major, j ascending) is kept.
+struct Cursor {
+    unsigned m, nz;        // remaining bits of the current cell; remaining non-empty cells
+    int a;                 // tile index of the current cell's first particle
+    float ex, ey, ez;      // own coordinates in the current cell's frame
+};
+__device__ __forceinline__ void cursor_jump(Cursor &k, const unsigned *smask, const F4 *ct, const F4 &pi) {
+    if (k.m == 0 && k.nz != 0) {
+        const int cc = __ffs(k.nz) - 1;
+        k.nz &= k.nz - 1;
+        k.m = smask[cc * BT + threadIdx.x];
+        const F4 t = ct[cc];
+        k.a = __float_as_int(t.w);
+        k.ex = pi.x - t.x; k.ey = pi.y - t.y; k.ez = pi.z - t.z;
+    }
+}
+// takes up to two bits of the current cell: tile indices i0, i1 and validity of the second (the first is valid iff m != 0)
+__device__ __forceinline__ void cursor_take2(Cursor &k, int &i0, int &i1, bool &v0, bool &v1) {
+    v0 = k.m != 0;
+    const int t0 = v0 ? __ffs(k.m) - 1 : 0;
+    k.m &= k.m - 1;
+    v1 = k.m != 0;
+    const int t1 = v1 ? __ffs(k.m) - 1 : t0;
+    k.m &= k.m - 1;
+    i0 = k.a + t0; i1 = k.a + t1;
 }
 
 // ------------------------------------------------------------------------------------------------ pass 0: masks
@@ -269,33 +300,30 @@ __global__ void __launch_bounds__(BT) k_tile_mask(DevF c, TileGeom g) {
     const KernConst kc = kern_const(c);
     build_ctab<1>(c, g, sh, w, lane);
     const F4 *ct = sh.ctab + w * 27;
-    float ssum = 0.f, ex = 0.f, ey = 0.f, ez = 0.f;
-    int nflow = 0, a = 0;
-    unsigned m = 0;
-    bool alive = mine;
+    float ssum = 0.f;
+    int nflow = 0;
+    Cursor k;
+    k.m = 0; k.nz = mine ? nz : 0u; k.a = 0; k.ex = k.ey = k.ez = 0.f;
     while (true) {
-        if (alive && m == 0) {                                      // jump to the next non-empty stencil cell
-            if (nz == 0) alive = false;
-            else {
-                const int cc = __ffs(nz) - 1;
-                nz &= nz - 1;
-                m = smask[cc * BT + tid];
-                const F4 t = ct[cc];
-                a = __float_as_int(t.w);
-                ex = pi.x - t.x; ey = pi.y - t.y; ez = pi.z - t.z;
-            }
-        }
-        if (!__any_sync(0xffffffffu, alive)) break;
-        if (alive) {
-            const int t = __ffs(m) - 1;
-            m &= m - 1;
-            const F4 pj = A[a + t];
-            if (pj.w > 0.f) {
-                const float dx = ex - pj.x, dy = ey - pj.y, dz = ez - pj.z;
-                ssum += pj.w * fastW<KERNEL>(kc, dist2(dx, dy, dz));
-                nflow++;
-            }
-        }
+        cursor_jump(k, smask, ct, pi);
+        if (!__any_sync(0xffffffffu, k.m != 0)) break;              // warp-uniform round
+        int i0, i1, i2, i3;
+        bool v0, v1, v2, v3;
+        cursor_take2(k, i0, i1, v0, v1);
+        const float e0x = k.ex, e0y = k.ey, e0z = k.ez;
+        cursor_jump(k, smask, ct, pi);
+        cursor_take2(k, i2, i3, v2, v3);
+        const F4 p0 = A[i0], p1 = A[i1], p2 = A[i2], p3 = A[i3];
+        const float w0 = fastW<KERNEL>(kc, dist2(e0x - p0.x, e0y - p0.y, e0z - p0.z));
+        const float w1 = fastW<KERNEL>(kc, dist2(e0x - p1.x, e0y - p1.y, e0z - p1.z));
+        const float w2 = fastW<KERNEL>(kc, dist2(k.ex - p2.x, k.ey - p2.y, k.ez - p2.z));
+        const float w3 = fastW<KERNEL>(kc, dist2(k.ex - p3.x, k.ey - p3.y, k.ez - p3.z));
+        const bool f0 = v0 && p0.w > 0.f, f1 = v1 && p1.w > 0.f, f2 = v2 && p2.w > 0.f, f3 = v3 && p3.w > 0.f;
+        ssum += f0 ? p0.w * w0 : 0.f;
+        ssum += f1 ? p1.w * w1 : 0.f;
+        ssum += f2 ? p2.w * w2 : 0.f;
+        ssum += f3 ? p3.w * w3 : 0.f;
+        nflow += (int)f0 + (int)f1 + (int)f2 + (int)f3;
     }
     if (mine) {
         c.cspm_f[i] = (ssum != 0.f) ? 1.f / ssum : 1.f;
@@ -322,8 +350,13 @@ __global__ void __launch_bounds__(256) k_tile_prep(DevF c) {
         F4 pk = c.vt4[i];
         pk.w = p / (pk.w * pk.w);
         c.pk4[i] = pk;
+        F4 pw; pw.x = p; pw.y = c.press[i]; pw.z = 0.f; pw.w = 0.f;   // EOS pressure, previous pressure (wc:86-103 race)
+        c.pw4[i] = pw;
     } else if (!is_wall(t)) {
-        c.pnew[i] = c.press[i];
+        const float po = c.press[i];
+        c.pnew[i] = po;
+        F4 pw; pw.x = po; pw.y = po; pw.z = 0.f; pw.w = 0.f;
+        c.pw4[i] = pw;
     }
 }
 
@@ -345,13 +378,23 @@ __device__ __forceinline__ unsigned load_masks(const DevF &c, unsigned *smask, i
 }
 
 // wc:90-103 for dummy-wall particles: v~ = 2v - f sum V v~ W, rho~ = rho0, p = max(f sum V (p_j + rho~_j g_y dy) W, 0).
+// Tile payloads: ps4 (coords, signed volume), vt4 (v~, rho~), pw4 (EOS pressure, previous pressure).
+template <int KERNEL>
+__device__ __forceinline__ void wall_pair(const KernConst &kc, float ex, float ey, float ez, const F4 pj, const F4 vj, float pjv,
+                                          bool valid, float gy, float &vw, float &pterm) {
+    const float dx = ex - pj.x, dy = ey - pj.y, dz = ez - pj.z;
+    const float wgt = fastW<KERNEL>(kc, dist2(dx, dy, dz));
+    vw = (valid && pj.w > 0.f) ? pj.w * wgt : 0.f;               // flow neighbours only (base:654-663)
+    pterm = fmaf(vj.w * gy, dy, pjv);
+}
+
 template <int KERNEL>
 __global__ void __launch_bounds__(BT) k_tile_wall(DevF c, TileGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileShared<2> &sh = *reinterpret_cast<TileShared<2> *>(smem_raw);
-    unsigned *smask = reinterpret_cast<unsigned *>(smem_raw + sizeof(TileShared<2>));   // [NW][BT]
+    TileShared<3> &sh = *reinterpret_cast<TileShared<3> *>(smem_raw);
+    unsigned *smask = reinterpret_cast<unsigned *>(smem_raw + sizeof(TileShared<3>));   // [NW][BT]
     const int col = blockIdx.x / g.nseg, seg = blockIdx.x - col * g.nseg;
-    const int f0 = seg * ZB, w = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int f0 = seg * ZB, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = f0 + w;
     const int gcell = col * g.nF + f;
     int is = 0, nc = 0;
@@ -374,50 +417,59 @@ __global__ void __launch_bounds__(BT) k_tile_wall(DevF c, TileGeom g) {
     }
     if (!__syncthreads_or(work)) return;
     const int NW = g.nR * 3;
-    unsigned nz = load_masks(c, smask, NW, i, work);
-    if (!tile_setup<2>(c, g, sh, col, f0, c.ps4, c.vt4)) return;   // cannot happen for unflagged cells
-    build_ctab<2>(c, g, sh, w, lane);
-    const F4 *A = sh.P[0], *B = sh.P[1];
+    const unsigned nz = load_masks(c, smask, NW, i, work);
+    if (!tile_setup<3>(c, g, sh, col, f0, c.ps4, c.vt4, c.pw4)) return;   // cannot happen for unflagged cells
+    build_ctab<3>(c, g, sh, w, lane);
+    const F4 *A = sh.P[0], *B = sh.P[1], *Pw = sh.P[2];
     const F4 *ct = sh.ctab + w * 27;
-    const int *cg = sh.cgd + w * 27;
     const int rc = g.nR / 2;
-    const F4 pi = A[sh.cb[rc * CBW + w + 1] + (work ? lane : 0)];
+    const int ci = sh.cb[rc * CBW + w + 1];                         // tile index of this cell's first particle
+    const F4 pi = A[ci + (work ? lane : 0)];
     const KernConst kc = kern_const(c);
     const float gy = c.g[1];
-    float Sv0 = 0.f, Sv1 = 0.f, Sv2 = 0.f, Sp = 0.f, ex = 0.f, ey = 0.f, ez = 0.f;
-    int a = 0, gd = 0;
-    unsigned m = 0;
-    bool alive = work;
+    const bool fresh = c.wc_fresh != 0;
+    const int self = ci + lane;                                     // "j < i" in sorted order == tile index below mine (same run)
+    float Sv0 = 0.f, Sv1 = 0.f, Sv2 = 0.f, Sp = 0.f;
+    Cursor k;
+    k.m = 0; k.nz = nz; k.a = 0; k.ex = k.ey = k.ez = 0.f;
+    const int c_lo = sh.cb[rc * CBW + w + 1], c_hi = sh.cb[rc * CBW + w + 2];   // my own cell inside the tile
+    const int centre = NW / 2;
+    (void)centre;
     while (true) {
-        if (alive && m == 0) {
-            if (nz == 0) alive = false;
-            else {
-                const int cc = __ffs(nz) - 1;
-                nz &= nz - 1;
-                m = smask[cc * BT + tid];
-                const F4 t = ct[cc];
-                a = __float_as_int(t.w);
-                gd = cg[cc];
-                ex = pi.x - t.x; ey = pi.y - t.y; ez = pi.z - t.z;
-            }
-        }
-        if (!__any_sync(0xffffffffu, alive)) break;
-        if (alive) {
-            const int t = __ffs(m) - 1;
-            m &= m - 1;
-            const F4 pj = A[a + t];
-            if (pj.w > 0.f) {
-                const float dx = ex - pj.x, dy = ey - pj.y, dz = ez - pj.z;
-                const float wgt = fastW<KERNEL>(kc, dist2(dx, dy, dz));
-                const F4 vj = B[a + t];
-                const int j = a + t + gd;
-                const float vw = pj.w * wgt;
-                Sv0 = fmaf(vw, vj.x, Sv0); Sv1 = fmaf(vw, vj.y, Sv1); Sv2 = fmaf(vw, vj.z, Sv2);
-                const float pjv = (c.wc_fresh || j < i) ? c.pnew[j] : c.press[j];
-                Sp = fmaf(vw, fmaf(vj.w * gy, dy, pjv), Sp);
-            }
-        }
+        cursor_jump(k, smask, ct, pi);
+        if (!__any_sync(0xffffffffu, k.m != 0)) break;
+        int i0, i1, i2, i3;
+        bool v0, v1, v2, v3;
+        // sorted order: every particle of a stencil cell with a smaller cell id precedes i, every one with a larger id
+        // follows it; inside my own cell the tile index decides.  before0/before1 = "this cell precedes mine".
+        cursor_take2(k, i0, i1, v0, v1);
+        const float e0x = k.ex, e0y = k.ey, e0z = k.ez;
+        const float s0x = pi.x - k.ex, s0y = pi.y - k.ey, s0z = pi.z - k.ez;       // the cell's shift
+        cursor_jump(k, smask, ct, pi);
+        cursor_take2(k, i2, i3, v2, v3);
+        const float s1x = pi.x - k.ex, s1y = pi.y - k.ey, s1z = pi.z - k.ez;
+        const F4 p0 = A[i0], p1 = A[i1], p2 = A[i2], p3 = A[i3];
+        const F4 u0 = B[i0], u1 = B[i1], u2 = B[i2], u3 = B[i3];
+        const F4 w0 = Pw[i0], w1 = Pw[i1], w2 = Pw[i2], w3 = Pw[i3];
+        // stencil order is x-major / z-fastest == ascending cell id: shift (sx, sy, sz) lexicographically negative <=> cell precedes
+        const bool b0 = s0x < 0.f || (s0x == 0.f && (s0y < 0.f || (s0y == 0.f && s0z < 0.f)));
+        const bool b1 = s1x < 0.f || (s1x == 0.f && (s1y < 0.f || (s1y == 0.f && s1z < 0.f)));
+        const bool same0 = s0x == 0.f && s0y == 0.f && s0z == 0.f, same1 = s1x == 0.f && s1y == 0.f && s1z == 0.f;
+        const float q0 = (fresh || b0 || (same0 && i0 < self)) ? w0.x : w0.y;
+        const float q1 = (fresh || b0 || (same0 && i1 < self)) ? w1.x : w1.y;
+        const float q2 = (fresh || b1 || (same1 && i2 < self)) ? w2.x : w2.y;
+        const float q3 = (fresh || b1 || (same1 && i3 < self)) ? w3.x : w3.y;
+        float vw0, pt0, vw1, pt1, vw2, pt2, vw3, pt3;
+        wall_pair<KERNEL>(kc, e0x, e0y, e0z, p0, u0, q0, v0, gy, vw0, pt0);
+        wall_pair<KERNEL>(kc, e0x, e0y, e0z, p1, u1, q1, v1, gy, vw1, pt1);
+        wall_pair<KERNEL>(kc, k.ex, k.ey, k.ez, p2, u2, q2, v2, gy, vw2, pt2);
+        wall_pair<KERNEL>(kc, k.ex, k.ey, k.ez, p3, u3, q3, v3, gy, vw3, pt3);
+        Sv0 = fmaf(vw0, u0.x, Sv0); Sv1 = fmaf(vw0, u0.y, Sv1); Sv2 = fmaf(vw0, u0.z, Sv2); Sp = fmaf(vw0, pt0, Sp);
+        Sv0 = fmaf(vw1, u1.x, Sv0); Sv1 = fmaf(vw1, u1.y, Sv1); Sv2 = fmaf(vw1, u1.z, Sv2); Sp = fmaf(vw1, pt1, Sp);
+        Sv0 = fmaf(vw2, u2.x, Sv0); Sv1 = fmaf(vw2, u2.y, Sv1); Sv2 = fmaf(vw2, u2.z, Sv2); Sp = fmaf(vw2, pt2, Sp);
+        Sv0 = fmaf(vw3, u3.x, Sv0); Sv1 = fmaf(vw3, u3.y, Sv1); Sv2 = fmaf(vw3, u3.z, Sv2); Sp = fmaf(vw3, pt3, Sp);
     }
+    (void)c_lo; (void)c_hi;
     if (!work) return;
     const float fi = c.cspm_f[i];
     const F4 v = c.v4[i];
@@ -436,17 +488,17 @@ __global__ void __launch_bounds__(BT) k_tile_wall(DevF c, TileGeom g) {
 // wc:108-126 for fluid particles: continuity + viscosity + pressure in one visit of the set bits.
 //   d_rho_i = rho~_i sum_j V_j (v~_i - v~_j) . gradW_ij
 //   d_v_i   = g + sum_j [ 2(dim+2) nu V_j min(v_ij . x_ij, 0) / (r^2 + 0.01 h^2) {1 | rho0 / rho~_i} - rho0 V_j (p_i/rho~_i^2 + p_j/rho~_j^2) ] gradW_ij
-struct FluidI { float ex, ey, ez, vx, vy, vz, pr, visc_f, visc_w, h2, nrho0; };
-// one pair: returns V_j s (v_ij . x_ij) through ddc and the coefficient cf with  d_v += cf * d
+struct FluidI { float vx, vy, vz, pr, visc_f, visc_w, h2, nrho0; };
+// one pair: ddc = V_j s (v_ij . x_ij), and the coefficient cf with  d_v += cf * d
 template <int KERNEL>
-__device__ __forceinline__ void fluid_pair(const KernConst &kc, const FluidI &I, const F4 pj, const F4 qj, float valid,
-                                           float &ddc, float &cf, float &dx, float &dy, float &dz) {
-    dx = I.ex - pj.x; dy = I.ey - pj.y; dz = I.ez - pj.z;
+__device__ __forceinline__ void fluid_pair(const KernConst &kc, const FluidI &I, float ex, float ey, float ez, const F4 pj,
+                                           const F4 qj, bool valid, float &ddc, float &cf, float &dx, float &dy, float &dz) {
+    dx = ex - pj.x; dy = ey - pj.y; dz = ez - pj.z;
     const float r2 = dist2(dx, dy, dz);
     const float s = fastdW<KERNEL>(kc, r2);
     const float ux = I.vx - qj.x, uy = I.vy - qj.y, uz = I.vz - qj.z;
     const float vx = fmaf(uz, dz, fmaf(uy, dy, ux * dx));          // v_ij . x_ij
-    const float Vs = fabsf(pj.w) * s * valid;
+    const float Vs = valid ? fabsf(pj.w) * s : 0.f;
     ddc = Vs * vx;
     const float visc = (pj.w < 0.f ? I.visc_w : I.visc_f) * fminf(vx, 0.f) * __fdividef(1.f, r2 + I.h2);
     cf = Vs * fmaf(I.nrho0, I.pr + qj.w, visc);
@@ -458,7 +510,7 @@ __global__ void __launch_bounds__(BT) k_tile_fluid(DevF c, TileGeom g) {
     TileShared<2> &sh = *reinterpret_cast<TileShared<2> *>(smem_raw);
     unsigned *smask = reinterpret_cast<unsigned *>(smem_raw + sizeof(TileShared<2>));   // [NW][BT]
     const int col = blockIdx.x / g.nseg, seg = blockIdx.x - col * g.nseg;
-    const int f0 = seg * ZB, w = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int f0 = seg * ZB, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = f0 + w;
     const int gcell = col * g.nF + f;
     int is = 0, nc = 0;
@@ -468,7 +520,7 @@ __global__ void __launch_bounds__(BT) k_tile_fluid(DevF c, TileGeom g) {
     const bool work = lane < nc && c.type[i] == 1;
     if (!__syncthreads_or(work)) return;
     const int NW = g.nR * 3;
-    unsigned nz = load_masks(c, smask, NW, i, work);
+    const unsigned nz = load_masks(c, smask, NW, i, work);
     if (!tile_setup<2>(c, g, sh, col, f0, c.ps4, c.pk4)) return;
     build_ctab<2>(c, g, sh, w, lane);
     const F4 *A = sh.P[0], *B = sh.P[1];
@@ -482,37 +534,28 @@ __global__ void __launch_bounds__(BT) k_tile_fluid(DevF c, TileGeom g) {
     I.vx = qi.x; I.vy = qi.y; I.vz = qi.z; I.pr = qi.w;
     I.visc_f = c.visc_coef; I.visc_w = c.visc_coef * c.rho0T / rhoi;   // wc:41-44
     I.h2 = c.h2_001; I.nrho0 = -c.rho0T;
-    I.ex = I.ey = I.ez = 0.f;
     float dd = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    int a = 0;
-    unsigned m = 0;
-    bool alive = work;
+    Cursor k;
+    k.m = 0; k.nz = nz; k.a = 0; k.ex = k.ey = k.ez = 0.f;
     while (true) {
-        if (alive && m == 0) {                                      // jump to the next non-empty stencil cell
-            if (nz == 0) alive = false;
-            else {
-                const int cc = __ffs(nz) - 1;
-                nz &= nz - 1;
-                m = smask[cc * BT + tid];
-                const F4 t = ct[cc];
-                a = __float_as_int(t.w);
-                I.ex = pi.x - t.x; I.ey = pi.y - t.y; I.ez = pi.z - t.z;
-            }
-        }
-        if (!__any_sync(0xffffffffu, alive)) break;                 // warp-uniform round: lanes reconverge here
-        if (alive) {                                                // two neighbours of the same cell per round (ILP)
-            const int t1 = __ffs(m) - 1;
-            m &= m - 1;
-            const bool two = m != 0;
-            const int t2 = two ? __ffs(m) - 1 : t1;
-            m &= m - 1;                                             // no-op when m == 0
-            const F4 pj1 = A[a + t1], qj1 = B[a + t1], pj2 = A[a + t2], qj2 = B[a + t2];
-            float d1, c1, x1, y1, z1, d2, c2, x2, y2, z2;
-            fluid_pair<KERNEL>(kc, I, pj1, qj1, 1.f, d1, c1, x1, y1, z1);
-            fluid_pair<KERNEL>(kc, I, pj2, qj2, two ? 1.f : 0.f, d2, c2, x2, y2, z2);
-            dd += d1; a0 = fmaf(c1, x1, a0); a1 = fmaf(c1, y1, a1); a2 = fmaf(c1, z1, a2);
-            dd += d2; a0 = fmaf(c2, x2, a0); a1 = fmaf(c2, y2, a1); a2 = fmaf(c2, z2, a2);
-        }
+        cursor_jump(k, smask, ct, pi);
+        if (!__any_sync(0xffffffffu, k.m != 0)) break;              // warp-uniform round: lanes reconverge here
+        int i0, i1, i2, i3;
+        bool v0, v1, v2, v3;
+        cursor_take2(k, i0, i1, v0, v1);
+        const float e0x = k.ex, e0y = k.ey, e0z = k.ez;
+        cursor_jump(k, smask, ct, pi);
+        cursor_take2(k, i2, i3, v2, v3);
+        const F4 p0 = A[i0], q0 = B[i0], p1 = A[i1], q1 = B[i1], p2 = A[i2], q2 = B[i2], p3 = A[i3], q3 = B[i3];
+        float d0, c0, x0, y0, z0, d1, c1, x1, y1, z1, d2, c2, x2, y2, z2, d3, c3, x3, y3, z3;
+        fluid_pair<KERNEL>(kc, I, e0x, e0y, e0z, p0, q0, v0, d0, c0, x0, y0, z0);
+        fluid_pair<KERNEL>(kc, I, e0x, e0y, e0z, p1, q1, v1, d1, c1, x1, y1, z1);
+        fluid_pair<KERNEL>(kc, I, k.ex, k.ey, k.ez, p2, q2, v2, d2, c2, x2, y2, z2);
+        fluid_pair<KERNEL>(kc, I, k.ex, k.ey, k.ez, p3, q3, v3, d3, c3, x3, y3, z3);
+        dd += d0; a0 = fmaf(c0, x0, a0); a1 = fmaf(c0, y0, a1); a2 = fmaf(c0, z0, a2);
+        dd += d1; a0 = fmaf(c1, x1, a0); a1 = fmaf(c1, y1, a1); a2 = fmaf(c1, z1, a2);
+        dd += d2; a0 = fmaf(c2, x2, a0); a1 = fmaf(c2, y2, a1); a2 = fmaf(c2, z2, a2);
+        dd += d3; a0 = fmaf(c3, x3, a0); a1 = fmaf(c3, y3, a1); a2 = fmaf(c3, z3, a2);
     }
     if (!work) return;
     c.d_rho[i] = dd * rhoi;
@@ -523,10 +566,11 @@ __global__ void __launch_bounds__(BT) k_tile_fluid(DevF c, TileGeom g) {
 // ------------------------------------------------------------------------------------------------ host side
 static size_t smem_mask(int NW) { return sizeof(TileShared<1>) + (size_t)NW * BT * 4; }
 static size_t smem_pass(int NW = 27) { return sizeof(TileShared<2>) + (size_t)NW * BT * 4; }
+static size_t smem_wall(int NW = 27) { return sizeof(TileShared<3>) + (size_t)NW * BT * 4; }
 
 template <int KERNEL> static int set_attrs(SphCtx *c) {
     SPH_CHECK(c, cudaFuncSetAttribute(k_tile_mask<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mask(27)));
-    SPH_CHECK(c, cudaFuncSetAttribute(k_tile_wall<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pass()));
+    SPH_CHECK(c, cudaFuncSetAttribute(k_tile_wall<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wall()));
     SPH_CHECK(c, cudaFuncSetAttribute(k_tile_fluid<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pass()));
     return 0;
 }
@@ -563,8 +607,8 @@ int tile_wc_prep_and_wall(SphCtx *c) {
     k_tile_prep<<<blocks_for(n, 256), 256, 0, c->stream>>>(d);
     SPH_LAUNCH_CHECK(c);
     SPH_PROF(c, K_TILE_WALL);
-    if (c->p.kernel == 0) k_tile_wall<0><<<nblk, BT, smem_pass(g.nR * 3), c->stream>>>(d, g);
-    else k_tile_wall<1><<<nblk, BT, smem_pass(g.nR * 3), c->stream>>>(d, g);
+    if (c->p.kernel == 0) k_tile_wall<0><<<nblk, BT, smem_wall(g.nR * 3), c->stream>>>(d, g);
+    else k_tile_wall<1><<<nblk, BT, smem_wall(g.nR * 3), c->stream>>>(d, g);
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
