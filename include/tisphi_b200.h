@@ -83,6 +83,8 @@ enum SphField {
     SPH_F_CELL_END,       /* i32 x C: inclusive scan = grid_particle_num after prefix_sum.run (ps:256) */
     SPH_F_CELL_COUNT,     /* i32 x C: histogram = grid_particle_num_temp (ps:235-236)                 */
     SPH_F_ID_NEW,         /* i32: destination index of the last sort, pt.id_new (ps:245)              */
+    SPH_F_PK4,            /* real x4: v_tmp.xyz, pressure / density_tmp^2 -- tile payload of the fluid pass; only
+                             allocated when the cell-tile fast path is (MIXED precision WCSPH without CSPM_L)  */
     SPH_F_NUM
 };
 
@@ -145,8 +147,36 @@ int sph_profile_enable(SphCtx *ctx, int on);
 int sph_profile_num_kernels(void);
 const char *sph_profile_name(int id);
 int sph_profile_read(SphCtx *ctx, double *ms_by_kernel, int64_t *launches_by_kernel);
-/* multi-GPU slab support: see tisphi_b200/parallel notes in DESIGN.md */
-int sph_set_ghost_range(SphCtx *ctx, int64_t n_owned_begin, int64_t n_owned_end);
+
+/* ---- multi-GPU slab decomposition (DESIGN.md "Multi-GPU"; the reference is single-device) -----------
+ * A rank owns the x-columns [cx_begin, cx_end) of the GLOBAL grid and additionally holds one ghost column on each
+ * side.  The flattened cell id is x-major (ps:221-222), so after sph_grid_build every column is ONE contiguous
+ * index range of every member array: halo and migration messages are plain ranges, never gathers.
+ * A message is a device buffer holding, for each listed member in order, `count` consecutive elements of that
+ * member (element = stride x sizeof(kind)), each section padded to 16 bytes.                                      */
+/* <Solver>.one_step split at its top-level loops (the points where ghost columns must be refreshed):
+ *   WCSPH  0: loop A (EOS + wall extrapolation, wc:86-106)        1: loop B (continuity + momentum, wc:108-126)
+ *   mu(I)  0: loop 1 (muI:67-92)   1: loop 2 walls (muI:95-109)   2: loop 3 momentum (muI:115-128)
+ *   DP     0: loop 1 (dp:215-217)  1: loop 2 walls (dp:220-231)   2: loop 3 (dp:237-270)                          */
+int sph_num_phases(SphCtx *ctx);
+int sph_one_step_phase(SphCtx *ctx, int phase);
+/* sweeps only update particles whose cell column lies in [cx_begin, cx_end); pointwise kernels still run on all.
+ * (0, grid_num[0]) restores the single-GPU behaviour. */
+int sph_set_owned_columns(SphCtx *ctx, int32_t cx_begin, int32_t cx_end);
+/* index of the first particle of each listed column (cx <= 0 -> 0, cx >= grid_num[0] -> n) after the last
+ * sph_grid_build.  Synchronises the stream. */
+int sph_column_starts(SphCtx *ctx, int32_t ncols, const int32_t *cx, int64_t *start_out);
+/* the members that travel with a particle through the sort (the migration / halo record); returns their number */
+int sph_state_fields(SphCtx *ctx, int32_t *fields_out, int32_t capacity);
+int64_t sph_message_bytes(SphCtx *ctx, int32_t nfields, const int32_t *fields, int64_t count);
+int sph_pack_fields(SphCtx *ctx, int32_t nfields, const int32_t *fields, int64_t first, int64_t count, void *msg_dev);
+int sph_unpack_fields(SphCtx *ctx, int32_t nfields, const int32_t *fields, int64_t first, int64_t count,
+                      const void *msg_dev);
+/* particle set := [n_left particles of left_msg][keep_count current particles from keep_first][n_right of right_msg]
+ * (messages hold the sph_state_fields members).  Arrivals from the lower-x neighbour go in front and those from
+ * the higher-x neighbour behind, so that the next stable sort reproduces the single-GPU global order. */
+int sph_replace_particles(SphCtx *ctx, int64_t keep_first, int64_t keep_count, const void *left_msg, int64_t n_left,
+                          const void *right_msg, int64_t n_right);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,8 @@ def lib():
             getattr(L, fn).restype = None
         L.orc_set_params.argtypes = [C.c_void_p, C.POINTER(OrcParams)]
         L.orc_advect.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_one_step_phase.argtypes = [C.c_void_p, C.c_int]
+        L.orc_one_step_phase.restype = None
         L.orc_grid_build.argtypes = [C.c_void_p]
         L.orc_grid_build.restype = C.c_int64
         L.orc_step.argtypes = [C.c_void_p]

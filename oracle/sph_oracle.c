@@ -354,10 +354,14 @@ static inline double eos_wc(const OrcParams *p, double rho) {
     double v = p->stiff * (pow(rho / p->rho0, p->gamma_) - 1.0);
     return v > 0.0 ? v : 0.0;
 }
-static void one_step_wc(Orc *o) {
+/* phase: -1 = the whole one_step; 0, 1, (2) = one top-level loop only (used by the slab-decomposition tests, which
+ * refresh ghost columns between the loops exactly as tisphi_b200/parallel.py does on the GPUs) */
+#define PHASE(k) if (phase == -1 || phase == (k))
+static void one_step_wc(Orc *o, int phase) {
     const OrcParams *p = &o->p;
     int64_t n = o->n;
     double *pr = o->f[F_PRESSURE], *pold = o->scratch;            /* snapshot of pressure before loop A */
+    PHASE(0) {
     memcpy(pold, pr, sizeof(double) * n);
     /* loop A (wc:86-106).  In-place read of p_j emulated pointwise: j < i -> new EOS value, j > i -> old value. */
 #pragma omp parallel for schedule(dynamic, 256)
@@ -386,7 +390,9 @@ static void one_step_wc(Orc *o) {
             pr[i] = v > 0.0 ? v : 0.0;
         }
     }
+    }
     /* loop B (wc:108-126) */
+    PHASE(1)
 #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t i = 0; i < n; i++) {
         if (!is_fluid(TYPE(o, i))) continue;
@@ -446,9 +452,10 @@ static inline double dev_component(const double *t) {    /* type_define.py:26-28
 }
 
 /* ------------------------------------------------------------------------------------ mu(I) (muI:62-156) */
-static void one_step_mui(Orc *o) {
+static void one_step_mui(Orc *o, int phase) {
     const OrcParams *p = &o->p;
     int64_t n = o->n;
+    PHASE(0)
 #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t i = 0; i < n; i++) {                    /* loop 1 (muI:67-92) */
         if (!is_soil(TYPE(o, i))) continue;
@@ -473,6 +480,7 @@ static void one_step_mui(Orc *o) {
         se[0] -= tr / 3.0; se[4] -= tr / 3.0; se[8] -= tr / 3.0;
         o->f[F_D_STRAIN_EQU][i] = dev_component(se);
     }
+    PHASE(1)
 #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t i = 0; i < n; i++) {                    /* loop 2 (muI:95-109) */
         int t = TYPE(o, i);
@@ -484,6 +492,7 @@ static void one_step_mui(Orc *o) {
         o->f[F_DENSITY_TMP][i] = rt > p->rho0 ? rt : p->rho0;
         for (int a = 0; a < 9; a++) o->f[F_STRESS_TMP][9 * i + a] = Ss[a] * f;
     }
+    PHASE(2)
 #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t i = 0; i < n; i++) {                    /* loop 3 (muI:115-128) */
         if (!is_soil(TYPE(o, i))) continue;
@@ -561,11 +570,13 @@ static void bui2008(const OrcParams *p, const double *st, const double *vg, doub
         *dsep = dev_component(ep);
     }
 }
-static void one_step_dp(Orc *o) {
+static void one_step_dp(Orc *o, int phase) {
     const OrcParams *p = &o->p;
     int64_t n = o->n;
+    PHASE(0)
     for (int64_t i = 0; i < n; i++)                      /* loop 1 (dp:215-217) */
         if (is_soil(TYPE(o, i))) adapt_stress(p, &o->f[F_STRESS_TMP][9 * i]);
+    PHASE(1)
 #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t i = 0; i < n; i++) {                    /* loop 2 (dp:220-231) */
         int t = TYPE(o, i);
@@ -576,6 +587,7 @@ static void one_step_dp(Orc *o) {
         o->f[F_DENSITY_TMP][i] = p->rho0;
         for (int a = 0; a < 9; a++) o->f[F_STRESS_TMP][9 * i + a] = Ss[a] * f;
     }
+    PHASE(2)
 #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t i = 0; i < n; i++) {                    /* loop 3 (dp:237-270) */
         if (!is_soil(TYPE(o, i))) continue;
@@ -590,11 +602,12 @@ static void one_step_dp(Orc *o) {
     }
 }
 
-void orc_one_step(Orc *o) {
-    if (o->p.solver == 1) one_step_wc(o);
-    else if (o->p.solver == 2) one_step_mui(o);
-    else one_step_dp(o);
+void orc_one_step_phase(Orc *o, int phase) {
+    if (o->p.solver == 1) one_step_wc(o, phase);
+    else if (o->p.solver == 2) one_step_mui(o, phase);
+    else one_step_dp(o, phase);
 }
+void orc_one_step(Orc *o) { orc_one_step_phase(o, -1); }
 
 /* DP constructor's init_stress (base:249-260, dp:35) */
 void orc_init_stress(Orc *o) {

@@ -14,7 +14,7 @@ SOLVER_WC, SOLVER_MUI, SOLVER_DP = 1, 2, 3
 FIELDS = ["X", "V", "MASS", "M_V", "DENSITY", "DENSITY_TMP", "V_TMP", "PRESSURE", "MAT_TYPE", "ID0", "GRID_IDS",
           "STRESS", "STRESS_TMP", "STRAIN_EQU", "STRAIN_EQU_P", "FLAG_RETMAP", "CSPM_F", "CSPM_L", "D_DENSITY", "D_VEL",
           "D_STRESS", "V_GRAD", "D_STRAIN_EQU", "D_STRAIN_EQU_P", "D_DENSITY_RK", "D_VEL_RK", "D_STRESS_RK", "XS",
-          "CELL_END", "CELL_COUNT", "ID_NEW"]
+          "CELL_END", "CELL_COUNT", "ID_NEW", "PK4"]
 FIELD_ID = {name: k for k, name in enumerate(FIELDS)}
 
 # every symbol include/tisphi_b200.h declares (tests check that the library exports all of them)
@@ -22,7 +22,9 @@ SYMBOLS = ["sph_arena_bytes", "sph_create", "sph_destroy", "sph_last_error", "sp
            "sph_add_particles", "sph_num_particles", "sph_clear_particles", "sph_read_state", "sph_grid_build",
            "sph_calc_kernel_corr", "sph_init_real2tmp", "sph_one_step", "sph_advect", "sph_advect_pos", "sph_post_step",
            "sph_init_stress", "sph_step", "sph_neighbor_count", "sph_density_sum", "sph_read_bad_cells",
-           "sph_launch_count", "sph_set_ghost_range", "sph_profile_enable", "sph_profile_num_kernels",
+           "sph_launch_count", "sph_num_phases", "sph_one_step_phase", "sph_set_owned_columns",
+           "sph_column_starts", "sph_state_fields", "sph_message_bytes", "sph_pack_fields", "sph_unpack_fields",
+           "sph_replace_particles", "sph_profile_enable", "sph_profile_num_kernels",
            "sph_profile_name", "sph_profile_read", "sph_params_size"]
 
 
@@ -71,7 +73,15 @@ def load():
     L.sph_density_sum.restype, L.sph_density_sum.argtypes = C.c_int, [vp, vp]
     L.sph_read_bad_cells.restype, L.sph_read_bad_cells.argtypes = i64, [vp]
     L.sph_launch_count.restype, L.sph_launch_count.argtypes = i64, [vp]
-    L.sph_set_ghost_range.restype, L.sph_set_ghost_range.argtypes = C.c_int, [vp, i64, i64]
+    L.sph_num_phases.restype, L.sph_num_phases.argtypes = C.c_int, [vp]
+    L.sph_one_step_phase.restype, L.sph_one_step_phase.argtypes = C.c_int, [vp, C.c_int]
+    L.sph_set_owned_columns.restype, L.sph_set_owned_columns.argtypes = C.c_int, [vp, i32, i32]
+    L.sph_column_starts.restype, L.sph_column_starts.argtypes = C.c_int, [vp, i32, C.POINTER(i32), C.POINTER(i64)]
+    L.sph_state_fields.restype, L.sph_state_fields.argtypes = C.c_int, [vp, C.POINTER(i32), i32]
+    L.sph_message_bytes.restype, L.sph_message_bytes.argtypes = i64, [vp, i32, C.POINTER(i32), i64]
+    L.sph_pack_fields.restype, L.sph_pack_fields.argtypes = C.c_int, [vp, i32, C.POINTER(i32), i64, i64, vp]
+    L.sph_unpack_fields.restype, L.sph_unpack_fields.argtypes = C.c_int, [vp, i32, C.POINTER(i32), i64, i64, vp]
+    L.sph_replace_particles.restype, L.sph_replace_particles.argtypes = C.c_int, [vp, i64, i64, vp, i64, vp, i64]
     L.sph_profile_enable.restype, L.sph_profile_enable.argtypes = C.c_int, [vp, C.c_int]
     L.sph_profile_num_kernels.restype, L.sph_profile_num_kernels.argtypes = C.c_int, []
     L.sph_profile_name.restype, L.sph_profile_name.argtypes = C.c_char_p, [C.c_int]

@@ -10,7 +10,7 @@ namespace {
 
 inline int64_t align_up(int64_t v, int64_t a = 256) { return (v + a - 1) / a * a; }
 
-struct FieldSpec { int ncomp, stride, kind; bool carried; int need; };   // need: 0 always, 1 soil, 2 rk, 3 cspm_L, 4 soil+rk
+struct FieldSpec { int ncomp, stride, kind; bool carried; int need; };   // need: 0 always, 1 soil, 2 rk, 3 cspm_L, 4 soil+rk, 5 fast
 // order == enum FieldSlot
 const FieldSpec SPEC[SPH_F_NUM] = {
     /* X            */ {3, 3, 0, true, 0},
@@ -44,6 +44,7 @@ const FieldSpec SPEC[SPH_F_NUM] = {
     /* CELL_END     */ {1, 1, 2, false, 0},
     /* CELL_COUNT   */ {1, 1, 2, false, 0},
     /* ID_NEW       */ {1, 1, 2, false, 0},
+    /* PK4          */ {4, 4, 1, false, 5},
 };
 
 inline int elem_bytes(int kind, int real_bytes) { return kind == 0 ? 8 : (kind == 1 ? real_bytes : 4); }
@@ -55,10 +56,13 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
     const int rb = p->precision == SPH_PREC_F64 ? 8 : 4;
     const bool soil = p->solver != SPH_SOLVER_WC, rk = p->ti == 4, hasL = p->kcorr == 1;
     const int64_t C = n_cells(p);
+    // cell-tile fast path scratch: MIXED precision WCSPH without CSPM_L
+    const bool fast = p->fast && p->precision == SPH_PREC_MIXED && p->solver == SPH_SOLVER_WC && p->kcorr == 0;
     int64_t off = 0;
     for (int f = 0; f < SPH_F_NUM; f++) {
         const FieldSpec &s = SPEC[f];
-        bool present = s.need == 0 || (s.need == 1 && soil) || (s.need == 2 && rk) || (s.need == 3 && hasL) || (s.need == 4 && soil && rk);
+        bool present = s.need == 0 || (s.need == 1 && soil) || (s.need == 2 && rk) || (s.need == 3 && hasL) ||
+                       (s.need == 4 && soil && rk) || (s.need == 5 && fast);
         if (f == SPH_F_MASS || f == SPH_F_M_V) present = true;
         int64_t count = (f == SPH_F_CELL_END || f == SPH_F_CELL_COUNT) ? C + 1 : n_max;
         int64_t bytes = align_up(count * s.stride * elem_bytes(s.kind, rb));
@@ -82,14 +86,11 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
     int64_t o_bad = off; off += 256;
     const int64_t nt = (C + 2047) / 2048 + 1;
     int64_t o_tiles = off; off += align_up(nt * 4);
-    // cell-tile fast path scratch: MIXED precision WCSPH without CSPM_L
-    const bool fast = p->fast && p->precision == SPH_PREC_MIXED && p->solver == SPH_SOLVER_WC && p->kcorr == 0;
     const int mask_words = p->dim == 3 ? 27 : 9;
     int64_t o_pw4 = 0;
     int64_t o_ps4 = 0, o_pk4 = 0, o_mask = 0, o_nflow = 0, o_cflag = 0, o_nflag = 0;
     if (fast) {
         o_ps4 = off; off += align_up(n_max * 16);
-        o_pk4 = off; off += align_up(n_max * 16);
         o_pw4 = off; off += align_up(n_max * 16);
         o_mask = off; off += align_up(n_max * 4 * mask_words);
         o_nflow = off; off += align_up(n_max);
@@ -98,7 +99,7 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
     }
     if (c) {
         c->off_pw4 = o_pw4;
-        c->off_ps4 = o_ps4; c->off_pk4 = o_pk4; c->off_mask = o_mask; c->off_nflow = o_nflow; c->off_cellflag = o_cflag;
+        c->off_ps4 = o_ps4; c->off_pk4 = fast ? c->f[SPH_F_PK4].off[0] : o_pk4; c->off_mask = o_mask; c->off_nflow = o_nflow; c->off_cellflag = o_cflag;
         c->off_nflag = o_nflag; c->fast = fast; c->mask_words = mask_words;
         c->off_gid_unsorted = o_gid; c->off_slot = o_slot; c->off_perm = o_perm; c->off_tmpidx = o_tmp;
         c->off_bad = o_bad; c->off_scan_tiles = o_tiles;
@@ -178,6 +179,7 @@ template <typename T> Dev<T> make_dev(SphCtx *c, int which) {
     for (int a = 0; a < 3; a++) { d.gn[a] = p.gn[a]; d.vstart[a] = p.vstart[a]; d.g[a] = (T)p.g[a]; }
     if (p.dim == 2) d.gn[2] = 1;
     d.C = c->C;
+    d.own0 = c->own0; d.own1 = c->own1;
     d.gs = p.grid_size; d.dt = p.dt; d.m_V0d = p.m_V0;
     d.h = (T)p.h; d.hinv = (T)(1.0 / p.h); d.support = (T)p.support;
     d.r2thr = sizeof(T) == 8 ? (T)c->r2thr64 : (T)c->r2thr32;
@@ -310,6 +312,7 @@ SphCtx *sph_create(const SphParams *p, int64_t n_max, void *arena, int64_t arena
     c->arena_bytes = arena_bytes;
     c->stream = (cudaStream_t)stream;
     layout(p, n_max, c);
+    c->own0 = 0; c->own1 = p->gn[0];
     c->r2thr64 = r2_threshold64(p->support);
     c->r2thr32 = r2_threshold32((float)p->support);
     if (cudaMemsetAsync(arena, 0, (size_t)layout(p, n_max, nullptr), c->stream) != cudaSuccess) { delete c; return nullptr; }
@@ -432,6 +435,12 @@ int sph_profile_read(SphCtx *c, double *ms_by_kernel, int64_t *launches_by_kerne
     ps->used = 0;
     return 0;
 }
-int sph_set_ghost_range(SphCtx *c, int64_t b, int64_t e) { (void)c; (void)b; (void)e; return 0; }
+int sph_num_phases(SphCtx *c) { return c->p.solver == SPH_SOLVER_WC ? 2 : 3; }
+int sph_one_step_phase(SphCtx *c, int phase) { return DISPATCH(c, one_step_phase, c, phase); }
+int sph_set_owned_columns(SphCtx *c, int32_t b, int32_t e) {
+    if (b < 0 || e > c->p.gn[0] || b >= e) { snprintf(c->err, sizeof(c->err), "owned columns [%d, %d) outside the grid", b, e); return -2; }
+    c->own0 = b; c->own1 = e;
+    return 0;
+}
 
 }  // extern "C"

@@ -46,6 +46,7 @@ template <typename T> struct Dev {
     int dim, kernel, kcorr, solver, xsph, wc_fresh;
     int gn[3];
     int C;
+    int own0, own1;      // owned x-columns [own0, own1): sweeps skip particles of other columns (ghosts)
     // geometry (float64: cell ids are always computed in float64 like the reference, ps:216-226)
     double vstart[3], gs;
     double dt, m_V0d;

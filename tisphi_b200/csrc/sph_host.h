@@ -39,6 +39,7 @@ struct SphCtx {
     int64_t launches_by_kernel[32];
     void *prof_state;
     float r2thr32;
+    int own0, own1;      // owned x-columns [own0, own1) (multi-GPU slabs); the whole grid on one GPU
 };
 
 #define SPH_CHECK(ctx, call)                                                                          \
@@ -82,6 +83,7 @@ template <typename T> int grid_build(SphCtx *c);
 // sweeps.cu
 template <typename T> int calc_kernel_corr(SphCtx *c);
 template <typename T> int one_step(SphCtx *c);
+template <typename T> int one_step_phase(SphCtx *c, int phase);
 template <typename T> int advect_pos(SphCtx *c);
 template <typename T> int post_step(SphCtx *c);
 template <typename T> int neighbor_count(SphCtx *c, int32_t *out);

@@ -13,7 +13,13 @@ namespace sph {
 
 // --------------------------------------------------------------------------------------------- kernel correction
 // flagged-only mode: the cell-tile kernels handled every particle except those of flagged cells
+template <typename T> __device__ __forceinline__ bool not_owned(const Dev<T> &c, int i) {
+    if (c.own1 - c.own0 >= c.gn[0]) return false;
+    const int cx = c.gid[i] / (c.gn[1] * c.gn[2]);
+    return cx < c.own0 || cx >= c.own1;
+}
 template <typename T> __device__ __forceinline__ bool skip_unflagged(const Dev<T> &c, int i) {
+    if (not_owned(c, i)) return true;
     if (!c.flagged_only) return false;
     if (*c.nflag == 0) return true;
     return c.cellflag[c.gid[i]] == 0;
@@ -36,6 +42,7 @@ template <typename T> __device__ __forceinline__ T det3(const T *m) {
 template <typename T> __global__ void __launch_bounds__(128) k_cspm_L(Dev<T> c) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n) return;
+    if (not_owned(c, i)) return;
     T L[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     const int ti = c.type[i];
     if (is_flow(ti)) {
@@ -200,6 +207,7 @@ template <typename T> __global__ void __launch_bounds__(128) k_soil_wall(Dev<T> 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n) return;
     if (!is_wall(c.type[i])) return;
+    if (not_owned(c, i)) return;
     T Sv0 = 0, Sv1 = 0, Sv2 = 0, Sr = 0, Ss[6] = {0, 0, 0, 0, 0, 0};
     for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
         if (is_flow(c.type[j])) {
@@ -279,6 +287,7 @@ template <typename T> __global__ void __launch_bounds__(128) k_mui_soil1(Dev<T> 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n) return;
     if (!is_soil(c.type[i])) return;
+    if (not_owned(c, i)) return;
     T vg[9], dd, mom[3];
     soil_sweep<T, true, false>(c, i, vg, &dd, mom);
 #pragma unroll
@@ -310,6 +319,7 @@ template <typename T> __global__ void __launch_bounds__(128) k_mui_soil3(Dev<T> 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n) return;
     if (!is_soil(c.type[i])) return;
+    if (not_owned(c, i)) return;
     T vg[9], dd, mom[3];
     soil_sweep<T, false, true>(c, i, vg, &dd, mom);
     const Vec4<T> vi = c.vt4[i];
@@ -415,6 +425,7 @@ template <typename T> __global__ void __launch_bounds__(128) k_dp_soil(Dev<T> c)
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n) return;
     if (!is_soil(c.type[i])) return;
+    if (not_owned(c, i)) return;
     T vg[9], dd, mom[3];
     soil_sweep<T, true, true>(c, i, vg, &dd, mom);
 #pragma unroll
@@ -433,63 +444,87 @@ template <typename T> __global__ void __launch_bounds__(128) k_dp_soil(Dev<T> c)
     c.d_vel[i] = dv;
 }
 
-template <typename T> int one_step(SphCtx *c) {
+// one top-level loop of <Solver>.one_step (phases documented in include/tisphi_b200.h: sph_one_step_phase)
+template <typename T> int one_step_phase(SphCtx *c, int phase) {
     if (c->n == 0) return 0;
     const int n = (int)c->n;
     cudaStream_t st = c->stream;
-    if (c->p.solver == SPH_SOLVER_WC && c->fast) {
-        int r = tile_wc_prep_and_wall(c);
-        if (r) return r;
+    const int solver = c->p.solver;
+    if (phase < 0 || phase >= (solver == SPH_SOLVER_WC ? 2 : 3)) {
+        snprintf(c->err, sizeof(c->err), "solver %d has no phase %d", solver, phase);
+        return -2;
+    }
+    if (solver == SPH_SOLVER_WC && c->fast) {
+        if (phase == 0) {
+            int r = tile_wc_prep_and_wall(c);
+            if (r) return r;
+            Dev<T> d = make_dev<T>(c);
+            d.flagged_only = 1;
+            SPH_PROF(c, K_WC_WALL);
+            k_wc_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+            SPH_LAUNCH_CHECK(c);
+            flip(c, SPH_F_PRESSURE);
+        } else {
+            int r = tile_wc_fluid(c);
+            if (r) return r;
+            Dev<T> d = make_dev<T>(c);
+            d.flagged_only = 1;
+            SPH_PROF(c, K_WC_FLUID);
+            k_wc_fluid<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+            SPH_LAUNCH_CHECK(c);
+        }
+    } else if (solver == SPH_SOLVER_WC) {
         Dev<T> d = make_dev<T>(c);
-        d.flagged_only = 1;
-        SPH_PROF(c, K_WC_WALL);
-        k_wc_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
-        SPH_LAUNCH_CHECK(c);
-        flip(c, SPH_F_PRESSURE);
-        if ((r = tile_wc_fluid(c))) return r;
-        d = make_dev<T>(c);
-        d.flagged_only = 1;
-        SPH_PROF(c, K_WC_FLUID);
-        k_wc_fluid<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
-        SPH_LAUNCH_CHECK(c);
-    } else if (c->p.solver == SPH_SOLVER_WC) {
+        if (phase == 0) {
+            SPH_PROF(c, K_WC_EOS);
+            k_wc_eos<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
+            SPH_LAUNCH_CHECK(c);
+            SPH_PROF(c, K_WC_WALL);
+            k_wc_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+            SPH_LAUNCH_CHECK(c);
+            flip(c, SPH_F_PRESSURE);               // pnew becomes pt.pressure
+        } else {
+            SPH_PROF(c, K_WC_FLUID);
+            k_wc_fluid<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+            SPH_LAUNCH_CHECK(c);
+        }
+    } else if (solver == SPH_SOLVER_MUI) {
         Dev<T> d = make_dev<T>(c);
-        SPH_PROF(c, K_WC_EOS);
-        k_wc_eos<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
+        if (phase == 0) {
+            SPH_PROF(c, K_MUI_SOIL1);
+            k_mui_soil1<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        } else if (phase == 1) {
+            SPH_PROF(c, K_SOIL_WALL);
+            k_soil_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        } else {
+            SPH_PROF(c, K_MUI_SOIL3);
+            k_mui_soil3<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        }
         SPH_LAUNCH_CHECK(c);
-        SPH_PROF(c, K_WC_WALL);
-        k_wc_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
-        SPH_LAUNCH_CHECK(c);
-        flip(c, SPH_F_PRESSURE);               // pnew becomes pt.pressure
-        d = make_dev<T>(c);
-        SPH_PROF(c, K_WC_FLUID);
-        k_wc_fluid<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
-        SPH_LAUNCH_CHECK(c);
-    } else if (c->p.solver == SPH_SOLVER_MUI) {
+    } else if (solver == SPH_SOLVER_DP) {
         Dev<T> d = make_dev<T>(c);
-        SPH_PROF(c, K_MUI_SOIL1);
-        k_mui_soil1<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
-        SPH_LAUNCH_CHECK(c);
-        SPH_PROF(c, K_SOIL_WALL);
-        k_soil_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
-        SPH_LAUNCH_CHECK(c);
-        SPH_PROF(c, K_MUI_SOIL3);
-        k_mui_soil3<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
-        SPH_LAUNCH_CHECK(c);
-    } else if (c->p.solver == SPH_SOLVER_DP) {
-        Dev<T> d = make_dev<T>(c);
-        SPH_PROF(c, K_DP_ADAPT);
-        k_dp_adapt<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
-        SPH_LAUNCH_CHECK(c);
-        SPH_PROF(c, K_SOIL_WALL);
-        k_soil_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
-        SPH_LAUNCH_CHECK(c);
-        SPH_PROF(c, K_DP_SOIL);
-        k_dp_soil<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        if (phase == 0) {
+            SPH_PROF(c, K_DP_ADAPT);
+            k_dp_adapt<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
+        } else if (phase == 1) {
+            SPH_PROF(c, K_SOIL_WALL);
+            k_soil_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        } else {
+            SPH_PROF(c, K_DP_SOIL);
+            k_dp_soil<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        }
         SPH_LAUNCH_CHECK(c);
     } else {
-        snprintf(c->err, sizeof(c->err), "unknown solver %d", c->p.solver);
+        snprintf(c->err, sizeof(c->err), "unknown solver %d", solver);
         return -2;
+    }
+    return 0;
+}
+template <typename T> int one_step(SphCtx *c) {
+    const int np = c->p.solver == SPH_SOLVER_WC ? 2 : 3;
+    for (int ph = 0; ph < np; ph++) {
+        int r = one_step_phase<T>(c, ph);
+        if (r) return r;
     }
     return 0;
 }
@@ -598,6 +633,7 @@ template <typename T> __global__ void __launch_bounds__(128) k_post_mui_b(Dev<T>
     if (i >= c.n) return;
     const int ti = c.type[i];
     if (!is_soil(ti)) return;
+    if (not_owned(c, i)) return;
     T acc[6] = {0, 0, 0, 0, 0, 0};
     for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
         if (c.type[j] == ti) {
@@ -671,6 +707,7 @@ template <typename T> int density_sum(SphCtx *c, void *out) {
 #define INST(T)                                            \
     template int calc_kernel_corr<T>(SphCtx *);            \
     template int one_step<T>(SphCtx *);                    \
+    template int one_step_phase<T>(SphCtx *, int);                    \
     template int advect_pos<T>(SphCtx *);                  \
     template int post_step<T>(SphCtx *);                   \
     template int neighbor_count<T>(SphCtx *, int32_t *);   \

@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(BT) k_tile_mask(DevF c, TileGeom g) {
     TileShared<1> &sh = *reinterpret_cast<TileShared<1> *>(smem_raw);
     unsigned *smask = reinterpret_cast<unsigned *>(smem_raw + sizeof(TileShared<1>));   // [NW][BT]
     const int col = blockIdx.x / g.nseg, seg = blockIdx.x - col * g.nseg;
+    if (col / g.ny < c.own0 || col / g.ny >= c.own1) return;        // ghost column of a slab (block-uniform)
     const int f0 = seg * ZB, w = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int f = f0 + w;
     const int gcell = col * g.nF + f;
@@ -394,6 +395,7 @@ __global__ void __launch_bounds__(BT) k_tile_wall(DevF c, TileGeom g) {
     TileShared<3> &sh = *reinterpret_cast<TileShared<3> *>(smem_raw);
     unsigned *smask = reinterpret_cast<unsigned *>(smem_raw + sizeof(TileShared<3>));   // [NW][BT]
     const int col = blockIdx.x / g.nseg, seg = blockIdx.x - col * g.nseg;
+    if (col / g.ny < c.own0 || col / g.ny >= c.own1) return;        // ghost column of a slab (block-uniform)
     const int f0 = seg * ZB, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = f0 + w;
     const int gcell = col * g.nF + f;
@@ -510,6 +512,7 @@ __global__ void __launch_bounds__(BT) k_tile_fluid(DevF c, TileGeom g) {
     TileShared<2> &sh = *reinterpret_cast<TileShared<2> *>(smem_raw);
     unsigned *smask = reinterpret_cast<unsigned *>(smem_raw + sizeof(TileShared<2>));   // [NW][BT]
     const int col = blockIdx.x / g.nseg, seg = blockIdx.x - col * g.nseg;
+    if (col / g.ny < c.own0 || col / g.ny >= c.own1) return;        // ghost column of a slab (block-uniform)
     const int f0 = seg * ZB, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = f0 + w;
     const int gcell = col * g.nF + f;

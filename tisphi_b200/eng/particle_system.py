@@ -74,7 +74,7 @@ class _ParticleFields:
 
 
 class ParticleSystem:
-    def __init__(self, config: SimConfiger, device="cuda:0", precision=None) -> None:
+    def __init__(self, config: SimConfiger, device="cuda:0", precision=None, slab=None) -> None:
         import torch
         self._torch = torch
         self.cfg = config
@@ -168,13 +168,19 @@ class ParticleSystem:
             P.g[a] = float(grav[a])
         P.h, P.support, P.grid_size, P.m_V0, P.eps = self.smoothing_len, self.support_radius, self.grid_size, self.m_V0, 1e-8
         self.params = P
-        self.engine = _lib.Engine(P, max(self.particle_max_num, 1), device=device)
         self.pt = _ParticleFields(self)
         self.pt_buf = self.pt            # the ping-pong buffers are internal to the engine
         self._const = {k: [] for k in _CONST}
         self._const_cache = {}
-
-        self.initialize_particles()
+        self._slab = slab
+        self._device = device
+        if slab is None:
+            self.engine = _lib.Engine(P, max(self.particle_max_num, 1), device=device)
+            self.initialize_particles()
+        else:
+            self._pending = []           # host arrays of the whole scene; only this rank's columns are uploaded
+            self.initialize_particles()
+            self._upload_slab()
         self.set_id0()
         print("Particle system construction complete!")
 
@@ -202,16 +208,53 @@ class ParticleSystem:
                        new_particle_density, new_particle_pressure, new_particles_material_id,
                        new_particles_material_type, new_particles_is_dynamic, new_particles_color):
         """ps:289-314: append host arrays to the device arrays (pressure is always 0 at creation, ps:283)."""
-        self.engine.add_particles(new_particles_positions, new_particles_velocity, new_particle_density,
-                                  new_particles_material_type)
         n = int(new_particles_num)
+        if self._slab is not None:
+            self._pending.append((np.asarray(new_particles_positions, dtype=np.float64),
+                                  np.asarray(new_particles_velocity, dtype=np.float64),
+                                  np.asarray(new_particle_density, dtype=np.float64),
+                                  np.asarray(new_particles_material_type, dtype=np.int32)))
+        else:
+            self.engine.add_particles(new_particles_positions, new_particles_velocity, new_particle_density,
+                                      new_particles_material_type)
         self._const["obj_id"].append(np.full(n, object_id, dtype=np.int32))
         self._const["mat_id"].append(np.asarray(new_particles_material_id, dtype=np.int32))
         self._const["is_dynamic"].append(np.asarray(new_particles_is_dynamic, dtype=np.int32))
         self._const["color"].append(np.asarray(new_particles_color, dtype=np.float32))
         self._const["x0"].append(np.asarray(new_particles_positions, dtype=np.float64))
         self._const_cache.clear()
+        if self._slab is None:
+            self.particle_num[None] = self.engine.n
+
+    def _upload_slab(self):
+        """Multi-GPU: choose the column partition from the whole scene, upload this rank's columns, keep GLOBAL id0."""
+        from ..parallel import column_weights, partition_columns
+        slab = self._slab
+        x = np.concatenate([p[0] for p in self._pending])
+        v = np.concatenate([p[1] for p in self._pending])
+        rho = np.concatenate([p[2] for p in self._pending])
+        typ = np.concatenate([p[3] for p in self._pending])
+        self._pending = None
+        n_cols = int(self.grid_num[0])
+        w, cx = column_weights(x[:, 0], typ, float(self.vdomain_start[0]), self.grid_size, n_cols,
+                               slab.get("wall_weight", 0.15))
+        self.slab_columns = slab.get("columns") or partition_columns(w, slab["world"])
+        a, b = self.slab_columns[slab["rank"]]
+        mine = np.nonzero((cx >= a) & (cx < b))[0]
+        counts = np.bincount(cx, minlength=n_cols)
+        ghosts = int(counts[max(a - 1, 0):a].sum() + counts[b:b + 1].sum())
+        # capacity: this rank's particles + both ghost columns, with head-room for inflow (a dam break front can
+        # multiply the population of an initially dry slab); override with the optional scene key "slabCapacity"
+        cap = self.cfg.get_opt("slabCapacity", None)
+        if cap is None:
+            cap = int(1.5 * (len(mine) + ghosts)) + 4 * int(counts.max()) + 1024
+        self.global_particle_num = len(x)
+        self.engine = _lib.Engine(self.params, max(int(cap), 1), device=self._device)
+        if len(mine):
+            self.engine.add_particles(x[mine], v[mine], rho[mine], typ[mine])
+            self.engine.field("ID0").copy_(self._torch.from_numpy(mine.astype(np.int32)).to(self.engine.device))
         self.particle_num[None] = self.engine.n
+        print(f"slab rank {slab['rank']}/{slab['world']}: columns [{a}, {b}) of {n_cols}, {len(mine)} particles, capacity {cap}")
 
     def _const_dev(self, name):
         if name not in self._const_cache:

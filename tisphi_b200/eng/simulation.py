@@ -9,12 +9,13 @@ _SOLVERS = {1: WCSPHSolver, 2: MUISPHSolver, 3: DPSPHSolver}
 
 
 class Simulation:
-    def __init__(self, config: SimConfiger, device="cuda:0") -> None:
+    def __init__(self, config: SimConfiger, device="cuda:0", slab=None) -> None:
+        """``slab``: dict(rank, world, wall_weight, columns) for one rank of a multi-GPU run (tisphi_b200/parallel.py)."""
         self.cfg = config
         self.solver_type = self.cfg.get_cfg("simulationMethod")
         if self.solver_type not in _SOLVERS:      # the reference fails after building the particle system
             raise NotImplementedError(f"Solver type {self.solver_type} has not been implemented.")
-        self.ps = ParticleSystem(self.cfg, device=device)
+        self.ps = ParticleSystem(self.cfg, device=device, slab=slab)
         self.solver = self.build_solver()
 
     def build_solver(self):
