@@ -113,7 +113,7 @@ def cpu_reference(scale, steps, warmup=0):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return          # under torchrun only rank 0 times the CPU reference arm
     base, n, dt = cpu_reference(args.cpu_scale, max(1, args.steps), warmup=min(args.warmup, 1))
     line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / max(1, args.steps) * 1e3, "higher_is_better": True,
@@ -151,8 +151,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        from tisphi_b200.parallel import run_bench_multi
-        return run_bench_multi(args, rank, local, world)
+        return run_ours_multi(args, rank, local, world)
     torch.cuda.set_device(local)
     from tisphi_b200 import scenes
     from tisphi_b200.eng.simulation import Simulation, SimConfiger
@@ -251,6 +250,125 @@ def run_ours(args):
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "real_particle_updates_per_s": n_fluid * args.steps / (ms * 1e-3)}
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- our arm, N > 1
+def run_ours_multi(args, rank, local, world):
+    """C4 slab-partitioned over `world` GPUs (strong scaling): one process per GPU, neighbour send/recv over NCCL."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    from tisphi_b200 import scenes
+    from tisphi_b200.eng.simulation import SimConfiger
+    from tisphi_b200.parallel import SlabSimulation
+
+    scene = scenes.dambreak3d(scale=args.scale, precision=args.precision)
+    t0 = time.time()
+    sim = SlabSimulation(SimConfiger(config=scene), f"cuda:{local}", rank, world)
+    eng, drv, ps = sim.ps.engine, sim.driver, sim.ps
+    n_global = ps.global_particle_num
+    n_own0 = eng.n
+    log(f"[rank {rank}] slab built: columns {sim.columns}, {n_own0} of {n_global} particles, {time.time() - t0:.1f}s")
+
+    # host copy of this rank's initial state for the end-to-end leg (pinned)
+    pin = lambda t: t.detach().cpu().contiguous().pin_memory()
+    h_x, h_rho, h_typ, h_id = pin(ps.pt.x), pin(ps.pt.density), pin(ps.pt.mat_type), pin(ps.pt.id0)
+    h_v = pin(ps.pt.v.double())
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    sim.run_steps(args.warmup)
+    barrier()
+    launches0 = eng.L.sph_launch_count(eng.h)
+    bytes0, ex0 = drv.bytes_sent, drv.exchanges
+    if rank == 0:
+        eng.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record(eng.stream)
+        sim.run_steps(args.steps)
+        e1.record(eng.stream)
+        barrier()
+    ms_t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms = float(ms_t)
+    prof = eng.profile_read() if rank == 0 else {}
+    if rank == 0:
+        eng.profile(False)
+    launches = torch.tensor([eng.L.sph_launch_count(eng.h) - launches0, drv.own_count, drv.bytes_sent - bytes0,
+                             drv.exchanges - ex0], dtype=torch.int64, device=f"cuda:{local}")
+    allv = [torch.zeros_like(launches) for _ in range(world)]
+    dist.all_gather(allv, launches)
+    assert bool(torch.isfinite(ps.pt.v).all()), "non-finite velocities after the timed region"
+    assert sum(int(v[1]) for v in allv) == n_global, "particles lost or duplicated by the migration"
+    value = n_global * args.steps / (ms * 1e-3)
+
+    # end to end: every step uploads this rank's particles from pinned host memory and reads its owned state back
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    n0 = len(h_rho)
+    cap = eng.n_max
+    out_x = torch.empty((cap, 3), dtype=torch.float64).pin_memory()
+    out_v = torch.empty((cap, 4), dtype=eng.real).pin_memory()
+    out_rho = torch.empty(cap, dtype=torch.float64).pin_memory()
+    out_p = torch.empty(cap, dtype=eng.real).pin_memory()
+    out_id = torch.empty(cap, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        eng.call("sph_clear_particles")
+        eng.call("sph_add_particles", n0, h_x.data_ptr(), h_v.data_ptr(), h_rho.data_ptr(), h_typ.data_ptr())
+        eng.field("ID0").copy_(h_id, non_blocking=True)
+        drv.own_first, drv.own_count = 0, n0
+        drv.step()
+        eng.call("sph_read_state", out_x.data_ptr(), out_v.data_ptr(), out_rho.data_ptr(), out_p.data_ptr(), out_id.data_ptr())
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_t)
+    io = torch.tensor([n0 * (24 + 24 + 8 + 4 + 4), eng.n * (24 + 4 * out_v.element_size() + 8 + out_p.element_size() + 4)],
+                      dtype=torch.int64, device=f"cuda:{local}")
+    dist.all_reduce(io)
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        n_loc = eng.n
+        typ = ps.pt.mat_type
+        nf_loc = int((typ == 1).sum())
+        roofline = None
+        if prof:
+            dom_name, (dom_ms, dom_cnt) = max(prof.items(), key=lambda kv: kv[1][0])
+            ab = algorithmic_bytes(dom_name, n_loc, nf_loc, n_loc - nf_loc, ps.grid_num_total)
+            achieved = ab / (dom_ms / dom_cnt * 1e-3) / 1e9 if ab else None
+            roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak if achieved else None, "traffic": None, "peak_kind": peak_kind,
+                        "rank": 0, "note": "rank 0's slab; neighbour sweeps are fp32-issue bound, not HBM bound",
+                        "kernel_share_of_step": {k: round(v[0] / ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+                        "kernel_ms": {k: round(v[0] / v[1], 4) for k, v in prof.items()}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32" if args.precision != "f64" else "f64", "data": "synthetic",
+                "config": {"workload": f"C4 3D WCSPH dambreak (Wendland C2, dummy walls, LF): N={n_global}, cells={ps.grid_num_total}, "
+                                       f"scale={args.scale}, slab-partitioned over {world} GPUs along x",
+                           "precision": "mixed: fp32 sweeps, fp64 positions+densities" if args.precision != "f64" else "f64",
+                           "columns": [list(c) for c in ps.slab_columns],
+                           "owned_particles": [int(v[1]) for v in allv],
+                           "halo_bytes_sent_per_step": [int(v[2]) // args.steps for v in allv],
+                           "exchanges_per_step": int(allv[0][3]) / args.steps,
+                           "l2": "state larger than L2, no flush needed"},
+                "clocks": clocks.summary(),
+                "e2e": {"value": n_global * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(io[0]),
+                        "d2h_bytes_per_step": int(io[1]), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
+                "gpu_launches": int(sum(int(v[0]) for v in allv)), "roofline": roofline, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
 
 
 def main():
