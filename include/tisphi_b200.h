@@ -115,6 +115,9 @@ int sph_read_state(SphCtx *ctx, double *x, double *v, double *density, double *p
 int sph_grid_build(SphCtx *ctx);
 /* SPHBase.calc_kernel_corr (base:363-368): CSPM_f always, CSPM_L when kcorr == 1 */
 int sph_calc_kernel_corr(SphCtx *ctx);
+/* the same, except that on the cell-tile path (MIXED precision WCSPH) the CSPM_f of particles whose sums the next
+ * one_step forms anyway (walls: loop A, fluid: loop B) is completed by that one_step instead of an extra sweep. */
+int sph_calc_kernel_corr_deferred(SphCtx *ctx);
 /* SPHBase.init_real2tmp (base:67-74) */
 int sph_init_real2tmp(SphCtx *ctx);
 /* <Solver>.one_step (wc:82-126, muI:62-132, dp:210-274) */
@@ -134,6 +137,9 @@ int sph_step(SphCtx *ctx, int nsteps);
 /* stand-alone sweeps on the current grid (BASELINE config C5; parity of the neighbour predicate, ps:259-269) */
 int sph_neighbor_count(SphCtx *ctx, int32_t *out_dev);          /* n int32  */
 int sph_density_sum(SphCtx *ctx, void *out_dev);                /* n real: sum_j mass_j W_ij (wc:30-31) */
+/* cell-tile path only, after sph_calc_kernel_corr: the count read back from the per-step neighbour bit masks for
+ * flow particles of representable cells, -1 for every other particle (parity probe of the mask kernel) */
+int sph_neighbor_count_masks(SphCtx *ctx, int32_t *out_dev);
 
 /* number of particles whose cell fell outside the grid since the last call.  Synchronises. */
 int64_t sph_read_bad_cells(SphCtx *ctx);

@@ -781,9 +781,10 @@ void orc_neighbor_count_f32(Orc *o, int32_t *out) {
 }
 
 /* float32 predicate of the MIXED engine: coordinates local to the cell each particle is stored in (grid_ids),
- * xs = (float)(x - (vstart + cell*gs)) with unfused float64 ops, neighbour coordinates shifted by
- * d = (xs_i - (float)(cell_j - cell_i) * (float)gs) - xs_j, r2 = fma(dz,dz, fma(dy,dy, fl(dx*dx))),
- * sqrtf(r2) < (float)support. */
+ * xs = (float)(x - (vstart + cell*gs)) with unfused float64 ops.  A pair is evaluated from the side of the LOWER cell
+ * id in the frame of the higher cell: lo in cell A, hi in cell B > A, s = (float)(B - A) * (float)gs,
+ * d = (xs_lo - s) - xs_hi (same cell: d = xs_i - xs_j), r2 = fma(dz,dz, fma(dy,dy, fl(dx*dx))), sqrtf(r2) < (float)support.
+ * The relation is exactly symmetric, which the CUDA mask kernel exploits (one evaluation per cell pair + transpose). */
 static inline void unflatten(const OrcParams *p, int64_t g, int c[3]) {
     int64_t nyz = (int64_t)p->gn[1] * p->gn[2];
     c[0] = (int)(g / nyz);
@@ -822,8 +823,14 @@ void orc_neighbor_count_f32local(Orc *o, int32_t *out) {
                 float xj[3];
                 unflatten(p, o->ia[I_GRID_IDS][j], sj);
                 local_xs(o, j, sj, xj);
-                float ex = xi[0] - sh[0], ey = xi[1] - sh[1], ez = xi[2] - sh[2];
-                float dx = ex - xj[0], dy = ey - xj[1], dz = ez - xj[2];
+                float dx, dy, dz;
+                if (g >= o->ia[I_GRID_IDS][i]) {
+                    float ex = xi[0] - sh[0], ey = xi[1] - sh[1], ez = xi[2] - sh[2];
+                    dx = ex - xj[0]; dy = ey - xj[1]; dz = ez - xj[2];
+                } else {                           /* j's cell precedes i's: evaluate from j's side (shift negated) */
+                    float ex = xj[0] + sh[0], ey = xj[1] + sh[1], ez = xj[2] + sh[2];
+                    dx = ex - xi[0]; dy = ey - xi[1]; dz = ez - xi[2];
+                }
                 float xx = dx * dx;
                 float r2 = fmaf(dz, dz, fmaf(dy, dy, xx));
                 if (sqrtf(r2) < sup) c++;

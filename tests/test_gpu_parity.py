@@ -281,6 +281,33 @@ def test_tile_path_equals_generic_path(name):
         assert relmax(fa[k][ok], fb[k][ok]) < 1e-5, k
 
 
+@pytest.mark.parametrize("name", ["wc2d_small_lf", "wc3d_tiny_lf", "c1_test1_wc_lf"])
+def test_tile_masks_reproduce_the_neighbour_predicate(name):
+    """The per-step neighbour bit masks (one evaluation per cell pair + warp transpose) must select exactly the pairs
+    of the float32 predicate: popcounts of every flow particle == generic neighbour count == the oracle's restatement."""
+    import torch
+    from oracle import oracle as orc
+    g = Golden(name)
+    sim = make_sim(g.scene, precision="f32")
+    o = orc.Oracle.from_scene(g.scene, serial=0)
+    eng = sim.ps.engine
+    for s in range(4):
+        sim.ps.initialize_particle_system()
+        sim.solver.calc_kernel_corr()
+        out = torch.empty(eng.n, dtype=torch.int32, device=eng.device)
+        eng.call("sph_neighbor_count_masks", out.data_ptr())
+        got = out.cpu().numpy()
+        want = sim.ps.neighbor_count().cpu().numpy()
+        flow = sim.ps.pt.mat_type.cpu().numpy() > 0
+        assert (got[flow] >= 0).all(), "a flow particle was left to the generic path on a lattice scene"
+        assert np.array_equal(got[flow], want[flow]), (name, s)
+        o.x[:] = sim.ps.pt.x.cpu().numpy()
+        o.grid_build()
+        assert np.array_equal(want, o.neighbor_count(f32=True)), (name, s)
+        sim.solver.step()
+        o.x[:] = sim.ps.pt.x.cpu().numpy()
+
+
 def test_tile_path_crowded_cells_fall_back():
     """kh = 2 puts 4^3 = 64 particles in a cell (> 32): every cell is flagged and the generic kernels must take over."""
     import copy

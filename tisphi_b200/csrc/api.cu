@@ -93,7 +93,7 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
         o_ps4 = off; off += align_up(n_max * 16);
         o_pw4 = off; off += align_up(n_max * 16);
         o_mask = off; off += align_up(n_max * 4 * mask_words);
-        o_nflow = off; off += align_up(n_max);
+        o_nflow = off; off += align_up(n_max * 4);
         o_cflag = off; off += align_up(C + 1);
         o_nflag = off; off += 256;
     }
@@ -234,7 +234,7 @@ template <typename T> Dev<T> make_dev(SphCtx *c, int which) {
         d.pk4 = (Vec4<T> *)(c->arena + c->off_pk4);
         d.pw4 = (Vec4<T> *)(c->arena + c->off_pw4);
         d.mask = (unsigned *)(c->arena + c->off_mask);
-        d.nflow = (unsigned char *)(c->arena + c->off_nflow);
+        d.nzw = (unsigned *)(c->arena + c->off_nflow);
         d.cellflag = (unsigned char *)(c->arena + c->off_cellflag);
         d.nflag = (int *)(c->arena + c->off_nflag);
     }
@@ -251,7 +251,7 @@ namespace {
 template <typename T> int step_once(SphCtx *c) {
     int r;
     if ((r = grid_build<T>(c))) return r;
-    if ((r = calc_kernel_corr<T>(c))) return r;
+    if ((r = calc_kernel_corr<T>(c, false))) return r;
     if ((r = init_real2tmp<T>(c))) return r;
     switch (c->p.ti) {
     case 1:
@@ -391,7 +391,8 @@ int sph_read_state(SphCtx *c, double *x, double *v, double *density, double *pre
 }
 
 int sph_grid_build(SphCtx *c) { return DISPATCH(c, grid_build, c); }
-int sph_calc_kernel_corr(SphCtx *c) { return DISPATCH(c, calc_kernel_corr, c); }
+int sph_calc_kernel_corr(SphCtx *c) { return DISPATCH(c, calc_kernel_corr, c, true); }
+int sph_calc_kernel_corr_deferred(SphCtx *c) { return DISPATCH(c, calc_kernel_corr, c, false); }
 int sph_init_real2tmp(SphCtx *c) { return DISPATCH(c, init_real2tmp, c); }
 int sph_one_step(SphCtx *c) { return DISPATCH(c, one_step, c); }
 int sph_advect(SphCtx *c, int kind, int m) { return DISPATCH(c, advect, c, kind, m); }
@@ -401,6 +402,11 @@ int sph_init_stress(SphCtx *c) { return DISPATCH(c, init_stress, c); }
 int sph_step(SphCtx *c, int nsteps) { return DISPATCH(c, dispatch_step, c, nsteps); }
 int sph_neighbor_count(SphCtx *c, int32_t *out_dev) { return DISPATCH(c, neighbor_count, c, out_dev); }
 int sph_density_sum(SphCtx *c, void *out_dev) { return DISPATCH(c, density_sum, c, out_dev); }
+int sph_neighbor_count_masks(SphCtx *c, int32_t *out_dev) {
+    if (!c->fast) { snprintf(c->err, sizeof(c->err), "neighbour masks exist only on the cell-tile path (MIXED precision WCSPH)"); return -2; }
+    if (c->n == 0) return 0;
+    return tile_mask_count(c, out_dev);
+}
 
 int64_t sph_read_bad_cells(SphCtx *c) {
     unsigned long long v = 0;

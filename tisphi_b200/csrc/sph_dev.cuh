@@ -74,8 +74,9 @@ template <typename T> struct Dev {
     Vec4<T> *ps4;        // sweep coords xyz, +m_V for flow particles / -m_V otherwise (tile payload A)
     Vec4<T> *pk4;        // v_tmp.xyz, pressure / density_tmp^2                        (tile payload B of the fluid pass)
     Vec4<T> *pw4;        // EOS pressure, previous pressure, 0, 0                       (tile payload C of the wall pass)
-    unsigned *mask;      // neighbour bit masks, word-major: mask[word * n + i], word = neighbour cell (x-major, z fastest)
-    unsigned char *nflow;     // min(number of flow neighbours, 255) per particle
+    unsigned *mask;      // neighbour bit masks, word-major: mask[word * n + i], word = neighbour cell (x-major, z fastest);
+                         // bit b = the b-th particle of that cell.  Wall particles keep their FLOW neighbours only.
+    unsigned *nzw;            // per particle: bitmap of its non-zero mask words
     unsigned char *cellflag;  // 1: this centre cell cannot use the tile path (a cell of its stencil holds > 32 particles ...)
     int *nflag;               // number of flagged cells (device counter)
     int flagged_only;         // generic kernels: process only particles of flagged cells
@@ -135,13 +136,18 @@ template <typename T> __device__ __forceinline__ T kernel_dW_over_r(const Dev<T>
 
 // ------------------------------------------------------------------ generic neighbour iteration (ps:259-269)
 // Centre cell from the CURRENT master position (ps:261); 3^dim cells x-major / z-fastest; j ascending; out-of-range
-// cells per axis are empty; strict r < support evaluated as r2 < r2thr (same predicate, no sqrt);
-// d = (x_i - cell shift) - x_j: the own coordinate is moved into the frame of the neighbour's cell once per cell.   body(j, dx, dy, dz, r, V_j)
+// cells per axis are empty; strict r < support evaluated as r2 < r2thr (same predicate, no sqrt).
+// MIXED precision: coordinates are local to the cell a particle is STORED in, and a pair is always evaluated from
+// the side of the lower cell id, in the frame of the higher cell:  lo in cell A, hi in cell B > A, s = (B - A) * gs,
+//   d_canon = (x_lo - s) - x_hi ,   d(lo -> hi) = d_canon ,   d(hi -> lo) = -d_canon
+// so the neighbour relation and every pair geometry are EXACTLY antisymmetric (the cell-tile mask kernel relies on
+// it: it evaluates a cell pair once and transposes the bit matrix).   body(j, dx, dy, dz, r, V_j)
 template <typename T, typename F> __device__ __forceinline__ void for_neighbors(const Dev<T> &c, int i, F &&body) {
     int cc[3], sc[3] = {0, 0, 0};
     const double xi[3] = {c.x[3 * (size_t)i], c.x[3 * (size_t)i + 1], c.x[3 * (size_t)i + 2]};
     pos_to_cell(c, xi, cc);
-    if (sizeof(T) == 4) unflatten(c, c.gid[i], sc);           // the cell xs4[i] is local to
+    const int gi = sizeof(T) == 4 ? c.gid[i] : 0;
+    if (sizeof(T) == 4) unflatten(c, gi, sc);                 // the cell xs4[i] is local to
     const Vec4<T> pi = c.xs4[i];
     const int z0 = (c.dim == 2) ? 0 : -1, z1 = (c.dim == 2) ? 0 : 1;
     for (int ox = -1; ox <= 1; ox++) {
@@ -158,10 +164,14 @@ template <typename T, typename F> __device__ __forceinline__ void for_neighbors(
                 T sz = (T)(cz - sc[2]) * c.gsT;
                 int g = flatten(c, cx, cy, cz);
                 int jb = g > 0 ? c.cell_end[g - 1] : 0, je = c.cell_end[g];
+                const bool rev = sizeof(T) == 4 && g < gi;    // the neighbour's cell precedes mine: evaluate from its side
+                const T ex = pi.x - sx, ey = pi.y - sy, ez = pi.z - sz;
                 for (int j = jb; j < je; j++) {
                     if (j == i) continue;
                     Vec4<T> pj = c.xs4[j];
-                    T dx = (pi.x - sx) - pj.x, dy = (pi.y - sy) - pj.y, dz = (pi.z - sz) - pj.z;
+                    T dx, dy, dz;
+                    if (!rev) { dx = ex - pj.x; dy = ey - pj.y; dz = ez - pj.z; }
+                    else { dx = -((pj.x + sx) - pi.x); dy = -((pj.y + sy) - pi.y); dz = -((pj.z + sz) - pi.z); }
                     T r2 = dist2(dx, dy, dz);
                     if (r2 < c.r2thr) body(j, dx, dy, dz, sqrt_rn(r2), pj.w);
                 }

@@ -39,6 +39,8 @@ struct SphCtx {
     int64_t launches_by_kernel[32];
     void *prof_state;
     float r2thr32;
+    bool shep_wall_pending;
+    bool shep_pending;   // tile path: CSPM_f of flow particles is still to be formed by the next fluid pass
     int own0, own1;      // owned x-columns [own0, own1) (multi-GPU slabs); the whole grid on one GPU
 };
 
@@ -81,7 +83,7 @@ inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) /
 // grid.cu
 template <typename T> int grid_build(SphCtx *c);
 // sweeps.cu
-template <typename T> int calc_kernel_corr(SphCtx *c);
+template <typename T> int calc_kernel_corr(SphCtx *c, bool standalone);
 template <typename T> int one_step(SphCtx *c);
 template <typename T> int one_step_phase(SphCtx *c, int phase);
 template <typename T> int advect_pos(SphCtx *c);
@@ -89,7 +91,8 @@ template <typename T> int post_step(SphCtx *c);
 template <typename T> int neighbor_count(SphCtx *c, int32_t *out);
 template <typename T> int density_sum(SphCtx *c, void *out);
 // sweeps_tile.cu (float only)
-int tile_mask(SphCtx *c);
+int tile_mask(SphCtx *c, bool shepard);
+int tile_mask_count(SphCtx *c, int32_t *out);
 int tile_wc_prep_and_wall(SphCtx *c);
 int tile_wc_fluid(SphCtx *c);
 // integrate.cu

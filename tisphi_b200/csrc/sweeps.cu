@@ -79,11 +79,13 @@ template <typename T> __global__ void __launch_bounds__(128) k_cspm_L(Dev<T> c) 
     for (int a = 0; a < 9; a++) c.cspm_L[9 * (size_t)i + a] = L[a];
 }
 
-template <typename T> int calc_kernel_corr(SphCtx *c) {
+// standalone: every CSPM_f is final on return (the API call).  Otherwise (inside sph_step) the tile path leaves the
+// Shepard sums of unflagged cells to the wall pass and the first fluid pass, which visit the same neighbours anyway.
+template <typename T> int calc_kernel_corr(SphCtx *c, bool standalone) {
     if (c->n == 0) return 0;
     Dev<T> d = make_dev<T>(c);
-    if (c->fast) {                       // tile path: masks + CSPM_f; the generic kernel completes flagged cells
-        int r = tile_mask(c);
+    if (c->fast) {                       // tile path: masks (+ CSPM_f); the generic kernel completes flagged cells
+        int r = tile_mask(c, standalone);
         if (r) return r;
         d.flagged_only = 1;
     }
@@ -705,7 +707,7 @@ template <typename T> int density_sum(SphCtx *c, void *out) {
 }
 
 #define INST(T)                                            \
-    template int calc_kernel_corr<T>(SphCtx *);            \
+    template int calc_kernel_corr<T>(SphCtx *, bool);            \
     template int one_step<T>(SphCtx *);                    \
     template int one_step_phase<T>(SphCtx *, int);                    \
     template int advect_pos<T>(SphCtx *);                  \

@@ -1,45 +1,55 @@
 // sweeps_tile.cu -- cell-major neighbour sweeps for the WCSPH hot loop (MIXED precision), hand-written for sm_100a.
 //
-// Work decomposition.  A thread block owns ZB consecutive cells along the fastest grid axis (z in 3D, y in 2D) of
-// one cell column; warp w owns cell f0 + w and lane l owns the l-th particle of that cell.  Because the flattened
-// cell id is fastest-axis-major (ps:221-222), the particles of the 3 x ... x (ZB + 2) cells a block needs form nR
-// contiguous spans of the sorted arrays (nR = 9 in 3D, 3 in 2D): each span is brought into shared memory with ONE
-// 1-D TMA bulk copy (cp.async.bulk ... mbarrier::complete_tx), raw, with no transformation.
+// Work decomposition.  A thread block owns a footprint of BX x BY cell columns (3D; BX columns in 2D) times ZB
+// consecutive cells along the fastest grid axis (z in 3D, y in 2D); warp w owns ONE cell of the footprint and lane l
+// owns the l-th particle of that cell.  Because the flattened cell id is fastest-axis-major (ps:221-222), the
+// particles of the (BX+2) x (BY+2) x (ZB+2) cells a block needs form NR = (BX+2)(BY+2) contiguous spans ("runs") of
+// the sorted arrays: each run is brought into shared memory with ONE 1-D TMA bulk copy per payload array
+// (cp.async.bulk ... mbarrier::complete_tx), raw, with no transformation.
 //
-// Neighbour predicate.  The own coordinate is moved into the frame of each neighbour cell once per cell
-// (e = x_i - shift), then d = e - x_j, r2 = fma(dz,dz, fma(dy,dy, dx*dx)), r2 < r2thr: the expression of
-// sph_dev.cuh::for_neighbors in float32, so the tile kernels and the generic kernels select identical pairs in
-// identical order (cells x-major / z-fastest, j ascending) -- summation order is preserved.
+// Neighbour predicate.  Evaluated ONCE per step (positions are frozen inside a step; they only change in
+// advect_pos) by k_tile_mask into one 32-bit word per (particle, stencil cell): bit b = the b-th particle of that
+// cell is a neighbour.  The predicate is the float32 expression of sph_dev.cuh::for_neighbors, which is exactly
+// symmetric, so a cell pair (A, B > A) is evaluated once by A's warp and the 32 x 32 bit matrix is transposed with
+// warp shuffles to give B's words.  Wall particles keep only their FLOW neighbours (all a wall sum ever reads,
+// base:647-669): dry walls end up with empty masks and cost nothing.
 //
-// Positions are frozen inside a step (they only change in advect_pos), so the predicate is evaluated ONCE per step
-// (k_tile_mask) into one 32-bit word per (particle, neighbour cell); the wall pass and the fluid pass of both
-// one_steps then only visit set bits.  Cells that cannot be represented (more than 32 particles in a stencil cell,
-// or more than TILE_CAP particles in the block's tile) are flagged and processed by the generic kernels of sweeps.cu.
+// The wall pass and the fluid pass of both one_steps then only visit set bits, four neighbours per round in stencil
+// order (cells x-major / z-fastest, j ascending), with the mask words streamed from global memory one cell ahead.
+// Cells that cannot be represented (more than 32 particles in a stencil cell, or a tile that overflows) are flagged
+// together with their stencil neighbours and processed by the generic kernels of sweeps.cu.
 //
 // Replaces, for this configuration: calc_CSPM_f (base:386-398), WCSPH one_step loops A and B (wc:82-126).
 #include "sph_host.h"
 
 namespace sph {
 
-constexpr int ZB = 4;                 // cells (warps) per block along the fastest axis
-constexpr int BT = ZB * 32;           // threads per block
-constexpr int TILE_CAP = 1536;        // particles per block tile (3D rest lattice: 9 * 6 * 27 = 1458)
-constexpr int NRMAX = 9;
-constexpr int CBW = ZB + 3;           // cell boundaries per run
-
+constexpr int ZB = 4;                 // cells per footprint along the fastest axis
 typedef Vec4<float> F4;
 typedef Dev<float> DevF;
 
-// NPAY payload arrays of TILE_CAP float4 (+8 entries of slack: the chunked test loop may read past a cell's end)
-template <int NPAY> struct TileShared {
-    F4 P[NPAY][TILE_CAP + 8];
-    unsigned long long bar;           // mbarrier
-    int cb[NRMAX * CBW];              // tile index of the first particle of each (run, cell)
-    int gdelta[NRMAX];                // global index = tile index + gdelta[run]
-    int total, overflow;
-    F4 ctab[ZB * 27];                 // per (warp, neighbour cell): shift xyz, tile index of the cell's first particle (int bits)
-    int cgd[ZB * 27];                 // per (warp, neighbour cell): global index - tile index
+template <bool D3, int BX_, int BY_> struct Foot {
+    static constexpr bool d3 = D3;
+    static constexpr int BX = BX_, BY = D3 ? BY_ : 1;
+    static constexpr int NRX = BX + 2, NRY = D3 ? BY + 2 : 1, NR = NRX * NRY;       // runs
+    static constexpr int NWARP = BX * BY * ZB, BT = NWARP * 32;
+    static constexpr int NW = D3 ? 27 : 9, CENTRE = NW / 2;                          // stencil cells
+    static constexpr int CBW = ZB + 3;                                               // cell boundaries per run
+    static constexpr int REST = NR * (ZB + 2) * (D3 ? 27 : 9);                       // rest-lattice tile population
+    static constexpr int CAP = (REST + REST / 6 + 63) / 64 * 64;                     // + ~17 % head-room
+    static constexpr int SENT = CAP;                                                 // all-zero sentinel entry
 };
+
+// NP payload arrays of CAP float4 (+8 entries of slack: the sentinel, and the chunked test loop may read past a cell)
+template <class FT, int NP> struct TileShared {
+    F4 P[NP][FT::CAP + 8];
+    unsigned long long bar;           // mbarrier
+    int cb[FT::NR * FT::CBW];         // tile index of the first particle of each (run, cell)
+    int gdelta[FT::NR];               // global index = tile index + gdelta[run]
+    int total, overflow;
+    F4 ctab[FT::NWARP * FT::NW];      // per (warp, stencil cell): shift xyz, tile index of the cell's first particle | flags
+};
+constexpr unsigned CT_BEFORE = 1u << 30, CT_SAME = 1u << 29, CT_IDX = (1u << 24) - 1;
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -65,101 +75,104 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
             "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
 }
+__device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // ------------------------------------------------------------------------------------------------ geometry
-struct TileGeom {
-    int nF, nR, nseg, ny, nslow0, nslow1;   // 3D: slow axes (x, y); 2D: slow axis x only (nslow1 = 1)
-};
-__host__ __device__ inline TileGeom make_geom(int dim, const int gn[3]) {
+struct TileGeom { int nF, n0, n1, nb0, nb1, nseg; };   // fast axis cells; slow axes (x, y | x, 1); blocks per slow axis; segments
+template <class FT> __host__ inline TileGeom make_geom(const int gn[3]) {
     TileGeom g;
-    if (dim == 3) { g.nF = gn[2]; g.nR = 9; g.nslow0 = gn[0]; g.nslow1 = gn[1]; }
-    else { g.nF = gn[1]; g.nR = 3; g.nslow0 = gn[0]; g.nslow1 = 1; }
-    g.ny = g.nslow1;
+    if (FT::d3) { g.nF = gn[2]; g.n0 = gn[0]; g.n1 = gn[1]; }
+    else { g.nF = gn[1]; g.n0 = gn[0]; g.n1 = 1; }
+    g.nb0 = (g.n0 + FT::BX - 1) / FT::BX;
+    g.nb1 = (g.n1 + FT::BY - 1) / FT::BY;
     g.nseg = (g.nF + ZB - 1) / ZB;
     return g;
 }
-// shift of neighbour cell (run r, fast offset dzi in 0..2) relative to the centre cell
-__device__ __forceinline__ void cell_shift(const DevF &c, const TileGeom &g, int r, int dzi, float &sx, float &sy, float &sz) {
-    if (g.nR == 9) {
-        const int rx = r / 3;
-        sx = (float)(rx - 1) * c.gsT; sy = (float)(r - 3 * rx - 1) * c.gsT; sz = (float)(dzi - 1) * c.gsT;
-    } else { sx = (float)(r - 1) * c.gsT; sy = (float)(dzi - 1) * c.gsT; sz = 0.f; }
-}
-
-// per-warp table of the stencil cells, so that advancing to the next cell costs one shared load
-template <int NPAY>
-__device__ __forceinline__ void build_ctab(const DevF &c, const TileGeom &g, TileShared<NPAY> &sh, int w, int lane) {
-    const int NW = g.nR * 3;
-    if (lane < NW) {
-        const int r = lane / 3, dzi = lane - 3 * r;
-        F4 t;
-        if (g.nR == 9) {
-            const int rx = r / 3;
-            t.x = (float)(rx - 1) * c.gsT; t.y = (float)(r - 3 * rx - 1) * c.gsT; t.z = (float)(dzi - 1) * c.gsT;
-        } else { t.x = (float)(r - 1) * c.gsT; t.y = (float)(dzi - 1) * c.gsT; t.z = 0.f; }
-        t.w = __int_as_float(sh.cb[r * CBW + w + dzi]);
-        sh.ctab[w * 27 + lane] = t;
-        sh.cgd[w * 27 + lane] = sh.gdelta[r];
-    }
-    __syncwarp();
-}
-
 __device__ __forceinline__ int cell_start(const int *cell_end, int g) { return g > 0 ? cell_end[g - 1] : 0; }
 
-// Computes spans and cell boundaries, issues the TMA copies of NPAY payload arrays and waits for them.
+// what a warp knows about its cell
+struct WarpCell { int b0, b1, f0, wx, wy, wz, cx, cy, f, gcell, is, nc; };
+template <class FT> __device__ __forceinline__ WarpCell warp_cell(const DevF &c, const TileGeom &g) {
+    WarpCell w;
+    const int seg = blockIdx.x % g.nseg, t = blockIdx.x / g.nseg;
+    w.b1 = t % g.nb1; w.b0 = t / g.nb1; w.f0 = seg * ZB;
+    const int wi = threadIdx.x >> 5;
+    w.wz = wi % ZB; w.wy = (wi / ZB) % FT::BY; w.wx = wi / (ZB * FT::BY);
+    w.cx = w.b0 * FT::BX + w.wx; w.cy = w.b1 * FT::BY + w.wy; w.f = w.f0 + w.wz;
+    w.gcell = 0; w.is = 0; w.nc = 0;
+    if (w.cx < g.n0 && w.cy < g.n1 && w.f < g.nF && w.cx >= c.own0 && w.cx < c.own1) {     // ghost columns of a slab idle
+        w.gcell = (w.cx * g.n1 + w.cy) * g.nF + w.f;
+        w.is = cell_start(c.cell_end, w.gcell);
+        w.nc = c.cell_end[w.gcell] - w.is;
+    }
+    return w;
+}
+// stencil cell cc of a warp -> (run, boundary index) and the offsets
+template <class FT> __device__ __forceinline__ void stencil(int cc, int &ox, int &oy, int &of) {
+    if (FT::d3) { ox = cc / 9 - 1; oy = (cc / 3) % 3 - 1; of = cc % 3 - 1; }
+    else { ox = cc / 3 - 1; oy = 0; of = cc % 3 - 1; }
+}
+template <class FT> __device__ __forceinline__ int stencil_cb(const WarpCell &w, int ox, int oy, int of) {
+    const int r = (w.wx + ox + 1) * FT::NRY + (FT::d3 ? w.wy + oy + 1 : 0);
+    return r * FT::CBW + (w.wz + of + 1);
+}
+
+// Computes spans and cell boundaries, issues the TMA copies of the NP payload arrays and waits for them.
 // Returns false (uniformly) when the tile does not fit.
-template <int NPAY>
-__device__ __forceinline__ bool tile_setup(const DevF &c, const TileGeom &g, TileShared<NPAY> &sh, int col, int f0,
-                                           const F4 *src0, const F4 *src1, const F4 *src2 = nullptr) {
+template <class FT, int NP>
+__device__ __forceinline__ bool tile_setup(const DevF &c, const TileGeom &g, TileShared<FT, NP> &sh, const WarpCell &w,
+                                           const F4 *src0, const F4 *src1 = nullptr, const F4 *src2 = nullptr) {
     const int tid = threadIdx.x;
-    const int f_lo = max(f0 - 1, 0), f_hi = min(f0 + ZB, g.nF - 1);
+    const int f0 = w.f0, f_lo = max(f0 - 1, 0), f_hi = min(f0 + ZB, g.nF - 1);
     if (tid < 32) {
         int len = 0, S = 0, gb = 0;
         bool valid = false;
-        if (tid < g.nR) {
-            int s0 = col / g.ny, s1 = col - s0 * g.ny;          // slow coordinates of the block's column
-            int n0 = s0, n1 = s1;
-            if (g.nR == 9) { n0 += tid / 3 - 1; n1 += tid % 3 - 1; }
-            else { n0 += tid - 1; }
-            valid = n0 >= 0 && n0 < g.nslow0 && n1 >= 0 && n1 < g.nslow1;
+        if (tid < FT::NR) {
+            const int n0 = w.b0 * FT::BX + tid / FT::NRY - 1;
+            const int n1 = FT::d3 ? w.b1 * FT::BY + tid % FT::NRY - 1 : 0;
+            valid = n0 >= 0 && n0 < g.n0 && n1 >= 0 && n1 < g.n1;
             if (valid) {
-                gb = (n0 * g.ny + n1) * g.nF;
+                gb = (n0 * g.n1 + n1) * g.nF;
                 S = cell_start(c.cell_end, gb + f_lo);
                 len = c.cell_end[gb + f_hi] - S;
             }
         }
-        int inc = len;                                            // inclusive scan over the first nR lanes
+        int inc = len;                                            // inclusive scan over the first NR lanes
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
+        for (int o = 1; o < 32; o <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, inc, o);
             if (tid >= o) inc += t;
         }
         const int roff = inc - len;
-        if (tid < g.nR) {
+        if (tid < FT::NR) {
             sh.gdelta[tid] = S - roff;
-            for (int k = 0; k < CBW; k++) {
+            for (int k = 0; k < FT::CBW; k++) {
                 const int f = f0 - 1 + k;
                 int v;
                 if (!valid || f < f_lo) v = roff;
                 else if (f > f_hi) v = roff + len;
                 else v = roff + cell_start(c.cell_end, gb + f) - S;
-                sh.cb[tid * CBW + k] = v;
+                sh.cb[tid * FT::CBW + k] = v;
             }
         }
-        const int total = __shfl_sync(0xffffffffu, inc, g.nR - 1);
+        const int total = __shfl_sync(0xffffffffu, inc, FT::NR - 1);
         if (tid == 0) {
             sh.total = total;
-            sh.overflow = total > TILE_CAP;
+            sh.overflow = total > FT::CAP;
             mbar_init(&sh.bar, 1);
+            F4 z; z.x = z.y = z.z = z.w = 0.f;
+#pragma unroll
+            for (int p = 0; p < NP; p++) sh.P[p][FT::SENT] = z;
         }
         __syncwarp();
-        if (total <= TILE_CAP) {
-            if (tid == 0) mbar_expect_tx(&sh.bar, (unsigned)(total * 16 * NPAY));
+        if (total <= FT::CAP) {
+            if (tid == 0) mbar_expect_tx(&sh.bar, (unsigned)(total * 16 * NP));
             __syncwarp();
-            if (tid < g.nR && len > 0) {
+            if (tid < FT::NR && len > 0) {
                 tma_load_1d(&sh.P[0][roff], src0 + S, (unsigned)(len * 16), &sh.bar);
-                if (NPAY > 1) tma_load_1d(&sh.P[1][roff], src1 + S, (unsigned)(len * 16), &sh.bar);
-                if (NPAY > 2) tma_load_1d(&sh.P[NPAY - 1][roff], src2 + S, (unsigned)(len * 16), &sh.bar);
+                if (NP > 1) tma_load_1d(&sh.P[1][roff], src1 + S, (unsigned)(len * 16), &sh.bar);
+                if (NP > 2) tma_load_1d(&sh.P[NP - 1][roff], src2 + S, (unsigned)(len * 16), &sh.bar);
             }
         }
     }
@@ -169,9 +182,28 @@ __device__ __forceinline__ bool tile_setup(const DevF &c, const TileGeom &g, Til
     return true;
 }
 
+// per-warp table of the stencil cells, so that advancing to the next cell costs one shared load
+template <class FT, int NP>
+__device__ __forceinline__ void build_ctab(const DevF &c, TileShared<FT, NP> &sh, const WarpCell &w, int lane) {
+    if (lane < FT::NW) {
+        int ox, oy, of;
+        stencil<FT>(lane, ox, oy, of);
+        F4 t;
+        if (FT::d3) { t.x = (float)ox * c.gsT; t.y = (float)oy * c.gsT; t.z = (float)of * c.gsT; }
+        else { t.x = (float)ox * c.gsT; t.y = (float)of * c.gsT; t.z = 0.f; }
+        unsigned v = (unsigned)sh.cb[stencil_cb<FT>(w, ox, oy, of)];
+        if (lane < FT::CENTRE) v |= CT_BEFORE;                 // stencil order == ascending cell id
+        if (lane == FT::CENTRE) v |= CT_SAME;
+        t.w = __uint_as_float(v);
+        sh.ctab[(threadIdx.x >> 5) * FT::NW + lane] = t;
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------ float32 kernels
 // Division-free float32 forms of base:278-358 on the squared distance (MUFU.RSQ instead of IEEE sqrt/div).
-// Guards: r > 1e-8 and q <= 2 as in the reference.  KERNEL: 0 cubic spline, 1 Wendland C2.
+// The reference's guards (r > 1e-8, q <= 2) become clamps: r2 is clamped from below before the rsqrt and (1 - q/2)
+// resp. (2 - q) from below at 0 -- pairs selected by the mask have r < support = 2h up to rounding.
 struct KernConst { float hinv, eps2, knorm, c_grad; };   // c_grad = -5 knorm / h^2 (Wendland) | knorm / h^2 (cubic)
 __device__ __forceinline__ KernConst kern_const(const DevF &c) {
     KernConst k;
@@ -180,156 +212,213 @@ __device__ __forceinline__ KernConst kern_const(const DevF &c) {
     return k;
 }
 template <int KERNEL> __device__ __forceinline__ float fastW(const KernConst &k, float r2) {
-    const float rinv = rsqrtf(r2), q = r2 * rinv * k.hinv;
-    float w;
-    if (KERNEL == 1) { const float q1 = fmaf(-0.5f, q, 1.f), q2 = q1 * q1; w = k.knorm * (q2 * q2) * fmaf(2.f, q, 1.f); }
-    else {
-        const float t = 2.f - q;
-        w = q <= 1.f ? k.knorm * (q * q * fmaf(0.5f, q, -1.f) + (float)(2.0 / 3.0)) : k.knorm * (1.f / 6.f) * t * t * t;
+    const float r2c = fmaxf(r2, k.eps2), r = r2c * rsqrt_fast(r2c);
+    if (KERNEL == 1) {
+        const float q1 = fmaxf(fmaf(-0.5f * k.hinv, r, 1.f), 0.f), q2 = q1 * q1;
+        return (k.knorm * q2) * (q2 * fmaf(2.f * k.hinv, r, 1.f));
     }
-    return (r2 > k.eps2 && q <= 2.f) ? w : 0.f;
-}
-// s with gradW = s * d
-template <int KERNEL> __device__ __forceinline__ float fastdW(const KernConst &k, float r2) {
-    const float rinv = rsqrtf(r2), q = r2 * rinv * k.hinv;
-    float s;
-    if (KERNEL == 1) { const float q1 = fmaf(-0.5f, q, 1.f); s = k.c_grad * (q1 * q1 * q1); }
-    else {
-        const float t = 2.f - q;
-        s = q <= 1.f ? k.c_grad * fmaf(1.5f, q, -2.f) : -0.5f * k.c_grad * t * t * (rinv / k.hinv);
-    }
-    return (r2 > k.eps2 && q <= 2.f) ? s : 0.f;
+    const float q = r * k.hinv, t = fmaxf(2.f - q, 0.f);
+    return q <= 1.f ? k.knorm * (q * q * fmaf(0.5f, q, -1.f) + (float)(2.0 / 3.0)) : k.knorm * (1.f / 6.f) * t * t * t;
 }
 
 // ------------------------------------------------------------------------------------------------ bit iteration
 // Per-lane cursor over the set bits of the neighbour masks in stencil order.  A round takes up to four neighbours:
 // two from the current cell, then (after an optional jump to the next non-empty cell) two more.  Slots that find no
-// bit are marked invalid and contribute exactly zero, so the summation order (cells x-major, j ascending) is kept.
+// bit read the all-zero sentinel entry (volume 0) and contribute exactly zero, so the summation order (cells
+// x-major, j ascending) is kept.  The mask word of the NEXT non-empty cell is always in flight from global memory.
 struct Cursor {
-    unsigned m, nz;        // remaining bits of the current cell; remaining non-empty cells
-    int a;                 // tile index of the current cell's first particle
-    float ex, ey, ez;      // own coordinates in the current cell's frame
+    unsigned m, nz, mnext;   // remaining bits of the current cell; remaining non-empty cells; prefetched word
+    unsigned flags;          // CT_BEFORE / CT_SAME of the current cell
+    int a;                   // tile index of the current cell's first particle
+    float ex, ey, ez;        // own coordinates in the current cell's frame
 };
-__device__ __forceinline__ void cursor_jump(Cursor &k, const unsigned *smask, const F4 *ct, const F4 &pi) {
+__device__ __forceinline__ void cursor_init(Cursor &k, const unsigned *mrow, size_t n, unsigned nz) {
+    k.m = 0; k.nz = nz; k.mnext = 0; k.flags = 0; k.a = 0; k.ex = k.ey = k.ez = 0.f;
+    if (nz) k.mnext = __ldg(mrow + (size_t)(__ffs(nz) - 1) * n);
+}
+__device__ __forceinline__ void cursor_jump(Cursor &k, const unsigned *mrow, size_t n, const F4 *ct, const F4 &pi) {
     if (k.m == 0 && k.nz != 0) {
         const int cc = __ffs(k.nz) - 1;
         k.nz &= k.nz - 1;
-        k.m = smask[cc * BT + threadIdx.x];
+        k.m = k.mnext;
+        if (k.nz) k.mnext = __ldg(mrow + (size_t)(__ffs(k.nz) - 1) * n);
         const F4 t = ct[cc];
-        k.a = __float_as_int(t.w);
+        const unsigned v = __float_as_uint(t.w);
+        k.a = (int)(v & CT_IDX); k.flags = v;
         k.ex = pi.x - t.x; k.ey = pi.y - t.y; k.ez = pi.z - t.z;
     }
 }
-// takes up to two bits of the current cell: tile indices i0, i1 and validity of the second (the first is valid iff m != 0)
-__device__ __forceinline__ void cursor_take2(Cursor &k, int &i0, int &i1, bool &v0, bool &v1) {
-    v0 = k.m != 0;
-    const int t0 = v0 ? __ffs(k.m) - 1 : 0;
-    k.m &= k.m - 1;
-    v1 = k.m != 0;
-    const int t1 = v1 ? __ffs(k.m) - 1 : t0;
-    k.m &= k.m - 1;
-    i0 = k.a + t0; i1 = k.a + t1;
+// takes up to two bits of the current cell: tile indices (the sentinel when there is no bit)
+template <int SENT> __device__ __forceinline__ void cursor_take2(Cursor &k, int &i0, int &i1) {
+    const unsigned m0 = k.m;
+    const int t0 = __ffs(m0) - 1;
+    const unsigned m1 = m0 & (m0 - 1);
+    const int t1 = __ffs(m1) - 1;
+    k.m = m1 & (m1 - 1);
+    i0 = m0 ? k.a + t0 : SENT;
+    i1 = m1 ? k.a + t1 : SENT;
+}
+
+// 32 x 32 bit-matrix transpose across the lanes of a warp: in: lane i holds row i, out: lane j holds column j
+__device__ __forceinline__ unsigned warp_transpose32(unsigned a, int lane) {
+    const unsigned mk[5] = {0x0000FFFFu, 0x00FF00FFu, 0x0F0F0F0Fu, 0x33333333u, 0x55555555u};
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+        const int s = 16 >> q;
+        const unsigned o = __shfl_xor_sync(0xffffffffu, a, s);
+        a = (lane & s) ? ((a & ~mk[q]) | ((o >> s) & mk[q])) : ((a & mk[q]) | ((o << s) & ~mk[q]));
+    }
+    return a;
 }
 
 // ------------------------------------------------------------------------------------------------ pass 0: masks
-// One launch per step, right after the grid build: neighbour masks, flow-neighbour counts and the Shepard factor
-// CSPM_f (base:386-398) of every particle.
-template <int KERNEL>
-__global__ void __launch_bounds__(BT) k_tile_mask(DevF c, TileGeom g) {
+// One launch per step, right after the grid build.  nzw (bitmap of non-zero words per particle) must be zero on entry.
+template <class FT> __global__ void __launch_bounds__(FT::BT) k_tile_mask(DevF c, TileGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileShared<1> &sh = *reinterpret_cast<TileShared<1> *>(smem_raw);
-    unsigned *smask = reinterpret_cast<unsigned *>(smem_raw + sizeof(TileShared<1>));   // [NW][BT]
-    const int col = blockIdx.x / g.nseg, seg = blockIdx.x - col * g.nseg;
-    if (col / g.ny < c.own0 || col / g.ny >= c.own1) return;        // ghost column of a slab (block-uniform)
-    const int f0 = seg * ZB, w = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-    const int f = f0 + w;
-    const int gcell = col * g.nF + f;
-    int is = 0, nc = 0;
-    if (f < g.nF) { is = cell_start(c.cell_end, gcell); nc = c.cell_end[gcell] - is; }
-    if (!__syncthreads_or(nc > 0)) return;                         // empty segment
-    const bool ok = tile_setup<1>(c, g, sh, col, f0, c.ps4, nullptr);
-    if (nc == 0) return;
+    TileShared<FT, 1> &sh = *reinterpret_cast<TileShared<FT, 1> *>(smem_raw);
+    const WarpCell w = warp_cell<FT>(c, g);
+    const int lane = threadIdx.x & 31;
+    if (!__syncthreads_or(w.nc > 0)) return;                       // nothing owned in this footprint
+    const bool ok = tile_setup<FT, 1>(c, g, sh, w, c.ps4);
+    if (w.nc == 0) return;
     // can this cell be represented?  (uniform per warp)
-    bool flagged = !ok || nc > 32;
-    const int NW = g.nR * 3;
+    bool flagged = !ok || w.nc > 32;
+    int ox = 0, oy = 0, of = 0;
+    if (lane < FT::NW) stencil<FT>(lane, ox, oy, of);
     if (!flagged) {
-        for (int cc = lane; cc < NW; cc += 32) {
-            const int r = cc / 3, dzi = cc - 3 * r;
-            if (sh.cb[r * CBW + w + dzi + 1] - sh.cb[r * CBW + w + dzi] > 32) flagged = true;
+        bool big = false;
+        if (lane < FT::NW) {
+            const int q = stencil_cb<FT>(w, ox, oy, of);
+            big = sh.cb[q + 1] - sh.cb[q] > 32;
         }
-        flagged = __any_sync(0xffffffffu, flagged);
+        flagged = __any_sync(0xffffffffu, big);
     }
-    if (flagged) {
-        if (lane == 0) { c.cellflag[gcell] = 1; atomicAdd(c.nflag, 1); }
+    if (flagged) {                                                 // my neighbours wait for words only I can write: flag them too
+        if (lane < FT::NW) {
+            const int nx = w.cx + ox, ny = w.cy + oy, nf = w.f + of;
+            if (nx >= 0 && nx < g.n0 && ny >= 0 && ny < g.n1 && nf >= 0 && nf < g.nF) c.cellflag[(nx * g.n1 + ny) * g.nF + nf] = 1;
+        }
+        if (lane == 0) atomicAdd(c.nflag, 1);
         return;
     }
-    const bool mine = lane < nc;
-    const int i = is + lane;
+    const bool mine = lane < w.nc;
+    const int i = w.is + lane;
     const F4 *A = sh.P[0];
-    const int rc = g.nR / 2;                                       // centre run
-    const F4 pi = A[sh.cb[rc * CBW + w + 1] + (mine ? lane : 0)];
+    const int own = sh.cb[stencil_cb<FT>(w, 0, 0, 0)];
+    const F4 pi = A[own + (mine ? lane : 0)];
+    const bool myflow = pi.w > 0.f;
+    const unsigned flowA = __ballot_sync(0xffffffffu, mine && myflow);
     const float thr = c.r2thr;
-    unsigned nz = 0;                                               // which stencil cells hold at least one neighbour
-    // ---- predicate: every lane tests every candidate of the 3^dim stencil (broadcast reads, 8-way ILP)
-    for (int cc = 0; cc < NW; cc++) {
-        const int r = cc / 3, dzi = cc - 3 * r;
-        const int a = sh.cb[r * CBW + w + dzi], nb = sh.cb[r * CBW + w + dzi + 1] - a;
+    const size_t n = (size_t)c.n;
+    unsigned nz = 0;
+#pragma unroll 1
+    for (int cc = 0; cc < FT::NW; cc++) {
+        int bx, by, bf;
+        stencil<FT>(cc, bx, by, bf);
+        const int q = stencil_cb<FT>(w, bx, by, bf);
+        const int a = sh.cb[q], nb = sh.cb[q + 1] - a;
+        if (nb == 0) {                                             // empty or outside the grid: nobody else writes this word
+            if (mine) c.mask[(size_t)cc * n + i] = 0u;
+            continue;
+        }
+        const bool same = cc == FT::CENTRE, upper = cc > FT::CENTRE;
+        const int ncx = w.cx + bx;
+        const bool b_owned = ncx >= c.own0 && ncx < c.own1;        // B's warp runs on this rank
+        if (!same && !upper && b_owned) continue;                  // B's warp evaluates the pair and writes my word
         float sx, sy, sz;
-        cell_shift(c, g, r, dzi, sx, sy, sz);
-        const float ex = pi.x - sx, ey = pi.y - sy, ez = pi.z - sz;
+        if (FT::d3) { sx = (float)bx * c.gsT; sy = (float)by * c.gsT; sz = (float)bf * c.gsT; }
+        else { sx = (float)bx * c.gsT; sy = (float)bf * c.gsT; sz = 0.f; }
         unsigned m = 0;
-        for (int t0 = 0; t0 < nb; t0 += 8) {
-            unsigned cm = 0;
-            F4 pj[8];
+        if (upper || same) {                                       // lower side: d = (x_i - s) - x_j
+            const float ex = pi.x - sx, ey = pi.y - sy, ez = pi.z - sz;
+            for (int t0 = 0; t0 < nb; t0 += 8) {
+                unsigned cm = 0;
+                F4 pj[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) pj[u] = A[a + t0 + u];     // may run past the cell: masked below
+                for (int u = 0; u < 8; u++) pj[u] = A[a + t0 + u];     // may run past the cell: masked below
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const float dx = ex - pj[u].x, dy = ey - pj[u].y, dz = ez - pj[u].z;
-                if (dist2(dx, dy, dz) < thr) cm |= 1u << u;
+                for (int u = 0; u < 8; u++) {
+                    const float dx = ex - pj[u].x, dy = ey - pj[u].y, dz = ez - pj[u].z;
+                    if (dist2(dx, dy, dz) < thr) cm |= 1u << u;
+                }
+                m |= cm << t0;
             }
-            m |= cm << t0;
+        } else {                                                   // B precedes A and is a ghost column: d' = (x_j + s) - x_i
+            for (int t0 = 0; t0 < nb; t0 += 8) {
+                unsigned cm = 0;
+                F4 pj[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) pj[u] = A[a + t0 + u];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const float dx = (pj[u].x + sx) - pi.x, dy = (pj[u].y + sy) - pi.y, dz = (pj[u].z + sz) - pi.z;
+                    if (dist2(dx, dy, dz) < thr) cm |= 1u << u;
+                }
+                m |= cm << t0;
+            }
         }
         m &= nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
-        if (cc == NW / 2) m &= ~(1u << lane);                      // i != j
+        if (same) m &= ~(1u << lane);                              // i != j
         if (!mine) m = 0;
-        smask[cc * BT + tid] = m;
-        if (m) nz |= 1u << cc;
-        if (mine) c.mask[(size_t)cc * c.n + i] = m;
+        const bool bflow = lane < nb && A[a + lane].w > 0.f;
+        const unsigned flowB = __ballot_sync(0xffffffffu, bflow);
+        const unsigned mi = myflow ? m : (m & flowB);              // walls keep their flow neighbours only
+        if (mine) c.mask[(size_t)cc * n + i] = mi;
+        if (mi) nz |= 1u << cc;
+        if (upper && b_owned) {                                    // the same pairs seen from B: transpose
+            const unsigned t = warp_transpose32(m, lane);
+            const unsigned tj = bflow ? t : (t & flowA);
+            if (lane < nb) {
+                const int r = q / FT::CBW;
+                const int j = a + lane + sh.gdelta[r];
+                const int ccm = FT::NW - 1 - cc;
+                c.mask[(size_t)ccm * n + j] = tj;
+                if (tj) atomicOr(&c.nzw[j], 1u << ccm);
+            }
+        }
     }
-    // ---- Shepard sum over flow neighbours in stencil order (cells x-major, j ascending): warp-uniform rounds
+    if (mine && nz) atomicOr(&c.nzw[i], nz);
+}
+
+// ------------------------------------------------------------------------------------------------ Shepard factor alone
+// calc_CSPM_f (base:386-398) for every particle of unflagged cells, when sph_calc_kernel_corr is called on its own;
+// inside sph_step the same sums are formed by the wall pass and the first fluid pass.
+template <int KERNEL, class FT> __global__ void __launch_bounds__(FT::BT) k_tile_shepard(DevF c, TileGeom g) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileShared<FT, 1> &sh = *reinterpret_cast<TileShared<FT, 1> *>(smem_raw);
+    WarpCell w = warp_cell<FT>(c, g);
+    const int lane = threadIdx.x & 31;
+    if (w.nc > 0 && c.cellflag[w.gcell]) w.nc = 0;
+    if (!__syncthreads_or(w.nc > 0)) return;
+    if (!tile_setup<FT, 1>(c, g, sh, w, c.ps4)) return;
+    build_ctab<FT, 1>(c, sh, w, lane);
+    if (w.nc == 0) return;
+    const bool mine = lane < w.nc;
+    const int i = w.is + (mine ? lane : 0);
+    const F4 *A = sh.P[0];
+    const F4 *ct = sh.ctab + (threadIdx.x >> 5) * FT::NW;
+    const F4 pi = A[sh.cb[stencil_cb<FT>(w, 0, 0, 0)] + (mine ? lane : 0)];
     const KernConst kc = kern_const(c);
-    build_ctab<1>(c, g, sh, w, lane);
-    const F4 *ct = sh.ctab + w * 27;
-    float ssum = 0.f;
-    int nflow = 0;
+    const size_t n = (size_t)c.n;
+    const unsigned *mrow = c.mask + i;
     Cursor k;
-    k.m = 0; k.nz = mine ? nz : 0u; k.a = 0; k.ex = k.ey = k.ez = 0.f;
+    cursor_init(k, mrow, n, mine ? c.nzw[i] : 0u);
+    float ssum = 0.f;
     while (true) {
-        cursor_jump(k, smask, ct, pi);
-        if (!__any_sync(0xffffffffu, k.m != 0)) break;              // warp-uniform round
+        cursor_jump(k, mrow, n, ct, pi);
+        if (!__any_sync(0xffffffffu, k.m != 0)) break;
         int i0, i1, i2, i3;
-        bool v0, v1, v2, v3;
-        cursor_take2(k, i0, i1, v0, v1);
+        cursor_take2<FT::SENT>(k, i0, i1);
         const float e0x = k.ex, e0y = k.ey, e0z = k.ez;
-        cursor_jump(k, smask, ct, pi);
-        cursor_take2(k, i2, i3, v2, v3);
+        cursor_jump(k, mrow, n, ct, pi);
+        cursor_take2<FT::SENT>(k, i2, i3);
         const F4 p0 = A[i0], p1 = A[i1], p2 = A[i2], p3 = A[i3];
-        const float w0 = fastW<KERNEL>(kc, dist2(e0x - p0.x, e0y - p0.y, e0z - p0.z));
-        const float w1 = fastW<KERNEL>(kc, dist2(e0x - p1.x, e0y - p1.y, e0z - p1.z));
-        const float w2 = fastW<KERNEL>(kc, dist2(k.ex - p2.x, k.ey - p2.y, k.ez - p2.z));
-        const float w3 = fastW<KERNEL>(kc, dist2(k.ex - p3.x, k.ey - p3.y, k.ez - p3.z));
-        const bool f0 = v0 && p0.w > 0.f, f1 = v1 && p1.w > 0.f, f2 = v2 && p2.w > 0.f, f3 = v3 && p3.w > 0.f;
-        ssum += f0 ? p0.w * w0 : 0.f;
-        ssum += f1 ? p1.w * w1 : 0.f;
-        ssum += f2 ? p2.w * w2 : 0.f;
-        ssum += f3 ? p3.w * w3 : 0.f;
-        nflow += (int)f0 + (int)f1 + (int)f2 + (int)f3;
+        ssum += fmaxf(p0.w, 0.f) * fastW<KERNEL>(kc, dist2(e0x - p0.x, e0y - p0.y, e0z - p0.z));
+        ssum += fmaxf(p1.w, 0.f) * fastW<KERNEL>(kc, dist2(e0x - p1.x, e0y - p1.y, e0z - p1.z));
+        ssum += fmaxf(p2.w, 0.f) * fastW<KERNEL>(kc, dist2(k.ex - p2.x, k.ey - p2.y, k.ez - p2.z));
+        ssum += fmaxf(p3.w, 0.f) * fastW<KERNEL>(kc, dist2(k.ex - p3.x, k.ey - p3.y, k.ez - p3.z));
     }
-    if (mine) {
-        c.cspm_f[i] = (ssum != 0.f) ? 1.f / ssum : 1.f;
-        c.nflow[i] = (unsigned char)min(nflow, 255);
-    }
+    if (mine) c.cspm_f[i] = (ssum != 0.f) ? 1.f / ssum : 1.f;
 }
 
 // ------------------------------------------------------------------------------------------------ prep (pointwise)
@@ -362,118 +451,92 @@ __global__ void __launch_bounds__(256) k_tile_prep(DevF c) {
 }
 
 // ------------------------------------------------------------------------------------------------ pass A: walls
-// loads the NW mask words of this thread's particle into shared memory (coalesced, all in flight at once) and
-// returns the bitmap of non-empty stencil cells
-__device__ __forceinline__ unsigned load_masks(const DevF &c, unsigned *smask, int NW, int i, bool work) {
-    unsigned nz = 0;
-    if (work) {
-        const unsigned *mp = c.mask + i;
-#pragma unroll 9
-        for (int cc = 0; cc < NW; cc++) {
-            const unsigned m = mp[(size_t)cc * c.n];
-            smask[cc * BT + threadIdx.x] = m;
-            if (m) nz |= 1u << cc;
-        }
-    }
-    return nz;
-}
-
-// wc:90-103 for dummy-wall particles: v~ = 2v - f sum V v~ W, rho~ = rho0, p = max(f sum V (p_j + rho~_j g_y dy) W, 0).
+// wc:90-103 for dummy-wall particles: v~ = 2v - f sum V v~ W, rho~ = rho0, p = max(f sum V (p_j + rho~_j g_y dy) W, 0)
+// SHEP (the first wall pass after the masks were built): f = 1 / sum V W (calc_CSPM_f) is formed in the same visit and
+// stored; later passes of the step reuse the stored f like the reference does (m_V changes with the stage density).
+// Masks of wall particles hold flow neighbours only.
 // Tile payloads: ps4 (coords, signed volume), vt4 (v~, rho~), pw4 (EOS pressure, previous pressure).
 template <int KERNEL>
 __device__ __forceinline__ void wall_pair(const KernConst &kc, float ex, float ey, float ez, const F4 pj, const F4 vj, float pjv,
-                                          bool valid, float gy, float &vw, float &pterm) {
+                                          float gy, float &vw, float &pterm) {
     const float dx = ex - pj.x, dy = ey - pj.y, dz = ez - pj.z;
-    const float wgt = fastW<KERNEL>(kc, dist2(dx, dy, dz));
-    vw = (valid && pj.w > 0.f) ? pj.w * wgt : 0.f;               // flow neighbours only (base:654-663)
+    vw = pj.w * fastW<KERNEL>(kc, dist2(dx, dy, dz));            // flow neighbour: w = +V; sentinel: 0
     pterm = fmaf(vj.w * gy, dy, pjv);
 }
 
-template <int KERNEL>
-__global__ void __launch_bounds__(BT) k_tile_wall(DevF c, TileGeom g) {
+template <int KERNEL, class FT, bool SHEP> __global__ void __launch_bounds__(FT::BT) k_tile_wall(DevF c, TileGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileShared<3> &sh = *reinterpret_cast<TileShared<3> *>(smem_raw);
-    unsigned *smask = reinterpret_cast<unsigned *>(smem_raw + sizeof(TileShared<3>));   // [NW][BT]
-    const int col = blockIdx.x / g.nseg, seg = blockIdx.x - col * g.nseg;
-    if (col / g.ny < c.own0 || col / g.ny >= c.own1) return;        // ghost column of a slab (block-uniform)
-    const int f0 = seg * ZB, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int f = f0 + w;
-    const int gcell = col * g.nF + f;
-    int is = 0, nc = 0;
-    if (f < g.nF) { is = cell_start(c.cell_end, gcell); nc = c.cell_end[gcell] - is; }
-    if (nc > 0 && c.cellflag[gcell]) nc = 0;                        // flagged cells belong to the generic kernels
-    const int i = is + lane;
+    TileShared<FT, 3> &sh = *reinterpret_cast<TileShared<FT, 3> *>(smem_raw);
+    WarpCell w = warp_cell<FT>(c, g);
+    const int lane = threadIdx.x & 31;
+    if (w.nc > 0 && c.cellflag[w.gcell]) w.nc = 0;                  // flagged cells belong to the generic kernels
+    const int i = w.is + lane;
     bool wall = false, work = false;
-    if (lane < nc) {
+    unsigned nz = 0;
+    if (lane < w.nc) {
         wall = c.ps4[i].w < 0.f;
-        work = wall && c.nflow[i] > 0;
-        if (wall && !work) {                                        // no flow neighbour: the sums are empty
+        if (wall) nz = c.nzw[i];
+        work = nz != 0;
+        if (wall && !work) {                                        // no flow neighbour: the sums are empty, f = 1
             const F4 v = c.v4[i];
             F4 vt; vt.x = 2.f * v.x; vt.y = 2.f * v.y; vt.z = 2.f * v.z; vt.w = c.rho0T;
             c.vt4[i] = vt;
             c.rho_t[i] = c.rho0;
             c.pnew[i] = 0.f;
+            if (SHEP) c.cspm_f[i] = 1.f;
             F4 pk = vt; pk.w = 0.f;
             c.pk4[i] = pk;
         }
     }
     if (!__syncthreads_or(work)) return;
-    const int NW = g.nR * 3;
-    const unsigned nz = load_masks(c, smask, NW, i, work);
-    if (!tile_setup<3>(c, g, sh, col, f0, c.ps4, c.vt4, c.pw4)) return;   // cannot happen for unflagged cells
-    build_ctab<3>(c, g, sh, w, lane);
+    if (!tile_setup<FT, 3>(c, g, sh, w, c.ps4, c.vt4, c.pw4)) return;   // cannot happen for unflagged cells
+    build_ctab<FT, 3>(c, sh, w, lane);
+    if (!__any_sync(0xffffffffu, work)) return;
     const F4 *A = sh.P[0], *B = sh.P[1], *Pw = sh.P[2];
-    const F4 *ct = sh.ctab + w * 27;
-    const int rc = g.nR / 2;
-    const int ci = sh.cb[rc * CBW + w + 1];                         // tile index of this cell's first particle
+    const F4 *ct = sh.ctab + (threadIdx.x >> 5) * FT::NW;
+    const int ci = sh.cb[stencil_cb<FT>(w, 0, 0, 0)];               // tile index of this cell's first particle
     const F4 pi = A[ci + (work ? lane : 0)];
     const KernConst kc = kern_const(c);
     const float gy = c.g[1];
     const bool fresh = c.wc_fresh != 0;
-    const int self = ci + lane;                                     // "j < i" in sorted order == tile index below mine (same run)
-    float Sv0 = 0.f, Sv1 = 0.f, Sv2 = 0.f, Sp = 0.f;
+    const int self = ci + lane;                                     // "j < i" inside my own cell == tile index below mine
+    const size_t n = (size_t)c.n;
+    const unsigned *mrow = c.mask + (work ? i : w.is);
+    float Sv0 = 0.f, Sv1 = 0.f, Sv2 = 0.f, Sp = 0.f, Sw = 0.f;
     Cursor k;
-    k.m = 0; k.nz = nz; k.a = 0; k.ex = k.ey = k.ez = 0.f;
-    const int c_lo = sh.cb[rc * CBW + w + 1], c_hi = sh.cb[rc * CBW + w + 2];   // my own cell inside the tile
-    const int centre = NW / 2;
-    (void)centre;
+    cursor_init(k, mrow, n, nz);
     while (true) {
-        cursor_jump(k, smask, ct, pi);
+        cursor_jump(k, mrow, n, ct, pi);
         if (!__any_sync(0xffffffffu, k.m != 0)) break;
         int i0, i1, i2, i3;
-        bool v0, v1, v2, v3;
-        // sorted order: every particle of a stencil cell with a smaller cell id precedes i, every one with a larger id
-        // follows it; inside my own cell the tile index decides.  before0/before1 = "this cell precedes mine".
-        cursor_take2(k, i0, i1, v0, v1);
+        cursor_take2<FT::SENT>(k, i0, i1);
         const float e0x = k.ex, e0y = k.ey, e0z = k.ez;
-        const float s0x = pi.x - k.ex, s0y = pi.y - k.ey, s0z = pi.z - k.ez;       // the cell's shift
-        cursor_jump(k, smask, ct, pi);
-        cursor_take2(k, i2, i3, v2, v3);
-        const float s1x = pi.x - k.ex, s1y = pi.y - k.ey, s1z = pi.z - k.ez;
+        // sorted order: every particle of a stencil cell with a smaller cell id precedes i, inside my own cell the index decides
+        const bool b0 = fresh || (k.flags & CT_BEFORE), s0 = (k.flags & CT_SAME) != 0;
+        cursor_jump(k, mrow, n, ct, pi);
+        cursor_take2<FT::SENT>(k, i2, i3);
+        const bool b1 = fresh || (k.flags & CT_BEFORE), s1 = (k.flags & CT_SAME) != 0;
         const F4 p0 = A[i0], p1 = A[i1], p2 = A[i2], p3 = A[i3];
         const F4 u0 = B[i0], u1 = B[i1], u2 = B[i2], u3 = B[i3];
         const F4 w0 = Pw[i0], w1 = Pw[i1], w2 = Pw[i2], w3 = Pw[i3];
-        // stencil order is x-major / z-fastest == ascending cell id: shift (sx, sy, sz) lexicographically negative <=> cell precedes
-        const bool b0 = s0x < 0.f || (s0x == 0.f && (s0y < 0.f || (s0y == 0.f && s0z < 0.f)));
-        const bool b1 = s1x < 0.f || (s1x == 0.f && (s1y < 0.f || (s1y == 0.f && s1z < 0.f)));
-        const bool same0 = s0x == 0.f && s0y == 0.f && s0z == 0.f, same1 = s1x == 0.f && s1y == 0.f && s1z == 0.f;
-        const float q0 = (fresh || b0 || (same0 && i0 < self)) ? w0.x : w0.y;
-        const float q1 = (fresh || b0 || (same0 && i1 < self)) ? w1.x : w1.y;
-        const float q2 = (fresh || b1 || (same1 && i2 < self)) ? w2.x : w2.y;
-        const float q3 = (fresh || b1 || (same1 && i3 < self)) ? w3.x : w3.y;
+        const float q0 = (b0 || (s0 && i0 < self)) ? w0.x : w0.y;
+        const float q1 = (b0 || (s0 && i1 < self)) ? w1.x : w1.y;
+        const float q2 = (b1 || (s1 && i2 < self)) ? w2.x : w2.y;
+        const float q3 = (b1 || (s1 && i3 < self)) ? w3.x : w3.y;
         float vw0, pt0, vw1, pt1, vw2, pt2, vw3, pt3;
-        wall_pair<KERNEL>(kc, e0x, e0y, e0z, p0, u0, q0, v0, gy, vw0, pt0);
-        wall_pair<KERNEL>(kc, e0x, e0y, e0z, p1, u1, q1, v1, gy, vw1, pt1);
-        wall_pair<KERNEL>(kc, k.ex, k.ey, k.ez, p2, u2, q2, v2, gy, vw2, pt2);
-        wall_pair<KERNEL>(kc, k.ex, k.ey, k.ez, p3, u3, q3, v3, gy, vw3, pt3);
-        Sv0 = fmaf(vw0, u0.x, Sv0); Sv1 = fmaf(vw0, u0.y, Sv1); Sv2 = fmaf(vw0, u0.z, Sv2); Sp = fmaf(vw0, pt0, Sp);
-        Sv0 = fmaf(vw1, u1.x, Sv0); Sv1 = fmaf(vw1, u1.y, Sv1); Sv2 = fmaf(vw1, u1.z, Sv2); Sp = fmaf(vw1, pt1, Sp);
-        Sv0 = fmaf(vw2, u2.x, Sv0); Sv1 = fmaf(vw2, u2.y, Sv1); Sv2 = fmaf(vw2, u2.z, Sv2); Sp = fmaf(vw2, pt2, Sp);
-        Sv0 = fmaf(vw3, u3.x, Sv0); Sv1 = fmaf(vw3, u3.y, Sv1); Sv2 = fmaf(vw3, u3.z, Sv2); Sp = fmaf(vw3, pt3, Sp);
+        wall_pair<KERNEL>(kc, e0x, e0y, e0z, p0, u0, q0, gy, vw0, pt0);
+        wall_pair<KERNEL>(kc, e0x, e0y, e0z, p1, u1, q1, gy, vw1, pt1);
+        wall_pair<KERNEL>(kc, k.ex, k.ey, k.ez, p2, u2, q2, gy, vw2, pt2);
+        wall_pair<KERNEL>(kc, k.ex, k.ey, k.ez, p3, u3, q3, gy, vw3, pt3);
+        Sw += vw0; Sv0 = fmaf(vw0, u0.x, Sv0); Sv1 = fmaf(vw0, u0.y, Sv1); Sv2 = fmaf(vw0, u0.z, Sv2); Sp = fmaf(vw0, pt0, Sp);
+        Sw += vw1; Sv0 = fmaf(vw1, u1.x, Sv0); Sv1 = fmaf(vw1, u1.y, Sv1); Sv2 = fmaf(vw1, u1.z, Sv2); Sp = fmaf(vw1, pt1, Sp);
+        Sw += vw2; Sv0 = fmaf(vw2, u2.x, Sv0); Sv1 = fmaf(vw2, u2.y, Sv1); Sv2 = fmaf(vw2, u2.z, Sv2); Sp = fmaf(vw2, pt2, Sp);
+        Sw += vw3; Sv0 = fmaf(vw3, u3.x, Sv0); Sv1 = fmaf(vw3, u3.y, Sv1); Sv2 = fmaf(vw3, u3.z, Sv2); Sp = fmaf(vw3, pt3, Sp);
     }
-    (void)c_lo; (void)c_hi;
     if (!work) return;
-    const float fi = c.cspm_f[i];
+    float fi;
+    if (SHEP) { fi = (Sw != 0.f) ? 1.f / Sw : 1.f; c.cspm_f[i] = fi; }
+    else fi = c.cspm_f[i];
     const F4 v = c.v4[i];
     F4 vt;
     vt.x = 2.f * v.x - Sv0 * fi; vt.y = 2.f * v.y - Sv1 * fi; vt.z = 2.f * v.z - Sv2 * fi; vt.w = c.rho0T;
@@ -490,138 +553,210 @@ __global__ void __launch_bounds__(BT) k_tile_wall(DevF c, TileGeom g) {
 // wc:108-126 for fluid particles: continuity + viscosity + pressure in one visit of the set bits.
 //   d_rho_i = rho~_i sum_j V_j (v~_i - v~_j) . gradW_ij
 //   d_v_i   = g + sum_j [ 2(dim+2) nu V_j min(v_ij . x_ij, 0) / (r^2 + 0.01 h^2) {1 | rho0 / rho~_i} - rho0 V_j (p_i/rho~_i^2 + p_j/rho~_j^2) ] gradW_ij
-struct FluidI { float vx, vy, vz, pr, visc_f, visc_w, h2, nrho0; };
-// one pair: ddc = V_j s (v_ij . x_ij), and the coefficient cf with  d_v += cf * d
-template <int KERNEL>
+// SHEP: also the Shepard sum over flow neighbours (calc_CSPM_f, base:386-398) -- the first fluid pass of a step.  The
+// volumes read there belong to the FIRST one_step, whose m_V is still the step-start value calc_CSPM_f would see.
+struct FluidI { float vx, vy, vz, npr, visc_f, visc_w, h2, nrho0; };      // npr = -rho0 p_i / rho~_i^2
+template <int KERNEL, bool SHEP>
 __device__ __forceinline__ void fluid_pair(const KernConst &kc, const FluidI &I, float ex, float ey, float ez, const F4 pj,
-                                           const F4 qj, bool valid, float &ddc, float &cf, float &dx, float &dy, float &dz) {
-    dx = ex - pj.x; dy = ey - pj.y; dz = ez - pj.z;
+                                           const F4 qj, float &dd, float &a0, float &a1, float &a2, float &ssum) {
+    const float dx = ex - pj.x, dy = ey - pj.y, dz = ez - pj.z;
     const float r2 = dist2(dx, dy, dz);
-    const float s = fastdW<KERNEL>(kc, r2);
+    const float r2c = fmaxf(r2, kc.eps2), rinv = rsqrt_fast(r2c), r = r2c * rinv;
+    float s;
+    if (KERNEL == 1) {
+        const float q1 = fmaxf(fmaf(-0.5f * kc.hinv, r, 1.f), 0.f), q2 = q1 * q1;
+        s = (kc.c_grad * q1) * q2;
+        if (SHEP) ssum = fmaf(fmaxf(pj.w, 0.f) * (kc.knorm * q2), q2 * fmaf(2.f * kc.hinv, r, 1.f), ssum);
+    } else {
+        const float q = r * kc.hinv, t = fmaxf(2.f - q, 0.f);
+        s = q <= 1.f ? kc.c_grad * fmaf(1.5f, q, -2.f) : -0.5f * kc.c_grad * t * t * (rinv / kc.hinv);
+        if (SHEP) ssum = fmaf(fmaxf(pj.w, 0.f), fastW<0>(kc, r2), ssum);
+    }
     const float ux = I.vx - qj.x, uy = I.vy - qj.y, uz = I.vz - qj.z;
     const float vx = fmaf(uz, dz, fmaf(uy, dy, ux * dx));          // v_ij . x_ij
-    const float Vs = valid ? fabsf(pj.w) * s : 0.f;
-    ddc = Vs * vx;
-    const float visc = (pj.w < 0.f ? I.visc_w : I.visc_f) * fminf(vx, 0.f) * __fdividef(1.f, r2 + I.h2);
-    cf = Vs * fmaf(I.nrho0, I.pr + qj.w, visc);
+    const float Vs = fabsf(pj.w) * s;                              // sentinel: 0
+    dd = fmaf(Vs, vx, dd);
+    const float visc = ((pj.w < 0.f ? I.visc_w : I.visc_f) * fminf(vx, 0.f)) * rcp_fast(r2 + I.h2);
+    const float cf = Vs * (fmaf(I.nrho0, qj.w, I.npr) + visc);
+    a0 = fmaf(cf, dx, a0); a1 = fmaf(cf, dy, a1); a2 = fmaf(cf, dz, a2);
 }
 
-template <int KERNEL>
-__global__ void __launch_bounds__(BT) k_tile_fluid(DevF c, TileGeom g) {
+template <int KERNEL, class FT, bool SHEP> __global__ void __launch_bounds__(FT::BT, 2) k_tile_fluid(DevF c, TileGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileShared<2> &sh = *reinterpret_cast<TileShared<2> *>(smem_raw);
-    unsigned *smask = reinterpret_cast<unsigned *>(smem_raw + sizeof(TileShared<2>));   // [NW][BT]
-    const int col = blockIdx.x / g.nseg, seg = blockIdx.x - col * g.nseg;
-    if (col / g.ny < c.own0 || col / g.ny >= c.own1) return;        // ghost column of a slab (block-uniform)
-    const int f0 = seg * ZB, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int f = f0 + w;
-    const int gcell = col * g.nF + f;
-    int is = 0, nc = 0;
-    if (f < g.nF) { is = cell_start(c.cell_end, gcell); nc = c.cell_end[gcell] - is; }
-    if (nc > 0 && c.cellflag[gcell]) nc = 0;
-    const int i = is + lane;
-    const bool work = lane < nc && c.type[i] == 1;
+    TileShared<FT, 2> &sh = *reinterpret_cast<TileShared<FT, 2> *>(smem_raw);
+    WarpCell w = warp_cell<FT>(c, g);
+    const int lane = threadIdx.x & 31;
+    if (w.nc > 0 && c.cellflag[w.gcell]) w.nc = 0;
+    const int i = w.is + lane;
+    const bool work = lane < w.nc && c.ps4[i].w > 0.f;              // flow particle (fluid: the only flow type of WCSPH)
+    const unsigned nz = work ? c.nzw[i] : 0u;
     if (!__syncthreads_or(work)) return;
-    const int NW = g.nR * 3;
-    const unsigned nz = load_masks(c, smask, NW, i, work);
-    if (!tile_setup<2>(c, g, sh, col, f0, c.ps4, c.pk4)) return;
-    build_ctab<2>(c, g, sh, w, lane);
+    if (!tile_setup<FT, 2>(c, g, sh, w, c.ps4, c.pk4)) return;
+    build_ctab<FT, 2>(c, sh, w, lane);
+    if (!__any_sync(0xffffffffu, work)) return;
     const F4 *A = sh.P[0], *B = sh.P[1];
-    const F4 *ct = sh.ctab + w * 27;
-    const int rc = g.nR / 2;
-    const int ci = sh.cb[rc * CBW + w + 1] + (work ? lane : 0);
+    const F4 *ct = sh.ctab + (threadIdx.x >> 5) * FT::NW;
+    const int ci = sh.cb[stencil_cb<FT>(w, 0, 0, 0)] + (work ? lane : 0);
     const F4 pi = A[ci], qi = B[ci];                               // qi = v~_i, p_i / rho~_i^2
     const float rhoi = work ? c.vt4[i].w : 1.f;
     const KernConst kc = kern_const(c);
     FluidI I;
-    I.vx = qi.x; I.vy = qi.y; I.vz = qi.z; I.pr = qi.w;
+    I.vx = qi.x; I.vy = qi.y; I.vz = qi.z; I.nrho0 = -c.rho0T; I.npr = I.nrho0 * qi.w;
     I.visc_f = c.visc_coef; I.visc_w = c.visc_coef * c.rho0T / rhoi;   // wc:41-44
-    I.h2 = c.h2_001; I.nrho0 = -c.rho0T;
-    float dd = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    I.h2 = c.h2_001;
+    float dd = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, ssum = 0.f;
+    const size_t n = (size_t)c.n;
+    const unsigned *mrow = c.mask + (work ? i : w.is);
     Cursor k;
-    k.m = 0; k.nz = nz; k.a = 0; k.ex = k.ey = k.ez = 0.f;
+    cursor_init(k, mrow, n, nz);
     while (true) {
-        cursor_jump(k, smask, ct, pi);
+        cursor_jump(k, mrow, n, ct, pi);
         if (!__any_sync(0xffffffffu, k.m != 0)) break;              // warp-uniform round: lanes reconverge here
         int i0, i1, i2, i3;
-        bool v0, v1, v2, v3;
-        cursor_take2(k, i0, i1, v0, v1);
+        cursor_take2<FT::SENT>(k, i0, i1);
         const float e0x = k.ex, e0y = k.ey, e0z = k.ez;
-        cursor_jump(k, smask, ct, pi);
-        cursor_take2(k, i2, i3, v2, v3);
+        cursor_jump(k, mrow, n, ct, pi);
+        cursor_take2<FT::SENT>(k, i2, i3);
         const F4 p0 = A[i0], q0 = B[i0], p1 = A[i1], q1 = B[i1], p2 = A[i2], q2 = B[i2], p3 = A[i3], q3 = B[i3];
-        float d0, c0, x0, y0, z0, d1, c1, x1, y1, z1, d2, c2, x2, y2, z2, d3, c3, x3, y3, z3;
-        fluid_pair<KERNEL>(kc, I, e0x, e0y, e0z, p0, q0, v0, d0, c0, x0, y0, z0);
-        fluid_pair<KERNEL>(kc, I, e0x, e0y, e0z, p1, q1, v1, d1, c1, x1, y1, z1);
-        fluid_pair<KERNEL>(kc, I, k.ex, k.ey, k.ez, p2, q2, v2, d2, c2, x2, y2, z2);
-        fluid_pair<KERNEL>(kc, I, k.ex, k.ey, k.ez, p3, q3, v3, d3, c3, x3, y3, z3);
-        dd += d0; a0 = fmaf(c0, x0, a0); a1 = fmaf(c0, y0, a1); a2 = fmaf(c0, z0, a2);
-        dd += d1; a0 = fmaf(c1, x1, a0); a1 = fmaf(c1, y1, a1); a2 = fmaf(c1, z1, a2);
-        dd += d2; a0 = fmaf(c2, x2, a0); a1 = fmaf(c2, y2, a1); a2 = fmaf(c2, z2, a2);
-        dd += d3; a0 = fmaf(c3, x3, a0); a1 = fmaf(c3, y3, a1); a2 = fmaf(c3, z3, a2);
+        fluid_pair<KERNEL, SHEP>(kc, I, e0x, e0y, e0z, p0, q0, dd, a0, a1, a2, ssum);
+        fluid_pair<KERNEL, SHEP>(kc, I, e0x, e0y, e0z, p1, q1, dd, a0, a1, a2, ssum);
+        fluid_pair<KERNEL, SHEP>(kc, I, k.ex, k.ey, k.ez, p2, q2, dd, a0, a1, a2, ssum);
+        fluid_pair<KERNEL, SHEP>(kc, I, k.ex, k.ey, k.ez, p3, q3, dd, a0, a1, a2, ssum);
     }
     if (!work) return;
     c.d_rho[i] = dd * rhoi;
     F4 dv; dv.x = a0 + c.g[0]; dv.y = a1 + c.g[1]; dv.z = a2 + c.g[2]; dv.w = 0.f;
     c.d_vel[i] = dv;
+    if (SHEP) c.cspm_f[i] = (ssum != 0.f) ? 1.f / ssum : 1.f;
+}
+
+// ------------------------------------------------------------------------------------------------ mask-based count
+// number of neighbours per FLOW particle of unflagged cells from the masks (parity probe of k_tile_mask); -1 elsewhere
+__global__ void __launch_bounds__(256) k_mask_count(DevF c, int nw, int *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    int cnt = -1;
+    if (c.ps4[i].w > 0.f && !c.cellflag[c.gid[i]]) {
+        cnt = 0;
+        for (int cc = 0; cc < nw; cc++) cnt += __popc(c.mask[(size_t)cc * c.n + i]);
+    }
+    out[i] = cnt;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-static size_t smem_mask(int NW) { return sizeof(TileShared<1>) + (size_t)NW * BT * 4; }
-static size_t smem_pass(int NW = 27) { return sizeof(TileShared<2>) + (size_t)NW * BT * 4; }
-static size_t smem_wall(int NW = 27) { return sizeof(TileShared<3>) + (size_t)NW * BT * 4; }
+typedef Foot<true, 2, 2> F3M;      // 3D: masks / Shepard / fluid pass -- 16 warps, 16 runs
+typedef Foot<true, 1, 1> F3W;      // 3D: wall pass (three payload arrays) -- 4 warps, 9 runs
+typedef Foot<false, 4, 1> F2M;     // 2D: 16 warps, 6 runs
+typedef Foot<false, 2, 1> F2W;
 
-template <int KERNEL> static int set_attrs(SphCtx *c) {
-    SPH_CHECK(c, cudaFuncSetAttribute(k_tile_mask<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mask(27)));
-    SPH_CHECK(c, cudaFuncSetAttribute(k_tile_wall<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wall()));
-    SPH_CHECK(c, cudaFuncSetAttribute(k_tile_fluid<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pass()));
+template <class FT, int NP> static size_t smem_of() { return sizeof(TileShared<FT, NP>); }
+
+template <typename K> static int set_smem(SphCtx *c, K kern, size_t bytes) {
+    SPH_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return 0;
 }
-static int ensure_attrs(SphCtx *c) {
-    static bool done = false;
-    if (done) return 0;
-    int r = set_attrs<0>(c);
-    if (!r) r = set_attrs<1>(c);
-    done = r == 0;
+template <int KERNEL> static int set_attrs(SphCtx *c) {
+    int r = 0;
+    if (!r) r = set_smem(c, k_tile_shepard<KERNEL, F3M>, smem_of<F3M, 1>());
+    if (!r) r = set_smem(c, k_tile_shepard<KERNEL, F2M>, smem_of<F2M, 1>());
+    if (!r) r = set_smem(c, k_tile_wall<KERNEL, F3W, false>, smem_of<F3W, 3>());
+    if (!r) r = set_smem(c, k_tile_wall<KERNEL, F3W, true>, smem_of<F3W, 3>());
+    if (!r) r = set_smem(c, k_tile_wall<KERNEL, F2W, false>, smem_of<F2W, 3>());
+    if (!r) r = set_smem(c, k_tile_wall<KERNEL, F2W, true>, smem_of<F2W, 3>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, F3M, false>, smem_of<F3M, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, F3M, true>, smem_of<F3M, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, F2M, false>, smem_of<F2M, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, F2M, true>, smem_of<F2M, 2>());
     return r;
 }
+static int ensure_attrs(SphCtx *c) {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || done[dev]) return 0;
+    int r = set_attrs<0>(c);
+    if (!r) r = set_attrs<1>(c);
+    if (!r) r = set_smem(c, k_tile_mask<F3M>, smem_of<F3M, 1>());
+    if (!r) r = set_smem(c, k_tile_mask<F2M>, smem_of<F2M, 1>());
+    done[dev] = r == 0;
+    return r;
+}
+template <class FT> static int nblocks(const TileGeom &g) { return g.nb0 * g.nb1 * g.nseg; }
 
-int tile_mask(SphCtx *c) {
+// masks (+ the Shepard factor of every particle when `shepard`: the stand-alone sph_calc_kernel_corr)
+int tile_mask(SphCtx *c, bool shepard) {
     DevF d = make_dev<float>(c);
-    const TileGeom g = make_geom(c->p.dim, d.gn);
-    const int nblk = g.nslow0 * g.nslow1 * g.nseg;
     int r = ensure_attrs(c);
     if (r) return r;
+    const bool d3 = c->p.dim == 3;
     SPH_CHECK(c, cudaMemsetAsync(d.cellflag, 0, (size_t)c->C, c->stream));
     SPH_CHECK(c, cudaMemsetAsync(d.nflag, 0, 4, c->stream));
+    SPH_CHECK(c, cudaMemsetAsync(d.nzw, 0, (size_t)c->n * 4, c->stream));
     SPH_PROF(c, K_TILE_MASK);
-    if (c->p.kernel == 0) k_tile_mask<0><<<nblk, BT, smem_mask(g.nR * 3), c->stream>>>(d, g);
-    else k_tile_mask<1><<<nblk, BT, smem_mask(g.nR * 3), c->stream>>>(d, g);
+    if (d3) { const TileGeom g = make_geom<F3M>(d.gn); k_tile_mask<F3M><<<nblocks<F3M>(g), F3M::BT, smem_of<F3M, 1>(), c->stream>>>(d, g); }
+    else { const TileGeom g = make_geom<F2M>(d.gn); k_tile_mask<F2M><<<nblocks<F2M>(g), F2M::BT, smem_of<F2M, 1>(), c->stream>>>(d, g); }
+    SPH_LAUNCH_CHECK(c);
+    c->shep_pending = c->shep_wall_pending = !shepard;
+    if (!shepard) return 0;
+    SPH_PROF(c, K_CSPM_F);
+    if (d3) {
+        const TileGeom g = make_geom<F3M>(d.gn);
+        if (c->p.kernel == 0) k_tile_shepard<0, F3M><<<nblocks<F3M>(g), F3M::BT, smem_of<F3M, 1>(), c->stream>>>(d, g);
+        else k_tile_shepard<1, F3M><<<nblocks<F3M>(g), F3M::BT, smem_of<F3M, 1>(), c->stream>>>(d, g);
+    } else {
+        const TileGeom g = make_geom<F2M>(d.gn);
+        if (c->p.kernel == 0) k_tile_shepard<0, F2M><<<nblocks<F2M>(g), F2M::BT, smem_of<F2M, 1>(), c->stream>>>(d, g);
+        else k_tile_shepard<1, F2M><<<nblocks<F2M>(g), F2M::BT, smem_of<F2M, 1>(), c->stream>>>(d, g);
+    }
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
 
+template <int KERNEL, class FT> static void launch_wall(SphCtx *c, const DevF &d, bool shep) {
+    const TileGeom g = make_geom<FT>(d.gn);
+    if (shep) k_tile_wall<KERNEL, FT, true><<<nblocks<FT>(g), FT::BT, smem_of<FT, 3>(), c->stream>>>(d, g);
+    else k_tile_wall<KERNEL, FT, false><<<nblocks<FT>(g), FT::BT, smem_of<FT, 3>(), c->stream>>>(d, g);
+}
 // WCSPH one_step (wc:82-126) on the tile path; flagged cells are completed by the generic kernels (flagged_only).
 int tile_wc_prep_and_wall(SphCtx *c) {
     DevF d = make_dev<float>(c);
-    const TileGeom g = make_geom(c->p.dim, d.gn);
-    const int nblk = g.nslow0 * g.nslow1 * g.nseg, n = (int)c->n;
+    const int n = (int)c->n;
     SPH_PROF(c, K_WC_EOS);
     k_tile_prep<<<blocks_for(n, 256), 256, 0, c->stream>>>(d);
     SPH_LAUNCH_CHECK(c);
+    const bool shep = c->shep_wall_pending;
+    c->shep_wall_pending = false;
     SPH_PROF(c, K_TILE_WALL);
-    if (c->p.kernel == 0) k_tile_wall<0><<<nblk, BT, smem_wall(g.nR * 3), c->stream>>>(d, g);
-    else k_tile_wall<1><<<nblk, BT, smem_wall(g.nR * 3), c->stream>>>(d, g);
+    if (c->p.dim == 3) {
+        if (c->p.kernel == 0) launch_wall<0, F3W>(c, d, shep); else launch_wall<1, F3W>(c, d, shep);
+    } else {
+        if (c->p.kernel == 0) launch_wall<0, F2W>(c, d, shep); else launch_wall<1, F2W>(c, d, shep);
+    }
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
+template <int KERNEL, class FT> static void launch_fluid(SphCtx *c, const DevF &d, bool shep) {
+    const TileGeom g = make_geom<FT>(d.gn);
+    if (shep) k_tile_fluid<KERNEL, FT, true><<<nblocks<FT>(g), FT::BT, smem_of<FT, 2>(), c->stream>>>(d, g);
+    else k_tile_fluid<KERNEL, FT, false><<<nblocks<FT>(g), FT::BT, smem_of<FT, 2>(), c->stream>>>(d, g);
+}
 int tile_wc_fluid(SphCtx *c) {
     DevF d = make_dev<float>(c);
-    const TileGeom g = make_geom(c->p.dim, d.gn);
-    const int nblk = g.nslow0 * g.nslow1 * g.nseg;
+    const bool shep = c->shep_pending;
+    c->shep_pending = false;
     SPH_PROF(c, K_TILE_FLUID);
-    if (c->p.kernel == 0) k_tile_fluid<0><<<nblk, BT, smem_pass(g.nR * 3), c->stream>>>(d, g);
-    else k_tile_fluid<1><<<nblk, BT, smem_pass(g.nR * 3), c->stream>>>(d, g);
+    if (c->p.dim == 3) {
+        if (c->p.kernel == 0) launch_fluid<0, F3M>(c, d, shep); else launch_fluid<1, F3M>(c, d, shep);
+    } else {
+        if (c->p.kernel == 0) launch_fluid<0, F2M>(c, d, shep); else launch_fluid<1, F2M>(c, d, shep);
+    }
+    SPH_LAUNCH_CHECK(c);
+    return 0;
+}
+int tile_mask_count(SphCtx *c, int32_t *out) {
+    DevF d = make_dev<float>(c);
+    SPH_PROF(c, K_NEIGHBOR_COUNT);
+    k_mask_count<<<blocks_for(c->n, 256), 256, 0, c->stream>>>(d, c->p.dim == 3 ? 27 : 9, out);
     SPH_LAUNCH_CHECK(c);
     return 0;
 }

@@ -303,7 +303,7 @@ class CudaSlabEngine:
         self.e.call("sph_grid_build")
 
     def calc_kernel_corr(self):
-        self.e.call("sph_calc_kernel_corr")
+        self.e.call("sph_calc_kernel_corr_deferred")
 
     def init_real2tmp(self):
         self.e.call("sph_init_real2tmp")
