@@ -88,7 +88,7 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
     int64_t o_tiles = off; off += align_up(nt * 4);
     const int mask_words = p->dim == 3 ? 27 : 9;
     int64_t o_pw4 = 0;
-    int64_t o_ps4 = 0, o_pk4 = 0, o_mask = 0, o_nflow = 0, o_cflag = 0, o_nflag = 0;
+    int64_t o_ps4 = 0, o_pk4 = 0, o_mask = 0, o_nflow = 0, o_cflag = 0, o_nflag = 0, o_cinfo = 0, o_wl = 0;
     if (fast) {
         o_ps4 = off; off += align_up(n_max * 16);
         o_pw4 = off; off += align_up(n_max * 16);
@@ -96,11 +96,13 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
         o_nflow = off; off += align_up(n_max * 4);
         o_cflag = off; off += align_up(C + 1);
         o_nflag = off; off += 256;
+        o_cinfo = off; off += align_up(C + 1);
+        o_wl = off; off += 3 * align_up((C + 1) * 4);     // work lists: occupied / flow / wall segments
     }
     if (c) {
         c->off_pw4 = o_pw4;
         c->off_ps4 = o_ps4; c->off_pk4 = fast ? c->f[SPH_F_PK4].off[0] : o_pk4; c->off_mask = o_mask; c->off_nflow = o_nflow; c->off_cellflag = o_cflag;
-        c->off_nflag = o_nflag; c->fast = fast; c->mask_words = mask_words;
+        c->off_nflag = o_nflag; c->off_cellinfo = o_cinfo; c->off_worklist = o_wl; c->fast = fast; c->mask_words = mask_words;
         c->off_gid_unsorted = o_gid; c->off_slot = o_slot; c->off_perm = o_perm; c->off_tmpidx = o_tmp;
         c->off_bad = o_bad; c->off_scan_tiles = o_tiles;
         c->real_bytes = rb; c->soil = soil; c->rk = rk; c->has_L = hasL; c->C = (int)C;
@@ -237,6 +239,9 @@ template <typename T> Dev<T> make_dev(SphCtx *c, int which) {
         d.nzw = (unsigned *)(c->arena + c->off_nflow);
         d.cellflag = (unsigned char *)(c->arena + c->off_cellflag);
         d.nflag = (int *)(c->arena + c->off_nflag);
+        d.cellinfo = (unsigned char *)(c->arena + c->off_cellinfo);
+        for (int k = 0; k < 3; k++) d.worklist[k] = (int *)(c->arena + c->off_worklist + k * align_up(((int64_t)c->C + 1) * 4));
+        d.wcount = d.nflag + 4;              // three counters after the flag counter
     }
     return d;
 }

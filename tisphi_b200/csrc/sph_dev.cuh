@@ -79,6 +79,10 @@ template <typename T> struct Dev {
     unsigned *nzw;            // per particle: bitmap of its non-zero mask words
     unsigned char *cellflag;  // 1: this centre cell cannot use the tile path (a cell of its stencil holds > 32 particles ...)
     int *nflag;               // number of flagged cells (device counter)
+    unsigned char *cellinfo;  // per cell, written by the mask kernel: 1 has flow particles, 2 has wall particles,
+                              // 4 has wall particles AND a stencil cell with flow particles (candidate for the wall pass)
+    int *worklist[3];         // footprint segments with work: 0 occupied (mask pass), 1 flow (fluid pass), 2 wall pass
+    int *wcount;              // their lengths (3 ints)
     int flagged_only;         // generic kernels: process only particles of flagged cells
 };
 

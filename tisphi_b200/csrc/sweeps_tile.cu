@@ -46,7 +46,7 @@ template <class FT, int NP> struct TileShared {
     unsigned long long bar;           // mbarrier
     int cb[FT::NR * FT::CBW];         // tile index of the first particle of each (run, cell)
     int gdelta[FT::NR];               // global index = tile index + gdelta[run]
-    int total, overflow;
+    int total, overflow, item;
     F4 ctab[FT::NWARP * FT::NW];      // per (warp, stencil cell): shift xyz, tile index of the cell's first particle | flags
 };
 constexpr unsigned CT_BEFORE = 1u << 30, CT_SAME = 1u << 29, CT_IDX = (1u << 24) - 1;
@@ -93,9 +93,9 @@ __device__ __forceinline__ int cell_start(const int *cell_end, int g) { return g
 
 // what a warp knows about its cell
 struct WarpCell { int b0, b1, f0, wx, wy, wz, cx, cy, f, gcell, is, nc; };
-template <class FT> __device__ __forceinline__ WarpCell warp_cell(const DevF &c, const TileGeom &g) {
+template <class FT> __device__ __forceinline__ WarpCell warp_cell(const DevF &c, const TileGeom &g, int blk) {
     WarpCell w;
-    const int seg = blockIdx.x % g.nseg, t = blockIdx.x / g.nseg;
+    const int seg = blk % g.nseg, t = blk / g.nseg;
     w.b1 = t % g.nb1; w.b0 = t / g.nb1; w.f0 = seg * ZB;
     const int wi = threadIdx.x >> 5;
     w.wz = wi % ZB; w.wy = (wi / ZB) % FT::BY; w.wx = wi / (ZB * FT::BY);
@@ -120,9 +120,19 @@ template <class FT> __device__ __forceinline__ int stencil_cb(const WarpCell &w,
 
 // Computes spans and cell boundaries, issues the TMA copies of the NP payload arrays and waits for them.
 // Returns false (uniformly) when the tile does not fit.
+// once per block: the mbarrier (reused with alternating parity by every work item) and the sentinel entries
+template <class FT, int NP> __device__ __forceinline__ void tile_init(TileShared<FT, NP> &sh) {
+    if (threadIdx.x == 0) {
+        mbar_init(&sh.bar, 1);
+        F4 z; z.x = z.y = z.z = z.w = 0.f;
+#pragma unroll
+        for (int p = 0; p < NP; p++) sh.P[p][FT::SENT] = z;
+    }
+    __syncthreads();
+}
 template <class FT, int NP>
 __device__ __forceinline__ bool tile_setup(const DevF &c, const TileGeom &g, TileShared<FT, NP> &sh, const WarpCell &w,
-                                           const F4 *src0, const F4 *src1 = nullptr, const F4 *src2 = nullptr) {
+                                           unsigned parity, const F4 *src0, const F4 *src1 = nullptr, const F4 *src2 = nullptr) {
     const int tid = threadIdx.x;
     const int f0 = w.f0, f_lo = max(f0 - 1, 0), f_hi = min(f0 + ZB, g.nF - 1);
     if (tid < 32) {
@@ -160,13 +170,11 @@ __device__ __forceinline__ bool tile_setup(const DevF &c, const TileGeom &g, Til
         if (tid == 0) {
             sh.total = total;
             sh.overflow = total > FT::CAP;
-            mbar_init(&sh.bar, 1);
-            F4 z; z.x = z.y = z.z = z.w = 0.f;
-#pragma unroll
-            for (int p = 0; p < NP; p++) sh.P[p][FT::SENT] = z;
         }
         __syncwarp();
-        if (total <= FT::CAP) {
+        if (total > FT::CAP) {                                    // nothing is loaded: complete the phase so that the parity still flips
+            if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sh.bar)) : "memory");
+        } else {
             if (tid == 0) mbar_expect_tx(&sh.bar, (unsigned)(total * 16 * NP));
             __syncwarp();
             if (tid < FT::NR && len > 0) {
@@ -178,9 +186,26 @@ __device__ __forceinline__ bool tile_setup(const DevF &c, const TileGeom &g, Til
     }
     __syncthreads();
     if (sh.overflow) return false;
-    mbar_wait(&sh.bar, 0);
+    mbar_wait(&sh.bar, parity);
     return true;
 }
+// Persistent blocks walk a work list of footprint segments.  BODY(blk, parity) returns true when it used the tile
+// (block-uniform), which flips the mbarrier parity for the next item.
+#define TILE_PERSISTENT_LOOP(SH, LIST, COUNT, CURSOR, CALL)                           \
+    {                                                                                 \
+        unsigned uses_ = 0;                                                           \
+        const int items_ = *(COUNT);                                                  \
+        while (true) {                                                                \
+            if (threadIdx.x == 0) (SH).item = atomicAdd((CURSOR), 1);                 \
+            __syncthreads();                                                          \
+            const int it_ = (SH).item;                                                \
+            if (it_ >= items_) break;                                                 \
+            const int blk = (LIST)[it_];                                              \
+            const unsigned parity = uses_ & 1u;                                       \
+            if (CALL) uses_++;                                                        \
+            __syncthreads();                                                          \
+        }                                                                             \
+    }
 
 // per-warp table of the stencil cells, so that advancing to the next cell costs one shared load
 template <class FT, int NP>
@@ -273,33 +298,25 @@ __device__ __forceinline__ unsigned warp_transpose32(unsigned a, int lane) {
 
 // ------------------------------------------------------------------------------------------------ pass 0: masks
 // One launch per step, right after the grid build.  nzw (bitmap of non-zero words per particle) must be zero on entry.
-template <class FT> __global__ void __launch_bounds__(FT::BT) k_tile_mask(DevF c, TileGeom g) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileShared<FT, 1> &sh = *reinterpret_cast<TileShared<FT, 1> *>(smem_raw);
-    const WarpCell w = warp_cell<FT>(c, g);
+template <class FT>
+__device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, TileShared<FT, 1> &sh, int blk, unsigned parity) {
+    const WarpCell w = warp_cell<FT>(c, g, blk);
     const int lane = threadIdx.x & 31;
-    if (!__syncthreads_or(w.nc > 0)) return;                       // nothing owned in this footprint
-    const bool ok = tile_setup<FT, 1>(c, g, sh, w, c.ps4);
-    if (w.nc == 0) return;
-    // can this cell be represented?  (uniform per warp)
-    bool flagged = !ok || w.nc > 32;
-    int ox = 0, oy = 0, of = 0;
-    if (lane < FT::NW) stencil<FT>(lane, ox, oy, of);
-    if (!flagged) {
-        bool big = false;
-        if (lane < FT::NW) {
-            const int q = stencil_cb<FT>(w, ox, oy, of);
-            big = sh.cb[q + 1] - sh.cb[q] > 32;
-        }
-        flagged = __any_sync(0xffffffffu, big);
-    }
+    const bool ok = tile_setup<FT, 1>(c, g, sh, w, parity, c.ps4);
+    if (w.nc == 0) return true;
+    // can this cell be represented?  (uniform per warp; branch-free so that the warp stays converged)
+    int ox, oy, of;
+    stencil<FT>(min(lane, FT::NW - 1), ox, oy, of);
+    const int q0 = stencil_cb<FT>(w, ox, oy, of);
+    const bool big = lane < FT::NW && sh.cb[q0 + 1] - sh.cb[q0] > 32;
+    const bool flagged = __any_sync(0xffffffffu, big) || !ok || w.nc > 32;
     if (flagged) {                                                 // my neighbours wait for words only I can write: flag them too
         if (lane < FT::NW) {
             const int nx = w.cx + ox, ny = w.cy + oy, nf = w.f + of;
             if (nx >= 0 && nx < g.n0 && ny >= 0 && ny < g.n1 && nf >= 0 && nf < g.nF) c.cellflag[(nx * g.n1 + ny) * g.nF + nf] = 1;
         }
         if (lane == 0) atomicAdd(c.nflag, 1);
-        return;
+        return true;
     }
     const bool mine = lane < w.nc;
     const int i = w.is + lane;
@@ -308,11 +325,14 @@ template <class FT> __global__ void __launch_bounds__(FT::BT) k_tile_mask(DevF c
     const F4 pi = A[own + (mine ? lane : 0)];
     const bool myflow = pi.w > 0.f;
     const unsigned flowA = __ballot_sync(0xffffffffu, mine && myflow);
+    const bool has_wall = __any_sync(0xffffffffu, mine && !myflow);
+    bool near_flow = flowA != 0;
     const float thr = c.r2thr;
     const size_t n = (size_t)c.n;
     unsigned nz = 0;
 #pragma unroll 1
     for (int cc = 0; cc < FT::NW; cc++) {
+        __syncwarp();
         int bx, by, bf;
         stencil<FT>(cc, bx, by, bf);
         const int q = stencil_cb<FT>(w, bx, by, bf);
@@ -324,7 +344,10 @@ template <class FT> __global__ void __launch_bounds__(FT::BT) k_tile_mask(DevF c
         const bool same = cc == FT::CENTRE, upper = cc > FT::CENTRE;
         const int ncx = w.cx + bx;
         const bool b_owned = ncx >= c.own0 && ncx < c.own1;        // B's warp runs on this rank
-        if (!same && !upper && b_owned) continue;                  // B's warp evaluates the pair and writes my word
+        if (!same && !upper && b_owned) {                          // B's warp evaluates the pair and writes my word
+            if (has_wall && !near_flow) near_flow = __any_sync(0xffffffffu, lane < nb && A[a + lane].w > 0.f);
+            continue;
+        }
         float sx, sy, sz;
         if (FT::d3) { sx = (float)bx * c.gsT; sy = (float)by * c.gsT; sz = (float)bf * c.gsT; }
         else { sx = (float)bx * c.gsT; sy = (float)bf * c.gsT; sz = 0.f; }
@@ -362,6 +385,7 @@ template <class FT> __global__ void __launch_bounds__(FT::BT) k_tile_mask(DevF c
         if (!mine) m = 0;
         const bool bflow = lane < nb && A[a + lane].w > 0.f;
         const unsigned flowB = __ballot_sync(0xffffffffu, bflow);
+        near_flow = near_flow || flowB != 0;
         const unsigned mi = myflow ? m : (m & flowB);              // walls keep their flow neighbours only
         if (mine) c.mask[(size_t)cc * n + i] = mi;
         if (mi) nz |= 1u << cc;
@@ -378,21 +402,47 @@ template <class FT> __global__ void __launch_bounds__(FT::BT) k_tile_mask(DevF c
         }
     }
     if (mine && nz) atomicOr(&c.nzw[i], nz);
+    if (lane == 0) c.cellinfo[w.gcell] = (unsigned char)((flowA ? 1 : 0) | (has_wall ? 2 : 0) | (has_wall && near_flow ? 4 : 0));
+    return true;
+}
+template <class FT> __global__ void __launch_bounds__(FT::BT) k_tile_mask(DevF c, TileGeom g) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileShared<FT, 1> &sh = *reinterpret_cast<TileShared<FT, 1> *>(smem_raw);
+    tile_init<FT, 1>(sh);
+    TILE_PERSISTENT_LOOP(sh, c.worklist[0], c.wcount + 0, c.wcount + 4, (mask_body<FT>(c, g, sh, blk, parity)))
+}
+
+// ------------------------------------------------------------------------------------------------ work lists
+// footprint segments that hold work: mode 0: any own (and owned) cell is occupied; mode 1: any own cell has flow
+// particles; mode 2: any own cell has wall particles next to flow particles (cellinfo, written by the mask kernel)
+template <class FT> __global__ void __launch_bounds__(256) k_tile_worklist(DevF c, TileGeom g, int nblk, int mode) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const int seg = b % g.nseg, t = b / g.nseg, b1 = t % g.nb1, b0 = t / g.nb1;
+    bool any = false;
+    for (int wx = 0; wx < FT::BX; wx++)
+        for (int wy = 0; wy < FT::BY; wy++) {
+            const int cx = b0 * FT::BX + wx, cy = b1 * FT::BY + wy;
+            if (cx >= g.n0 || cy >= g.n1 || cx < c.own0 || cx >= c.own1) continue;
+            const int base = (cx * g.n1 + cy) * g.nF, f0 = seg * ZB, f1 = min(f0 + ZB, g.nF);
+            if (mode == 0) any = any || c.cell_end[base + f1 - 1] > cell_start(c.cell_end, base + f0);
+            else for (int f = f0; f < f1; f++) any = any || (c.cellinfo[base + f] & (mode == 1 ? 1 : 4)) != 0;
+        }
+    if (any) c.worklist[mode][atomicAdd(c.wcount + mode, 1)] = b;
 }
 
 // ------------------------------------------------------------------------------------------------ Shepard factor alone
 // calc_CSPM_f (base:386-398) for every particle of unflagged cells, when sph_calc_kernel_corr is called on its own;
 // inside sph_step the same sums are formed by the wall pass and the first fluid pass.
-template <int KERNEL, class FT> __global__ void __launch_bounds__(FT::BT) k_tile_shepard(DevF c, TileGeom g) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileShared<FT, 1> &sh = *reinterpret_cast<TileShared<FT, 1> *>(smem_raw);
-    WarpCell w = warp_cell<FT>(c, g);
+template <int KERNEL, class FT>
+__device__ __forceinline__ bool shepard_body(const DevF &c, const TileGeom &g, TileShared<FT, 1> &sh, int blk, unsigned parity) {
+    WarpCell w = warp_cell<FT>(c, g, blk);
     const int lane = threadIdx.x & 31;
     if (w.nc > 0 && c.cellflag[w.gcell]) w.nc = 0;
-    if (!__syncthreads_or(w.nc > 0)) return;
-    if (!tile_setup<FT, 1>(c, g, sh, w, c.ps4)) return;
+    if (!__syncthreads_or(w.nc > 0)) return false;
+    if (!tile_setup<FT, 1>(c, g, sh, w, parity, c.ps4)) return true;
     build_ctab<FT, 1>(c, sh, w, lane);
-    if (w.nc == 0) return;
+    if (w.nc == 0) return true;
     const bool mine = lane < w.nc;
     const int i = w.is + (mine ? lane : 0);
     const F4 *A = sh.P[0];
@@ -419,6 +469,13 @@ template <int KERNEL, class FT> __global__ void __launch_bounds__(FT::BT) k_tile
         ssum += fmaxf(p3.w, 0.f) * fastW<KERNEL>(kc, dist2(k.ex - p3.x, k.ey - p3.y, k.ez - p3.z));
     }
     if (mine) c.cspm_f[i] = (ssum != 0.f) ? 1.f / ssum : 1.f;
+    return true;
+}
+template <int KERNEL, class FT> __global__ void __launch_bounds__(FT::BT) k_tile_shepard(DevF c, TileGeom g) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileShared<FT, 1> &sh = *reinterpret_cast<TileShared<FT, 1> *>(smem_raw);
+    tile_init<FT, 1>(sh);
+    TILE_PERSISTENT_LOOP(sh, c.worklist[0], c.wcount + 0, c.wcount + 5, (shepard_body<KERNEL, FT>(c, g, sh, blk, parity)))
 }
 
 // ------------------------------------------------------------------------------------------------ prep (pointwise)
@@ -464,10 +521,9 @@ __device__ __forceinline__ void wall_pair(const KernConst &kc, float ex, float e
     pterm = fmaf(vj.w * gy, dy, pjv);
 }
 
-template <int KERNEL, class FT, bool SHEP> __global__ void __launch_bounds__(FT::BT) k_tile_wall(DevF c, TileGeom g) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileShared<FT, 3> &sh = *reinterpret_cast<TileShared<FT, 3> *>(smem_raw);
-    WarpCell w = warp_cell<FT>(c, g);
+template <int KERNEL, class FT, bool SHEP>
+__device__ __forceinline__ bool wall_body(const DevF &c, const TileGeom &g, TileShared<FT, 3> &sh, int blk, unsigned parity) {
+    WarpCell w = warp_cell<FT>(c, g, blk);
     const int lane = threadIdx.x & 31;
     if (w.nc > 0 && c.cellflag[w.gcell]) w.nc = 0;                  // flagged cells belong to the generic kernels
     const int i = w.is + lane;
@@ -476,22 +532,12 @@ template <int KERNEL, class FT, bool SHEP> __global__ void __launch_bounds__(FT:
     if (lane < w.nc) {
         wall = c.ps4[i].w < 0.f;
         if (wall) nz = c.nzw[i];
-        work = nz != 0;
-        if (wall && !work) {                                        // no flow neighbour: the sums are empty, f = 1
-            const F4 v = c.v4[i];
-            F4 vt; vt.x = 2.f * v.x; vt.y = 2.f * v.y; vt.z = 2.f * v.z; vt.w = c.rho0T;
-            c.vt4[i] = vt;
-            c.rho_t[i] = c.rho0;
-            c.pnew[i] = 0.f;
-            if (SHEP) c.cspm_f[i] = 1.f;
-            F4 pk = vt; pk.w = 0.f;
-            c.pk4[i] = pk;
-        }
+        work = nz != 0;                                             // dry walls: k_tile_wall_dry
     }
-    if (!__syncthreads_or(work)) return;
-    if (!tile_setup<FT, 3>(c, g, sh, w, c.ps4, c.vt4, c.pw4)) return;   // cannot happen for unflagged cells
+    if (!__syncthreads_or(work)) return false;
+    if (!tile_setup<FT, 3>(c, g, sh, w, parity, c.ps4, c.vt4, c.pw4)) return true;   // cannot happen for unflagged cells
     build_ctab<FT, 3>(c, sh, w, lane);
-    if (!__any_sync(0xffffffffu, work)) return;
+    if (!__any_sync(0xffffffffu, work)) return true;
     const F4 *A = sh.P[0], *B = sh.P[1], *Pw = sh.P[2];
     const F4 *ct = sh.ctab + (threadIdx.x >> 5) * FT::NW;
     const int ci = sh.cb[stencil_cb<FT>(w, 0, 0, 0)];               // tile index of this cell's first particle
@@ -533,7 +579,7 @@ template <int KERNEL, class FT, bool SHEP> __global__ void __launch_bounds__(FT:
         Sw += vw2; Sv0 = fmaf(vw2, u2.x, Sv0); Sv1 = fmaf(vw2, u2.y, Sv1); Sv2 = fmaf(vw2, u2.z, Sv2); Sp = fmaf(vw2, pt2, Sp);
         Sw += vw3; Sv0 = fmaf(vw3, u3.x, Sv0); Sv1 = fmaf(vw3, u3.y, Sv1); Sv2 = fmaf(vw3, u3.z, Sv2); Sp = fmaf(vw3, pt3, Sp);
     }
-    if (!work) return;
+    if (!work) return true;
     float fi;
     if (SHEP) { fi = (Sw != 0.f) ? 1.f / Sw : 1.f; c.cspm_f[i] = fi; }
     else fi = c.cspm_f[i];
@@ -547,6 +593,27 @@ template <int KERNEL, class FT, bool SHEP> __global__ void __launch_bounds__(FT:
     c.pnew[i] = pc;
     F4 pk = vt; pk.w = pc / (c.rho0T * c.rho0T);
     c.pk4[i] = pk;
+    return true;
+}
+// dry wall particles (no flow neighbour: empty masks) never reach the work list: their constant result is pointwise
+__global__ void __launch_bounds__(256) k_tile_wall_dry(DevF c, int shep) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    if (!(c.ps4[i].w < 0.f) || c.nzw[i] != 0u || c.cellflag[c.gid[i]]) return;
+    const F4 v = c.v4[i];
+    F4 vt; vt.x = 2.f * v.x; vt.y = 2.f * v.y; vt.z = 2.f * v.z; vt.w = c.rho0T;
+    c.vt4[i] = vt;
+    c.rho_t[i] = c.rho0;
+    c.pnew[i] = 0.f;
+    if (shep) c.cspm_f[i] = 1.f;
+    F4 pk = vt; pk.w = 0.f;
+    c.pk4[i] = pk;
+}
+template <int KERNEL, class FT, bool SHEP> __global__ void __launch_bounds__(FT::BT) k_tile_wall(DevF c, TileGeom g) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileShared<FT, 3> &sh = *reinterpret_cast<TileShared<FT, 3> *>(smem_raw);
+    tile_init<FT, 3>(sh);
+    TILE_PERSISTENT_LOOP(sh, c.worklist[2], c.wcount + 2, c.wcount + 6, (wall_body<KERNEL, FT, SHEP>(c, g, sh, blk, parity)))
 }
 
 // ------------------------------------------------------------------------------------------------ pass B: fluid
@@ -581,19 +648,18 @@ __device__ __forceinline__ void fluid_pair(const KernConst &kc, const FluidI &I,
     a0 = fmaf(cf, dx, a0); a1 = fmaf(cf, dy, a1); a2 = fmaf(cf, dz, a2);
 }
 
-template <int KERNEL, class FT, bool SHEP> __global__ void __launch_bounds__(FT::BT, 2) k_tile_fluid(DevF c, TileGeom g) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileShared<FT, 2> &sh = *reinterpret_cast<TileShared<FT, 2> *>(smem_raw);
-    WarpCell w = warp_cell<FT>(c, g);
+template <int KERNEL, class FT, bool SHEP>
+__device__ __forceinline__ bool fluid_body(const DevF &c, const TileGeom &g, TileShared<FT, 2> &sh, int blk, unsigned parity) {
+    WarpCell w = warp_cell<FT>(c, g, blk);
     const int lane = threadIdx.x & 31;
     if (w.nc > 0 && c.cellflag[w.gcell]) w.nc = 0;
     const int i = w.is + lane;
     const bool work = lane < w.nc && c.ps4[i].w > 0.f;              // flow particle (fluid: the only flow type of WCSPH)
     const unsigned nz = work ? c.nzw[i] : 0u;
-    if (!__syncthreads_or(work)) return;
-    if (!tile_setup<FT, 2>(c, g, sh, w, c.ps4, c.pk4)) return;
+    if (!__syncthreads_or(work)) return false;
+    if (!tile_setup<FT, 2>(c, g, sh, w, parity, c.ps4, c.pk4)) return true;
     build_ctab<FT, 2>(c, sh, w, lane);
-    if (!__any_sync(0xffffffffu, work)) return;
+    if (!__any_sync(0xffffffffu, work)) return true;
     const F4 *A = sh.P[0], *B = sh.P[1];
     const F4 *ct = sh.ctab + (threadIdx.x >> 5) * FT::NW;
     const int ci = sh.cb[stencil_cb<FT>(w, 0, 0, 0)] + (work ? lane : 0);
@@ -623,11 +689,18 @@ template <int KERNEL, class FT, bool SHEP> __global__ void __launch_bounds__(FT:
         fluid_pair<KERNEL, SHEP>(kc, I, k.ex, k.ey, k.ez, p2, q2, dd, a0, a1, a2, ssum);
         fluid_pair<KERNEL, SHEP>(kc, I, k.ex, k.ey, k.ez, p3, q3, dd, a0, a1, a2, ssum);
     }
-    if (!work) return;
+    if (!work) return true;
     c.d_rho[i] = dd * rhoi;
     F4 dv; dv.x = a0 + c.g[0]; dv.y = a1 + c.g[1]; dv.z = a2 + c.g[2]; dv.w = 0.f;
     c.d_vel[i] = dv;
     if (SHEP) c.cspm_f[i] = (ssum != 0.f) ? 1.f / ssum : 1.f;
+    return true;
+}
+template <int KERNEL, class FT, bool SHEP> __global__ void __launch_bounds__(FT::BT, 2) k_tile_fluid(DevF c, TileGeom g) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileShared<FT, 2> &sh = *reinterpret_cast<TileShared<FT, 2> *>(smem_raw);
+    tile_init<FT, 2>(sh);
+    TILE_PERSISTENT_LOOP(sh, c.worklist[1], c.wcount + 1, c.wcount + 7, (fluid_body<KERNEL, FT, SHEP>(c, g, sh, blk, parity)))
 }
 
 // ------------------------------------------------------------------------------------------------ mask-based count
@@ -682,6 +755,31 @@ static int ensure_attrs(SphCtx *c) {
     return r;
 }
 template <class FT> static int nblocks(const TileGeom &g) { return g.nb0 * g.nb1 * g.nseg; }
+// persistent grid: the blocks that are resident at once (occupancy x SMs), never more than there are segments; the
+// work items are handed out dynamically (atomic cursor), so a bigger grid would only add a tail
+template <typename K> static int pgrid(K kern, int threads, size_t smem, int nb) {
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return nb < per_sm * sms ? nb : per_sm * sms;
+}
+// launches a persistent tile kernel over its work list; `cursor` = index of the dynamic cursor in wcount
+#define TILE_LAUNCH(KERN, FT, NP, CURSOR)                                                                         \
+    do {                                                                                                          \
+        const TileGeom g_ = make_geom<FT>(d.gn);                                                                  \
+        cudaMemsetAsync(d.wcount + (CURSOR), 0, 4, c->stream);                                                     \
+        KERN<<<pgrid(KERN, FT::BT, smem_of<FT, NP>(), nblocks<FT>(g_)), FT::BT, smem_of<FT, NP>(), c->stream>>>(d, g_); \
+    } while (0)
+template <class FT> static int build_worklist(SphCtx *c, const DevF &d, int mode) {
+    const TileGeom g = make_geom<FT>(d.gn);
+    const int nb = nblocks<FT>(g);
+    SPH_CHECK(c, cudaMemsetAsync(d.wcount + mode, 0, 4, c->stream));
+    SPH_PROF(c, K_OTHER);
+    k_tile_worklist<FT><<<blocks_for(nb, 256), 256, 0, c->stream>>>(d, g, nb, mode);
+    SPH_LAUNCH_CHECK(c);
+    return 0;
+}
 
 // masks (+ the Shepard factor of every particle when `shepard`: the stand-alone sph_calc_kernel_corr)
 int tile_mask(SphCtx *c, bool shepard) {
@@ -692,30 +790,29 @@ int tile_mask(SphCtx *c, bool shepard) {
     SPH_CHECK(c, cudaMemsetAsync(d.cellflag, 0, (size_t)c->C, c->stream));
     SPH_CHECK(c, cudaMemsetAsync(d.nflag, 0, 4, c->stream));
     SPH_CHECK(c, cudaMemsetAsync(d.nzw, 0, (size_t)c->n * 4, c->stream));
+    SPH_CHECK(c, cudaMemsetAsync(d.cellinfo, 0, (size_t)c->C, c->stream));
+    if ((r = d3 ? build_worklist<F3M>(c, d, 0) : build_worklist<F2M>(c, d, 0))) return r;
     SPH_PROF(c, K_TILE_MASK);
-    if (d3) { const TileGeom g = make_geom<F3M>(d.gn); k_tile_mask<F3M><<<nblocks<F3M>(g), F3M::BT, smem_of<F3M, 1>(), c->stream>>>(d, g); }
-    else { const TileGeom g = make_geom<F2M>(d.gn); k_tile_mask<F2M><<<nblocks<F2M>(g), F2M::BT, smem_of<F2M, 1>(), c->stream>>>(d, g); }
+    if (d3) TILE_LAUNCH(k_tile_mask<F3M>, F3M, 1, 4);
+    else TILE_LAUNCH(k_tile_mask<F2M>, F2M, 1, 4);
     SPH_LAUNCH_CHECK(c);
+    if ((r = d3 ? build_worklist<F3M>(c, d, 1) : build_worklist<F2M>(c, d, 1))) return r;
+    if ((r = d3 ? build_worklist<F3W>(c, d, 2) : build_worklist<F2W>(c, d, 2))) return r;
     c->shep_pending = c->shep_wall_pending = !shepard;
     if (!shepard) return 0;
     SPH_PROF(c, K_CSPM_F);
     if (d3) {
-        const TileGeom g = make_geom<F3M>(d.gn);
-        if (c->p.kernel == 0) k_tile_shepard<0, F3M><<<nblocks<F3M>(g), F3M::BT, smem_of<F3M, 1>(), c->stream>>>(d, g);
-        else k_tile_shepard<1, F3M><<<nblocks<F3M>(g), F3M::BT, smem_of<F3M, 1>(), c->stream>>>(d, g);
+        if (c->p.kernel == 0) TILE_LAUNCH((k_tile_shepard<0, F3M>), F3M, 1, 5); else TILE_LAUNCH((k_tile_shepard<1, F3M>), F3M, 1, 5);
     } else {
-        const TileGeom g = make_geom<F2M>(d.gn);
-        if (c->p.kernel == 0) k_tile_shepard<0, F2M><<<nblocks<F2M>(g), F2M::BT, smem_of<F2M, 1>(), c->stream>>>(d, g);
-        else k_tile_shepard<1, F2M><<<nblocks<F2M>(g), F2M::BT, smem_of<F2M, 1>(), c->stream>>>(d, g);
+        if (c->p.kernel == 0) TILE_LAUNCH((k_tile_shepard<0, F2M>), F2M, 1, 5); else TILE_LAUNCH((k_tile_shepard<1, F2M>), F2M, 1, 5);
     }
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
 
 template <int KERNEL, class FT> static void launch_wall(SphCtx *c, const DevF &d, bool shep) {
-    const TileGeom g = make_geom<FT>(d.gn);
-    if (shep) k_tile_wall<KERNEL, FT, true><<<nblocks<FT>(g), FT::BT, smem_of<FT, 3>(), c->stream>>>(d, g);
-    else k_tile_wall<KERNEL, FT, false><<<nblocks<FT>(g), FT::BT, smem_of<FT, 3>(), c->stream>>>(d, g);
+    if (shep) TILE_LAUNCH((k_tile_wall<KERNEL, FT, true>), FT, 3, 6);
+    else TILE_LAUNCH((k_tile_wall<KERNEL, FT, false>), FT, 3, 6);
 }
 // WCSPH one_step (wc:82-126) on the tile path; flagged cells are completed by the generic kernels (flagged_only).
 int tile_wc_prep_and_wall(SphCtx *c) {
@@ -727,6 +824,9 @@ int tile_wc_prep_and_wall(SphCtx *c) {
     const bool shep = c->shep_wall_pending;
     c->shep_wall_pending = false;
     SPH_PROF(c, K_TILE_WALL);
+    k_tile_wall_dry<<<blocks_for(n, 256), 256, 0, c->stream>>>(d, shep ? 1 : 0);
+    SPH_LAUNCH_CHECK(c);
+    SPH_PROF(c, K_TILE_WALL);
     if (c->p.dim == 3) {
         if (c->p.kernel == 0) launch_wall<0, F3W>(c, d, shep); else launch_wall<1, F3W>(c, d, shep);
     } else {
@@ -736,9 +836,8 @@ int tile_wc_prep_and_wall(SphCtx *c) {
     return 0;
 }
 template <int KERNEL, class FT> static void launch_fluid(SphCtx *c, const DevF &d, bool shep) {
-    const TileGeom g = make_geom<FT>(d.gn);
-    if (shep) k_tile_fluid<KERNEL, FT, true><<<nblocks<FT>(g), FT::BT, smem_of<FT, 2>(), c->stream>>>(d, g);
-    else k_tile_fluid<KERNEL, FT, false><<<nblocks<FT>(g), FT::BT, smem_of<FT, 2>(), c->stream>>>(d, g);
+    if (shep) TILE_LAUNCH((k_tile_fluid<KERNEL, FT, true>), FT, 2, 7);
+    else TILE_LAUNCH((k_tile_fluid<KERNEL, FT, false>), FT, 2, 7);
 }
 int tile_wc_fluid(SphCtx *c) {
     DevF d = make_dev<float>(c);
