@@ -257,16 +257,27 @@ struct Cursor {
     int a;                   // tile index of the current cell's first particle
     float ex, ey, ez;        // own coordinates in the current cell's frame
 };
+// Masks and the non-empty-cell bitmaps are stored BIT-REVERSED (particle / cell b at bit 31 - b): the next element in
+// ascending order is then one FLO (count-leading-zeros) instead of BREV + FLO, which halves the load on the XU pipe.
+__device__ __forceinline__ unsigned rbit(int b) { return 0x80000000u >> b; }
 __device__ __forceinline__ void cursor_init(Cursor &k, const unsigned *mrow, size_t n, unsigned nz) {
     k.m = 0; k.nz = nz; k.mnext = 0; k.flags = 0; k.a = 0; k.ex = k.ey = k.ez = 0.f;
-    if (nz) k.mnext = __ldg(mrow + (size_t)(__ffs(nz) - 1) * n);
+    if (nz) k.mnext = __ldg(mrow + (size_t)__clz(nz) * n);
+}
+// L2 prefetch of every mask line this lane will read (issued once per work item, long before the first use)
+__device__ __forceinline__ void cursor_prefetch(const unsigned *mrow, size_t n, unsigned nz) {
+    while (nz) {
+        const int cc = __clz(nz);
+        nz &= ~rbit(cc);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(mrow + (size_t)cc * n));
+    }
 }
 __device__ __forceinline__ void cursor_jump(Cursor &k, const unsigned *mrow, size_t n, const F4 *ct, const F4 &pi) {
     if (k.m == 0 && k.nz != 0) {
-        const int cc = __ffs(k.nz) - 1;
-        k.nz &= k.nz - 1;
+        const int cc = __clz(k.nz);
+        k.nz &= ~rbit(cc);
         k.m = k.mnext;
-        if (k.nz) k.mnext = __ldg(mrow + (size_t)(__ffs(k.nz) - 1) * n);
+        if (k.nz) k.mnext = __ldg(mrow + (size_t)__clz(k.nz) * n);
         const F4 t = ct[cc];
         const unsigned v = __float_as_uint(t.w);
         k.a = (int)(v & CT_IDX); k.flags = v;
@@ -276,10 +287,10 @@ __device__ __forceinline__ void cursor_jump(Cursor &k, const unsigned *mrow, siz
 // takes up to two bits of the current cell: tile indices (the sentinel when there is no bit)
 template <int SENT> __device__ __forceinline__ void cursor_take2(Cursor &k, int &i0, int &i1) {
     const unsigned m0 = k.m;
-    const int t0 = __ffs(m0) - 1;
-    const unsigned m1 = m0 & (m0 - 1);
-    const int t1 = __ffs(m1) - 1;
-    k.m = m1 & (m1 - 1);
+    const int t0 = __clz(m0);
+    const unsigned m1 = m0 & ~rbit(t0 & 31);
+    const int t1 = __clz(m1);
+    k.m = m1 & ~rbit(t1 & 31);
     i0 = m0 ? k.a + t0 : SENT;
     i1 = m1 ? k.a + t1 : SENT;
 }
@@ -387,8 +398,8 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Tile
         const unsigned flowB = __ballot_sync(0xffffffffu, bflow);
         near_flow = near_flow || flowB != 0;
         const unsigned mi = myflow ? m : (m & flowB);              // walls keep their flow neighbours only
-        if (mine) c.mask[(size_t)cc * n + i] = mi;
-        if (mi) nz |= 1u << cc;
+        if (mine) c.mask[(size_t)cc * n + i] = __brev(mi);
+        if (mi) nz |= rbit(cc);
         if (upper && b_owned) {                                    // the same pairs seen from B: transpose
             const unsigned t = warp_transpose32(m, lane);
             const unsigned tj = bflow ? t : (t & flowA);
@@ -396,8 +407,8 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Tile
                 const int r = q / FT::CBW;
                 const int j = a + lane + sh.gdelta[r];
                 const int ccm = FT::NW - 1 - cc;
-                c.mask[(size_t)ccm * n + j] = tj;
-                if (tj) atomicOr(&c.nzw[j], 1u << ccm);
+                c.mask[(size_t)ccm * n + j] = __brev(tj);
+                if (tj) atomicOr(&c.nzw[j], rbit(ccm));
             }
         }
     }
@@ -535,6 +546,7 @@ __device__ __forceinline__ bool wall_body(const DevF &c, const TileGeom &g, Tile
         work = nz != 0;                                             // dry walls: k_tile_wall_dry
     }
     if (!__syncthreads_or(work)) return false;
+    cursor_prefetch(c.mask + i, (size_t)c.n, nz);
     if (!tile_setup<FT, 3>(c, g, sh, w, parity, c.ps4, c.vt4, c.pw4)) return true;   // cannot happen for unflagged cells
     build_ctab<FT, 3>(c, sh, w, lane);
     if (!__any_sync(0xffffffffu, work)) return true;
@@ -657,6 +669,7 @@ __device__ __forceinline__ bool fluid_body(const DevF &c, const TileGeom &g, Til
     const bool work = lane < w.nc && c.ps4[i].w > 0.f;              // flow particle (fluid: the only flow type of WCSPH)
     const unsigned nz = work ? c.nzw[i] : 0u;
     if (!__syncthreads_or(work)) return false;
+    cursor_prefetch(c.mask + i, (size_t)c.n, nz);
     if (!tile_setup<FT, 2>(c, g, sh, w, parity, c.ps4, c.pk4)) return true;
     build_ctab<FT, 2>(c, sh, w, lane);
     if (!__any_sync(0xffffffffu, work)) return true;
