@@ -273,16 +273,22 @@ __device__ __forceinline__ void cursor_prefetch(const unsigned *mrow, size_t n, 
     }
 }
 __device__ __forceinline__ void cursor_jump(Cursor &k, const unsigned *mrow, size_t n, const F4 *ct, const F4 &pi) {
-    if (k.m == 0 && k.nz != 0) {
+    const bool jump = k.m == 0 && k.nz != 0;
+    if (jump) {
         const int cc = __clz(k.nz);
         k.nz &= ~rbit(cc);
         k.m = k.mnext;
-        if (k.nz) k.mnext = __ldg(mrow + (size_t)__clz(k.nz) * n);
         const F4 t = ct[cc];
         const unsigned v = __float_as_uint(t.w);
         k.a = (int)(v & CT_IDX); k.flags = v;
         k.ex = pi.x - t.x; k.ey = pi.y - t.y; k.ez = pi.z - t.z;
     }
+    // The word of the NEXT non-empty cell is requested here, outside the divergent region and as a predicated load
+    // INTO the loop-carried register: a plain assignment inside the branch makes ptxas load into a temporary and
+    // move it at the reconvergence point, which waits for the load at once and exposes the whole memory latency.
+    const unsigned go = jump ? k.nz : 0u;
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p ld.global.nc.u32 %0, [%1];\n}"
+                 : "+r"(k.mnext) : "l"(mrow + (size_t)(__clz(go) & 31) * n), "r"(go));
 }
 // takes up to two bits of the current cell: tile indices (the sentinel when there is no bit)
 template <int SENT> __device__ __forceinline__ void cursor_take2(Cursor &k, int &i0, int &i1) {
