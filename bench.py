@@ -300,7 +300,8 @@ def run_ours_multi(args, rank, local, world):
     if rank == 0:
         eng.profile(False)
     launches = torch.tensor([eng.L.sph_launch_count(eng.h) - launches0, drv.own_count, drv.bytes_sent - bytes0,
-                             drv.exchanges - ex0], dtype=torch.int64, device=f"cuda:{local}")
+                             drv.exchanges - ex0, int(e0.elapsed_time(e1) * 1000), int(drv.t_compute * 1e6),
+                             int(drv.t_comm * 1e6)], dtype=torch.int64, device=f"cuda:{local}")
     allv = [torch.zeros_like(launches) for _ in range(world)]
     dist.all_gather(allv, launches)
     assert bool(torch.isfinite(ps.pt.v).all()), "non-finite velocities after the timed region"
@@ -321,7 +322,7 @@ def run_ours_multi(args, rank, local, world):
         eng.call("sph_clear_particles")
         eng.call("sph_add_particles", n0, h_x.data_ptr(), h_v.data_ptr(), h_rho.data_ptr(), h_typ.data_ptr())
         eng.field("ID0").copy_(h_id, non_blocking=True)
-        drv.own_first, drv.own_count = 0, n0
+        drv.reset()
         drv.step()
         eng.call("sph_read_state", out_x.data_ptr(), out_v.data_ptr(), out_rho.data_ptr(), out_p.data_ptr(), out_id.data_ptr())
 
@@ -362,6 +363,8 @@ def run_ours_multi(args, rank, local, world):
                            "owned_particles": [int(v[1]) for v in allv],
                            "halo_bytes_sent_per_step": [int(v[2]) // args.steps for v in allv],
                            "exchanges_per_step": int(allv[0][3]) / args.steps,
+                           "rank_ms_per_step": [round(int(v[4]) / 1000 / args.steps, 3) for v in allv],
+                           "rank_host_wait_ms_per_step": [round(int(v[6]) / 1000 / args.steps, 3) for v in allv],
                            "l2": "state larger than L2, no flush needed"},
                 "clocks": clocks.summary(),
                 "e2e": {"value": n_global * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(io[0]),

@@ -178,6 +178,12 @@ int64_t sph_message_bytes(SphCtx *ctx, int32_t nfields, const int32_t *fields, i
 int sph_pack_fields(SphCtx *ctx, int32_t nfields, const int32_t *fields, int64_t first, int64_t count, void *msg_dev);
 int sph_unpack_fields(SphCtx *ctx, int32_t nfields, const int32_t *fields, int64_t first, int64_t count,
                       const void *msg_dev);
+/* Migration without a sort: a STABLE index list (previous order kept) of the particles of [first, first + count)
+ * whose NEW cell column lies in [cx_lo, cx_hi]; two lists can be pending (which = 0 | 1).  sph_select_counts
+ * returns both lengths (synchronises); sph_pack_selected gathers the listed particles into a message. */
+int sph_select_columns(SphCtx *ctx, int32_t which, int64_t first, int64_t count, int32_t cx_lo, int32_t cx_hi);
+int sph_select_counts(SphCtx *ctx, int64_t *n0, int64_t *n1);
+int sph_pack_selected(SphCtx *ctx, int32_t which, int32_t nfields, const int32_t *fields, int64_t count, void *msg_dev);
 /* particle set := [n_left particles of left_msg][keep_count current particles from keep_first][n_right of right_msg]
  * (messages hold the sph_state_fields members).  Arrivals from the lower-x neighbour go in front and those from
  * the higher-x neighbour behind, so that the next stable sort reproduces the single-GPU global order. */

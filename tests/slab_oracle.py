@@ -83,7 +83,29 @@ class OracleSlabEngine:
     def unpack(self, fields, first, count, buf):
         self._unpack_into(self.o, fields, first, count, buf)
 
+    def select_columns(self, which, first, count, cx_lo, cx_hi):
+        x = self.o.x[first:first + count, 0]
+        cx = ((x - self.P.vstart[0]) / self.P.grid_size).astype(np.int64)           # ps:216-218
+        if not hasattr(self, "_sel"):
+            self._sel = {}
+        self._sel[which] = first + np.nonzero((cx >= cx_lo) & (cx <= cx_hi))[0]       # stable: previous order kept
+
+    def select_counts(self):
+        sel = getattr(self, "_sel", {})
+        out = (len(sel.get(0, ())), len(sel.get(1, ())))
+        return out
+
+    def pack_selected(self, which, fields, count, buf):
+        idx = self._sel[which]
+        assert len(idx) == count
+        b, off = buf.numpy(), 0
+        for f in fields:
+            raw = np.ascontiguousarray(self._arr(f)[idx]).view(np.uint8).reshape(-1)
+            b[off:off + raw.size] = raw
+            off += raw.size
+
     def replace(self, keep_first, keep_count, left, n_left, right, n_right):
+        self._sel = {}
         new = self._alloc(n_left + keep_count + n_right)
         for f in STATE:
             getattr(new, f)[n_left:n_left + keep_count] = self._arr(f)[keep_first:keep_first + keep_count]

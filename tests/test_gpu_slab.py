@@ -32,8 +32,10 @@ def _worker(rank, world, port, name, prec, nsteps, extra):
     from tisphi_b200.eng.simulation import Simulation, SimConfiger
     from tisphi_b200.parallel import SlabSimulation
     torch.cuda.set_device(rank)
+    import datetime
+    import traceback
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
-                            device_id=torch.device(f"cuda:{rank}"))
+                            device_id=torch.device(f"cuda:{rank}"), timeout=datetime.timedelta(seconds=90))
     try:
         g = Golden(name)
         scene = copy.deepcopy(g.scene)
@@ -53,8 +55,11 @@ def _worker(rank, world, port, name, prec, nsteps, extra):
                     want = getattr(ref.ps.pt, f).detach().cpu().numpy()
                     assert got.shape == want.shape, (name, prec, s, f, got.shape, want.shape)
                     assert np.array_equal(got, want), f"{name}[{prec}] step {s + 1}: {f} differs from the single-GPU run"
-    finally:
-        dist.destroy_process_group()
+    except BaseException:           # fail fast: a peer blocked in a collective must not wait for the NCCL watchdog
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
+    dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("name,prec,extra", [

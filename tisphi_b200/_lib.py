@@ -24,7 +24,7 @@ SYMBOLS = ["sph_arena_bytes", "sph_create", "sph_destroy", "sph_last_error", "sp
            "sph_init_stress", "sph_step", "sph_neighbor_count", "sph_neighbor_count_masks", "sph_density_sum", "sph_read_bad_cells",
            "sph_launch_count", "sph_num_phases", "sph_one_step_phase", "sph_set_owned_columns",
            "sph_column_starts", "sph_state_fields", "sph_message_bytes", "sph_pack_fields", "sph_unpack_fields",
-           "sph_replace_particles", "sph_profile_enable", "sph_profile_num_kernels",
+           "sph_replace_particles", "sph_select_columns", "sph_select_counts", "sph_pack_selected", "sph_profile_enable", "sph_profile_num_kernels",
            "sph_profile_name", "sph_profile_read", "sph_params_size"]
 
 
@@ -82,6 +82,9 @@ def load():
     L.sph_message_bytes.restype, L.sph_message_bytes.argtypes = i64, [vp, i32, C.POINTER(i32), i64]
     L.sph_pack_fields.restype, L.sph_pack_fields.argtypes = C.c_int, [vp, i32, C.POINTER(i32), i64, i64, vp]
     L.sph_unpack_fields.restype, L.sph_unpack_fields.argtypes = C.c_int, [vp, i32, C.POINTER(i32), i64, i64, vp]
+    L.sph_select_columns.restype, L.sph_select_columns.argtypes = C.c_int, [vp, i32, i64, i64, i32, i32]
+    L.sph_select_counts.restype, L.sph_select_counts.argtypes = C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.sph_pack_selected.restype, L.sph_pack_selected.argtypes = C.c_int, [vp, i32, i32, C.POINTER(i32), i64, vp]
     L.sph_replace_particles.restype, L.sph_replace_particles.argtypes = C.c_int, [vp, i64, i64, vp, i64, vp, i64]
     L.sph_profile_enable.restype, L.sph_profile_enable.argtypes = C.c_int, [vp, C.c_int]
     L.sph_profile_num_kernels.restype, L.sph_profile_num_kernels.argtypes = C.c_int, []

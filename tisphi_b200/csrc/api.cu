@@ -84,7 +84,7 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
     int64_t o_perm = off; off += ib;
     int64_t o_tmp = off; off += ib;
     int64_t o_bad = off; off += 256;
-    const int64_t nt = (C + 2047) / 2048 + 1;
+    const int64_t nt = ((C > n_max ? C : n_max) + 2047) / 2048 + 2;    // scan tiles: cells (grid build) or particles (selection)
     int64_t o_tiles = off; off += align_up(nt * 4);
     const int mask_words = p->dim == 3 ? 27 : 9;
     int64_t o_pw4 = 0;

@@ -160,6 +160,53 @@ __global__ void __launch_bounds__(256) k_reorder(Dev<T> a, Dev<T> b, const int *
     }
 }
 
+// ------------------------------------------------------------------------------------------------ column selection
+// Multi-GPU migration (tisphi_b200/parallel.py): the particles of [first, first + count) whose NEW cell column lies in
+// [cx_lo, cx_hi], as a STABLE index list (previous order kept -- what the receiver's stable counting sort needs).
+template <typename T>
+__global__ void __launch_bounds__(256) k_flag_columns(Dev<T> c, int first, int count, int lo, int hi, int *__restrict__ flags) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const size_t i = (size_t)first + t;
+    const int cx = (int)__ddiv_rn(__dsub_rn(c.x[3 * i], c.vstart[0]), c.gs);
+    flags[t] = (cx >= lo && cx <= hi) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) k_compact(int first, int count, const int *__restrict__ flags, const int *__restrict__ incl,
+                                                 int *__restrict__ idx, int *__restrict__ total) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    if (flags[t]) idx[incl[t] - 1] = first + t;
+    if (t == count - 1) *total = incl[t];
+}
+template <typename T> int select_columns(SphCtx *c, int which, int64_t first, int64_t count, int lo, int hi) {
+    int *total = (int *)(c->arena + c->off_bad + 16) + which;
+    cudaStream_t st = c->stream;
+    if (count == 0) { SPH_CHECK(c, cudaMemsetAsync(total, 0, 4, st)); return 0; }
+    Dev<T> d = make_dev<T>(c);
+    int *flags = (int *)(c->arena + c->off_perm), *incl = (int *)(c->arena + c->off_tmpidx);
+    int *idx = (int *)(c->arena + (which == 0 ? c->off_slot : c->off_gid_unsorted));
+    int *tiles = (int *)(c->arena + c->off_scan_tiles);
+    const int n = (int)count, nt = (n + SCAN_TILE - 1) / SCAN_TILE;
+    SPH_PROF(c, K_HALO);
+    k_flag_columns<T><<<blocks_for(n, 256), 256, 0, st>>>(d, (int)first, n, lo, hi, flags);
+    SPH_LAUNCH_CHECK(c);
+    SPH_PROF(c, K_SCAN);
+    k_scan_reduce<<<nt, SCAN_THREADS, 0, st>>>(flags, n, tiles);
+    SPH_LAUNCH_CHECK(c);
+    SPH_PROF(c, K_SCAN);
+    k_scan_tiles<<<1, 1024, 0, st>>>(tiles, nt);
+    SPH_LAUNCH_CHECK(c);
+    SPH_PROF(c, K_SCAN);
+    k_scan_apply<<<nt, SCAN_THREADS, 0, st>>>(flags, n, tiles, incl);
+    SPH_LAUNCH_CHECK(c);
+    SPH_PROF(c, K_HALO);
+    k_compact<<<blocks_for(n, 256), 256, 0, st>>>((int)first, n, flags, incl, idx, total);
+    SPH_LAUNCH_CHECK(c);
+    return 0;
+}
+template int select_columns<float>(SphCtx *, int, int64_t, int64_t, int, int);
+template int select_columns<double>(SphCtx *, int, int64_t, int64_t, int, int);
+
 template <typename T> int grid_build(SphCtx *c) {
     const int n = (int)c->n;
     if (n == 0) return 0;

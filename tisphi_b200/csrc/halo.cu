@@ -7,18 +7,35 @@
 
 namespace sph {
 
-struct CopyDesc { const uint32_t *src; uint32_t *dst; long long nwords; };
+struct CopyDesc { const uint32_t *src; uint32_t *dst; long long nwords; int wpe; };   // wpe: 4-byte words per particle
 constexpr int MAX_COPY = 16;
 struct CopyBatch { CopyDesc d[MAX_COPY]; int n; long long total; };
 
-// all ranges are 4-byte aligned (members are int32 / float32 / float64 arrays); grid-stride, coalesced both sides
-__global__ void __launch_bounds__(256) k_multi_copy(CopyBatch b) {
+// all ranges are 4-byte aligned (members are int32 / float32 / float64 arrays); grid-stride, coalesced both sides.
+// W = uint4 when every range is 16-byte aligned and a multiple of 16 bytes (nwords then counts 16-byte units).
+template <typename W> __global__ void __launch_bounds__(256) k_multi_copy(CopyBatch b) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < b.total; t += stride) {
         long long r = t;
 #pragma unroll 1
         for (int k = 0; k < b.n; k++) {
-            if (r < b.d[k].nwords) { b.d[k].dst[r] = b.d[k].src[r]; break; }
+            if (r < b.d[k].nwords) { ((W *)b.d[k].dst)[r] = ((const W *)b.d[k].src)[r]; break; }
+            r -= b.d[k].nwords;
+        }
+    }
+}
+// gather: destination section k holds, for t < count, the particle idx[t] of member k (wpe words each)
+__global__ void __launch_bounds__(256) k_multi_gather(CopyBatch b, const int *__restrict__ idx, int count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < b.total; t += stride) {
+        long long r = t;
+#pragma unroll 1
+        for (int k = 0; k < b.n; k++) {
+            if (r < b.d[k].nwords) {
+                const int wpe = b.d[k].wpe, p = (int)(r / wpe), w = (int)(r - (long long)p * wpe);
+                b.d[k].dst[r] = b.d[k].src[(long long)idx[p] * wpe + w];
+                break;
+            }
             r -= b.d[k].nwords;
         }
     }
@@ -37,12 +54,18 @@ static bool field_ref(SphCtx *c, int f, bool alt, char **ptr, int *elem_bytes) {
     return true;
 }
 
-static int launch_copy(SphCtx *c, const CopyBatch &b) {
-    if (b.total == 0) return 0;
+static int launch_copy(SphCtx *c, const CopyBatch &b_in) {
+    if (b_in.total == 0) return 0;
+    CopyBatch b = b_in;
+    bool wide = true;
+    for (int k = 0; k < b.n; k++)
+        wide = wide && (((uintptr_t)b.d[k].src | (uintptr_t)b.d[k].dst) & 15) == 0 && (b.d[k].nwords & 3) == 0;
+    if (wide) { b.total = 0; for (int k = 0; k < b.n; k++) { b.d[k].nwords /= 4; b.total += b.d[k].nwords; } }
     long long blocks = (b.total + 256 * 4 - 1) / (256 * 4);
     if (blocks > 148 * 16) blocks = 148 * 16;
     SPH_PROF(c, K_HALO);
-    k_multi_copy<<<(int)blocks, 256, 0, c->stream>>>(b);
+    if (wide) k_multi_copy<uint4><<<(int)blocks, 256, 0, c->stream>>>(b);
+    else k_multi_copy<uint32_t><<<(int)blocks, 256, 0, c->stream>>>(b);
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
@@ -63,6 +86,7 @@ static int message_copy(SphCtx *c, int nf, const int32_t *fields, int64_t first,
         d.src = (const uint32_t *)(dir == 0 ? a : m);
         d.dst = (uint32_t *)(dir == 0 ? m : a);
         d.nwords = count * eb / 4;
+        d.wpe = eb / 4;
         b.total += d.nwords;
         off += align16(count * eb);
     }
@@ -124,12 +148,52 @@ int sph_replace_particles(SphCtx *c, int64_t keep_first, int64_t keep_count, con
             d.src = (const uint32_t *)(cur + keep_first * eb);
             d.dst = (uint32_t *)(alt + nl * eb);
             d.nwords = keep_count * eb / 4;
+            d.wpe = eb / 4;
             b.total += d.nwords;
         }
         if ((r = launch_copy(c, b))) return r;
     }
     for (int k = 0; k < nf; k++) flip(c, fields[k]);
     c->n = total;
+    return 0;
+}
+
+// ---- migration without a sort: stable selection of the particles whose NEW cell column lies in [cx_lo, cx_hi]
+int sph_select_columns(SphCtx *c, int32_t which, int64_t first, int64_t count, int32_t cx_lo, int32_t cx_hi) {
+    if (which < 0 || which > 1 || first < 0 || count < 0 || first + count > c->n) { snprintf(c->err, sizeof(c->err), "sph_select_columns: bad range"); return -2; }
+    return c->p.precision == SPH_PREC_F64 ? select_columns<double>(c, which, first, count, cx_lo, cx_hi)
+                                          : select_columns<float>(c, which, first, count, cx_lo, cx_hi);
+}
+int sph_select_counts(SphCtx *c, int64_t *n0, int64_t *n1) {
+    int v[2] = {0, 0};
+    SPH_CHECK(c, cudaMemcpyAsync(v, c->arena + c->off_bad + 16, 8, cudaMemcpyDeviceToHost, c->stream));
+    SPH_CHECK(c, cudaStreamSynchronize(c->stream));
+    *n0 = v[0]; *n1 = v[1];
+    return 0;
+}
+int sph_pack_selected(SphCtx *c, int32_t which, int32_t nf, const int32_t *fields, int64_t count, void *msg) {
+    if (count == 0) return 0;
+    if (nf > MAX_COPY || which < 0 || which > 1) { snprintf(c->err, sizeof(c->err), "sph_pack_selected: bad arguments"); return -2; }
+    const int *idx = (const int *)(c->arena + (which == 0 ? c->off_slot : c->off_gid_unsorted));
+    CopyBatch b;
+    b.n = 0; b.total = 0;
+    int64_t off = 0;
+    for (int k = 0; k < nf; k++) {
+        char *p; int eb;
+        if (!field_ref(c, fields[k], false, &p, &eb)) { snprintf(c->err, sizeof(c->err), "member %d cannot travel in a message", fields[k]); return -2; }
+        CopyDesc &d = b.d[b.n++];
+        d.src = (const uint32_t *)p;
+        d.dst = (uint32_t *)((char *)msg + off);
+        d.nwords = count * eb / 4;
+        d.wpe = eb / 4;
+        b.total += d.nwords;
+        off += align16(count * eb);
+    }
+    long long blocks = (b.total + 256 * 4 - 1) / (256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    SPH_PROF(c, K_HALO);
+    k_multi_gather<<<(int)blocks, 256, 0, c->stream>>>(b, idx, (int)count);
+    SPH_LAUNCH_CHECK(c);
     return 0;
 }
 

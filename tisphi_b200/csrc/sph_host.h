@@ -82,6 +82,7 @@ inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) /
 
 // grid.cu
 template <typename T> int grid_build(SphCtx *c);
+template <typename T> int select_columns(SphCtx *c, int which, int64_t first, int64_t count, int lo, int hi);
 // sweeps.cu
 template <typename T> int calc_kernel_corr(SphCtx *c, bool standalone);
 template <typename T> int one_step(SphCtx *c);

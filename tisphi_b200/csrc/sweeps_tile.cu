@@ -246,6 +246,10 @@ template <int KERNEL> __device__ __forceinline__ float fastW(const KernConst &k,
     return q <= 1.f ? k.knorm * (q * q * fmaf(0.5f, q, -1.f) + (float)(2.0 / 3.0)) : k.knorm * (1.f / 6.f) * t * t * t;
 }
 
+// One term of the Shepard sum (calc_CSPM_f): S += max(V_j signed, 0) * W.  Written with explicit roundings so that the
+// stand-alone kernel and the sums fused into the wall / fluid passes give bit-identical CSPM_f (no FMA contraction).
+__device__ __forceinline__ float shep_add(float s, float vsigned, float w) { return __fadd_rn(s, __fmul_rn(fmaxf(vsigned, 0.f), w)); }
+
 // ------------------------------------------------------------------------------------------------ bit iteration
 // Per-lane cursor over the set bits of the neighbour masks in stencil order.  A round takes up to four neighbours:
 // two from the current cell, then (after an optional jump to the next non-empty cell) two more.  Slots that find no
@@ -480,10 +484,10 @@ __device__ __forceinline__ bool shepard_body(const DevF &c, const TileGeom &g, T
         cursor_jump(k, mrow, n, ct, pi);
         cursor_take2<FT::SENT>(k, i2, i3);
         const F4 p0 = A[i0], p1 = A[i1], p2 = A[i2], p3 = A[i3];
-        ssum += fmaxf(p0.w, 0.f) * fastW<KERNEL>(kc, dist2(e0x - p0.x, e0y - p0.y, e0z - p0.z));
-        ssum += fmaxf(p1.w, 0.f) * fastW<KERNEL>(kc, dist2(e0x - p1.x, e0y - p1.y, e0z - p1.z));
-        ssum += fmaxf(p2.w, 0.f) * fastW<KERNEL>(kc, dist2(k.ex - p2.x, k.ey - p2.y, k.ez - p2.z));
-        ssum += fmaxf(p3.w, 0.f) * fastW<KERNEL>(kc, dist2(k.ex - p3.x, k.ey - p3.y, k.ez - p3.z));
+        ssum = shep_add(ssum, p0.w, fastW<KERNEL>(kc, dist2(e0x - p0.x, e0y - p0.y, e0z - p0.z)));
+        ssum = shep_add(ssum, p1.w, fastW<KERNEL>(kc, dist2(e0x - p1.x, e0y - p1.y, e0z - p1.z)));
+        ssum = shep_add(ssum, p2.w, fastW<KERNEL>(kc, dist2(k.ex - p2.x, k.ey - p2.y, k.ez - p2.z)));
+        ssum = shep_add(ssum, p3.w, fastW<KERNEL>(kc, dist2(k.ex - p3.x, k.ey - p3.y, k.ez - p3.z)));
     }
     if (mine) c.cspm_f[i] = (ssum != 0.f) ? 1.f / ssum : 1.f;
     return true;
@@ -534,7 +538,7 @@ template <int KERNEL>
 __device__ __forceinline__ void wall_pair(const KernConst &kc, float ex, float ey, float ez, const F4 pj, const F4 vj, float pjv,
                                           float gy, float &vw, float &pterm) {
     const float dx = ex - pj.x, dy = ey - pj.y, dz = ez - pj.z;
-    vw = pj.w * fastW<KERNEL>(kc, dist2(dx, dy, dz));            // flow neighbour: w = +V; sentinel: 0
+    vw = __fmul_rn(fmaxf(pj.w, 0.f), fastW<KERNEL>(kc, dist2(dx, dy, dz)));   // flow neighbour: w = +V; sentinel: 0
     pterm = fmaf(vj.w * gy, dy, pjv);
 }
 
@@ -592,10 +596,10 @@ __device__ __forceinline__ bool wall_body(const DevF &c, const TileGeom &g, Tile
         wall_pair<KERNEL>(kc, e0x, e0y, e0z, p1, u1, q1, gy, vw1, pt1);
         wall_pair<KERNEL>(kc, k.ex, k.ey, k.ez, p2, u2, q2, gy, vw2, pt2);
         wall_pair<KERNEL>(kc, k.ex, k.ey, k.ez, p3, u3, q3, gy, vw3, pt3);
-        Sw += vw0; Sv0 = fmaf(vw0, u0.x, Sv0); Sv1 = fmaf(vw0, u0.y, Sv1); Sv2 = fmaf(vw0, u0.z, Sv2); Sp = fmaf(vw0, pt0, Sp);
-        Sw += vw1; Sv0 = fmaf(vw1, u1.x, Sv0); Sv1 = fmaf(vw1, u1.y, Sv1); Sv2 = fmaf(vw1, u1.z, Sv2); Sp = fmaf(vw1, pt1, Sp);
-        Sw += vw2; Sv0 = fmaf(vw2, u2.x, Sv0); Sv1 = fmaf(vw2, u2.y, Sv1); Sv2 = fmaf(vw2, u2.z, Sv2); Sp = fmaf(vw2, pt2, Sp);
-        Sw += vw3; Sv0 = fmaf(vw3, u3.x, Sv0); Sv1 = fmaf(vw3, u3.y, Sv1); Sv2 = fmaf(vw3, u3.z, Sv2); Sp = fmaf(vw3, pt3, Sp);
+        Sw = __fadd_rn(Sw, vw0); Sv0 = fmaf(vw0, u0.x, Sv0); Sv1 = fmaf(vw0, u0.y, Sv1); Sv2 = fmaf(vw0, u0.z, Sv2); Sp = fmaf(vw0, pt0, Sp);
+        Sw = __fadd_rn(Sw, vw1); Sv0 = fmaf(vw1, u1.x, Sv0); Sv1 = fmaf(vw1, u1.y, Sv1); Sv2 = fmaf(vw1, u1.z, Sv2); Sp = fmaf(vw1, pt1, Sp);
+        Sw = __fadd_rn(Sw, vw2); Sv0 = fmaf(vw2, u2.x, Sv0); Sv1 = fmaf(vw2, u2.y, Sv1); Sv2 = fmaf(vw2, u2.z, Sv2); Sp = fmaf(vw2, pt2, Sp);
+        Sw = __fadd_rn(Sw, vw3); Sv0 = fmaf(vw3, u3.x, Sv0); Sv1 = fmaf(vw3, u3.y, Sv1); Sv2 = fmaf(vw3, u3.z, Sv2); Sp = fmaf(vw3, pt3, Sp);
     }
     if (!work) return true;
     float fi;
@@ -651,11 +655,11 @@ __device__ __forceinline__ void fluid_pair(const KernConst &kc, const FluidI &I,
     if (KERNEL == 1) {
         const float q1 = fmaxf(fmaf(-0.5f * kc.hinv, r, 1.f), 0.f), q2 = q1 * q1;
         s = (kc.c_grad * q1) * q2;
-        if (SHEP) ssum = fmaf(fmaxf(pj.w, 0.f) * (kc.knorm * q2), q2 * fmaf(2.f * kc.hinv, r, 1.f), ssum);
+        if (SHEP) ssum = shep_add(ssum, pj.w, (kc.knorm * q2) * (q2 * fmaf(2.f * kc.hinv, r, 1.f)));   // == fastW<1>
     } else {
         const float q = r * kc.hinv, t = fmaxf(2.f - q, 0.f);
         s = q <= 1.f ? kc.c_grad * fmaf(1.5f, q, -2.f) : -0.5f * kc.c_grad * t * t * (rinv / kc.hinv);
-        if (SHEP) ssum = fmaf(fmaxf(pj.w, 0.f), fastW<0>(kc, r2), ssum);
+        if (SHEP) ssum = shep_add(ssum, pj.w, fastW<0>(kc, r2));
     }
     const float ux = I.vx - qj.x, uy = I.vy - qj.y, uz = I.vz - qj.z;
     const float vx = fmaf(uz, dz, fmaf(uy, dy, ux * dx));          // v_ij . x_ij

@@ -12,10 +12,10 @@ The reference is single-device; this module is what lets one process
     single-GPU global order -- cell ids, order and every floating-point sum are bit-identical to a 1-GPU run.
 
 Per step and rank (neighbours L = rank - 1, R = rank + 1):
-  1. drop last step's ghosts, sort the particles this rank owned by their NEW cells                 (build #1)
-  2. send L everything in columns <= a (migrants + my first column), send R everything in columns >= b - 1;
-     what arrives holds the neighbour's boundary column (my ghosts) and its migrants into my slab    (1 exchange)
-  3. sort [from L][mine][from R]                                                                     (build #2)
+  1. stable selection (no sort) of the owned particles whose NEW column is <= a, resp. >= b - 1
+  2. send them to L / R (migrants + my boundary column in one message); what arrives holds the neighbour's
+     boundary column (my ghosts) and its migrants into my slab                                       (1 exchange)
+  3. ONE sort of [from L][mine, last step's ghosts dropped][from R]
   4. kernel correction, init_real2tmp, then for every phase of every one_step: run it on the owned columns,
      refresh the ghost columns with the members that phase wrote; integrator kernels run on ghosts too.
 There is no collective in the step: only neighbour send/recv (NCCL over NVLink on GPUs, gloo in the CPU tests).
@@ -62,6 +62,7 @@ class SlabDriver:
     """Runs SPHBase.step (eng/solver_sph_base.py:41-51) on one slab.  ``eng`` is a slab engine (see module doc):
 
     n, ti, xsph, solver; grid_build(), column_starts(list) -> list, state_fields, phase_fields(phase), deriv_fields,
+    select_columns(which, first, count, cx_lo, cx_hi), select_counts() -> (n0, n1), pack_selected(which, fields, count, buf),
     message_bytes(fields, count), new_buffer(nbytes), pack(fields, first, count, buf), unpack(fields, first, count, buf),
     replace(keep_first, keep_count, left_buf, n_left, right_buf, n_right), set_owned_columns(a, b),
     calc_kernel_corr(), init_real2tmp(), num_phases(), one_step_phase(p), advect(kind, m), advect_pos(), post_step(),
@@ -80,13 +81,22 @@ class SlabDriver:
         self.group = group
         self.check = check
         self.own_first, self.own_count = 0, eng.n          # before the first step a rank holds its own particles only
+        self.col_start = None                               # {column: first index} after the last sort
         self.ghost_l = (0, 0)                               # (first, count) of the ghost column a - 1
         self.ghost_r = (0, 0)
         self.send_l = (0, 0)                                # my column a      -> ghost column of L
         self.send_r = (0, 0)                                # my column b - 1  -> ghost column of R
         self.exchanges = 0
         self.bytes_sent = 0
+        self.t_compute = 0.0
+        self.t_comm = 0.0                                   # host seconds spent waiting in send/recv (incl. device drain)
         eng.set_owned_columns(self.a, self.b)
+
+    def reset(self):
+        """The engine's particle set was replaced from outside (fresh upload): it holds owned particles only, unsorted."""
+        self.own_first, self.own_count = 0, self.eng.n
+        self.col_start = None
+        self.ghost_l = self.ghost_r = self.send_l = self.send_r = (0, 0)
 
     # ---- transport ------------------------------------------------------------------------------------
     def _sendrecv(self, send_l, send_r, recv_l, recv_r):
@@ -106,8 +116,11 @@ class SlabDriver:
             if recv_r is not None and recv_r.numel():
                 ops.append(dist.P2POp(dist.irecv, recv_r, self.right, group=self.group))
         if ops:
+            import time
+            t0 = time.perf_counter()
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
+            self.t_comm += time.perf_counter() - t0
             self.exchanges += 1
 
     def _exchange_counts(self, n_to_l, n_to_r):
@@ -121,39 +134,53 @@ class SlabDriver:
 
     # ---- step 1-3: migration + halo -------------------------------------------------------------------
     def redistribute(self):
+        """One exchange that carries both the migrants and the neighbour's boundary column, then ONE sort.
+
+        Nothing is sorted before the exchange: the receiver's stable counting sort only needs arrivals in the sender's
+        previous order, so the sender picks them with a stable selection on the NEW cell column.  Particles move less
+        than a cell per step, so only the two old columns at each face have to be looked at."""
         e = self.eng
         a, b = self.a, self.b
-        if self.own_first != 0 or self.own_count != e.n:
-            e.replace(self.own_first, self.own_count, None, 0, None, 0)          # drop last step's ghosts
-        e.grid_build()
-        n = e.n
-        s_lo, s_a1, s_b1, s_hi = e.column_starts([a - 1, a + 1, b - 1, b + 1])
-        strays = s_lo + (n - s_hi)
-        if strays:
-            raise RuntimeError(f"rank {self.rank}: {strays} particles moved more than one column in a step")
-        n_to_l = s_a1 if self.left is not None else 0
-        n_to_r = n - s_b1 if self.right is not None else 0
+        of, oc = self.own_first, self.own_count
+        if self.col_start is None:                      # first step: no column table yet, look at everything owned
+            reg_l = reg_r = (of, oc)
+        else:
+            cs = self.col_start
+            reg_l = (cs[a], cs[min(a + 2, b)] - cs[a])
+            reg_r = (cs[max(b - 2, a)], cs[b] - cs[max(b - 2, a)])
+        if self.left is not None:
+            e.select_columns(0, reg_l[0], reg_l[1], -(1 << 30), a)         # migrants to L + my first column
+        if self.right is not None:
+            e.select_columns(1, reg_r[0], reg_r[1], b - 1, 1 << 30)        # my last column + migrants to R
+        n_to_l, n_to_r = e.select_counts() if (self.left is not None or self.right is not None) else (0, 0)
+        if self.left is None:
+            n_to_l = 0
+        if self.right is None:
+            n_to_r = 0
         n_from_l, n_from_r = self._exchange_counts(n_to_l, n_to_r)
         fields = e.state_fields
         buf = lambda cnt: e.new_buffer(e.message_bytes(fields, cnt)) if cnt else None
         out_l, out_r, in_l, in_r = buf(n_to_l), buf(n_to_r), buf(n_from_l), buf(n_from_r)
         if n_to_l:
-            e.pack(fields, 0, n_to_l, out_l)
+            e.pack_selected(0, fields, n_to_l, out_l)
         if n_to_r:
-            e.pack(fields, s_b1, n_to_r, out_r)
+            e.pack_selected(1, fields, n_to_r, out_r)
         self._sendrecv(out_l, out_r, in_l, in_r)
-        e.replace(s_lo, s_hi - s_lo, in_l, n_from_l, in_r, n_from_r)
+        e.replace(of, oc, in_l, n_from_l, in_r, n_from_r)                  # [from L][mine, ghosts dropped][from R]
         e.grid_build()
-        c = e.column_starts([a - 1, a, a + 1, b - 1, b, b + 1])
-        if c[0] != 0 or c[5] != e.n:
-            raise RuntimeError(f"rank {self.rank}: particles outside the slab and its ghost columns after migration")
-        self.ghost_l = (c[0], c[1] - c[0]) if self.left is not None else (0, 0)
-        self.ghost_r = (c[4], c[5] - c[4]) if self.right is not None else (0, 0)
-        self.own_first, self.own_count = c[1], c[4] - c[1]
-        self.send_l = (c[1], c[2] - c[1]) if self.left is not None else (0, 0)
-        self.send_r = (c[3], c[4] - c[3]) if self.right is not None else (0, 0)
-        if self.left is None and c[1] != 0 or self.right is None and c[4] != e.n:
+        cols = sorted({a - 1, a, a + 1, min(a + 2, b), max(b - 2, a), b - 1, b, b + 1})
+        c = dict(zip(cols, e.column_starts(cols)))
+        if c[a - 1] != 0 or c[b + 1] != e.n:
+            raise RuntimeError(f"rank {self.rank}: particles moved more than one column in a step "
+                               f"({c[a - 1]} below, {e.n - c[b + 1]} above the slab and its ghost columns)")
+        if self.left is None and c[a] != 0 or self.right is None and c[b] != e.n:
             raise RuntimeError(f"rank {self.rank}: particles beyond the outermost slab")
+        self.col_start = c
+        self.ghost_l = (c[a - 1], c[a] - c[a - 1]) if self.left is not None else (0, 0)
+        self.ghost_r = (c[b], c[b + 1] - c[b]) if self.right is not None else (0, 0)
+        self.own_first, self.own_count = c[a], c[b] - c[a]
+        self.send_l = (c[a], c[a + 1] - c[a]) if self.left is not None else (0, 0)
+        self.send_r = (c[b - 1], c[b] - c[b - 1]) if self.right is not None else (0, 0)
         if self.check:                          # both sides of a face must agree on the column population
             gl, gr = self._exchange_counts(self.send_l[1], self.send_r[1])
             assert (self.left is None or gl == self.ghost_l[1]) and (self.right is None or gr == self.ghost_r[1]), \
@@ -285,6 +312,17 @@ class CudaSlabEngine:
 
     def unpack(self, fields, first, count, buf):
         self.e.call("sph_unpack_fields", len(fields), self._ids(fields), int(first), int(count), buf.data_ptr())
+
+    def select_columns(self, which, first, count, cx_lo, cx_hi):
+        self.e.call("sph_select_columns", int(which), int(first), int(count), int(cx_lo), int(cx_hi))
+
+    def select_counts(self):
+        n0, n1 = C.c_int64(), C.c_int64()
+        self.e.call("sph_select_counts", C.byref(n0), C.byref(n1))
+        return int(n0.value), int(n1.value)
+
+    def pack_selected(self, which, fields, count, buf):
+        self.e.call("sph_pack_selected", int(which), len(fields), self._ids(fields), int(count), buf.data_ptr())
 
     def replace(self, keep_first, keep_count, left, n_left, right, n_right):
         self.e.call("sph_replace_particles", int(keep_first), int(keep_count), left.data_ptr() if left is not None else None,
