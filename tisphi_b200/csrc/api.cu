@@ -88,7 +88,8 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
     int64_t o_tiles = off; off += align_up(nt * 4);
     const int mask_words = p->dim == 3 ? 27 : 9;
     int64_t o_pw4 = 0;
-    int64_t o_ps4 = 0, o_pk4 = 0, o_mask = 0, o_nflow = 0, o_cflag = 0, o_nflag = 0, o_cinfo = 0, o_wl = 0;
+    int64_t o_ps4 = 0, o_pk4 = 0, o_mask = 0, o_nflow = 0, o_cflag = 0, o_nflag = 0, o_cinfo = 0, o_wl = 0, o_soa = 0, o_cflow = 0;
+    const int64_t soa_stride = align_up(n_max * 4 + 64), wl_stride = align_up((C + 1) * 4);
     if (fast) {
         o_ps4 = off; off += align_up(n_max * 16);
         o_pw4 = off; off += align_up(n_max * 16);
@@ -97,12 +98,15 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
         o_cflag = off; off += align_up(C + 1);
         o_nflag = off; off += 256;
         o_cinfo = off; off += align_up(C + 1);
-        o_wl = off; off += 3 * align_up((C + 1) * 4);     // work lists: occupied / flow / wall segments
+        o_wl = off; off += 4 * wl_stride;                 // work lists: occupied / flow / wall / mask segments
+        o_soa = off; off += 4 * soa_stride;               // psx, psy, psz, psf
+        o_cflow = off; off += align_up(C + 1);
     }
     if (c) {
         c->off_pw4 = o_pw4;
         c->off_ps4 = o_ps4; c->off_pk4 = fast ? c->f[SPH_F_PK4].off[0] : o_pk4; c->off_mask = o_mask; c->off_nflow = o_nflow; c->off_cellflag = o_cflag;
         c->off_nflag = o_nflag; c->off_cellinfo = o_cinfo; c->off_worklist = o_wl; c->fast = fast; c->mask_words = mask_words;
+        c->off_psoa = o_soa; c->off_cellflow = o_cflow; c->soa_stride = soa_stride; c->wl_stride = wl_stride;
         c->off_gid_unsorted = o_gid; c->off_slot = o_slot; c->off_perm = o_perm; c->off_tmpidx = o_tmp;
         c->off_bad = o_bad; c->off_scan_tiles = o_tiles;
         c->real_bytes = rb; c->soil = soil; c->rk = rk; c->has_L = hasL; c->C = (int)C;
@@ -240,8 +244,11 @@ template <typename T> Dev<T> make_dev(SphCtx *c, int which) {
         d.cellflag = (unsigned char *)(c->arena + c->off_cellflag);
         d.nflag = (int *)(c->arena + c->off_nflag);
         d.cellinfo = (unsigned char *)(c->arena + c->off_cellinfo);
-        for (int k = 0; k < 3; k++) d.worklist[k] = (int *)(c->arena + c->off_worklist + k * align_up(((int64_t)c->C + 1) * 4));
-        d.wcount = d.nflag + 4;              // three counters after the flag counter
+        for (int k = 0; k < 4; k++) d.worklist[k] = (int *)(c->arena + c->off_worklist + k * c->wl_stride);
+        d.wcount = d.nflag + 4;              // list lengths [0..3], cursors [4..] after the flag counter
+        d.psx = (T *)(c->arena + c->off_psoa); d.psy = (T *)(c->arena + c->off_psoa + c->soa_stride);
+        d.psz = (T *)(c->arena + c->off_psoa + 2 * c->soa_stride); d.psf = (T *)(c->arena + c->off_psoa + 3 * c->soa_stride);
+        d.cellflow = (unsigned char *)(c->arena + c->off_cellflow);
     }
     return d;
 }

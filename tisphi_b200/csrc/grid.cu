@@ -143,7 +143,12 @@ __global__ void __launch_bounds__(256) k_reorder(Dev<T> a, Dev<T> b, const int *
     xs.w = a.xs4[s].w;                              // m_V travels with the particle
     b.xs4[k] = xs;
     const int ty = a.type[s];
-    if (a.ps4) { Vec4<T> ps = xs; ps.w = is_flow(ty) ? xs.w : -xs.w; a.ps4[k] = ps; }
+    if (a.ps4) {                                    // cell-tile payloads: AoS for the passes, SoA for the mask kernel
+        const bool fl = is_flow(ty);
+        Vec4<T> ps = xs; ps.w = fl ? xs.w : -xs.w; a.ps4[k] = ps;
+        a.psx[k] = xs.x; a.psy[k] = xs.y; a.psz[k] = xs.z; a.psf[k] = fl ? (T)1 : (T)-1;
+        if (fl) a.cellflow[g] = 1;
+    }
     b.v4[k] = a.v4[s];
     b.vt4[k] = a.vt4[s];
     b.rho[k] = a.rho[s];
@@ -217,6 +222,7 @@ template <typename T> int grid_build(SphCtx *c) {
     int *id_new = (int *)(c->arena + c->f[SPH_F_ID_NEW].off[0]);
     cudaStream_t st = c->stream;
     SPH_CHECK(c, cudaMemsetAsync(a.cell_cnt, 0, sizeof(int) * (size_t)c->C, st));
+    if (c->fast) SPH_CHECK(c, cudaMemsetAsync(a.cellflow, 0, (size_t)c->C, st));
     SPH_PROF(c, K_CELL_ID);
     k_cell_id<T><<<blocks_for(n, 256), 256, 0, st>>>(a, gid_u, slot);
     SPH_LAUNCH_CHECK(c);

@@ -26,6 +26,7 @@ struct SphCtx {
     int64_t off_gid_unsorted, off_slot, off_perm, off_tmpidx, off_pnew, off_bad, off_scan_tiles, off_x_alt_unused;
     int64_t off_pw4;
     int64_t off_ps4, off_pk4, off_mask, off_nflow, off_cellflag, off_nflag, off_cellinfo, off_worklist;
+    int64_t off_psoa, off_cellflow, soa_stride, wl_stride;
     bool fast;           // cell-tile fast path allocated (MIXED precision, WCSPH, no CSPM_L)
     int mask_words;
     int scan_tiles;

@@ -25,9 +25,22 @@ template <typename T> __device__ __forceinline__ bool skip_unflagged(const Dev<T
     return c.cellflag[c.gid[i]] == 0;
 }
 
-template <typename T> __global__ void __launch_bounds__(128) k_cspm_f(Dev<T> c) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+// Flagged-only launches (the cell-tile kernels did everything else) are a fixed-size grid-stride grid that returns at
+// once when no cell is flagged -- the common case -- instead of n / 128 blocks that each find nothing to do.
+constexpr int FLAGGED_BLOCKS = 148 * 8;
+#define SPH_PARTICLE_KERNEL(NAME, BODY)                                                            \
+    template <typename T> __global__ void __launch_bounds__(128) NAME(Dev<T> c) {                  \
+        if (c.flagged_only) {                                                                      \
+            if (*c.nflag == 0) return;                                                             \
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) BODY(c, i); \
+        } else {                                                                                   \
+            const int i = blockIdx.x * blockDim.x + threadIdx.x;                                   \
+            if (i < c.n) BODY(c, i);                                                               \
+        }                                                                                          \
+    }
+template <typename T> inline int sweep_blocks(const Dev<T> &d) { return d.flagged_only ? FLAGGED_BLOCKS : blocks_for(d.n, 128); }
+
+template <typename T> __device__ __forceinline__ void body_cspm_f(const Dev<T> &c, int i) {
     if (skip_unflagged(c, i)) return;
     T s = 0;
     for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
@@ -35,6 +48,7 @@ template <typename T> __global__ void __launch_bounds__(128) k_cspm_f(Dev<T> c) 
     });
     c.cspm_f[i] = (s != (T)0) ? (T)1 / s : (T)1;
 }
+SPH_PARTICLE_KERNEL(k_cspm_f, body_cspm_f)
 
 template <typename T> __device__ __forceinline__ T det3(const T *m) {
     return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
@@ -90,7 +104,7 @@ template <typename T> int calc_kernel_corr(SphCtx *c, bool standalone) {
         d.flagged_only = 1;
     }
     SPH_PROF(c, K_CSPM_F);
-    k_cspm_f<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(d);
+    k_cspm_f<T><<<sweep_blocks(d), 128, 0, c->stream>>>(d);
     SPH_LAUNCH_CHECK(c);
     if (c->p.kcorr == 1) {
         SPH_PROF(c, K_CSPM_L);
@@ -135,9 +149,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_wc_eos(Dev<T> c) 
 }
 // loop A, wall branch (wc:90-103).  p_j is read "in place" by the reference; serial semantics are reproduced
 // pointwise: fluid j < i already holds EOS(rho~_j) (pnew), fluid j > i still holds the previous pressure (press).
-template <typename T> __global__ void __launch_bounds__(128) k_wc_wall(Dev<T> c) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+template <typename T> __device__ __forceinline__ void body_wc_wall(const Dev<T> &c, int i) {
     if (!is_wall(c.type[i])) return;
     if (skip_unflagged(c, i)) return;
     T Sv0 = 0, Sv1 = 0, Sv2 = 0, Sp = 0;
@@ -163,10 +175,9 @@ template <typename T> __global__ void __launch_bounds__(128) k_wc_wall(Dev<T> c)
     c.pnew[i] = pc;
     if (c.pk4) { Vec4<T> pk = vt; pk.w = pc / (c.rho0T * c.rho0T); c.pk4[i] = pk; }
 }
+SPH_PARTICLE_KERNEL(k_wc_wall, body_wc_wall)
 // loop B (wc:108-126): continuity (corrected gradient) + viscosity + pressure (plain gradient, H22)
-template <typename T> __global__ void __launch_bounds__(128) k_wc_fluid(Dev<T> c) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+template <typename T> __device__ __forceinline__ void body_wc_fluid(const Dev<T> &c, int i) {
     if (!is_fluid(c.type[i])) return;
     if (skip_unflagged(c, i)) return;
     const Vec4<T> vi = c.vt4[i];
@@ -196,6 +207,7 @@ template <typename T> __global__ void __launch_bounds__(128) k_wc_fluid(Dev<T> c
     Vec4<T> dv; dv.x = a0 + c.g[0]; dv.y = a1 + c.g[1]; dv.z = a2 + c.g[2]; dv.w = 0;
     c.d_vel[i] = dv;
 }
+SPH_PARTICLE_KERNEL(k_wc_fluid, body_wc_fluid)
 
 // ------------------------------------------------------------------------------------------ soil: shared pieces
 template <typename T> __device__ __forceinline__ T dev_component(const T *t) {     // type_define.py:26-28
@@ -463,7 +475,7 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
             Dev<T> d = make_dev<T>(c);
             d.flagged_only = 1;
             SPH_PROF(c, K_WC_WALL);
-            k_wc_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+            k_wc_wall<T><<<sweep_blocks(d), 128, 0, st>>>(d);
             SPH_LAUNCH_CHECK(c);
             flip(c, SPH_F_PRESSURE);
         } else {
@@ -472,7 +484,7 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
             Dev<T> d = make_dev<T>(c);
             d.flagged_only = 1;
             SPH_PROF(c, K_WC_FLUID);
-            k_wc_fluid<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+            k_wc_fluid<T><<<sweep_blocks(d), 128, 0, st>>>(d);
             SPH_LAUNCH_CHECK(c);
         }
     } else if (solver == SPH_SOLVER_WC) {
@@ -482,12 +494,12 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
             k_wc_eos<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
             SPH_LAUNCH_CHECK(c);
             SPH_PROF(c, K_WC_WALL);
-            k_wc_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+            k_wc_wall<T><<<sweep_blocks(d), 128, 0, st>>>(d);
             SPH_LAUNCH_CHECK(c);
             flip(c, SPH_F_PRESSURE);               // pnew becomes pt.pressure
         } else {
             SPH_PROF(c, K_WC_FLUID);
-            k_wc_fluid<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+            k_wc_fluid<T><<<sweep_blocks(d), 128, 0, st>>>(d);
             SPH_LAUNCH_CHECK(c);
         }
     } else if (solver == SPH_SOLVER_MUI) {

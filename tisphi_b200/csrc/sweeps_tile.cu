@@ -319,11 +319,111 @@ __device__ __forceinline__ unsigned warp_transpose32(unsigned a, int lane) {
 
 // ------------------------------------------------------------------------------------------------ pass 0: masks
 // One launch per step, right after the grid build.  nzw (bitmap of non-zero words per particle) must be zero on entry.
+//
+// The predicate loop is the hot spot of the step (729 candidates per particle in 3D, halved by symmetry), and it is
+// bound by instruction issue, not by the FP32 pipe.  It therefore runs on PACKED float32 pairs (sub / mul / fma
+// .f32x2 -> FADD2 / FMUL2 / FFMA2): one instruction evaluates one lane's particle against TWO candidates.  Each half
+// of a packed operation is the IEEE round-to-nearest scalar operation, so the predicate keeps the exact expression
+// of sph_dev.cuh::dist2 / for_neighbors.  To get candidate pairs into aligned 64-bit registers the mask kernel
+// stages a structure-of-arrays copy of the sweep coordinates (psx, psy, psz, flow sign psf): one LDS.128 brings the x
+// (or y, z) of four consecutive candidates.  TMA needs 16-byte aligned sources, so a run is copied from the 4-aligned
+// particle index below its start (the `lead` entries in front belong to another cell and are masked by position).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void up2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// two candidates against one particle: bit 0 / bit 1 = dist2(d) < thr, d given per component as packed pairs
+__device__ __forceinline__ unsigned test2(u64 dx, u64 dy, u64 dz, float thr) {
+    float lo, hi;
+    up2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), lo, hi);          // == dist2(dx, dy, dz) in each half
+    return (lo < thr ? 1u : 0u) | (hi < thr ? 2u : 0u);
+}
+
+template <class FT> struct MaskShared {
+    static constexpr int CAPS = FT::CAP + 8;          // the chunked test loop may read up to 7 entries past a cell
+    float X[CAPS], Y[CAPS], Z[CAPS], F[CAPS];
+    unsigned long long bar;
+    int cb[FT::NR * FT::CBW];         // tile index of the first particle of each (run, cell)
+    int gdelta[FT::NR];               // global index = tile index + gdelta[run]
+    int total, overflow, item;
+};
+template <class FT> __device__ __forceinline__ void mask_tile_init(MaskShared<FT> &sh) {
+    if (threadIdx.x == 0) mbar_init(&sh.bar, 1);
+    __syncthreads();
+}
+// Spans, cell boundaries and the TMA copies of the four SoA arrays.  Every run starts at a multiple of four entries
+// in the tile and is copied from the multiple of four particles at or below its first particle.
 template <class FT>
-__device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, TileShared<FT, 1> &sh, int blk, unsigned parity) {
+__device__ __forceinline__ bool mask_tile_setup(const DevF &c, const TileGeom &g, MaskShared<FT> &sh, const WarpCell &w, unsigned parity) {
+    const int tid = threadIdx.x;
+    const int f0 = w.f0, f_lo = max(f0 - 1, 0), f_hi = min(f0 + ZB, g.nF - 1);
+    if (tid < 32) {
+        int len = 0, S = 0, gb = 0, lead = 0, len4 = 0;
+        bool valid = false;
+        if (tid < FT::NR) {
+            const int n0 = w.b0 * FT::BX + tid / FT::NRY - 1;
+            const int n1 = FT::d3 ? w.b1 * FT::BY + tid % FT::NRY - 1 : 0;
+            valid = n0 >= 0 && n0 < g.n0 && n1 >= 0 && n1 < g.n1;
+            if (valid) {
+                gb = (n0 * g.n1 + n1) * g.nF;
+                S = cell_start(c.cell_end, gb + f_lo);
+                len = c.cell_end[gb + f_hi] - S;
+                if (len > 0) { lead = S & 3; len4 = (lead + len + 3) & ~3; }
+            }
+        }
+        int inc = len4;                                           // inclusive scan over the first NR lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= o) inc += t;
+        }
+        const int roff = inc - len4, first = roff + lead;         // tile index of the copy / of the run's first particle
+        if (tid < FT::NR) {
+            sh.gdelta[tid] = S - first;
+            for (int k = 0; k < FT::CBW; k++) {
+                const int f = f0 - 1 + k;
+                int v;
+                if (!valid || f < f_lo) v = first;
+                else if (f > f_hi) v = first + len;
+                else v = first + cell_start(c.cell_end, gb + f) - S;
+                sh.cb[tid * FT::CBW + k] = v;
+            }
+        }
+        const int total = __shfl_sync(0xffffffffu, inc, FT::NR - 1);
+        if (tid == 0) {
+            sh.total = total;
+            sh.overflow = total > FT::CAP;
+        }
+        __syncwarp();
+        if (total > FT::CAP) {                                    // nothing is loaded: complete the phase so that the parity still flips
+            if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sh.bar)) : "memory");
+        } else {
+            if (tid == 0) mbar_expect_tx(&sh.bar, (unsigned)(total * 16));
+            __syncwarp();
+            if (tid < FT::NR && len4 > 0) {
+                const int S4 = S - lead;
+                const unsigned bytes = (unsigned)(len4 * 4);
+                tma_load_1d(&sh.X[roff], c.psx + S4, bytes, &sh.bar);
+                tma_load_1d(&sh.Y[roff], c.psy + S4, bytes, &sh.bar);
+                tma_load_1d(&sh.Z[roff], c.psz + S4, bytes, &sh.bar);
+                tma_load_1d(&sh.F[roff], c.psf + S4, bytes, &sh.bar);
+            }
+        }
+    }
+    __syncthreads();
+    if (sh.overflow) return false;
+    mbar_wait(&sh.bar, parity);
+    return true;
+}
+
+template <class FT>
+__device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, MaskShared<FT> &sh, int blk, unsigned parity) {
     const WarpCell w = warp_cell<FT>(c, g, blk);
     const int lane = threadIdx.x & 31;
-    const bool ok = tile_setup<FT, 1>(c, g, sh, w, parity, c.ps4);
+    const bool ok = mask_tile_setup<FT>(c, g, sh, w, parity);
     if (w.nc == 0) return true;
     // can this cell be represented?  (uniform per warp; branch-free so that the warp stays converged)
     int ox, oy, of;
@@ -341,10 +441,10 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Tile
     }
     const bool mine = lane < w.nc;
     const int i = w.is + lane;
-    const F4 *A = sh.P[0];
-    const int own = sh.cb[stencil_cb<FT>(w, 0, 0, 0)];
-    const F4 pi = A[own + (mine ? lane : 0)];
-    const bool myflow = pi.w > 0.f;
+    const float *X = sh.X, *Y = sh.Y, *Z = sh.Z, *F = sh.F;
+    const int own = sh.cb[stencil_cb<FT>(w, 0, 0, 0)] + (mine ? lane : 0);
+    const float pix = X[own], piy = Y[own], piz = Z[own];
+    const bool myflow = F[own] > 0.f;
     const unsigned flowA = __ballot_sync(0xffffffffu, mine && myflow);
     const bool has_wall = __any_sync(0xffffffffu, mine && !myflow);
     bool near_flow = flowA != 0;
@@ -365,48 +465,52 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Tile
         const bool same = cc == FT::CENTRE, upper = cc > FT::CENTRE;
         const int ncx = w.cx + bx;
         const bool b_owned = ncx >= c.own0 && ncx < c.own1;        // B's warp runs on this rank
-        if (!same && !upper && b_owned) {                          // B's warp evaluates the pair and writes my word
-            if (has_wall && !near_flow) near_flow = __any_sync(0xffffffffu, lane < nb && A[a + lane].w > 0.f);
+        const bool bflow = lane < nb && F[a + lane] > 0.f;
+        const unsigned flowB = __ballot_sync(0xffffffffu, bflow);
+        near_flow = near_flow || flowB != 0;
+        if (!same && !upper && b_owned) continue;                  // B's warp evaluates the pair and writes my word
+        if (flowA == 0 && flowB == 0) {                            // walls keep flow neighbours only: both words are empty
+            if (mine) c.mask[(size_t)cc * n + i] = 0u;
+            if (upper && b_owned && lane < nb)
+                c.mask[(size_t)(FT::NW - 1 - cc) * n + (a + lane + sh.gdelta[q / FT::CBW])] = 0u;
             continue;
         }
         float sx, sy, sz;
         if (FT::d3) { sx = (float)bx * c.gsT; sy = (float)by * c.gsT; sz = (float)bf * c.gsT; }
         else { sx = (float)bx * c.gsT; sy = (float)bf * c.gsT; sz = 0.f; }
-        unsigned m = 0;
+        const int a4 = a & ~3, lead = a - a4, nslot = lead + nb;   // aligned chunk origin; candidate k sits at slot lead + k
+        u64 m64 = 0;
         if (upper || same) {                                       // lower side: d = (x_i - s) - x_j
-            const float ex = pi.x - sx, ey = pi.y - sy, ez = pi.z - sz;
-            for (int t0 = 0; t0 < nb; t0 += 8) {
-                unsigned cm = 0;
-                F4 pj[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) pj[u] = A[a + t0 + u];     // may run past the cell: masked below
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const float dx = ex - pj[u].x, dy = ey - pj[u].y, dz = ez - pj[u].z;
-                    if (dist2(dx, dy, dz) < thr) cm |= 1u << u;
-                }
-                m |= cm << t0;
+            const float ex = pix - sx, ey = piy - sy, ez = piz - sz;
+            const u64 Ex = pk2(ex, ex), Ey = pk2(ey, ey), Ez = pk2(ez, ez);
+            for (int t0 = 0; t0 < nslot; t0 += 8) {
+                const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(X + a4 + t0), x1 = *reinterpret_cast<const ulonglong2 *>(X + a4 + t0 + 4);
+                const ulonglong2 y0 = *reinterpret_cast<const ulonglong2 *>(Y + a4 + t0), y1 = *reinterpret_cast<const ulonglong2 *>(Y + a4 + t0 + 4);
+                const ulonglong2 z0 = *reinterpret_cast<const ulonglong2 *>(Z + a4 + t0), z1 = *reinterpret_cast<const ulonglong2 *>(Z + a4 + t0 + 4);
+                unsigned cm = test2(sub2(Ex, x0.x), sub2(Ey, y0.x), sub2(Ez, z0.x), thr);
+                cm |= test2(sub2(Ex, x0.y), sub2(Ey, y0.y), sub2(Ez, z0.y), thr) << 2;
+                cm |= test2(sub2(Ex, x1.x), sub2(Ey, y1.x), sub2(Ez, z1.x), thr) << 4;
+                cm |= test2(sub2(Ex, x1.y), sub2(Ey, y1.y), sub2(Ez, z1.y), thr) << 6;
+                m64 |= (u64)cm << t0;
             }
         } else {                                                   // B precedes A and is a ghost column: d' = (x_j + s) - x_i
-            for (int t0 = 0; t0 < nb; t0 += 8) {
-                unsigned cm = 0;
-                F4 pj[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) pj[u] = A[a + t0 + u];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const float dx = (pj[u].x + sx) - pi.x, dy = (pj[u].y + sy) - pi.y, dz = (pj[u].z + sz) - pi.z;
-                    if (dist2(dx, dy, dz) < thr) cm |= 1u << u;
-                }
-                m |= cm << t0;
+            const u64 Sx = pk2(sx, sx), Sy = pk2(sy, sy), Sz = pk2(sz, sz);
+            const u64 Px = pk2(pix, pix), Py = pk2(piy, piy), Pz = pk2(piz, piz);
+            for (int t0 = 0; t0 < nslot; t0 += 8) {
+                const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(X + a4 + t0), x1 = *reinterpret_cast<const ulonglong2 *>(X + a4 + t0 + 4);
+                const ulonglong2 y0 = *reinterpret_cast<const ulonglong2 *>(Y + a4 + t0), y1 = *reinterpret_cast<const ulonglong2 *>(Y + a4 + t0 + 4);
+                const ulonglong2 z0 = *reinterpret_cast<const ulonglong2 *>(Z + a4 + t0), z1 = *reinterpret_cast<const ulonglong2 *>(Z + a4 + t0 + 4);
+                unsigned cm = test2(sub2(add2(x0.x, Sx), Px), sub2(add2(y0.x, Sy), Py), sub2(add2(z0.x, Sz), Pz), thr);
+                cm |= test2(sub2(add2(x0.y, Sx), Px), sub2(add2(y0.y, Sy), Py), sub2(add2(z0.y, Sz), Pz), thr) << 2;
+                cm |= test2(sub2(add2(x1.x, Sx), Px), sub2(add2(y1.x, Sy), Py), sub2(add2(z1.x, Sz), Pz), thr) << 4;
+                cm |= test2(sub2(add2(x1.y, Sx), Px), sub2(add2(y1.y, Sy), Py), sub2(add2(z1.y, Sz), Pz), thr) << 6;
+                m64 |= (u64)cm << t0;
             }
         }
+        unsigned m = (unsigned)(m64 >> lead);
         m &= nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
         if (same) m &= ~(1u << lane);                              // i != j
         if (!mine) m = 0;
-        const bool bflow = lane < nb && A[a + lane].w > 0.f;
-        const unsigned flowB = __ballot_sync(0xffffffffu, bflow);
-        near_flow = near_flow || flowB != 0;
         const unsigned mi = myflow ? m : (m & flowB);              // walls keep their flow neighbours only
         if (mine) c.mask[(size_t)cc * n + i] = __brev(mi);
         if (mi) nz |= rbit(cc);
@@ -426,16 +530,18 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Tile
     if (lane == 0) c.cellinfo[w.gcell] = (unsigned char)((flowA ? 1 : 0) | (has_wall ? 2 : 0) | (has_wall && near_flow ? 4 : 0));
     return true;
 }
-template <class FT> __global__ void __launch_bounds__(FT::BT) k_tile_mask(DevF c, TileGeom g) {
+template <class FT> __global__ void __launch_bounds__(FT::BT, 2) k_tile_mask(DevF c, TileGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileShared<FT, 1> &sh = *reinterpret_cast<TileShared<FT, 1> *>(smem_raw);
-    tile_init<FT, 1>(sh);
-    TILE_PERSISTENT_LOOP(sh, c.worklist[0], c.wcount + 0, c.wcount + 4, (mask_body<FT>(c, g, sh, blk, parity)))
+    MaskShared<FT> &sh = *reinterpret_cast<MaskShared<FT> *>(smem_raw);
+    mask_tile_init<FT>(sh);
+    TILE_PERSISTENT_LOOP(sh, c.worklist[3], c.wcount + 3, c.wcount + 4, (mask_body<FT>(c, g, sh, blk, parity)))
 }
 
 // ------------------------------------------------------------------------------------------------ work lists
 // footprint segments that hold work: mode 0: any own (and owned) cell is occupied; mode 1: any own cell has flow
-// particles; mode 2: any own cell has wall particles next to flow particles (cellinfo, written by the mask kernel)
+// particles; mode 2: any own cell has wall particles next to flow particles (cellinfo, written by the mask kernel);
+// mode 3 (the mask kernel's list): occupied AND a flow particle somewhere in the footprint or its one-cell halo --
+// without one every mask word of the footprint is empty (walls keep flow neighbours only) and nzw stays zero.
 template <class FT> __global__ void __launch_bounds__(256) k_tile_worklist(DevF c, TileGeom g, int nblk, int mode) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblk) return;
@@ -446,9 +552,19 @@ template <class FT> __global__ void __launch_bounds__(256) k_tile_worklist(DevF 
             const int cx = b0 * FT::BX + wx, cy = b1 * FT::BY + wy;
             if (cx >= g.n0 || cy >= g.n1 || cx < c.own0 || cx >= c.own1) continue;
             const int base = (cx * g.n1 + cy) * g.nF, f0 = seg * ZB, f1 = min(f0 + ZB, g.nF);
-            if (mode == 0) any = any || c.cell_end[base + f1 - 1] > cell_start(c.cell_end, base + f0);
+            if (mode == 0 || mode == 3) any = any || c.cell_end[base + f1 - 1] > cell_start(c.cell_end, base + f0);
             else for (int f = f0; f < f1; f++) any = any || (c.cellinfo[base + f] & (mode == 1 ? 1 : 4)) != 0;
         }
+    if (any && mode == 3) {
+        bool flow = false;
+        const int f0 = max(seg * ZB - 1, 0), f1 = min(seg * ZB + ZB + 1, g.nF);
+        for (int cx = max(b0 * FT::BX - 1, 0); cx < min(b0 * FT::BX + FT::BX + 1, g.n0) && !flow; cx++)
+            for (int cy = max(b1 * FT::BY - 1, 0); cy < min(b1 * FT::BY + FT::BY + 1, g.n1) && !flow; cy++) {
+                const int base = (cx * g.n1 + cy) * g.nF;
+                for (int f = f0; f < f1; f++) flow = flow || c.cellflow[base + f] != 0;
+            }
+        any = flow;
+    }
     if (any) c.worklist[mode][atomicAdd(c.wcount + mode, 1)] = b;
 }
 
@@ -772,8 +888,8 @@ static int ensure_attrs(SphCtx *c) {
     if (dev < 0 || dev >= 64 || done[dev]) return 0;
     int r = set_attrs<0>(c);
     if (!r) r = set_attrs<1>(c);
-    if (!r) r = set_smem(c, k_tile_mask<F3M>, smem_of<F3M, 1>());
-    if (!r) r = set_smem(c, k_tile_mask<F2M>, smem_of<F2M, 1>());
+    if (!r) r = set_smem(c, k_tile_mask<F3M>, sizeof(MaskShared<F3M>));
+    if (!r) r = set_smem(c, k_tile_mask<F2M>, sizeof(MaskShared<F2M>));
     done[dev] = r == 0;
     return r;
 }
@@ -788,12 +904,13 @@ template <typename K> static int pgrid(K kern, int threads, size_t smem, int nb)
     return nb < per_sm * sms ? nb : per_sm * sms;
 }
 // launches a persistent tile kernel over its work list; `cursor` = index of the dynamic cursor in wcount
-#define TILE_LAUNCH(KERN, FT, NP, CURSOR)                                                                         \
+#define TILE_LAUNCH_SMEM(KERN, FT, SMEM, CURSOR)                                                                  \
     do {                                                                                                          \
         const TileGeom g_ = make_geom<FT>(d.gn);                                                                  \
         cudaMemsetAsync(d.wcount + (CURSOR), 0, 4, c->stream);                                                     \
-        KERN<<<pgrid(KERN, FT::BT, smem_of<FT, NP>(), nblocks<FT>(g_)), FT::BT, smem_of<FT, NP>(), c->stream>>>(d, g_); \
+        KERN<<<pgrid(KERN, FT::BT, (SMEM), nblocks<FT>(g_)), FT::BT, (SMEM), c->stream>>>(d, g_);                  \
     } while (0)
+#define TILE_LAUNCH(KERN, FT, NP, CURSOR) TILE_LAUNCH_SMEM(KERN, FT, (smem_of<FT, NP>()), CURSOR)
 template <class FT> static int build_worklist(SphCtx *c, const DevF &d, int mode) {
     const TileGeom g = make_geom<FT>(d.gn);
     const int nb = nblocks<FT>(g);
@@ -814,15 +931,16 @@ int tile_mask(SphCtx *c, bool shepard) {
     SPH_CHECK(c, cudaMemsetAsync(d.nflag, 0, 4, c->stream));
     SPH_CHECK(c, cudaMemsetAsync(d.nzw, 0, (size_t)c->n * 4, c->stream));
     SPH_CHECK(c, cudaMemsetAsync(d.cellinfo, 0, (size_t)c->C, c->stream));
-    if ((r = d3 ? build_worklist<F3M>(c, d, 0) : build_worklist<F2M>(c, d, 0))) return r;
+    if ((r = d3 ? build_worklist<F3M>(c, d, 3) : build_worklist<F2M>(c, d, 3))) return r;
     SPH_PROF(c, K_TILE_MASK);
-    if (d3) TILE_LAUNCH(k_tile_mask<F3M>, F3M, 1, 4);
-    else TILE_LAUNCH(k_tile_mask<F2M>, F2M, 1, 4);
+    if (d3) TILE_LAUNCH_SMEM(k_tile_mask<F3M>, F3M, sizeof(MaskShared<F3M>), 4);
+    else TILE_LAUNCH_SMEM(k_tile_mask<F2M>, F2M, sizeof(MaskShared<F2M>), 4);
     SPH_LAUNCH_CHECK(c);
     if ((r = d3 ? build_worklist<F3M>(c, d, 1) : build_worklist<F2M>(c, d, 1))) return r;
     if ((r = d3 ? build_worklist<F3W>(c, d, 2) : build_worklist<F2W>(c, d, 2))) return r;
     c->shep_pending = c->shep_wall_pending = !shepard;
     if (!shepard) return 0;
+    if ((r = d3 ? build_worklist<F3M>(c, d, 0) : build_worklist<F2M>(c, d, 0))) return r;
     SPH_PROF(c, K_CSPM_F);
     if (d3) {
         if (c->p.kernel == 0) TILE_LAUNCH((k_tile_shepard<0, F3M>), F3M, 1, 5); else TILE_LAUNCH((k_tile_shepard<1, F3M>), F3M, 1, 5);
