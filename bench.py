@@ -144,6 +144,14 @@ def algorithmic_bytes(kernel, n, n_fluid, n_wall, cells):
 
 
 # ---------------------------------------------------------------------------------------------- our arm
+def scene_options(args):
+    """Engine options (not part of the reference's scene schema) the bench can toggle for A/B runs."""
+    opt = {}
+    if args.lists is not None:
+        opt["neighbourLists"] = bool(args.lists)
+    return opt
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -156,7 +164,7 @@ def run_ours(args):
     from tisphi_b200 import scenes
     from tisphi_b200.eng.simulation import Simulation, SimConfiger
 
-    scene = scenes.dambreak3d(scale=args.scale, precision=args.precision)
+    scene = scenes.dambreak3d(scale=args.scale, precision=args.precision, **scene_options(args))
     t0 = time.time()
     sim = Simulation(SimConfiger(config=scene), device=f"cuda:{local}")
     ps, solver, eng = sim.ps, sim.solver, sim.ps.engine
@@ -263,7 +271,7 @@ def run_ours_multi(args, rank, local, world):
     from tisphi_b200.eng.simulation import SimConfiger
     from tisphi_b200.parallel import SlabSimulation
 
-    scene = scenes.dambreak3d(scale=args.scale, precision=args.precision)
+    scene = scenes.dambreak3d(scale=args.scale, precision=args.precision, **scene_options(args))
     t0 = time.time()
     sim = SlabSimulation(SimConfiger(config=scene), f"cuda:{local}", rank, world)
     eng, drv, ps = sim.ps.engine, sim.driver, sim.ps
@@ -386,6 +394,7 @@ def main():
     ap.add_argument("--cpu-scale", type=float, default=0.25, help="coarsening of the CPU-baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--lists", type=int, default=None, help="1 / 0: neighbour round lists on / off (default: engine default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -42,7 +42,8 @@ typedef struct SphParams {
     int32_t wc_fresh;       /* 0: wall pressure reads p_j as the serial reference does (EOS value for j < i, previous
                                value for j > i, wc:86-103); 1: race-free variant (EOS value for every j)            */
     int32_t gn[3];          /* grid_num                                           ps:57 */
-    int32_t fast;           /* 1: allow the cell-tile fast sweeps where they apply; 0: generic sweeps only        */
+    int32_t fast;           /* 0: generic sweeps only; 1: cell-tile fast sweeps where they apply; 2: additionally record
+                               the neighbours found by the first fluid pass of a step and replay them in the later ones */
     double h, support, grid_size, vstart[3], m_V0, g[3], dt, eps;
     double rho0, visc, stiff, gamma_;                                   /* wc:12-15 */
     double coh, fric, E, poi, dila, vsound, mu, alpha, kc, G, K, eps_f; /* muI:12-24, dp:12-29 */

@@ -277,7 +277,7 @@ def test_tile_path_equals_generic_path(name):
     g = Golden(name)
     a = make_sim(g.scene, precision="f32", fastSweeps=True)
     b = make_sim(g.scene, precision="f32", fastSweeps=False)
-    assert a.ps.engine.params.fast == 1 and b.ps.engine.params.fast == 0
+    assert a.ps.engine.params.fast == 2 and b.ps.engine.params.fast == 0
     a.ps.initialize_particle_system()
     b.ps.initialize_particle_system()
     a.solver.calc_kernel_corr()
@@ -294,6 +294,27 @@ def test_tile_path_equals_generic_path(name):
     ok = _well_conditioned(fa["CSPM_f"], fb["CSPM_f"])
     for k in ("x", "v", "density", "pressure", "d_vel", "d_density", "v_tmp", "CSPM_f"):
         assert relmax(fa[k][ok], fb[k][ok]) < 1e-5, k
+
+
+@pytest.mark.parametrize("name", ["wc2d_small_lf", "wc3d_tiny_lf", "c1_test1_wc_lf", "wc2d_small_rk4"])
+def test_neighbour_round_lists_replay_bit_exact(name):
+    """fast = 2 records the neighbours the first fluid pass of a step finds and replays them in the later one_steps
+    (LF: 1, RK4: 3): same pairs, same order, same arithmetic => bit-identical to walking the masks again (fast = 1)."""
+    import copy
+    if name == "wc2d_small_rk4":
+        scene = copy.deepcopy(Golden("wc2d_small_lf").scene)
+        scene["Configuration"]["timeIntegration"] = 4
+    else:
+        scene = Golden(name).scene
+    a = make_sim(scene, precision="f32", neighbourLists=True)
+    b = make_sim(scene, precision="f32", neighbourLists=False)
+    assert a.ps.engine.params.fast == 2 and b.ps.engine.params.fast == 1
+    for s in range(6):
+        a.solver.step()
+        b.solver.step()
+    fa, fb = engine_fields(a), engine_fields(b)
+    for k in ("id0", "x", "v", "density", "pressure", "d_vel", "d_density", "v_tmp", "CSPM_f"):
+        assert np.array_equal(fa[k], fb[k]), k
 
 
 @pytest.mark.parametrize("name", ["wc2d_small_lf", "wc3d_tiny_lf", "c1_test1_wc_lf"])

@@ -90,6 +90,8 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
     int64_t o_pw4 = 0;
     int64_t o_ps4 = 0, o_pk4 = 0, o_mask = 0, o_nflow = 0, o_cflag = 0, o_nflag = 0, o_cinfo = 0, o_wl = 0, o_soa = 0, o_cflow = 0;
     const int64_t soa_stride = align_up(n_max * 4 + 64), wl_stride = align_up((C + 1) * 4);
+    const bool lists = fast && p->fast >= 2 && p->ti != 1;     // SE has a single fluid pass per step: nothing to replay
+    int64_t o_nlist = 0, o_lrounds = 0;
     if (fast) {
         o_ps4 = off; off += align_up(n_max * 16);
         o_pw4 = off; off += align_up(n_max * 16);
@@ -101,12 +103,17 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
         o_wl = off; off += 4 * wl_stride;                 // work lists: occupied / flow / wall / mask segments
         o_soa = off; off += 4 * soa_stride;               // psx, psy, psz, psf
         o_cflow = off; off += align_up(C + 1);
+        if (lists) {
+            o_nlist = off; off += align_up(n_max * 8 * (int64_t)LIST_ROUNDS);
+            o_lrounds = off; off += align_up((C + 1) * 4);
+        }
     }
     if (c) {
         c->off_pw4 = o_pw4;
         c->off_ps4 = o_ps4; c->off_pk4 = fast ? c->f[SPH_F_PK4].off[0] : o_pk4; c->off_mask = o_mask; c->off_nflow = o_nflow; c->off_cellflag = o_cflag;
         c->off_nflag = o_nflag; c->off_cellinfo = o_cinfo; c->off_worklist = o_wl; c->fast = fast; c->mask_words = mask_words;
         c->off_psoa = o_soa; c->off_cellflow = o_cflow; c->soa_stride = soa_stride; c->wl_stride = wl_stride;
+        c->off_nlist = o_nlist; c->off_lrounds = o_lrounds; c->use_list = lists; c->list_valid = false;
         c->off_gid_unsorted = o_gid; c->off_slot = o_slot; c->off_perm = o_perm; c->off_tmpidx = o_tmp;
         c->off_bad = o_bad; c->off_scan_tiles = o_tiles;
         c->real_bytes = rb; c->soil = soil; c->rk = rk; c->has_L = hasL; c->C = (int)C;
@@ -249,6 +256,7 @@ template <typename T> Dev<T> make_dev(SphCtx *c, int which) {
         d.psx = (T *)(c->arena + c->off_psoa); d.psy = (T *)(c->arena + c->off_psoa + c->soa_stride);
         d.psz = (T *)(c->arena + c->off_psoa + 2 * c->soa_stride); d.psf = (T *)(c->arena + c->off_psoa + 3 * c->soa_stride);
         d.cellflow = (unsigned char *)(c->arena + c->off_cellflow);
+        if (c->use_list) { d.nlist = (uint2 *)(c->arena + c->off_nlist); d.lrounds = (int *)(c->arena + c->off_lrounds); }
     }
     return d;
 }

@@ -86,6 +86,12 @@ template <typename T> struct Dev {
     int *wcount;              // their lengths (4 ints), then the dynamic cursors of the persistent kernels
     T *psx, *psy, *psz, *psf; // SoA copy of the sweep coordinates + flow sign (+1 flow / -1 other): mask-kernel tiles
     unsigned char *cellflow;  // per cell: 1 when it holds a flow particle (written by the reorder kernel)
+    // neighbour round lists (fast >= 2): what the first fluid pass after the masks found, replayed by the later passes
+    // of the step.  For the cell whose first particle is `is` and
+    // which holds nc particles: nlist[is * LIST_ROUNDS + round * nc + k] (one contiguous block per cell) = two words {cc:5 | tile index:12 | tile index:12} = the four neighbour slots
+    // of that round; lrounds[cell] = rounds stored for the cell's warp, -1 when it needed more than LIST_ROUNDS.
+    uint2 *nlist;
+    int *lrounds;
     int flagged_only;         // generic kernels: process only particles of flagged cells
 };
 

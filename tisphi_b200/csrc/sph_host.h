@@ -26,7 +26,8 @@ struct SphCtx {
     int64_t off_gid_unsorted, off_slot, off_perm, off_tmpidx, off_pnew, off_bad, off_scan_tiles, off_x_alt_unused;
     int64_t off_pw4;
     int64_t off_ps4, off_pk4, off_mask, off_nflow, off_cellflag, off_nflag, off_cellinfo, off_worklist;
-    int64_t off_psoa, off_cellflow, soa_stride, wl_stride;
+    int64_t off_psoa, off_cellflow, soa_stride, wl_stride, off_nlist, off_lrounds;
+    bool use_list, list_valid;   // neighbour round lists allocated / filled by a fluid pass since the last mask build
     bool fast;           // cell-tile fast path allocated (MIXED precision, WCSPH, no CSPM_L)
     int mask_words;
     int scan_tiles;
@@ -76,6 +77,8 @@ void sph_prof_end(SphCtx *c);
     } while (0)
 
 namespace sph {
+
+constexpr int LIST_ROUNDS = 56;     // rounds (of four neighbour slots) a particle's list can hold
 
 template <typename T> Dev<T> make_dev(SphCtx *c, int which = -1);   // which = -1: current buffers, 1: alternates
 

@@ -49,7 +49,7 @@ template <class FT, int NP> struct TileShared {
     int total, overflow, item;
     F4 ctab[FT::NWARP * FT::NW];      // per (warp, stencil cell): shift xyz, tile index of the cell's first particle | flags
 };
-constexpr unsigned CT_BEFORE = 1u << 30, CT_SAME = 1u << 29, CT_IDX = (1u << 24) - 1;
+constexpr unsigned CT_BEFORE = 1u << 30, CT_SAME = 1u << 29, CT_IDX = (1u << 24) - 1, CT_CC = 0x1fu << 24;   // CT_CC: the stencil cell
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -216,7 +216,7 @@ __device__ __forceinline__ void build_ctab(const DevF &c, TileShared<FT, NP> &sh
         F4 t;
         if (FT::d3) { t.x = (float)ox * c.gsT; t.y = (float)oy * c.gsT; t.z = (float)of * c.gsT; }
         else { t.x = (float)ox * c.gsT; t.y = (float)of * c.gsT; t.z = 0.f; }
-        unsigned v = (unsigned)sh.cb[stencil_cb<FT>(w, ox, oy, of)];
+        unsigned v = (unsigned)sh.cb[stencil_cb<FT>(w, ox, oy, of)] | ((unsigned)lane << 24);
         if (lane < FT::CENTRE) v |= CT_BEFORE;                 // stencil order == ascending cell id
         if (lane == FT::CENTRE) v |= CT_SAME;
         t.w = __uint_as_float(v);
@@ -733,6 +733,152 @@ __device__ __forceinline__ bool wall_body(const DevF &c, const TileGeom &g, Tile
     c.pk4[i] = pk;
     return true;
 }
+// ------------------------------------------------------------------------------------------------ pass A: walls, gathered
+// The same wall pass without a tile: one warp per wall cell that has flow particles in reach (a compacted CELL list),
+// lane = particle, the mask bits walked in the same order with the same arithmetic, but the neighbour payloads are
+// gathered from global memory through L1 (the lanes of a warp share most of their neighbours).  Only ~5 % of the
+// particles take part in this pass and each has few (flow-only) neighbours, so staging 54 cells x 3 payloads per four
+// cells left the SMs idle behind TMA latency and block barriers (ncu: 12 % issue slots used, 9.6 warp-cycles of
+// barrier stall per issue).  Warps are independent here: no block barrier, 32 warps per SM.
+template <bool D3> __global__ void __launch_bounds__(256) k_wall_cells(DevF c) {
+    const int gcell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gcell >= c.C) return;
+    if (!(c.cellinfo[gcell] & 4) || c.cellflag[gcell]) return;
+    const int nF = D3 ? c.gn[2] : c.gn[1], n1 = D3 ? c.gn[1] : 1;
+    const int cx = gcell / (nF * n1);
+    if (cx < c.own0 || cx >= c.own1) return;                        // ghost columns of a slab idle
+    c.worklist[2][atomicAdd(c.wcount + 2, 1)] = gcell;
+}
+constexpr int WG_WARPS = 8;
+template <int KERNEL, bool D3, bool SHEP> __global__ void __launch_bounds__(WG_WARPS * 32) k_wall_gather(DevF c) {
+    constexpr int NW = D3 ? 27 : 9, CENTRE = NW / 2;
+    __shared__ F4 s_ct[WG_WARPS][NW];        // per warp and stencil cell: shift xyz, CT_BEFORE / CT_SAME
+    __shared__ int s_start[WG_WARPS][NW];    // global index of the stencil cell's first particle
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int items = c.wcount[2];
+    const int nF = D3 ? c.gn[2] : c.gn[1], n1 = D3 ? c.gn[1] : 1, n0 = c.gn[0];
+    const KernConst kc = kern_const(c);
+    const float gy = c.g[1];
+    const bool fresh = c.wc_fresh != 0;
+    const size_t n = (size_t)c.n;
+    const F4 *ct = s_ct[wi];
+    const int *cs = s_start[wi];
+    for (int it = blockIdx.x * WG_WARPS + wi; it < items; it += gridDim.x * WG_WARPS) {
+        const int gcell = c.worklist[2][it];
+        const int f = gcell % nF, t = gcell / nF, cy = t % n1, cx = t / n1;
+        const int is = cell_start(c.cell_end, gcell), nc = c.cell_end[gcell] - is;
+        __syncwarp();
+        if (lane < NW) {
+            int ox, oy, of;
+            if (D3) { ox = lane / 9 - 1; oy = (lane / 3) % 3 - 1; of = lane % 3 - 1; }
+            else { ox = lane / 3 - 1; oy = 0; of = lane % 3 - 1; }
+            const int nx = cx + ox, ny = cy + oy, nf = f + of;
+            int st = 0;
+            if (nx >= 0 && nx < n0 && ny >= 0 && ny < n1 && nf >= 0 && nf < nF) st = cell_start(c.cell_end, (nx * n1 + ny) * nF + nf);
+            F4 tt;
+            if (D3) { tt.x = (float)ox * c.gsT; tt.y = (float)oy * c.gsT; tt.z = (float)of * c.gsT; }
+            else { tt.x = (float)ox * c.gsT; tt.y = (float)of * c.gsT; tt.z = 0.f; }
+            unsigned v = 0;
+            if (lane < CENTRE) v |= CT_BEFORE;                     // stencil order == ascending cell id
+            if (lane == CENTRE) v |= CT_SAME;
+            tt.w = __uint_as_float(v);
+            s_ct[wi][lane] = tt;
+            s_start[wi][lane] = st;
+        }
+        __syncwarp();
+        const int i = is + lane;
+        bool work = false;
+        unsigned nz = 0;
+        F4 pi; pi.x = pi.y = pi.z = pi.w = 0.f;
+        if (lane < nc) {
+            pi = c.ps4[i];
+            if (pi.w < 0.f) { nz = c.nzw[i]; work = nz != 0; }      // dry walls: k_tile_wall_dry
+        }
+        if (!work) nz = 0;
+        if (!__any_sync(0xffffffffu, work)) continue;
+        const int safe = work ? i : is;                             // what an empty slot loads (its volume is zeroed)
+        const unsigned *mrow = c.mask + safe;
+        float Sv0 = 0.f, Sv1 = 0.f, Sv2 = 0.f, Sp = 0.f, Sw = 0.f;
+        // cursor state (see struct Cursor); the base of the current cell is a GLOBAL particle index here
+        unsigned m = 0, mnext = 0, flags = 0;
+        int a = 0;
+        float ex = 0.f, ey = 0.f, ez = 0.f;
+        if (nz) mnext = __ldg(mrow + (size_t)__clz(nz) * n);
+        auto jump = [&]() {
+            const bool jmp = m == 0 && nz != 0;
+            if (jmp) {
+                const int cc = __clz(nz);
+                nz &= ~rbit(cc);
+                m = mnext;
+                const F4 tt = ct[cc];
+                flags = __float_as_uint(tt.w);
+                a = cs[cc];
+                ex = pi.x - tt.x; ey = pi.y - tt.y; ez = pi.z - tt.z;
+            }
+            const unsigned go = jmp ? nz : 0u;
+            asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p ld.global.nc.u32 %0, [%1];\n}"
+                         : "+r"(mnext) : "l"(mrow + (size_t)(__clz(go) & 31) * n), "r"(go));
+        };
+        auto take2 = [&](int &j0, int &j1) {
+            const unsigned m0 = m;
+            const int t0 = __clz(m0);
+            const unsigned m1 = m0 & ~rbit(t0 & 31);
+            const int t1 = __clz(m1);
+            m = m1 & ~rbit(t1 & 31);
+            j0 = m0 ? a + t0 : -1;
+            j1 = m1 ? a + t1 : -1;
+        };
+        while (true) {
+            jump();
+            if (!__any_sync(0xffffffffu, m != 0)) break;
+            int j0, j1, j2, j3;
+            take2(j0, j1);
+            const float e0x = ex, e0y = ey, e0z = ez;
+            const bool b0 = fresh || (flags & CT_BEFORE), s0 = (flags & CT_SAME) != 0;
+            jump();
+            take2(j2, j3);
+            const bool b1 = fresh || (flags & CT_BEFORE), s1 = (flags & CT_SAME) != 0;
+            const int g0 = j0 >= 0 ? j0 : safe, g1 = j1 >= 0 ? j1 : safe, g2 = j2 >= 0 ? j2 : safe, g3 = j3 >= 0 ? j3 : safe;
+            F4 p0 = c.ps4[g0], p1 = c.ps4[g1], p2 = c.ps4[g2], p3 = c.ps4[g3];
+            const F4 u0 = c.vt4[g0], u1 = c.vt4[g1], u2 = c.vt4[g2], u3 = c.vt4[g3];
+            const F4 w0 = c.pw4[g0], w1 = c.pw4[g1], w2 = c.pw4[g2], w3 = c.pw4[g3];
+            if (j0 < 0) p0.w = 0.f;
+            if (j1 < 0) p1.w = 0.f;
+            if (j2 < 0) p2.w = 0.f;
+            if (j3 < 0) p3.w = 0.f;
+            const float q0 = (b0 || (s0 && g0 < i)) ? w0.x : w0.y;
+            const float q1 = (b0 || (s0 && g1 < i)) ? w1.x : w1.y;
+            const float q2 = (b1 || (s1 && g2 < i)) ? w2.x : w2.y;
+            const float q3 = (b1 || (s1 && g3 < i)) ? w3.x : w3.y;
+            float vw0, pt0, vw1, pt1, vw2, pt2, vw3, pt3;
+            wall_pair<KERNEL>(kc, e0x, e0y, e0z, p0, u0, q0, gy, vw0, pt0);
+            wall_pair<KERNEL>(kc, e0x, e0y, e0z, p1, u1, q1, gy, vw1, pt1);
+            wall_pair<KERNEL>(kc, ex, ey, ez, p2, u2, q2, gy, vw2, pt2);
+            wall_pair<KERNEL>(kc, ex, ey, ez, p3, u3, q3, gy, vw3, pt3);
+            Sw = __fadd_rn(Sw, vw0); Sv0 = fmaf(vw0, u0.x, Sv0); Sv1 = fmaf(vw0, u0.y, Sv1); Sv2 = fmaf(vw0, u0.z, Sv2); Sp = fmaf(vw0, pt0, Sp);
+            Sw = __fadd_rn(Sw, vw1); Sv0 = fmaf(vw1, u1.x, Sv0); Sv1 = fmaf(vw1, u1.y, Sv1); Sv2 = fmaf(vw1, u1.z, Sv2); Sp = fmaf(vw1, pt1, Sp);
+            Sw = __fadd_rn(Sw, vw2); Sv0 = fmaf(vw2, u2.x, Sv0); Sv1 = fmaf(vw2, u2.y, Sv1); Sv2 = fmaf(vw2, u2.z, Sv2); Sp = fmaf(vw2, pt2, Sp);
+            Sw = __fadd_rn(Sw, vw3); Sv0 = fmaf(vw3, u3.x, Sv0); Sv1 = fmaf(vw3, u3.y, Sv1); Sv2 = fmaf(vw3, u3.z, Sv2); Sp = fmaf(vw3, pt3, Sp);
+        }
+        // outputs are written after every lane of the warp has finished reading (vt4 of a wall particle is never a
+        // flow neighbour's payload, and pnew / pk4 / cspm_f are not read by this pass)
+        if (!work) continue;
+        float fi;
+        if (SHEP) { fi = (Sw != 0.f) ? 1.f / Sw : 1.f; c.cspm_f[i] = fi; }
+        else fi = c.cspm_f[i];
+        const F4 v = c.v4[i];
+        F4 vt;
+        vt.x = 2.f * v.x - Sv0 * fi; vt.y = 2.f * v.y - Sv1 * fi; vt.z = 2.f * v.z - Sv2 * fi; vt.w = c.rho0T;
+        c.vt4[i] = vt;
+        c.rho_t[i] = c.rho0;
+        const float p = Sp * fi;
+        const float pc = p > 0.f ? p : 0.f;
+        c.pnew[i] = pc;
+        F4 pk = vt; pk.w = pc / (c.rho0T * c.rho0T);
+        c.pk4[i] = pk;
+    }
+}
+
 // dry wall particles (no flow neighbour: empty masks) never reach the work list: their constant result is pointwise
 __global__ void __launch_bounds__(256) k_tile_wall_dry(DevF c, int shep) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -786,7 +932,10 @@ __device__ __forceinline__ void fluid_pair(const KernConst &kc, const FluidI &I,
     a0 = fmaf(cf, dx, a0); a1 = fmaf(cf, dy, a1); a2 = fmaf(cf, dz, a2);
 }
 
-template <int KERNEL, class FT, bool SHEP>
+// LIST (neighbour round lists): 0 none; 1 this pass walks the mask bits and RECORDS the four tile indices of
+// every round (the first fluid pass after the masks were built); 2 this pass REPLAYS the recorded rounds -- same
+// neighbours, same order, same arithmetic, without the bit cursor (cells whose list overflowed walk the bits again).
+template <int KERNEL, class FT, bool SHEP, int LIST>
 __device__ __forceinline__ bool fluid_body(const DevF &c, const TileGeom &g, TileShared<FT, 2> &sh, int blk, unsigned parity) {
     WarpCell w = warp_cell<FT>(c, g, blk);
     const int lane = threadIdx.x & 31;
@@ -795,7 +944,8 @@ __device__ __forceinline__ bool fluid_body(const DevF &c, const TileGeom &g, Til
     const bool work = lane < w.nc && c.ps4[i].w > 0.f;              // flow particle (fluid: the only flow type of WCSPH)
     const unsigned nz = work ? c.nzw[i] : 0u;
     if (!__syncthreads_or(work)) return false;
-    cursor_prefetch(c.mask + i, (size_t)c.n, nz);
+    const int rounds = (LIST == 2 && w.nc > 0) ? c.lrounds[w.gcell] : -1;     // warp-uniform
+    if (rounds < 0) cursor_prefetch(c.mask + i, (size_t)c.n, nz);
     if (!tile_setup<FT, 2>(c, g, sh, w, parity, c.ps4, c.pk4)) return true;
     build_ctab<FT, 2>(c, sh, w, lane);
     if (!__any_sync(0xffffffffu, work)) return true;
@@ -811,22 +961,55 @@ __device__ __forceinline__ bool fluid_body(const DevF &c, const TileGeom &g, Til
     I.h2 = c.h2_001;
     float dd = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, ssum = 0.f;
     const size_t n = (size_t)c.n;
-    const unsigned *mrow = c.mask + (work ? i : w.is);
-    Cursor k;
-    cursor_init(k, mrow, n, nz);
-    while (true) {
-        cursor_jump(k, mrow, n, ct, pi);
-        if (!__any_sync(0xffffffffu, k.m != 0)) break;              // warp-uniform round: lanes reconverge here
-        int i0, i1, i2, i3;
-        cursor_take2<FT::SENT>(k, i0, i1);
-        const float e0x = k.ex, e0y = k.ey, e0z = k.ez;
-        cursor_jump(k, mrow, n, ct, pi);
-        cursor_take2<FT::SENT>(k, i2, i3);
-        const F4 p0 = A[i0], q0 = B[i0], p1 = A[i1], q1 = B[i1], p2 = A[i2], q2 = B[i2], p3 = A[i3], q3 = B[i3];
-        fluid_pair<KERNEL, SHEP>(kc, I, e0x, e0y, e0z, p0, q0, dd, a0, a1, a2, ssum);
-        fluid_pair<KERNEL, SHEP>(kc, I, e0x, e0y, e0z, p1, q1, dd, a0, a1, a2, ssum);
-        fluid_pair<KERNEL, SHEP>(kc, I, k.ex, k.ey, k.ez, p2, q2, dd, a0, a1, a2, ssum);
-        fluid_pair<KERNEL, SHEP>(kc, I, k.ex, k.ey, k.ez, p3, q3, dd, a0, a1, a2, ssum);
+    constexpr unsigned SW = ((unsigned)FT::SENT << 12) | (unsigned)FT::SENT;   // a half round of two empty slots
+    if (LIST == 2 && rounds >= 0) {
+        const uint2 *lrow = c.nlist + ((size_t)w.is * LIST_ROUNDS + (work ? lane : 0));   // cell block: [round][particle of the cell]
+        uint2 cur = make_uint2(SW, SW);
+        if (work && rounds > 0) cur = __ldg(lrow);
+#pragma unroll 1
+        for (int r = 0; r < rounds; r++) {
+            lrow += w.nc;
+            uint2 nxt = make_uint2(SW, SW);
+            if (work && r + 1 < rounds) nxt = __ldg(lrow);          // one round ahead
+            const F4 t0 = ct[cur.x >> 24], t1 = ct[cur.y >> 24];
+            const int i0 = (cur.x >> 12) & 0xfff, i1 = cur.x & 0xfff, i2 = (cur.y >> 12) & 0xfff, i3 = cur.y & 0xfff;
+            const F4 p0 = A[i0], q0 = B[i0], p1 = A[i1], q1 = B[i1], p2 = A[i2], q2 = B[i2], p3 = A[i3], q3 = B[i3];
+            const float e0x = pi.x - t0.x, e0y = pi.y - t0.y, e0z = pi.z - t0.z;
+            const float e1x = pi.x - t1.x, e1y = pi.y - t1.y, e1z = pi.z - t1.z;
+            fluid_pair<KERNEL, SHEP>(kc, I, e0x, e0y, e0z, p0, q0, dd, a0, a1, a2, ssum);
+            fluid_pair<KERNEL, SHEP>(kc, I, e0x, e0y, e0z, p1, q1, dd, a0, a1, a2, ssum);
+            fluid_pair<KERNEL, SHEP>(kc, I, e1x, e1y, e1z, p2, q2, dd, a0, a1, a2, ssum);
+            fluid_pair<KERNEL, SHEP>(kc, I, e1x, e1y, e1z, p3, q3, dd, a0, a1, a2, ssum);
+            cur = nxt;
+        }
+    } else {
+        const unsigned *mrow = c.mask + (work ? i : w.is);
+        uint2 *lrow = LIST == 1 ? c.nlist + ((size_t)w.is * LIST_ROUNDS + (work ? lane : 0)) : nullptr;
+        int r = 0;
+        Cursor k;
+        cursor_init(k, mrow, n, nz);
+        while (true) {
+            cursor_jump(k, mrow, n, ct, pi);
+            if (!__any_sync(0xffffffffu, k.m != 0)) break;              // warp-uniform round: lanes reconverge here
+            int i0, i1, i2, i3;
+            cursor_take2<FT::SENT>(k, i0, i1);
+            const float e0x = k.ex, e0y = k.ey, e0z = k.ez;
+            const unsigned w0 = (k.flags & CT_CC) | ((unsigned)i0 << 12) | (unsigned)i1;
+            cursor_jump(k, mrow, n, ct, pi);
+            cursor_take2<FT::SENT>(k, i2, i3);
+            if (LIST == 1) {
+                const unsigned w1 = (k.flags & CT_CC) | ((unsigned)i2 << 12) | (unsigned)i3;
+                if (work && r < LIST_ROUNDS) *lrow = make_uint2(w0, w1);
+                lrow += w.nc;
+                r++;
+            }
+            const F4 p0 = A[i0], q0 = B[i0], p1 = A[i1], q1 = B[i1], p2 = A[i2], q2 = B[i2], p3 = A[i3], q3 = B[i3];
+            fluid_pair<KERNEL, SHEP>(kc, I, e0x, e0y, e0z, p0, q0, dd, a0, a1, a2, ssum);
+            fluid_pair<KERNEL, SHEP>(kc, I, e0x, e0y, e0z, p1, q1, dd, a0, a1, a2, ssum);
+            fluid_pair<KERNEL, SHEP>(kc, I, k.ex, k.ey, k.ez, p2, q2, dd, a0, a1, a2, ssum);
+            fluid_pair<KERNEL, SHEP>(kc, I, k.ex, k.ey, k.ez, p3, q3, dd, a0, a1, a2, ssum);
+        }
+        if (LIST == 1 && lane == 0) c.lrounds[w.gcell] = r <= LIST_ROUNDS ? r : -1;
     }
     if (!work) return true;
     c.d_rho[i] = dd * rhoi;
@@ -835,11 +1018,11 @@ __device__ __forceinline__ bool fluid_body(const DevF &c, const TileGeom &g, Til
     if (SHEP) c.cspm_f[i] = (ssum != 0.f) ? 1.f / ssum : 1.f;
     return true;
 }
-template <int KERNEL, class FT, bool SHEP> __global__ void __launch_bounds__(FT::BT, 2) k_tile_fluid(DevF c, TileGeom g) {
+template <int KERNEL, class FT, bool SHEP, int LIST> __global__ void __launch_bounds__(FT::BT, 2) k_tile_fluid(DevF c, TileGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileShared<FT, 2> &sh = *reinterpret_cast<TileShared<FT, 2> *>(smem_raw);
     tile_init<FT, 2>(sh);
-    TILE_PERSISTENT_LOOP(sh, c.worklist[1], c.wcount + 1, c.wcount + 7, (fluid_body<KERNEL, FT, SHEP>(c, g, sh, blk, parity)))
+    TILE_PERSISTENT_LOOP(sh, c.worklist[1], c.wcount + 1, c.wcount + 7, (fluid_body<KERNEL, FT, SHEP, LIST>(c, g, sh, blk, parity)))
 }
 
 // ------------------------------------------------------------------------------------------------ mask-based count
@@ -867,6 +1050,15 @@ template <typename K> static int set_smem(SphCtx *c, K kern, size_t bytes) {
     SPH_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return 0;
 }
+template <int KERNEL, class FT> static int set_fluid_attrs(SphCtx *c) {
+    int r = 0;
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 0>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, true, 0>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 1>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, true, 1>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 2>, smem_of<FT, 2>());
+    return r;
+}
 template <int KERNEL> static int set_attrs(SphCtx *c) {
     int r = 0;
     if (!r) r = set_smem(c, k_tile_shepard<KERNEL, F3M>, smem_of<F3M, 1>());
@@ -875,10 +1067,8 @@ template <int KERNEL> static int set_attrs(SphCtx *c) {
     if (!r) r = set_smem(c, k_tile_wall<KERNEL, F3W, true>, smem_of<F3W, 3>());
     if (!r) r = set_smem(c, k_tile_wall<KERNEL, F2W, false>, smem_of<F2W, 3>());
     if (!r) r = set_smem(c, k_tile_wall<KERNEL, F2W, true>, smem_of<F2W, 3>());
-    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, F3M, false>, smem_of<F3M, 2>());
-    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, F3M, true>, smem_of<F3M, 2>());
-    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, F2M, false>, smem_of<F2M, 2>());
-    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, F2M, true>, smem_of<F2M, 2>());
+    if (!r) r = set_fluid_attrs<KERNEL, F3M>(c);
+    if (!r) r = set_fluid_attrs<KERNEL, F2M>(c);
     return r;
 }
 static int ensure_attrs(SphCtx *c) {
@@ -937,8 +1127,13 @@ int tile_mask(SphCtx *c, bool shepard) {
     else TILE_LAUNCH_SMEM(k_tile_mask<F2M>, F2M, sizeof(MaskShared<F2M>), 4);
     SPH_LAUNCH_CHECK(c);
     if ((r = d3 ? build_worklist<F3M>(c, d, 1) : build_worklist<F2M>(c, d, 1))) return r;
-    if ((r = d3 ? build_worklist<F3W>(c, d, 2) : build_worklist<F2W>(c, d, 2))) return r;
+    SPH_CHECK(c, cudaMemsetAsync(d.wcount + 2, 0, 4, c->stream));           // wall CELLS with flow particles in reach
+    SPH_PROF(c, K_OTHER);
+    if (d3) k_wall_cells<true><<<blocks_for(c->C, 256), 256, 0, c->stream>>>(d);
+    else k_wall_cells<false><<<blocks_for(c->C, 256), 256, 0, c->stream>>>(d);
+    SPH_LAUNCH_CHECK(c);
     c->shep_pending = c->shep_wall_pending = !shepard;
+    c->list_valid = false;
     if (!shepard) return 0;
     if ((r = d3 ? build_worklist<F3M>(c, d, 0) : build_worklist<F2M>(c, d, 0))) return r;
     SPH_PROF(c, K_CSPM_F);
@@ -955,6 +1150,11 @@ template <int KERNEL, class FT> static void launch_wall(SphCtx *c, const DevF &d
     if (shep) TILE_LAUNCH((k_tile_wall<KERNEL, FT, true>), FT, 3, 6);
     else TILE_LAUNCH((k_tile_wall<KERNEL, FT, false>), FT, 3, 6);
 }
+template <int KERNEL, bool D3> static void launch_wall_gather(SphCtx *c, const DevF &d, bool shep) {
+    const int grid = 148 * 4;                                       // 4 blocks of 8 independent warps per SM, grid-stride over the cell list
+    if (shep) k_wall_gather<KERNEL, D3, true><<<grid, WG_WARPS * 32, 0, c->stream>>>(d);
+    else k_wall_gather<KERNEL, D3, false><<<grid, WG_WARPS * 32, 0, c->stream>>>(d);
+}
 // WCSPH one_step (wc:82-126) on the tile path; flagged cells are completed by the generic kernels (flagged_only).
 int tile_wc_prep_and_wall(SphCtx *c) {
     DevF d = make_dev<float>(c);
@@ -969,26 +1169,35 @@ int tile_wc_prep_and_wall(SphCtx *c) {
     SPH_LAUNCH_CHECK(c);
     SPH_PROF(c, K_TILE_WALL);
     if (c->p.dim == 3) {
-        if (c->p.kernel == 0) launch_wall<0, F3W>(c, d, shep); else launch_wall<1, F3W>(c, d, shep);
+        if (c->p.kernel == 0) launch_wall_gather<0, true>(c, d, shep); else launch_wall_gather<1, true>(c, d, shep);
     } else {
-        if (c->p.kernel == 0) launch_wall<0, F2W>(c, d, shep); else launch_wall<1, F2W>(c, d, shep);
+        if (c->p.kernel == 0) launch_wall_gather<0, false>(c, d, shep); else launch_wall_gather<1, false>(c, d, shep);
     }
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
-template <int KERNEL, class FT> static void launch_fluid(SphCtx *c, const DevF &d, bool shep) {
-    if (shep) TILE_LAUNCH((k_tile_fluid<KERNEL, FT, true>), FT, 2, 7);
-    else TILE_LAUNCH((k_tile_fluid<KERNEL, FT, false>), FT, 2, 7);
+// list: 0 no lists, 1 record, 2 replay (never together with the Shepard sums: those belong to the first pass)
+template <int KERNEL, class FT> static void launch_fluid(SphCtx *c, const DevF &d, bool shep, int list) {
+    if (list == 2) TILE_LAUNCH((k_tile_fluid<KERNEL, FT, false, 2>), FT, 2, 7);
+    else if (list == 1) {
+        if (shep) TILE_LAUNCH((k_tile_fluid<KERNEL, FT, true, 1>), FT, 2, 7);
+        else TILE_LAUNCH((k_tile_fluid<KERNEL, FT, false, 1>), FT, 2, 7);
+    } else {
+        if (shep) TILE_LAUNCH((k_tile_fluid<KERNEL, FT, true, 0>), FT, 2, 7);
+        else TILE_LAUNCH((k_tile_fluid<KERNEL, FT, false, 0>), FT, 2, 7);
+    }
 }
 int tile_wc_fluid(SphCtx *c) {
     DevF d = make_dev<float>(c);
     const bool shep = c->shep_pending;
     c->shep_pending = false;
+    const int list = !c->use_list ? 0 : ((c->list_valid && !shep) ? 2 : 1);
+    c->list_valid = c->use_list;
     SPH_PROF(c, K_TILE_FLUID);
     if (c->p.dim == 3) {
-        if (c->p.kernel == 0) launch_fluid<0, F3M>(c, d, shep); else launch_fluid<1, F3M>(c, d, shep);
+        if (c->p.kernel == 0) launch_fluid<0, F3M>(c, d, shep, list); else launch_fluid<1, F3M>(c, d, shep, list);
     } else {
-        if (c->p.kernel == 0) launch_fluid<0, F2M>(c, d, shep); else launch_fluid<1, F2M>(c, d, shep);
+        if (c->p.kernel == 0) launch_fluid<0, F2M>(c, d, shep, list); else launch_fluid<1, F2M>(c, d, shep, list);
     }
     SPH_LAUNCH_CHECK(c);
     return 0;

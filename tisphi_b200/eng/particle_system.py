@@ -160,7 +160,9 @@ class ParticleSystem:
         P.precision = {"f64": _lib.PREC_F64, "fp64": _lib.PREC_F64, "f32": _lib.PREC_MIXED, "fp32": _lib.PREC_MIXED,
                        "mixed": _lib.PREC_MIXED}[self.precision]
         P.wc_fresh = int(bool(self.cfg.get_opt("wcFresh", False)))
-        P.fast = int(bool(self.cfg.get_opt("fastSweeps", True)))
+        # 0: generic sweeps only; 1: cell-tile sweeps; 2: cell-tile sweeps + neighbour round lists replayed by the
+        # later one_steps of a step (LF / RK4)
+        P.fast = 0 if not self.cfg.get_opt("fastSweeps", True) else (2 if self.cfg.get_opt("neighbourLists", True) else 1)
         grav = self.cfg.get_cfg("gravitation")
         for a in range(3):
             P.gn[a] = int(self.grid_num[a])

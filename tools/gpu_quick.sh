@@ -12,3 +12,12 @@ d=json.loads(open("gpurun_out/${TAG}_bench.json").read().strip().splitlines()[-1
 print("ms_per_step", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"]["value"])
 print(json.dumps(d["roofline"]["kernel_ms"]))
 PY
+if [ -n "$2" ]; then
+python bench.py --steps 20 --warmup 3 --no-cpu $2 > gpurun_out/${TAG}_bench_b.json 2> gpurun_out/${TAG}_bench_b.err
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/${TAG}_bench_b.json").read().strip().splitlines()[-1])
+print("B: ms_per_step", d["ms_per_step"], "value", d["value"])
+print(json.dumps(d["roofline"]["kernel_ms"]))
+PY
+fi
