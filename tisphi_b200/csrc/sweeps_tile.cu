@@ -335,12 +335,17 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0,
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-// two candidates against one particle: bit 0 / bit 1 = dist2(d) < thr, d given per component as packed pairs
-__device__ __forceinline__ unsigned test2(u64 dx, u64 dy, u64 dz, float thr) {
+// Two more candidates against one particle: bits B and B + 1 of the chunk word are set when dist2(d) < thr.
+// The packed FP32 pipe is the busiest unit of this kernel (six packed operations per two candidates), so the compare
+// stays off it: one FSETP and one predicated OR with an immediate per candidate, both on the ALU pipe.
+template <int B> __device__ __forceinline__ unsigned push2(unsigned cm, u64 dx, u64 dy, u64 dz, float thr) {
     float lo, hi;
-    up2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), lo, hi);          // == dist2(dx, dy, dz) in each half
-    return (lo < thr ? 1u : 0u) | (hi < thr ? 2u : 0u);
+    up2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), lo, hi);                 // == dist2(dx, dy, dz) in each half
+    asm("{\n.reg .pred p, q;\nsetp.lt.f32 p, %1, %3;\nsetp.lt.f32 q, %2, %3;\n@p or.b32 %0, %0, %4;\n@q or.b32 %0, %0, %5;\n}"
+        : "+r"(cm) : "f"(lo), "f"(hi), "f"(thr), "n"(1u << B), "n"(2u << B));
+    return cm;
 }
+__device__ __forceinline__ u64 chunk_bits(unsigned cm, int t0) { return (u64)cm << t0; }
 
 template <class FT> struct MaskShared {
     static constexpr int CAPS = FT::CAP + 8;          // the chunked test loop may read up to 7 entries past a cell
@@ -349,6 +354,8 @@ template <class FT> struct MaskShared {
     int cb[FT::NR * FT::CBW];         // tile index of the first particle of each (run, cell)
     int gdelta[FT::NR];               // global index = tile index + gdelta[run]
     int total, overflow, item;
+    int4 tab[FT::NWARP][FT::NW];      // per (warp, stencil cell): tile index of its first particle, particle count,
+                                      // global - tile index, code = (ox+1) | (oy+1) << 2 | (of+1) << 4 | owned << 6 | has flow << 7
 };
 template <class FT> __device__ __forceinline__ void mask_tile_init(MaskShared<FT> &sh) {
     if (threadIdx.x == 0) mbar_init(&sh.bar, 1);
@@ -422,15 +429,27 @@ __device__ __forceinline__ bool mask_tile_setup(const DevF &c, const TileGeom &g
 template <class FT>
 __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, MaskShared<FT> &sh, int blk, unsigned parity) {
     const WarpCell w = warp_cell<FT>(c, g, blk);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const bool ok = mask_tile_setup<FT>(c, g, sh, w, parity);
     if (w.nc == 0) return true;
-    // can this cell be represented?  (uniform per warp; branch-free so that the warp stays converged)
+    // what this warp needs to know about its 27 (9) stencil cells, computed once by lane = stencil cell
     int ox, oy, of;
     stencil<FT>(min(lane, FT::NW - 1), ox, oy, of);
-    const int q0 = stencil_cb<FT>(w, ox, oy, of);
-    const bool big = lane < FT::NW && sh.cb[q0 + 1] - sh.cb[q0] > 32;
-    const bool flagged = __any_sync(0xffffffffu, big) || !ok || w.nc > 32;
+    int4 te = make_int4(0, 0, 0, 0);
+    bool bowned = false, bflowc = false;
+    if (lane < FT::NW) {
+        const int q = stencil_cb<FT>(w, ox, oy, of);
+        te.x = sh.cb[q];
+        te.y = sh.cb[q + 1] - te.x;
+        te.z = sh.gdelta[q / FT::CBW];
+        const int ncx = w.cx + ox;
+        bowned = ncx >= c.own0 && ncx < c.own1;                    // B's warp runs on this rank
+        if (te.y > 0) bflowc = c.cellflow[(ncx * g.n1 + (w.cy + oy)) * g.nF + (w.f + of)] != 0;
+        te.w = (ox + 1) | ((oy + 1) << 2) | ((of + 1) << 4) | (bowned ? 64 : 0) | (bflowc ? 128 : 0);
+        sh.tab[wi][lane] = te;
+    }
+    // can this cell be represented?  (uniform per warp)
+    const bool flagged = __any_sync(0xffffffffu, te.y > 32) || !ok || w.nc > 32;
     if (flagged) {                                                 // my neighbours wait for words only I can write: flag them too
         if (lane < FT::NW) {
             const int nx = w.cx + ox, ny = w.cy + oy, nf = w.f + of;
@@ -447,37 +466,28 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Mask
     const bool myflow = F[own] > 0.f;
     const unsigned flowA = __ballot_sync(0xffffffffu, mine && myflow);
     const bool has_wall = __any_sync(0xffffffffu, mine && !myflow);
-    bool near_flow = flowA != 0;
+    const bool near_flow = flowA != 0 || __any_sync(0xffffffffu, bflowc);
+    // Cell pairs this warp evaluates: itself and the cells after it (their warps get the transposed words), plus
+    // the cells before it that lie in a ghost column.  A pair of cells without any flow particle has empty words
+    // (walls keep flow neighbours only).  Empty words are never stored: readers only follow the bits of nzw.
+    unsigned todo = __ballot_sync(0xffffffffu, te.y > 0 && (lane >= FT::CENTRE || !bowned) && (flowA != 0 || bflowc));
     const float thr = c.r2thr;
     const size_t n = (size_t)c.n;
+    unsigned *mrow = c.mask + i;
     unsigned nz = 0;
-#pragma unroll 1
-    for (int cc = 0; cc < FT::NW; cc++) {
-        __syncwarp();
-        int bx, by, bf;
-        stencil<FT>(cc, bx, by, bf);
-        const int q = stencil_cb<FT>(w, bx, by, bf);
-        const int a = sh.cb[q], nb = sh.cb[q + 1] - a;
-        if (nb == 0) {                                             // empty or outside the grid: nobody else writes this word
-            if (mine) c.mask[(size_t)cc * n + i] = 0u;
-            continue;
-        }
-        const bool same = cc == FT::CENTRE, upper = cc > FT::CENTRE;
-        const int ncx = w.cx + bx;
-        const bool b_owned = ncx >= c.own0 && ncx < c.own1;        // B's warp runs on this rank
+    __syncwarp();
+    while (todo) {
+        const int cc = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int4 t = sh.tab[wi][cc];
+        const int a = t.x, nb = t.y;
+        const bool same = cc == FT::CENTRE, upper = cc > FT::CENTRE, b_owned = (t.w & 64) != 0;
+        const float bx = (float)((t.w & 3) - 1), by = (float)(((t.w >> 2) & 3) - 1), bf = (float)(((t.w >> 4) & 3) - 1);
+        float sx, sy, sz;
+        if (FT::d3) { sx = bx * c.gsT; sy = by * c.gsT; sz = bf * c.gsT; }
+        else { sx = bx * c.gsT; sy = bf * c.gsT; sz = 0.f; }
         const bool bflow = lane < nb && F[a + lane] > 0.f;
         const unsigned flowB = __ballot_sync(0xffffffffu, bflow);
-        near_flow = near_flow || flowB != 0;
-        if (!same && !upper && b_owned) continue;                  // B's warp evaluates the pair and writes my word
-        if (flowA == 0 && flowB == 0) {                            // walls keep flow neighbours only: both words are empty
-            if (mine) c.mask[(size_t)cc * n + i] = 0u;
-            if (upper && b_owned && lane < nb)
-                c.mask[(size_t)(FT::NW - 1 - cc) * n + (a + lane + sh.gdelta[q / FT::CBW])] = 0u;
-            continue;
-        }
-        float sx, sy, sz;
-        if (FT::d3) { sx = (float)bx * c.gsT; sy = (float)by * c.gsT; sz = (float)bf * c.gsT; }
-        else { sx = (float)bx * c.gsT; sy = (float)bf * c.gsT; sz = 0.f; }
         const int a4 = a & ~3, lead = a - a4, nslot = lead + nb;   // aligned chunk origin; candidate k sits at slot lead + k
         u64 m64 = 0;
         if (upper || same) {                                       // lower side: d = (x_i - s) - x_j
@@ -487,11 +497,11 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Mask
                 const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(X + a4 + t0), x1 = *reinterpret_cast<const ulonglong2 *>(X + a4 + t0 + 4);
                 const ulonglong2 y0 = *reinterpret_cast<const ulonglong2 *>(Y + a4 + t0), y1 = *reinterpret_cast<const ulonglong2 *>(Y + a4 + t0 + 4);
                 const ulonglong2 z0 = *reinterpret_cast<const ulonglong2 *>(Z + a4 + t0), z1 = *reinterpret_cast<const ulonglong2 *>(Z + a4 + t0 + 4);
-                unsigned cm = test2(sub2(Ex, x0.x), sub2(Ey, y0.x), sub2(Ez, z0.x), thr);
-                cm |= test2(sub2(Ex, x0.y), sub2(Ey, y0.y), sub2(Ez, z0.y), thr) << 2;
-                cm |= test2(sub2(Ex, x1.x), sub2(Ey, y1.x), sub2(Ez, z1.x), thr) << 4;
-                cm |= test2(sub2(Ex, x1.y), sub2(Ey, y1.y), sub2(Ez, z1.y), thr) << 6;
-                m64 |= (u64)cm << t0;
+                unsigned cm = push2<0>(0u, sub2(Ex, x0.x), sub2(Ey, y0.x), sub2(Ez, z0.x), thr);
+                cm = push2<2>(cm, sub2(Ex, x0.y), sub2(Ey, y0.y), sub2(Ez, z0.y), thr);
+                cm = push2<4>(cm, sub2(Ex, x1.x), sub2(Ey, y1.x), sub2(Ez, z1.x), thr);
+                cm = push2<6>(cm, sub2(Ex, x1.y), sub2(Ey, y1.y), sub2(Ez, z1.y), thr);
+                m64 |= chunk_bits(cm, t0);
             }
         } else {                                                   // B precedes A and is a ghost column: d' = (x_j + s) - x_i
             const u64 Sx = pk2(sx, sx), Sy = pk2(sy, sy), Sz = pk2(sz, sz);
@@ -500,11 +510,11 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Mask
                 const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(X + a4 + t0), x1 = *reinterpret_cast<const ulonglong2 *>(X + a4 + t0 + 4);
                 const ulonglong2 y0 = *reinterpret_cast<const ulonglong2 *>(Y + a4 + t0), y1 = *reinterpret_cast<const ulonglong2 *>(Y + a4 + t0 + 4);
                 const ulonglong2 z0 = *reinterpret_cast<const ulonglong2 *>(Z + a4 + t0), z1 = *reinterpret_cast<const ulonglong2 *>(Z + a4 + t0 + 4);
-                unsigned cm = test2(sub2(add2(x0.x, Sx), Px), sub2(add2(y0.x, Sy), Py), sub2(add2(z0.x, Sz), Pz), thr);
-                cm |= test2(sub2(add2(x0.y, Sx), Px), sub2(add2(y0.y, Sy), Py), sub2(add2(z0.y, Sz), Pz), thr) << 2;
-                cm |= test2(sub2(add2(x1.x, Sx), Px), sub2(add2(y1.x, Sy), Py), sub2(add2(z1.x, Sz), Pz), thr) << 4;
-                cm |= test2(sub2(add2(x1.y, Sx), Px), sub2(add2(y1.y, Sy), Py), sub2(add2(z1.y, Sz), Pz), thr) << 6;
-                m64 |= (u64)cm << t0;
+                unsigned cm = push2<0>(0u, sub2(add2(x0.x, Sx), Px), sub2(add2(y0.x, Sy), Py), sub2(add2(z0.x, Sz), Pz), thr);
+                cm = push2<2>(cm, sub2(add2(x0.y, Sx), Px), sub2(add2(y0.y, Sy), Py), sub2(add2(z0.y, Sz), Pz), thr);
+                cm = push2<4>(cm, sub2(add2(x1.x, Sx), Px), sub2(add2(y1.x, Sy), Py), sub2(add2(z1.x, Sz), Pz), thr);
+                cm = push2<6>(cm, sub2(add2(x1.y, Sx), Px), sub2(add2(y1.y, Sy), Py), sub2(add2(z1.y, Sz), Pz), thr);
+                m64 |= chunk_bits(cm, t0);
             }
         }
         unsigned m = (unsigned)(m64 >> lead);
@@ -512,17 +522,18 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Mask
         if (same) m &= ~(1u << lane);                              // i != j
         if (!mine) m = 0;
         const unsigned mi = myflow ? m : (m & flowB);              // walls keep their flow neighbours only
-        if (mine) c.mask[(size_t)cc * n + i] = __brev(mi);
-        if (mi) nz |= rbit(cc);
+        if (mi) {
+            mrow[(size_t)cc * n] = __brev(mi);
+            nz |= rbit(cc);
+        }
         if (upper && b_owned) {                                    // the same pairs seen from B: transpose
-            const unsigned t = warp_transpose32(m, lane);
-            const unsigned tj = bflow ? t : (t & flowA);
-            if (lane < nb) {
-                const int r = q / FT::CBW;
-                const int j = a + lane + sh.gdelta[r];
+            const unsigned tr = warp_transpose32(m, lane);
+            const unsigned tj = bflow ? tr : (tr & flowA);
+            if (lane < nb && tj) {
+                const int j = a + lane + t.z;
                 const int ccm = FT::NW - 1 - cc;
                 c.mask[(size_t)ccm * n + j] = __brev(tj);
-                if (tj) atomicOr(&c.nzw[j], rbit(ccm));
+                atomicOr(&c.nzw[j], rbit(ccm));
             }
         }
     }
@@ -1033,7 +1044,8 @@ __global__ void __launch_bounds__(256) k_mask_count(DevF c, int nw, int *__restr
     int cnt = -1;
     if (c.ps4[i].w > 0.f && !c.cellflag[c.gid[i]]) {
         cnt = 0;
-        for (int cc = 0; cc < nw; cc++) cnt += __popc(c.mask[(size_t)cc * c.n + i]);
+        const unsigned nz = c.nzw[i];                  // empty words are never stored
+        for (int cc = 0; cc < nw; cc++) if (nz & rbit(cc)) cnt += __popc(c.mask[(size_t)cc * c.n + i]);
     }
     out[i] = cnt;
 }
