@@ -255,6 +255,10 @@ __device__ __forceinline__ float shep_add(float s, float vsigned, float w) { ret
 // two from the current cell, then (after an optional jump to the next non-empty cell) two more.  Slots that find no
 // bit read the all-zero sentinel entry (volume 0) and contribute exactly zero, so the summation order (cells
 // x-major, j ascending) is kept.  The mask word of the NEXT non-empty cell is always in flight from global memory.
+// Mask storage: the words of a cell's particles form one contiguous block.  For the cell whose first particle is `is`
+// and which holds nc particles, the word of its k-th particle for stencil cell cc is mask[is * NW + cc * nc + k]: a
+// warp reads / writes nc consecutive words per stencil cell, and all offsets inside a block fit 32 bits.
+__device__ __forceinline__ unsigned *mask_row(unsigned *mask, int is, int nw, int k) { return mask + ((size_t)is * nw + k); }
 struct Cursor {
     unsigned m, nz, mnext;   // remaining bits of the current cell; remaining non-empty cells; prefetched word
     unsigned flags;          // CT_BEFORE / CT_SAME of the current cell
@@ -264,19 +268,20 @@ struct Cursor {
 // Masks and the non-empty-cell bitmaps are stored BIT-REVERSED (particle / cell b at bit 31 - b): the next element in
 // ascending order is then one FLO (count-leading-zeros) instead of BREV + FLO, which halves the load on the XU pipe.
 __device__ __forceinline__ unsigned rbit(int b) { return 0x80000000u >> b; }
-__device__ __forceinline__ void cursor_init(Cursor &k, const unsigned *mrow, size_t n, unsigned nz) {
+// mrow = mask_row(...) of the lane's particle; n = particles in its cell (the stride between the words of a particle)
+__device__ __forceinline__ void cursor_init(Cursor &k, const unsigned *mrow, unsigned n, unsigned nz) {
     k.m = 0; k.nz = nz; k.mnext = 0; k.flags = 0; k.a = 0; k.ex = k.ey = k.ez = 0.f;
-    if (nz) k.mnext = __ldg(mrow + (size_t)__clz(nz) * n);
+    if (nz) k.mnext = __ldg(mrow + (unsigned)__clz(nz) * n);
 }
 // L2 prefetch of every mask line this lane will read (issued once per work item, long before the first use)
-__device__ __forceinline__ void cursor_prefetch(const unsigned *mrow, size_t n, unsigned nz) {
+__device__ __forceinline__ void cursor_prefetch(const unsigned *mrow, unsigned n, unsigned nz) {
     while (nz) {
         const int cc = __clz(nz);
         nz &= ~rbit(cc);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(mrow + (size_t)cc * n));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(mrow + (unsigned)cc * n));
     }
 }
-__device__ __forceinline__ void cursor_jump(Cursor &k, const unsigned *mrow, size_t n, const F4 *ct, const F4 &pi) {
+__device__ __forceinline__ void cursor_jump(Cursor &k, const unsigned *mrow, unsigned n, const F4 *ct, const F4 &pi) {
     const bool jump = k.m == 0 && k.nz != 0;
     if (jump) {
         const int cc = __clz(k.nz);
@@ -292,7 +297,7 @@ __device__ __forceinline__ void cursor_jump(Cursor &k, const unsigned *mrow, siz
     // move it at the reconvergence point, which waits for the load at once and exposes the whole memory latency.
     const unsigned go = jump ? k.nz : 0u;
     asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p ld.global.nc.u32 %0, [%1];\n}"
-                 : "+r"(k.mnext) : "l"(mrow + (size_t)(__clz(go) & 31) * n), "r"(go));
+                 : "+r"(k.mnext) : "l"(mrow + (unsigned)(__clz(go) & 31) * n), "r"(go));
 }
 // takes up to two bits of the current cell: tile indices (the sentinel when there is no bit)
 template <int SENT> __device__ __forceinline__ void cursor_take2(Cursor &k, int &i0, int &i1) {
@@ -472,8 +477,8 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Mask
     // (walls keep flow neighbours only).  Empty words are never stored: readers only follow the bits of nzw.
     unsigned todo = __ballot_sync(0xffffffffu, te.y > 0 && (lane >= FT::CENTRE || !bowned) && (flowA != 0 || bflowc));
     const float thr = c.r2thr;
-    const size_t n = (size_t)c.n;
-    unsigned *mrow = c.mask + i;
+    // (mask words are addressed inside the cell blocks: mask_row)
+    unsigned *mrow = mask_row(c.mask, w.is, FT::NW, mine ? lane : 0);
     unsigned nz = 0;
     __syncwarp();
     while (todo) {
@@ -523,7 +528,7 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Mask
         if (!mine) m = 0;
         const unsigned mi = myflow ? m : (m & flowB);              // walls keep their flow neighbours only
         if (mi) {
-            mrow[(size_t)cc * n] = __brev(mi);
+            mrow[cc * w.nc] = __brev(mi);
             nz |= rbit(cc);
         }
         if (upper && b_owned) {                                    // the same pairs seen from B: transpose
@@ -532,7 +537,7 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Mask
             if (lane < nb && tj) {
                 const int j = a + lane + t.z;
                 const int ccm = FT::NW - 1 - cc;
-                c.mask[(size_t)ccm * n + j] = __brev(tj);
+                mask_row(c.mask, a + t.z, FT::NW, lane)[ccm * nb] = __brev(tj);
                 atomicOr(&c.nzw[j], rbit(ccm));
             }
         }
@@ -597,8 +602,8 @@ __device__ __forceinline__ bool shepard_body(const DevF &c, const TileGeom &g, T
     const F4 *ct = sh.ctab + (threadIdx.x >> 5) * FT::NW;
     const F4 pi = A[sh.cb[stencil_cb<FT>(w, 0, 0, 0)] + (mine ? lane : 0)];
     const KernConst kc = kern_const(c);
-    const size_t n = (size_t)c.n;
-    const unsigned *mrow = c.mask + i;
+    const unsigned n = (unsigned)w.nc;
+    const unsigned *mrow = mask_row(c.mask, w.is, FT::NW, mine ? lane : 0);
     Cursor k;
     cursor_init(k, mrow, n, mine ? c.nzw[i] : 0u);
     float ssum = 0.f;
@@ -669,81 +674,6 @@ __device__ __forceinline__ void wall_pair(const KernConst &kc, float ex, float e
     pterm = fmaf(vj.w * gy, dy, pjv);
 }
 
-template <int KERNEL, class FT, bool SHEP>
-__device__ __forceinline__ bool wall_body(const DevF &c, const TileGeom &g, TileShared<FT, 3> &sh, int blk, unsigned parity) {
-    WarpCell w = warp_cell<FT>(c, g, blk);
-    const int lane = threadIdx.x & 31;
-    if (w.nc > 0 && c.cellflag[w.gcell]) w.nc = 0;                  // flagged cells belong to the generic kernels
-    const int i = w.is + lane;
-    bool wall = false, work = false;
-    unsigned nz = 0;
-    if (lane < w.nc) {
-        wall = c.ps4[i].w < 0.f;
-        if (wall) nz = c.nzw[i];
-        work = nz != 0;                                             // dry walls: k_tile_wall_dry
-    }
-    if (!__syncthreads_or(work)) return false;
-    cursor_prefetch(c.mask + i, (size_t)c.n, nz);
-    if (!tile_setup<FT, 3>(c, g, sh, w, parity, c.ps4, c.vt4, c.pw4)) return true;   // cannot happen for unflagged cells
-    build_ctab<FT, 3>(c, sh, w, lane);
-    if (!__any_sync(0xffffffffu, work)) return true;
-    const F4 *A = sh.P[0], *B = sh.P[1], *Pw = sh.P[2];
-    const F4 *ct = sh.ctab + (threadIdx.x >> 5) * FT::NW;
-    const int ci = sh.cb[stencil_cb<FT>(w, 0, 0, 0)];               // tile index of this cell's first particle
-    const F4 pi = A[ci + (work ? lane : 0)];
-    const KernConst kc = kern_const(c);
-    const float gy = c.g[1];
-    const bool fresh = c.wc_fresh != 0;
-    const int self = ci + lane;                                     // "j < i" inside my own cell == tile index below mine
-    const size_t n = (size_t)c.n;
-    const unsigned *mrow = c.mask + (work ? i : w.is);
-    float Sv0 = 0.f, Sv1 = 0.f, Sv2 = 0.f, Sp = 0.f, Sw = 0.f;
-    Cursor k;
-    cursor_init(k, mrow, n, nz);
-    while (true) {
-        cursor_jump(k, mrow, n, ct, pi);
-        if (!__any_sync(0xffffffffu, k.m != 0)) break;
-        int i0, i1, i2, i3;
-        cursor_take2<FT::SENT>(k, i0, i1);
-        const float e0x = k.ex, e0y = k.ey, e0z = k.ez;
-        // sorted order: every particle of a stencil cell with a smaller cell id precedes i, inside my own cell the index decides
-        const bool b0 = fresh || (k.flags & CT_BEFORE), s0 = (k.flags & CT_SAME) != 0;
-        cursor_jump(k, mrow, n, ct, pi);
-        cursor_take2<FT::SENT>(k, i2, i3);
-        const bool b1 = fresh || (k.flags & CT_BEFORE), s1 = (k.flags & CT_SAME) != 0;
-        const F4 p0 = A[i0], p1 = A[i1], p2 = A[i2], p3 = A[i3];
-        const F4 u0 = B[i0], u1 = B[i1], u2 = B[i2], u3 = B[i3];
-        const F4 w0 = Pw[i0], w1 = Pw[i1], w2 = Pw[i2], w3 = Pw[i3];
-        const float q0 = (b0 || (s0 && i0 < self)) ? w0.x : w0.y;
-        const float q1 = (b0 || (s0 && i1 < self)) ? w1.x : w1.y;
-        const float q2 = (b1 || (s1 && i2 < self)) ? w2.x : w2.y;
-        const float q3 = (b1 || (s1 && i3 < self)) ? w3.x : w3.y;
-        float vw0, pt0, vw1, pt1, vw2, pt2, vw3, pt3;
-        wall_pair<KERNEL>(kc, e0x, e0y, e0z, p0, u0, q0, gy, vw0, pt0);
-        wall_pair<KERNEL>(kc, e0x, e0y, e0z, p1, u1, q1, gy, vw1, pt1);
-        wall_pair<KERNEL>(kc, k.ex, k.ey, k.ez, p2, u2, q2, gy, vw2, pt2);
-        wall_pair<KERNEL>(kc, k.ex, k.ey, k.ez, p3, u3, q3, gy, vw3, pt3);
-        Sw = __fadd_rn(Sw, vw0); Sv0 = fmaf(vw0, u0.x, Sv0); Sv1 = fmaf(vw0, u0.y, Sv1); Sv2 = fmaf(vw0, u0.z, Sv2); Sp = fmaf(vw0, pt0, Sp);
-        Sw = __fadd_rn(Sw, vw1); Sv0 = fmaf(vw1, u1.x, Sv0); Sv1 = fmaf(vw1, u1.y, Sv1); Sv2 = fmaf(vw1, u1.z, Sv2); Sp = fmaf(vw1, pt1, Sp);
-        Sw = __fadd_rn(Sw, vw2); Sv0 = fmaf(vw2, u2.x, Sv0); Sv1 = fmaf(vw2, u2.y, Sv1); Sv2 = fmaf(vw2, u2.z, Sv2); Sp = fmaf(vw2, pt2, Sp);
-        Sw = __fadd_rn(Sw, vw3); Sv0 = fmaf(vw3, u3.x, Sv0); Sv1 = fmaf(vw3, u3.y, Sv1); Sv2 = fmaf(vw3, u3.z, Sv2); Sp = fmaf(vw3, pt3, Sp);
-    }
-    if (!work) return true;
-    float fi;
-    if (SHEP) { fi = (Sw != 0.f) ? 1.f / Sw : 1.f; c.cspm_f[i] = fi; }
-    else fi = c.cspm_f[i];
-    const F4 v = c.v4[i];
-    F4 vt;
-    vt.x = 2.f * v.x - Sv0 * fi; vt.y = 2.f * v.y - Sv1 * fi; vt.z = 2.f * v.z - Sv2 * fi; vt.w = c.rho0T;
-    c.vt4[i] = vt;
-    c.rho_t[i] = c.rho0;
-    const float p = Sp * fi;
-    const float pc = p > 0.f ? p : 0.f;
-    c.pnew[i] = pc;
-    F4 pk = vt; pk.w = pc / (c.rho0T * c.rho0T);
-    c.pk4[i] = pk;
-    return true;
-}
 // ------------------------------------------------------------------------------------------------ pass A: walls, gathered
 // The same wall pass without a tile: one warp per wall cell that has flow particles in reach (a compacted CELL list),
 // lane = particle, the mask bits walked in the same order with the same arithmetic, but the neighbour payloads are
@@ -771,7 +701,7 @@ template <int KERNEL, bool D3, bool SHEP> __global__ void __launch_bounds__(WG_W
     const KernConst kc = kern_const(c);
     const float gy = c.g[1];
     const bool fresh = c.wc_fresh != 0;
-    const size_t n = (size_t)c.n;
+    // (the stride between a particle's mask words is its cell's particle count)
     const F4 *ct = s_ct[wi];
     const int *cs = s_start[wi];
     for (int it = blockIdx.x * WG_WARPS + wi; it < items; it += gridDim.x * WG_WARPS) {
@@ -808,13 +738,14 @@ template <int KERNEL, bool D3, bool SHEP> __global__ void __launch_bounds__(WG_W
         if (!work) nz = 0;
         if (!__any_sync(0xffffffffu, work)) continue;
         const int safe = work ? i : is;                             // what an empty slot loads (its volume is zeroed)
-        const unsigned *mrow = c.mask + safe;
+        const unsigned n = (unsigned)nc;
+        const unsigned *mrow = mask_row(c.mask, is, NW, work ? lane : 0);
         float Sv0 = 0.f, Sv1 = 0.f, Sv2 = 0.f, Sp = 0.f, Sw = 0.f;
         // cursor state (see struct Cursor); the base of the current cell is a GLOBAL particle index here
         unsigned m = 0, mnext = 0, flags = 0;
         int a = 0;
         float ex = 0.f, ey = 0.f, ez = 0.f;
-        if (nz) mnext = __ldg(mrow + (size_t)__clz(nz) * n);
+        if (nz) mnext = __ldg(mrow + (unsigned)__clz(nz) * n);
         auto jump = [&]() {
             const bool jmp = m == 0 && nz != 0;
             if (jmp) {
@@ -828,7 +759,7 @@ template <int KERNEL, bool D3, bool SHEP> __global__ void __launch_bounds__(WG_W
             }
             const unsigned go = jmp ? nz : 0u;
             asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p ld.global.nc.u32 %0, [%1];\n}"
-                         : "+r"(mnext) : "l"(mrow + (size_t)(__clz(go) & 31) * n), "r"(go));
+                         : "+r"(mnext) : "l"(mrow + (unsigned)(__clz(go) & 31) * n), "r"(go));
         };
         auto take2 = [&](int &j0, int &j1) {
             const unsigned m0 = m;
@@ -904,13 +835,6 @@ __global__ void __launch_bounds__(256) k_tile_wall_dry(DevF c, int shep) {
     F4 pk = vt; pk.w = 0.f;
     c.pk4[i] = pk;
 }
-template <int KERNEL, class FT, bool SHEP> __global__ void __launch_bounds__(FT::BT) k_tile_wall(DevF c, TileGeom g) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileShared<FT, 3> &sh = *reinterpret_cast<TileShared<FT, 3> *>(smem_raw);
-    tile_init<FT, 3>(sh);
-    TILE_PERSISTENT_LOOP(sh, c.worklist[2], c.wcount + 2, c.wcount + 6, (wall_body<KERNEL, FT, SHEP>(c, g, sh, blk, parity)))
-}
-
 // ------------------------------------------------------------------------------------------------ pass B: fluid
 // wc:108-126 for fluid particles: continuity + viscosity + pressure in one visit of the set bits.
 //   d_rho_i = rho~_i sum_j V_j (v~_i - v~_j) . gradW_ij
@@ -956,7 +880,7 @@ __device__ __forceinline__ bool fluid_body(const DevF &c, const TileGeom &g, Til
     const unsigned nz = work ? c.nzw[i] : 0u;
     if (!__syncthreads_or(work)) return false;
     const int rounds = (LIST == 2 && w.nc > 0) ? c.lrounds[w.gcell] : -1;     // warp-uniform
-    if (rounds < 0) cursor_prefetch(c.mask + i, (size_t)c.n, nz);
+    if (rounds < 0) cursor_prefetch(mask_row(c.mask, w.is, FT::NW, work ? lane : 0), (unsigned)w.nc, nz);
     if (!tile_setup<FT, 2>(c, g, sh, w, parity, c.ps4, c.pk4)) return true;
     build_ctab<FT, 2>(c, sh, w, lane);
     if (!__any_sync(0xffffffffu, work)) return true;
@@ -971,7 +895,7 @@ __device__ __forceinline__ bool fluid_body(const DevF &c, const TileGeom &g, Til
     I.visc_f = c.visc_coef; I.visc_w = c.visc_coef * c.rho0T / rhoi;   // wc:41-44
     I.h2 = c.h2_001;
     float dd = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, ssum = 0.f;
-    const size_t n = (size_t)c.n;
+    const unsigned n = (unsigned)w.nc;
     constexpr unsigned SW = ((unsigned)FT::SENT << 12) | (unsigned)FT::SENT;   // a half round of two empty slots
     if (LIST == 2 && rounds >= 0) {
         const uint2 *lrow = c.nlist + ((size_t)w.is * LIST_ROUNDS + (work ? lane : 0));   // cell block: [round][particle of the cell]
@@ -994,7 +918,7 @@ __device__ __forceinline__ bool fluid_body(const DevF &c, const TileGeom &g, Til
             cur = nxt;
         }
     } else {
-        const unsigned *mrow = c.mask + (work ? i : w.is);
+        const unsigned *mrow = mask_row(c.mask, w.is, FT::NW, work ? lane : 0);
         uint2 *lrow = LIST == 1 ? c.nlist + ((size_t)w.is * LIST_ROUNDS + (work ? lane : 0)) : nullptr;
         int r = 0;
         Cursor k;
@@ -1045,16 +969,16 @@ __global__ void __launch_bounds__(256) k_mask_count(DevF c, int nw, int *__restr
     if (c.ps4[i].w > 0.f && !c.cellflag[c.gid[i]]) {
         cnt = 0;
         const unsigned nz = c.nzw[i];                  // empty words are never stored
-        for (int cc = 0; cc < nw; cc++) if (nz & rbit(cc)) cnt += __popc(c.mask[(size_t)cc * c.n + i]);
+        const int g = c.gid[i], is = cell_start(c.cell_end, g), nc = c.cell_end[g] - is;
+        const unsigned *mrow = mask_row(c.mask, is, nw, i - is);
+        for (int cc = 0; cc < nw; cc++) if (nz & rbit(cc)) cnt += __popc(mrow[cc * nc]);
     }
     out[i] = cnt;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
 typedef Foot<true, 2, 2> F3M;      // 3D: masks / Shepard / fluid pass -- 16 warps, 16 runs
-typedef Foot<true, 1, 1> F3W;      // 3D: wall pass (three payload arrays) -- 4 warps, 9 runs
 typedef Foot<false, 4, 1> F2M;     // 2D: 16 warps, 6 runs
-typedef Foot<false, 2, 1> F2W;
 
 template <class FT, int NP> static size_t smem_of() { return sizeof(TileShared<FT, NP>); }
 
@@ -1075,10 +999,6 @@ template <int KERNEL> static int set_attrs(SphCtx *c) {
     int r = 0;
     if (!r) r = set_smem(c, k_tile_shepard<KERNEL, F3M>, smem_of<F3M, 1>());
     if (!r) r = set_smem(c, k_tile_shepard<KERNEL, F2M>, smem_of<F2M, 1>());
-    if (!r) r = set_smem(c, k_tile_wall<KERNEL, F3W, false>, smem_of<F3W, 3>());
-    if (!r) r = set_smem(c, k_tile_wall<KERNEL, F3W, true>, smem_of<F3W, 3>());
-    if (!r) r = set_smem(c, k_tile_wall<KERNEL, F2W, false>, smem_of<F2W, 3>());
-    if (!r) r = set_smem(c, k_tile_wall<KERNEL, F2W, true>, smem_of<F2W, 3>());
     if (!r) r = set_fluid_attrs<KERNEL, F3M>(c);
     if (!r) r = set_fluid_attrs<KERNEL, F2M>(c);
     return r;
@@ -1158,10 +1078,6 @@ int tile_mask(SphCtx *c, bool shepard) {
     return 0;
 }
 
-template <int KERNEL, class FT> static void launch_wall(SphCtx *c, const DevF &d, bool shep) {
-    if (shep) TILE_LAUNCH((k_tile_wall<KERNEL, FT, true>), FT, 3, 6);
-    else TILE_LAUNCH((k_tile_wall<KERNEL, FT, false>), FT, 3, 6);
-}
 template <int KERNEL, bool D3> static void launch_wall_gather(SphCtx *c, const DevF &d, bool shep) {
     const int grid = 148 * 4;                                       // 4 blocks of 8 independent warps per SM, grid-stride over the cell list
     if (shep) k_wall_gather<KERNEL, D3, true><<<grid, WG_WARPS * 32, 0, c->stream>>>(d);
