@@ -270,19 +270,26 @@ namespace {
 // SPHBase.step (base:41-51) + substep (base:53-61)
 template <typename T> int step_once(SphCtx *c) {
     int r;
+    // WCSPH without XSPH: pointwise stages ride in neighbouring kernels (identical operations, fewer HBM round trips):
+    // init_real2tmp in the reorder kernel, advect_LF_half in the EOS / payload kernel of the cell-tile path, and
+    // advect_SE|LF + advect_pos + advect_something in one kernel.
+    const bool wc_fused = c->p.solver == SPH_SOLVER_WC && !c->p.xsph && (c->p.ti == 1 || c->p.ti == 2);
+    c->fuse_init = wc_fused;
     if ((r = grid_build<T>(c))) return r;
+    c->fuse_init = false;
     if ((r = calc_kernel_corr<T>(c, false))) return r;
-    if ((r = init_real2tmp<T>(c))) return r;
+    if (!wc_fused && (r = init_real2tmp<T>(c))) return r;
     switch (c->p.ti) {
     case 1:
         if ((r = one_step<T>(c))) return r;
-        if ((r = advect<T>(c, 0, 0))) return r;
+        if (!wc_fused && (r = advect<T>(c, 0, 0))) return r;
         break;
     case 2:
         if ((r = one_step<T>(c))) return r;
-        if ((r = advect<T>(c, 1, 0))) return r;
+        if (wc_fused && c->fast) c->fuse_half = true;          // consumed by the next one_step's first kernel
+        else if ((r = advect<T>(c, 1, 0))) return r;
         if ((r = one_step<T>(c))) return r;
-        if ((r = advect<T>(c, 0, 0))) return r;
+        if (!wc_fused && (r = advect<T>(c, 0, 0))) return r;
         break;
     case 4: {
         static const int m[4] = {1, 2, 2, 1};
@@ -298,6 +305,7 @@ template <typename T> int step_once(SphCtx *c) {
         snprintf(c->err, sizeof(c->err), "timeIntegration %d is not runnable (3 is broken in the reference, base:126-130)", c->p.ti);
         return -2;
     }
+    if (wc_fused) return finish_step<T>(c);
     if ((r = advect_pos<T>(c))) return r;
     return post_step<T>(c);
 }

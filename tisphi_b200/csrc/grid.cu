@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) k_rank(int n, const int *__restrict__ gid
 // consecutive steps (particles move much less than a cell per step), so they are near-coalesced too.
 template <typename T>
 __global__ void __launch_bounds__(256) k_reorder(Dev<T> a, Dev<T> b, const int *__restrict__ perm,
-                                                 const int *__restrict__ gid_unsorted, int soil) {
+                                                 const int *__restrict__ gid_unsorted, int soil, int init_tmp) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.n) return;
     const int s = perm[k];
@@ -149,9 +149,15 @@ __global__ void __launch_bounds__(256) k_reorder(Dev<T> a, Dev<T> b, const int *
         a.psx[k] = xs.x; a.psy[k] = xs.y; a.psz[k] = xs.z; a.psf[k] = fl ? (T)1 : (T)-1;
         if (fl) a.cellflow[g] = 1;
     }
-    b.v4[k] = a.v4[s];
-    b.vt4[k] = a.vt4[s];
-    b.rho[k] = a.rho[s];
+    const Vec4<T> v = a.v4[s];
+    const double rho = a.rho[s];
+    b.v4[k] = v;
+    if (init_tmp && is_real(ty)) {                  // init_real2tmp (base:67-74) of the WCSPH step: tmp := real
+        Vec4<T> vt = v; vt.w = (T)rho;
+        b.vt4[k] = vt;
+        a.rho_t[k] = rho;                           // density_tmp is not carried: one buffer, sorted order
+    } else b.vt4[k] = a.vt4[s];
+    b.rho[k] = rho;
     b.press[k] = a.press[s];
     b.type[k] = ty;
     b.id0[k] = a.id0[s];
@@ -243,7 +249,9 @@ template <typename T> int grid_build(SphCtx *c) {
     k_rank<<<blocks_for(n, 256), 256, 0, st>>>(n, gid_u, a.cell_end, tmpidx, perm, id_new);
     SPH_LAUNCH_CHECK(c);
     SPH_PROF(c, K_REORDER);
-    k_reorder<T><<<blocks_for(n, 256), 256, 0, st>>>(a, b, perm, gid_u, c->soil ? 1 : 0);
+    const int init_tmp = (c->fuse_init && !c->soil) ? 1 : 0;
+    c->fuse_init = false;
+    k_reorder<T><<<blocks_for(n, 256), 256, 0, st>>>(a, b, perm, gid_u, c->soil ? 1 : 0, init_tmp);
     SPH_LAUNCH_CHECK(c);
     static const int carried[] = {SPH_F_X, SPH_F_XS, SPH_F_V, SPH_F_V_TMP, SPH_F_DENSITY, SPH_F_PRESSURE, SPH_F_MAT_TYPE, SPH_F_ID0};
     for (int f : carried) flip(c, f);

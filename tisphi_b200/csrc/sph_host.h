@@ -43,6 +43,7 @@ struct SphCtx {
     float r2thr32;
     bool shep_wall_pending;
     bool shep_pending;   // tile path: CSPM_f of flow particles is still to be formed by the next fluid pass
+    bool fuse_init, fuse_half;   // sph_step only: init_real2tmp rides in the reorder kernel / advect_LF_half in k_tile_prep
     int own0, own1;      // owned x-columns [own0, own1) (multi-GPU slabs); the whole grid on one GPU
 };
 
@@ -93,6 +94,7 @@ template <typename T> int one_step(SphCtx *c);
 template <typename T> int one_step_phase(SphCtx *c, int phase);
 template <typename T> int advect_pos(SphCtx *c);
 template <typename T> int post_step(SphCtx *c);
+template <typename T> int finish_step(SphCtx *c);      // advect_SE/LF + advect_pos + advect_something of WCSPH in one kernel
 template <typename T> int neighbor_count(SphCtx *c, int32_t *out);
 template <typename T> int density_sum(SphCtx *c, void *out);
 // sweeps_tile.cu (float only)

@@ -688,6 +688,36 @@ template <typename T> int post_step(SphCtx *c) {
     return 0;
 }
 
+// advect_SE / advect_LF (base:79-87, 106-114) + advect_pos without XSPH (base:228-238) + WCSPH advect_something
+// (wc:129-132) of one particle in one kernel: the same operations in the same order as k_advect(kind 0), k_advect_pos
+// and k_post_wc, without writing and re-reading density, velocity and volume in between (sph_step only).
+template <typename T> __global__ void __launch_bounds__(256) k_wc_finish(Dev<T> c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    const int t = c.type[i];
+    if (!is_real(t)) return;
+    Vec4<T> v = c.v4[i];
+    const Vec4<T> dv = c.d_vel[i];
+    const double dt = c.dt;
+    double r = c.rho[i] + dt * (double)c.d_rho[i];
+    v.x += (T)dt * dv.x; v.y += (T)dt * dv.y; v.z += (T)dt * dv.z;
+    c.v4[i] = v;
+    double *x = c.x + 3 * (size_t)i;
+    x[0] += dt * (double)v.x; x[1] += dt * (double)v.y; x[2] += dt * (double)v.z;
+    if (is_fluid(t) && r < c.rho0) r = c.rho0;                      // chk_density (base:214-221)
+    c.rho[i] = r;
+    Vec4<T> xs = c.xs4[i];
+    xs.w = (T)((double)v.w / r);
+    c.xs4[i] = xs;
+}
+template <typename T> int finish_step(SphCtx *c) {
+    if (c->n == 0) return 0;
+    SPH_PROF(c, K_ADVECT);
+    k_wc_finish<T><<<blocks_for(c->n, 256), 256, 0, c->stream>>>(make_dev<T>(c));
+    SPH_LAUNCH_CHECK(c);
+    return 0;
+}
+
 // -------------------------------------------------------------------------------------------- stand-alone sweeps
 template <typename T> __global__ void __launch_bounds__(128) k_neighbor_count(Dev<T> c, int *__restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -724,6 +754,7 @@ template <typename T> int density_sum(SphCtx *c, void *out) {
     template int one_step_phase<T>(SphCtx *, int);                    \
     template int advect_pos<T>(SphCtx *);                  \
     template int post_step<T>(SphCtx *);                   \
+    template int finish_step<T>(SphCtx *);                   \
     template int neighbor_count<T>(SphCtx *, int32_t *);   \
     template int density_sum<T>(SphCtx *, void *);
 INST(float)

@@ -632,22 +632,41 @@ template <int KERNEL, class FT> __global__ void __launch_bounds__(FT::BT) k_tile
 }
 
 // ------------------------------------------------------------------------------------------------ prep (pointwise)
-// wc:87-88 EOS in float64 into the NEW pressure buffer; signed volume of the tile payload; fluid half of pk4.
-__global__ void __launch_bounds__(256) k_tile_prep(DevF c) {
+// wc:87-88 EOS in float64 into the NEW pressure buffer; signed volume of the tile payload; fluid half of pk4; the
+// constant result of dry wall particles (no flow neighbour: empty masks, they never reach the wall pass).
+// ADV (inside sph_step only): the "LF" half-step update advect_LF_half (base:96-104, = k_advect kind 1) of the same
+// particle first, so that the stage state is written once and not read back by a second kernel.
+template <bool ADV> __global__ void __launch_bounds__(256) k_tile_prep(DevF c, int shep) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n) return;
     const int t = c.type[i];
-    const F4 xs = c.xs4[i];
+    F4 xs = c.xs4[i];
+    F4 vt;
+    double rt = 0.0;
+    bool have = false;
+    if (ADV && is_real(t)) {
+        vt = c.vt4[i];
+        const F4 dv = c.d_vel[i];
+        rt = c.rho_t[i] + 0.5 * c.dt * (double)c.d_rho[i];
+        c.rho_t[i] = rt;
+        xs.w = (float)((double)c.v4[i].w / rt);
+        c.xs4[i] = xs;
+        const float hdt = (float)(0.5 * c.dt);
+        vt.x += hdt * dv.x; vt.y += hdt * dv.y; vt.z += hdt * dv.z; vt.w = (float)rt;
+        c.vt4[i] = vt;
+        have = true;
+    }
     F4 ps = xs;
-    ps.w = is_flow(t) ? xs.w : -xs.w;
+    const bool fl = is_flow(t);
+    ps.w = fl ? xs.w : -xs.w;
     c.ps4[i] = ps;
     if (is_fluid(t)) {
-        const double rt = c.rho_t[i];
+        if (!have) { rt = c.rho_t[i]; vt = c.vt4[i]; }
         double v = c.stiff * (pow(rt / c.rho0, c.gamma_) - 1.0);
         v = v > 0.0 ? v : 0.0;
         const float p = (float)v;
         c.pnew[i] = p;
-        F4 pk = c.vt4[i];
+        F4 pk = vt;
         pk.w = p / (pk.w * pk.w);
         c.pk4[i] = pk;
         F4 pw; pw.x = p; pw.y = c.press[i]; pw.z = 0.f; pw.w = 0.f;   // EOS pressure, previous pressure (wc:86-103 race)
@@ -657,6 +676,16 @@ __global__ void __launch_bounds__(256) k_tile_prep(DevF c) {
         c.pnew[i] = po;
         F4 pw; pw.x = po; pw.y = po; pw.z = 0.f; pw.w = 0.f;
         c.pw4[i] = pw;
+    }
+    if (!fl && c.nzw[i] == 0u && !c.cellflag[c.gid[i]]) {           // dry: v~ = 2 v, rho~ = rho0, p = 0, f = 1
+        const F4 v = c.v4[i];
+        F4 wt; wt.x = 2.f * v.x; wt.y = 2.f * v.y; wt.z = 2.f * v.z; wt.w = c.rho0T;
+        c.vt4[i] = wt;
+        c.rho_t[i] = c.rho0;
+        c.pnew[i] = 0.f;
+        if (shep) c.cspm_f[i] = 1.f;
+        F4 pk = wt; pk.w = 0.f;
+        c.pk4[i] = pk;
     }
 }
 
@@ -733,7 +762,7 @@ template <int KERNEL, bool D3, bool SHEP> __global__ void __launch_bounds__(WG_W
         F4 pi; pi.x = pi.y = pi.z = pi.w = 0.f;
         if (lane < nc) {
             pi = c.ps4[i];
-            if (pi.w < 0.f) { nz = c.nzw[i]; work = nz != 0; }      // dry walls: k_tile_wall_dry
+            if (pi.w < 0.f) { nz = c.nzw[i]; work = nz != 0; }      // dry walls: k_tile_prep
         }
         if (!work) nz = 0;
         if (!__any_sync(0xffffffffu, work)) continue;
@@ -821,20 +850,6 @@ template <int KERNEL, bool D3, bool SHEP> __global__ void __launch_bounds__(WG_W
     }
 }
 
-// dry wall particles (no flow neighbour: empty masks) never reach the work list: their constant result is pointwise
-__global__ void __launch_bounds__(256) k_tile_wall_dry(DevF c, int shep) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
-    if (!(c.ps4[i].w < 0.f) || c.nzw[i] != 0u || c.cellflag[c.gid[i]]) return;
-    const F4 v = c.v4[i];
-    F4 vt; vt.x = 2.f * v.x; vt.y = 2.f * v.y; vt.z = 2.f * v.z; vt.w = c.rho0T;
-    c.vt4[i] = vt;
-    c.rho_t[i] = c.rho0;
-    c.pnew[i] = 0.f;
-    if (shep) c.cspm_f[i] = 1.f;
-    F4 pk = vt; pk.w = 0.f;
-    c.pk4[i] = pk;
-}
 // ------------------------------------------------------------------------------------------------ pass B: fluid
 // wc:108-126 for fluid particles: continuity + viscosity + pressure in one visit of the set bits.
 //   d_rho_i = rho~_i sum_j V_j (v~_i - v~_j) . gradW_ij
@@ -1087,13 +1102,13 @@ template <int KERNEL, bool D3> static void launch_wall_gather(SphCtx *c, const D
 int tile_wc_prep_and_wall(SphCtx *c) {
     DevF d = make_dev<float>(c);
     const int n = (int)c->n;
-    SPH_PROF(c, K_WC_EOS);
-    k_tile_prep<<<blocks_for(n, 256), 256, 0, c->stream>>>(d);
-    SPH_LAUNCH_CHECK(c);
     const bool shep = c->shep_wall_pending;
     c->shep_wall_pending = false;
-    SPH_PROF(c, K_TILE_WALL);
-    k_tile_wall_dry<<<blocks_for(n, 256), 256, 0, c->stream>>>(d, shep ? 1 : 0);
+    const bool adv = c->fuse_half;                                  // set by sph_step: the half-step update rides along
+    c->fuse_half = false;
+    SPH_PROF(c, K_WC_EOS);
+    if (adv) k_tile_prep<true><<<blocks_for(n, 256), 256, 0, c->stream>>>(d, shep ? 1 : 0);
+    else k_tile_prep<false><<<blocks_for(n, 256), 256, 0, c->stream>>>(d, shep ? 1 : 0);
     SPH_LAUNCH_CHECK(c);
     SPH_PROF(c, K_TILE_WALL);
     if (c->p.dim == 3) {
