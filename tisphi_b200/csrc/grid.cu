@@ -12,20 +12,32 @@
 namespace sph {
 
 // ------------------------------------------------------------------------------------------------ cell ids
+// After the first step the arrays are already almost sorted, so the lanes of a warp mostly fall into one or two cells:
+// the histogram update is aggregated per warp (one atomicAdd per distinct cell) with match.any.  Slots inside a cell
+// are arbitrary anyway -- k_rank recomputes the stable order.
 template <typename T>
 __global__ void __launch_bounds__(256) k_cell_id(Dev<T> c, int *__restrict__ gid_out, int *__restrict__ slot) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
-    const double x[3] = {c.x[3 * (size_t)i], c.x[3 * (size_t)i + 1], c.x[3 * (size_t)i + 2]};
-    int cc[3];
-    pos_to_cell(c, x, cc);
-    long long g = (long long)cc[0] * c.gn[1] * c.gn[2] + (long long)cc[1] * c.gn[2] + cc[2];
-    if (g < 0 || g >= c.C) {            // the reference has no check; we clamp and count
-        atomicAdd(c.bad, 1ull);
-        g = g < 0 ? 0 : c.C - 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = i < c.n;
+    long long g = -1 - lane;                    // idle lanes: distinct keys that match nobody
+    if (valid) {
+        const double x[3] = {c.x[3 * (size_t)i], c.x[3 * (size_t)i + 1], c.x[3 * (size_t)i + 2]};
+        int cc[3];
+        pos_to_cell(c, x, cc);
+        g = (long long)cc[0] * c.gn[1] * c.gn[2] + (long long)cc[1] * c.gn[2] + cc[2];
+        if (g < 0 || g >= c.C) {                // the reference has no check; we clamp and count
+            atomicAdd(c.bad, 1ull);
+            g = g < 0 ? 0 : c.C - 1;
+        }
+        gid_out[i] = (int)g;
     }
-    gid_out[i] = (int)g;
-    slot[i] = atomicAdd(&c.cell_cnt[(int)g], 1);
+    const unsigned peers = __match_any_sync(0xffffffffu, (int)g);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (valid && lane == leader) base = atomicAdd(&c.cell_cnt[(int)g], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (valid) slot[i] = base + __popc(peers & ((1u << lane) - 1u));
 }
 
 // ------------------------------------------------------------------------------------------------ scan

@@ -352,91 +352,92 @@ template <int B> __device__ __forceinline__ unsigned push2(unsigned cm, u64 dx, 
 }
 __device__ __forceinline__ u64 chunk_bits(unsigned cm, int t0) { return (u64)cm << t0; }
 
-template <class FT> struct MaskShared {
+// Two tile buffers: while the block evaluates the cell pairs of one work item, warp 0 has already fetched the next
+// item, computed its spans and issued its TMA copies into the other buffer (the tile is only 49 KB, two blocks of two
+// buffers fit an SM), so the copy latency and the cell_end look-ups are off the critical path.
+template <class FT> struct __align__(128) MaskTile {
     static constexpr int CAPS = FT::CAP + 8;          // the chunked test loop may read up to 7 entries past a cell
     float X[CAPS], Y[CAPS], Z[CAPS], F[CAPS];
-    unsigned long long bar;
     int cb[FT::NR * FT::CBW];         // tile index of the first particle of each (run, cell)
     int gdelta[FT::NR];               // global index = tile index + gdelta[run]
-    int total, overflow, item;
+    int total, overflow;
+};
+template <class FT> struct MaskShared {
+    MaskTile<FT> t[2];
+    unsigned long long bar[2];
+    int item[2];
     int4 tab[FT::NWARP][FT::NW];      // per (warp, stencil cell): tile index of its first particle, particle count,
                                       // global - tile index, code = (ox+1) | (oy+1) << 2 | (of+1) << 4 | owned << 6 | has flow << 7
 };
-template <class FT> __device__ __forceinline__ void mask_tile_init(MaskShared<FT> &sh) {
-    if (threadIdx.x == 0) mbar_init(&sh.bar, 1);
-    __syncthreads();
-}
-// Spans, cell boundaries and the TMA copies of the four SoA arrays.  Every run starts at a multiple of four entries
-// in the tile and is copied from the multiple of four particles at or below its first particle.
+// Warp 0 only.  Spans, cell boundaries and the TMA copies of the four SoA arrays of work item `blk` into `tl`.  Every
+// run starts at a multiple of four entries in the tile and is copied from the multiple of four particles at or
+// below its first particle.  Always completes exactly one phase of `bar`.
 template <class FT>
-__device__ __forceinline__ bool mask_tile_setup(const DevF &c, const TileGeom &g, MaskShared<FT> &sh, const WarpCell &w, unsigned parity) {
-    const int tid = threadIdx.x;
-    const int f0 = w.f0, f_lo = max(f0 - 1, 0), f_hi = min(f0 + ZB, g.nF - 1);
-    if (tid < 32) {
-        int len = 0, S = 0, gb = 0, lead = 0, len4 = 0;
-        bool valid = false;
-        if (tid < FT::NR) {
-            const int n0 = w.b0 * FT::BX + tid / FT::NRY - 1;
-            const int n1 = FT::d3 ? w.b1 * FT::BY + tid % FT::NRY - 1 : 0;
-            valid = n0 >= 0 && n0 < g.n0 && n1 >= 0 && n1 < g.n1;
-            if (valid) {
-                gb = (n0 * g.n1 + n1) * g.nF;
-                S = cell_start(c.cell_end, gb + f_lo);
-                len = c.cell_end[gb + f_hi] - S;
-                if (len > 0) { lead = S & 3; len4 = (lead + len + 3) & ~3; }
-            }
-        }
-        int inc = len4;                                           // inclusive scan over the first NR lanes
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (tid >= o) inc += t;
-        }
-        const int roff = inc - len4, first = roff + lead;         // tile index of the copy / of the run's first particle
-        if (tid < FT::NR) {
-            sh.gdelta[tid] = S - first;
-            for (int k = 0; k < FT::CBW; k++) {
-                const int f = f0 - 1 + k;
-                int v;
-                if (!valid || f < f_lo) v = first;
-                else if (f > f_hi) v = first + len;
-                else v = first + cell_start(c.cell_end, gb + f) - S;
-                sh.cb[tid * FT::CBW + k] = v;
-            }
-        }
-        const int total = __shfl_sync(0xffffffffu, inc, FT::NR - 1);
-        if (tid == 0) {
-            sh.total = total;
-            sh.overflow = total > FT::CAP;
-        }
-        __syncwarp();
-        if (total > FT::CAP) {                                    // nothing is loaded: complete the phase so that the parity still flips
-            if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sh.bar)) : "memory");
-        } else {
-            if (tid == 0) mbar_expect_tx(&sh.bar, (unsigned)(total * 16));
-            __syncwarp();
-            if (tid < FT::NR && len4 > 0) {
-                const int S4 = S - lead;
-                const unsigned bytes = (unsigned)(len4 * 4);
-                tma_load_1d(&sh.X[roff], c.psx + S4, bytes, &sh.bar);
-                tma_load_1d(&sh.Y[roff], c.psy + S4, bytes, &sh.bar);
-                tma_load_1d(&sh.Z[roff], c.psz + S4, bytes, &sh.bar);
-                tma_load_1d(&sh.F[roff], c.psf + S4, bytes, &sh.bar);
-            }
+__device__ __forceinline__ void mask_tile_issue(const DevF &c, const TileGeom &g, MaskTile<FT> &tl, unsigned long long *bar, int blk) {
+    const int tid = threadIdx.x;                                  // < 32
+    const int seg = blk % g.nseg, tq = blk / g.nseg, b1 = tq % g.nb1, b0 = tq / g.nb1;
+    const int f0 = seg * ZB, f_lo = max(f0 - 1, 0), f_hi = min(f0 + ZB, g.nF - 1);
+    int len = 0, S = 0, gb = 0, lead = 0, len4 = 0;
+    bool valid = false;
+    if (tid < FT::NR) {
+        const int n0 = b0 * FT::BX + tid / FT::NRY - 1;
+        const int n1 = FT::d3 ? b1 * FT::BY + tid % FT::NRY - 1 : 0;
+        valid = n0 >= 0 && n0 < g.n0 && n1 >= 0 && n1 < g.n1;
+        if (valid) {
+            gb = (n0 * g.n1 + n1) * g.nF;
+            S = cell_start(c.cell_end, gb + f_lo);
+            len = c.cell_end[gb + f_hi] - S;
+            if (len > 0) { lead = S & 3; len4 = (lead + len + 3) & ~3; }
         }
     }
-    __syncthreads();
-    if (sh.overflow) return false;
-    mbar_wait(&sh.bar, parity);
-    return true;
+    int inc = len4;                                               // inclusive scan over the first NR lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (tid >= o) inc += t;
+    }
+    const int roff = inc - len4, first = roff + lead;             // tile index of the copy / of the run's first particle
+    if (tid < FT::NR) {
+        tl.gdelta[tid] = S - first;
+        for (int k = 0; k < FT::CBW; k++) {
+            const int f = f0 - 1 + k;
+            int v;
+            if (!valid || f < f_lo) v = first;
+            else if (f > f_hi) v = first + len;
+            else v = first + cell_start(c.cell_end, gb + f) - S;
+            tl.cb[tid * FT::CBW + k] = v;
+        }
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, FT::NR - 1);
+    if (tid == 0) {
+        tl.total = total;
+        tl.overflow = total > FT::CAP;
+    }
+    __syncwarp();
+    if (total > FT::CAP) {                                        // nothing is loaded: complete the phase so that the parity still flips
+        if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    } else {
+        if (tid == 0) mbar_expect_tx(bar, (unsigned)(total * 16));
+        __syncwarp();
+        if (tid < FT::NR && len4 > 0) {
+            const int S4 = S - lead;
+            const unsigned bytes = (unsigned)(len4 * 4);
+            tma_load_1d(&tl.X[roff], c.psx + S4, bytes, bar);
+            tma_load_1d(&tl.Y[roff], c.psy + S4, bytes, bar);
+            tma_load_1d(&tl.Z[roff], c.psz + S4, bytes, bar);
+            tma_load_1d(&tl.F[roff], c.psf + S4, bytes, bar);
+        }
+    }
 }
 
 template <class FT>
-__device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, MaskShared<FT> &sh, int blk, unsigned parity) {
+__device__ __forceinline__ void mask_body(const DevF &c, const TileGeom &g, MaskShared<FT> &sm, const MaskTile<FT> &sh,
+                                          unsigned long long *bar, int blk, unsigned parity) {
     const WarpCell w = warp_cell<FT>(c, g, blk);
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-    const bool ok = mask_tile_setup<FT>(c, g, sh, w, parity);
-    if (w.nc == 0) return true;
+    const bool ok = !sh.overflow;
+    if (ok) mbar_wait(bar, parity);
+    if (w.nc == 0) return;
     // what this warp needs to know about its 27 (9) stencil cells, computed once by lane = stencil cell
     int ox, oy, of;
     stencil<FT>(min(lane, FT::NW - 1), ox, oy, of);
@@ -451,7 +452,7 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Mask
         bowned = ncx >= c.own0 && ncx < c.own1;                    // B's warp runs on this rank
         if (te.y > 0) bflowc = c.cellflow[(ncx * g.n1 + (w.cy + oy)) * g.nF + (w.f + of)] != 0;
         te.w = (ox + 1) | ((oy + 1) << 2) | ((of + 1) << 4) | (bowned ? 64 : 0) | (bflowc ? 128 : 0);
-        sh.tab[wi][lane] = te;
+        sm.tab[wi][lane] = te;
     }
     // can this cell be represented?  (uniform per warp)
     const bool flagged = __any_sync(0xffffffffu, te.y > 32) || !ok || w.nc > 32;
@@ -461,7 +462,7 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Mask
             if (nx >= 0 && nx < g.n0 && ny >= 0 && ny < g.n1 && nf >= 0 && nf < g.nF) c.cellflag[(nx * g.n1 + ny) * g.nF + nf] = 1;
         }
         if (lane == 0) atomicAdd(c.nflag, 1);
-        return true;
+        return;
     }
     const bool mine = lane < w.nc;
     const int i = w.is + lane;
@@ -484,7 +485,7 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Mask
     while (todo) {
         const int cc = __ffs(todo) - 1;
         todo &= todo - 1;
-        const int4 t = sh.tab[wi][cc];
+        const int4 t = sm.tab[wi][cc];
         const int a = t.x, nb = t.y;
         const bool same = cc == FT::CENTRE, upper = cc > FT::CENTRE, b_owned = (t.w & 64) != 0;
         const float bx = (float)((t.w & 3) - 1), by = (float)(((t.w >> 2) & 3) - 1), bf = (float)(((t.w >> 4) & 3) - 1);
@@ -544,13 +545,38 @@ __device__ __forceinline__ bool mask_body(const DevF &c, const TileGeom &g, Mask
     }
     if (mine && nz) atomicOr(&c.nzw[i], nz);
     if (lane == 0) c.cellinfo[w.gcell] = (unsigned char)((flowA ? 1 : 0) | (has_wall ? 2 : 0) | (has_wall && near_flow ? 4 : 0));
-    return true;
 }
 template <class FT> __global__ void __launch_bounds__(FT::BT, 2) k_tile_mask(DevF c, TileGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MaskShared<FT> &sh = *reinterpret_cast<MaskShared<FT> *>(smem_raw);
-    mask_tile_init<FT>(sh);
-    TILE_PERSISTENT_LOOP(sh, c.worklist[3], c.wcount + 3, c.wcount + 4, (mask_body<FT>(c, g, sh, blk, parity)))
+    const int tid = threadIdx.x;
+    const int items = c.wcount[3];
+    const int *list = c.worklist[3];
+    int *cursor = c.wcount + 4;
+    if (tid == 0) {
+        mbar_init(&sh.bar[0], 1);
+        mbar_init(&sh.bar[1], 1);
+        sh.item[0] = atomicAdd(cursor, 1);
+    }
+    __syncthreads();
+    if (tid < 32 && sh.item[0] < items) mask_tile_issue<FT>(c, g, sh.t[0], &sh.bar[0], list[sh.item[0]]);
+    __syncthreads();
+    unsigned par0 = 0, par1 = 0;
+    int b = 0;
+    while (true) {
+        const int it = sh.item[b];
+        if (it >= items) break;
+        if (tid < 32) {                                            // next item: fetch, spans, TMA into the other buffer
+            if (tid == 0) sh.item[b ^ 1] = atomicAdd(cursor, 1);
+            __syncwarp();
+            const int nit = sh.item[b ^ 1];
+            if (nit < items) mask_tile_issue<FT>(c, g, sh.t[b ^ 1], &sh.bar[b ^ 1], list[nit]);
+        }
+        mask_body<FT>(c, g, sh, sh.t[b], &sh.bar[b], list[it], b ? par1 : par0);
+        if (b) par1 ^= 1u; else par0 ^= 1u;
+        __syncthreads();                                           // tile b may be refilled; item / spans of the other buffer are visible
+        b ^= 1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ work lists
