@@ -34,6 +34,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def ncu_evidence(kernel):
+    """DRAM traffic per launch and the unit that actually bounds the kernel, from the committed ncu --set full captures
+    (profiles/r1_ncu_evidence.json, written by tools/ncu_evidence.py from the .ncu-rep of the same bench command)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_evidence.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -131,14 +141,19 @@ def algorithmic_bytes(kernel, n, n_fluid, n_wall, cells):
     table = {
         # read {x,y,z,V | v~x,v~y,v~z,rho~ | type | p} = 36 B of every particle, write {d_rho, d_vel} = 16 B per fluid
         "wc_fluid": 36 * n + 16 * n_fluid, "tile_fluid": 36 * n + 16 * n_fluid,
-        # read the same 36 B of every particle (+4 B previous pressure), write {v~, rho~, p} = 20 B per wall particle
-        "wc_wall": 40 * n + 20 * n_wall, "tile_wall": 40 * n + 20 * n_wall,
-        # read {x,y,z,V} + type = 20 B, write f = 4 B
-        "cspm_f": 24 * n, "tile_mask": 24 * n,
-        # read perm 4 + key 4 + carried payload, write payload + key: x 24, xs 16, v 16, v~ 16, rho 8, p 4, type 4, id0 4
-        "reorder": 8 * n + 2 * 92 * n + 4 * n,
+        # wall pass: read 36 B + write 16 B per wall particle (the gathered kernel only visits wall cells in reach of flow)
+        "wc_wall": 52 * n_wall, "tile_wall": 52 * n_wall,
+        # masks: read {x,y,z,flow} = 16 B per particle; the words themselves are internal traffic
+        "cspm_f": 24 * n, "tile_mask": 16 * n,
+        # reorder (+ init_real2tmp, + SoA / AoS tile payloads): read perm, key, x, m_V, v, rho, p, type, id0 = 84 B,
+        # write x, xs, ps4, SoA, v, v~, rho, rho~, p, type, id0, key = 136 B
+        "reorder": 220 * n,
         "cell_id": 24 * n + 8 * n, "rank": 12 * n, "scatter_index": 12 * n, "scan": 12 * cells,
-        "advect": 56 * n_fluid, "init_real2tmp": 52 * n_fluid, "wc_eos": 16 * n, "advect_pos": 64 * n_fluid, "post": 40 * n_fluid,
+        # EOS + tile payloads + dry walls (2 launches per LF step, the second carries advect_LF_half): average per launch
+        "wc_eos": 119 * n_fluid + 40 * n_wall,
+        # advect_LF + advect_pos + advect_something in one kernel: read 88 B, write 64 B per real particle
+        "advect": 152 * n_fluid,
+        "init_real2tmp": 52 * n_fluid, "advect_pos": 64 * n_fluid, "post": 40 * n_fluid,
     }
     return table.get(kernel)
 
@@ -211,10 +226,13 @@ def run_ours(args):
         if b:
             kernel_gbs[k] = round(b / (v[0] / v[1] * 1e-3) / 1e9, 1)
     step_bytes = 208 * n + 104 * n_wall + 12 * ps.grid_num_total          # SURVEY 8(d) formula, per step
+    ev = ncu_evidence(dom_name) or {}
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if achieved else None, "traffic": None, "peak_kind": peak_kind,
-                "note": "neighbour sweeps are fp32-issue bound, not HBM bound (SURVEY 8d); frac is the HBM view of the "
-                        "dominant kernel; per-kernel figures in kernel_gbs",
+                "frac": achieved / peak if achieved else None, "traffic": ev.get("dram_bytes_per_launch"), "peak_kind": peak_kind,
+                "note": "the neighbour sweeps are bound by shared-memory gather bandwidth and instruction issue, not by HBM "
+                        "(SURVEY 8d): frac is the HBM view of the dominant kernel, `limiter` the ncu view of what binds it; "
+                        "HBM-bound kernels (reorder, integrators) are in kernel_gbs",
+                "limiter": ev.get("limiter"),
                 "kernel_share_of_step": kernel_share, "kernel_ms": kernel_ms, "kernel_gbs": kernel_gbs,
                 "whole_step_algorithmic_gbs": step_bytes * args.steps / (ms * 1e-3) / 1e9}
 

@@ -277,7 +277,7 @@ def test_tile_path_equals_generic_path(name):
     g = Golden(name)
     a = make_sim(g.scene, precision="f32", fastSweeps=True)
     b = make_sim(g.scene, precision="f32", fastSweeps=False)
-    assert a.ps.engine.params.fast == 2 and b.ps.engine.params.fast == 0
+    assert a.ps.engine.params.fast >= 1 and b.ps.engine.params.fast == 0
     a.ps.initialize_particle_system()
     b.ps.initialize_particle_system()
     a.solver.calc_kernel_corr()

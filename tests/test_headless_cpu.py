@@ -1,0 +1,122 @@
+"""Host logic of the headless driver (tisphi_b200/eng/ui_sim.py): the reference's stop / exit / export rules
+(eng/ui_sim.py:211-241 of the reference), file stamps, CSV layout and the VTU writer.  No GPU."""
+import json
+import os
+
+import numpy as np
+
+from tisphi_b200.eng import ui_sim as U
+from tisphi_b200.eng.configer_builder import SimConfiger
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def cfg_with(**over):
+    scene = json.load(open(os.path.join(ROOT, "data", "scenes", "test1_db_water.json")))
+    scene["Configuration"].update(dict(stopEveryStep=0, stopAtStep=0, exitAtStep=0, stopAtTime=0, exitAtTime=0, exportEveryTime=0,
+                                       exportEveryRender=0, exportFrame=False, exportVTK=False, exportCSV=False, pauseAtStart=False))
+    scene["Configuration"].update(over)
+    return SimConfiger(config=scene)
+
+
+def run_rules(ctl, frames):
+    out, step = [], 0
+    for k in range(frames + 1):
+        export, paused, done = ctl.after_frame(step)
+        out.append((step, export, paused, done))
+        if paused or done:
+            break
+        step += ctl.substeps
+    return out
+
+
+def test_exit_at_step_and_export_every_render():
+    ctl = U.RunControl(cfg_with(stepsPerRenderUpdate=10, exitAtStep=50, exportEveryRender=2, exportCSV=True), dt=1e-4)
+    assert ctl.exports
+    log = run_rules(ctl, 100)
+    assert [s for s, e, p, d in log if e is not None] == [0, 20, 40]         # step 0, then every 2 renders x 10 steps
+    assert all(e[0] == "step" for s, e, p, d in log if e is not None)
+    assert log[-1][0] == 50 and log[-1][3] and not log[-1][2]               # ends exactly at exitAtStep
+
+
+def test_export_every_time_uses_simulated_time():
+    ctl = U.RunControl(cfg_with(stepsPerRenderUpdate=5, exitAtTime=0.0101, exportEveryTime=0.002, exportVTK=True), dt=1e-4)
+    log = run_rules(ctl, 1000)
+    stamps = [U.stamp_of(e) for s, e, p, d in log if e is not None]
+    assert stamps[0] == "time.secx1e6.0000000"
+    assert stamps[1:] == ["time.secx1e6.%07d" % (2000 * k) for k in range(1, 6)]
+    assert abs(log[-1][0] * 1e-4 - 0.0105) < 1e-12 and log[-1][3]           # first frame at or after exitAtTime
+
+
+def test_stop_rules_pause_the_run():
+    assert run_rules(U.RunControl(cfg_with(stepsPerRenderUpdate=10, stopAtStep=30), dt=1e-4), 100)[-1][:3:2] == (30, True)
+    assert run_rules(U.RunControl(cfg_with(stepsPerRenderUpdate=10, stopAtTime=0.0025), dt=1e-4), 100)[-1][:3:2] == (30, True)
+    assert run_rules(U.RunControl(cfg_with(stepsPerRenderUpdate=10, stopEveryStep=40), dt=1e-4), 100)[-1][:3:2] == (40, True)
+    # stopEveryStep smaller than a frame never fires (ui:215)
+    assert not any(p for s, e, p, d in run_rules(U.RunControl(cfg_with(stepsPerRenderUpdate=10, stopEveryStep=5), dt=1e-4), 20))
+
+
+def test_no_exports_without_a_format_or_a_schedule():
+    assert not U.RunControl(cfg_with(exportEveryRender=2), dt=1e-4).exports
+    assert not U.RunControl(cfg_with(exportCSV=True), dt=1e-4).exports
+    assert U.stamp_of(("step", 120)) == "000120"
+
+
+def test_vtu_round_trip(tmp_path):
+    rng = np.random.default_rng(3)
+    n = 1234
+    x, y, z = rng.normal(size=(3, n))
+    data = {"id0": np.arange(n, dtype=np.int64), "density": rng.uniform(900, 1100, n), "vel.x": rng.normal(size=n)}
+    f = U.write_vtu(str(tmp_path / "a.vtu"), x, y, z, data)
+    back = U.read_vtu(f)
+    assert np.array_equal(back["points"], np.stack([x, y, z], axis=1))
+    for k, v in data.items():
+        assert np.array_equal(back[k], v), k
+    assert np.array_equal(back["connectivity"], np.arange(n)) and np.array_equal(back["offsets"], np.arange(1, n + 1))
+    assert (back["types"] == 1).all()                                        # VTK_VERTEX
+    txt = open(f).read()
+    assert txt.startswith('<?xml version="1.0"?>') and f'NumberOfPoints="{n}"' in txt
+
+
+class _FakePS:
+    color_title = 7
+
+    def dump(self):
+        n = 5
+        pos = {"pos.x": np.arange(n) * 0.1, "pos.y": np.arange(n) * 0.2, "pos.z": np.zeros(n)}
+        data = {k: np.arange(n, dtype=np.float64) + j for j, k in enumerate(
+            ["id0", "objId", "material", "vel.x", "vel.y", "vel.z", "vel.norm", "density", "stress.xx", "stress.yy", "stress.zz",
+             "stress.xy", "stress.yz", "stress.zx", "strain_equ", "pressure"])}
+        return pos, data
+
+
+class _FakeCase:
+    ps = _FakePS()
+
+
+def test_csv_layout_matches_the_reference(tmp_path):
+    f = U.export_csv("000010", str(tmp_path), _FakeCase())
+    assert os.path.basename(f) == "sim.csv.000010.csv"
+    lines = open(f).read().splitlines()
+    assert lines[0] == "# id0, objId, material, pos.x, pos.y, pos.z, vel.x, vel.y, vel.z, density, stress.xx, stress.yy, " \
+                       "stress.zz, stress.xy, stress.yz, stress.zx, strain_equ"
+    rows = np.loadtxt(f, delimiter=",")
+    assert rows.shape == (5, 17)
+    assert np.allclose(rows[:, 3], np.arange(5) * 0.1) and np.allclose(rows[:, 9], np.arange(5) + 7)   # pos.x, density
+    g = U.export_frame("000010", str(tmp_path), _FakeCase())
+    z = np.load(g)
+    assert str(z["title"]) == "pressure" and np.array_equal(z["value"], np.arange(5) + 15.0)
+
+
+def test_scene_files_are_the_baseline_configs():
+    d = os.path.join(ROOT, "data", "scenes")
+    c1 = json.load(open(os.path.join(d, "test1_db_water.json")))["Configuration"]
+    assert (c1["simulationMethod"], c1["timeIntegration"], c1["kernel"], c1["boundary"], c1["is2D"]) == (1, 2, 1, 2, True)
+    c2 = json.load(open(os.path.join(d, "test2_cc_sand_muI.json")))["Configuration"]
+    assert (c2["simulationMethod"], c2["timeIntegration"], c2["xsph"]) == (2, 2, True)
+    c3 = json.load(open(os.path.join(d, "test2_cc_sand_dp_rk4_cspm.json")))["Configuration"]
+    assert (c3["simulationMethod"], c3["timeIntegration"], c3["kernelCorrection"]) == (3, 4, 1)
+    c4 = json.load(open(os.path.join(d, "c4_db3d_water_13M.json")))
+    assert c4["Configuration"]["is2D"] is False and c4["Blocks"][0]["size"] == [1.6, 1.0, 0.8]
+    for f in os.listdir(d):
+        assert "precision" not in json.load(open(os.path.join(d, f)))["Configuration"], f

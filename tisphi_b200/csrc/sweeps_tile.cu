@@ -960,7 +960,9 @@ __device__ __forceinline__ bool fluid_body(const DevF &c, const TileGeom &g, Til
         }
     } else {
         const unsigned *mrow = mask_row(c.mask, w.is, FT::NW, work ? lane : 0);
-        uint2 *lrow = LIST == 1 ? c.nlist + ((size_t)w.is * LIST_ROUNDS + (work ? lane : 0)) : nullptr;
+        // record: 32-bit offset of this lane's entry of the current round inside nlist, and where the cell's block ends
+        unsigned loff = (unsigned)w.is * LIST_ROUNDS + (work ? lane : 0);
+        const unsigned lend = ((unsigned)w.is + (unsigned)w.nc) * LIST_ROUNDS;
         int r = 0;
         Cursor k;
         cursor_init(k, mrow, n, nz);
@@ -975,8 +977,8 @@ __device__ __forceinline__ bool fluid_body(const DevF &c, const TileGeom &g, Til
             cursor_take2<FT::SENT>(k, i2, i3);
             if (LIST == 1) {
                 const unsigned w1 = (k.flags & CT_CC) | ((unsigned)i2 << 12) | (unsigned)i3;
-                if (work && r < LIST_ROUNDS) *lrow = make_uint2(w0, w1);
-                lrow += w.nc;
+                if (work && loff < lend) c.nlist[loff] = make_uint2(w0, w1);
+                loff += (unsigned)w.nc;
                 r++;
             }
             const F4 p0 = A[i0], q0 = B[i0], p1 = A[i1], q1 = B[i1], p2 = A[i2], q2 = B[i2], p3 = A[i3], q3 = B[i3];

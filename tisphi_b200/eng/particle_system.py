@@ -161,8 +161,11 @@ class ParticleSystem:
                        "mixed": _lib.PREC_MIXED}[self.precision]
         P.wc_fresh = int(bool(self.cfg.get_opt("wcFresh", False)))
         # 0: generic sweeps only; 1: cell-tile sweeps; 2: cell-tile sweeps + neighbour round lists replayed by the
-        # later one_steps of a step (LF / RK4)
-        P.fast = 0 if not self.cfg.get_opt("fastSweeps", True) else (2 if self.cfg.get_opt("neighbourLists", True) else 1)
+        # later one_steps of a step.  Measured on C4 (profiles/): a replayed pass is 8 % faster than walking the masks
+        # again but recording costs the first pass as much, so lists pay off with RK4 (three replays) and not with "LF"
+        # (one); they also take 448 B per particle.  Default: on for timeIntegration 4 only.
+        lists = self.cfg.get_opt("neighbourLists", P.ti == 4)
+        P.fast = 0 if not self.cfg.get_opt("fastSweeps", True) else (2 if lists else 1)
         grav = self.cfg.get_cfg("gravitation")
         for a in range(3):
             P.gn[a] = int(self.grid_num[a])
