@@ -236,31 +236,60 @@ def run_ours(args):
                 "kernel_share_of_step": kernel_share, "kernel_ms": kernel_ms, "kernel_gbs": kernel_gbs,
                 "whole_step_algorithmic_gbs": step_bytes * args.steps / (ms * 1e-3) / 1e9}
 
-    # end-to-end through the C ABI with host buffers
+    # end-to-end through the C ABI with HOST buffers: every step uploads the particle state from pinned host memory
+    # (sph_add_particles), runs sph_step(1) and reads the state back (sph_read_state*).  Steps are independent jobs, so
+    # they are pipelined over `depth` contexts on their own streams (upload of job k+1 | step of job k | download of
+    # job k-1 overlap; PCIe is full duplex); depth 1 is the strictly serial variant, reported alongside.
+    from tisphi_b200 import _lib as L_
+
+    def make_job(engine):
+        return {"eng": engine,
+                "x": torch.empty((n, 3), dtype=torch.float64).pin_memory(), "v": torch.empty((n, 4), dtype=engine.real).pin_memory(),
+                "rho": torch.empty(n, dtype=torch.float64).pin_memory(), "p": torch.empty(n, dtype=engine.real).pin_memory(),
+                "id": torch.empty(n, dtype=torch.int32).pin_memory()}
+
+    def submit(job):
+        e = job["eng"]
+        e.call("sph_clear_particles")
+        e.call("sph_add_particles", n, h_x.data_ptr(), h_v.data_ptr(), h_rho.data_ptr(), h_typ.data_ptr())
+        e.call("sph_step", 1)
+        e.call("sph_read_state_async", job["x"].data_ptr(), job["v"].data_ptr(), job["rho"].data_ptr(), job["p"].data_ptr(),
+               job["id"].data_ptr())
+
+    def run_e2e(jobs, steps):
+        for j in jobs:                                   # untimed warm-up of every context
+            submit(j)
+        for j in jobs:
+            j["eng"].call("sph_synchronize")
+        t0 = time.perf_counter()
+        for k in range(steps):
+            j = jobs[k % len(jobs)]
+            if k >= len(jobs):
+                j["eng"].call("sph_synchronize")         # the job that used this context before has been read back
+            submit(j)
+        for j in jobs:
+            j["eng"].call("sph_synchronize")
+        return time.perf_counter() - t0
+
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    out_x = torch.empty((n, 3), dtype=torch.float64).pin_memory()
-    out_v = torch.empty((n, 4), dtype=eng.real).pin_memory()
-    out_rho = torch.empty(n, dtype=torch.float64).pin_memory()
-    out_p = torch.empty(n, dtype=eng.real).pin_memory()
-    out_id = torch.empty(n, dtype=torch.int32).pin_memory()
-
-    def e2e_step():
-        eng.call("sph_clear_particles")
-        eng.call("sph_add_particles", n, h_x.data_ptr(), h_v.data_ptr(), h_rho.data_ptr(), h_typ.data_ptr())
-        eng.call("sph_step", 1)
-        eng.call("sph_read_state", out_x.data_ptr(), out_v.data_ptr(), out_rho.data_ptr(), out_p.data_ptr(), out_id.data_ptr())
-
-    e2e_step()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    jobs = [make_job(eng)]
+    serial_s = run_e2e(jobs, e2e_steps)
+    depth = max(1, args.e2e_depth)
+    for _ in range(depth - 1):
+        extra = L_.Engine(eng.params, eng.n_max, device=f"cuda:{local}", stream=torch.cuda.Stream(device=local))
+        jobs.append(make_job(extra))
+    pipe_steps = max(e2e_steps, 3 * depth)
+    e2e_s = run_e2e(jobs, pipe_steps) if depth > 1 else serial_s
+    if depth == 1:
+        pipe_steps = e2e_steps
+    assert bool(torch.isfinite(jobs[-1]["v"]).all()) and int(jobs[-1]["id"].max()) == n - 1, "end-to-end result is not a particle state"
     h2d = n * (24 + 24 + 8 + 4)
-    d2h = n * (24 + 4 * out_v.element_size() + 8 + out_p.element_size() + 4)
-    e2e = {"value": n * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3}
+    d2h = n * (24 + 4 * jobs[0]["v"].element_size() + 8 + jobs[0]["p"].element_size() + 4)
+    e2e = {"value": n * pipe_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": pipe_steps, "ms_per_step": e2e_s / pipe_steps * 1e3, "pipeline_depth": depth,
+           "serial_ms_per_step": serial_s / e2e_steps * 1e3, "serial_value": n * e2e_steps / serial_s}
+    for j in jobs[1:]:
+        j["eng"].close()
 
     cpu = None
     if not args.no_cpu:
@@ -409,6 +438,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="lattice refinement of the C4 scene (1 = 12.96 M particles)")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-depth", type=int, default=3, help="contexts the end-to-end jobs are pipelined over (1 = serial)")
     ap.add_argument("--cpu-scale", type=float, default=0.25, help="coarsening of the CPU-baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")

@@ -110,6 +110,10 @@ int sph_clear_particles(SphCtx *ctx);
 /* device -> host copies of the dump() state (ps:459-545) in current (sorted) order; any pointer may be NULL.
  * Synchronises the stream. */
 int sph_read_state(SphCtx *ctx, double *x, double *v, double *density, double *pressure, int32_t *id0);
+/* the same copies enqueued on the ctx's stream without waiting (pinned host buffers); sph_synchronize waits for
+ * everything enqueued on the ctx.  Several ctxs on different streams pipeline upload / step / download. */
+int sph_read_state_async(SphCtx *ctx, double *x, double *v, double *density, double *pressure, int32_t *id0);
+int sph_synchronize(SphCtx *ctx);
 
 /* ParticleSystem.initialize_particle_system (ps:254-257): cell ids, histogram, inclusive scan, stable counting
  * sort, reorder of every carried member. */

@@ -19,7 +19,8 @@ FIELD_ID = {name: k for k, name in enumerate(FIELDS)}
 
 # every symbol include/tisphi_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ["sph_arena_bytes", "sph_create", "sph_destroy", "sph_last_error", "sph_set_params", "sph_field_info",
-           "sph_add_particles", "sph_num_particles", "sph_clear_particles", "sph_read_state", "sph_grid_build",
+           "sph_add_particles", "sph_num_particles", "sph_clear_particles", "sph_read_state", "sph_read_state_async",
+           "sph_synchronize", "sph_grid_build",
            "sph_calc_kernel_corr", "sph_calc_kernel_corr_deferred", "sph_init_real2tmp", "sph_one_step", "sph_advect", "sph_advect_pos", "sph_post_step",
            "sph_init_stress", "sph_step", "sph_neighbor_count", "sph_neighbor_count_masks", "sph_density_sum", "sph_read_bad_cells",
            "sph_launch_count", "sph_num_phases", "sph_one_step_phase", "sph_set_owned_columns",
@@ -64,6 +65,8 @@ def load():
     L.sph_num_particles.restype, L.sph_num_particles.argtypes = i64, [vp]
     L.sph_clear_particles.restype, L.sph_clear_particles.argtypes = C.c_int, [vp]
     L.sph_read_state.restype, L.sph_read_state.argtypes = C.c_int, [vp, vp, vp, vp, vp, vp]
+    L.sph_read_state_async.restype, L.sph_read_state_async.argtypes = C.c_int, [vp, vp, vp, vp, vp, vp]
+    L.sph_synchronize.restype, L.sph_synchronize.argtypes = C.c_int, [vp]
     for fn in ("sph_grid_build", "sph_calc_kernel_corr", "sph_calc_kernel_corr_deferred", "sph_init_real2tmp", "sph_one_step", "sph_advect_pos",
                "sph_post_step", "sph_init_stress"):
         getattr(L, fn).restype, getattr(L, fn).argtypes = C.c_int, [vp]

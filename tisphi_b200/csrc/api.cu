@@ -405,7 +405,7 @@ int sph_clear_particles(SphCtx *c) {
     return 0;
 }
 
-int sph_read_state(SphCtx *c, double *x, double *v, double *density, double *pressure, int32_t *id0) {
+int sph_read_state_async(SphCtx *c, double *x, double *v, double *density, double *pressure, int32_t *id0) {
     const int64_t n = c->n;
     if (x) SPH_CHECK(c, cudaMemcpyAsync(x, c->arena + c->f[SPH_F_X].off[c->f[SPH_F_X].cur], (size_t)n * 24, cudaMemcpyDefault, c->stream));
     if (density) SPH_CHECK(c, cudaMemcpyAsync(density, c->arena + c->f[SPH_F_DENSITY].off[c->f[SPH_F_DENSITY].cur], (size_t)n * 8, cudaMemcpyDefault, c->stream));
@@ -414,8 +414,15 @@ int sph_read_state(SphCtx *c, double *x, double *v, double *density, double *pre
     // (v: n x 4 reals, pressure: n reals) when the engine is MIXED the caller passes float buffers.
     if (v) SPH_CHECK(c, cudaMemcpyAsync(v, c->arena + c->f[SPH_F_V].off[c->f[SPH_F_V].cur], (size_t)n * 4 * c->real_bytes, cudaMemcpyDefault, c->stream));
     if (pressure) SPH_CHECK(c, cudaMemcpyAsync(pressure, c->arena + c->f[SPH_F_PRESSURE].off[c->f[SPH_F_PRESSURE].cur], (size_t)n * c->real_bytes, cudaMemcpyDefault, c->stream));
+    return 0;
+}
+int sph_synchronize(SphCtx *c) {
     SPH_CHECK(c, cudaStreamSynchronize(c->stream));
     return 0;
+}
+int sph_read_state(SphCtx *c, double *x, double *v, double *density, double *pressure, int32_t *id0) {
+    int r = sph_read_state_async(c, x, v, density, pressure, id0);
+    return r ? r : sph_synchronize(c);
 }
 
 int sph_grid_build(SphCtx *c) { return DISPATCH(c, grid_build, c); }
