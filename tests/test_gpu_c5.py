@@ -1,0 +1,62 @@
+"""BASELINE config C5 (synthetic uniform box): neighbour counts bit-exact and density sums within tolerance against the
+oracle at a size the oracle finishes in seconds; size-independent properties at 1 M particles."""
+import numpy as np
+import pytest
+
+from helpers import relmax
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_box(x, n_side, f32):
+    from oracle import oracle as orc
+    from tisphi_b200.c5 import box_params
+    Pe = box_params(n_side)
+    P = orc.OrcParams()
+    P.dim, P.kernel, P.kcorr, P.ti, P.xsph, P.solver, P.serial, P.wc_fresh = 3, 1, 0, 1, 0, 1, 0, 0
+    for a in range(3):
+        P.gn[a], P.vstart[a], P.g[a] = Pe.gn[a], Pe.vstart[a], 0.0
+    P.h, P.support, P.grid_size, P.m_V0, P.eps = Pe.h, Pe.support, Pe.grid_size, Pe.m_V0, 1e-8
+    P.dt, P.rho0, P.visc, P.stiff, P.gamma_, P.vsound = Pe.dt, Pe.rho0, Pe.visc, Pe.stiff, Pe.gamma_, Pe.vsound
+    o = orc.Oracle(P, x, np.zeros_like(x), np.ones(len(x)), np.ones(len(x), dtype=np.int32))
+    o.grid_build()
+    return o
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_c5_small_box_matches_oracle(prec):
+    from tisphi_b200.c5 import UniformBox
+    box = UniformBox(27_000, precision=prec)
+    box.sweep()
+    o = oracle_box(box.x, box.n_side, prec == "f32")
+    eng = box.engine
+    assert np.array_equal(eng.field("ID0").cpu().numpy(), o.id0)                       # same sorted order
+    assert np.array_equal(eng.field("GRID_IDS").cpu().numpy(), o.grid_ids)
+    assert np.array_equal(box.count.cpu().numpy(), o.neighbor_count(f32=prec == "f32"))    # bit-exact counts
+    assert relmax(box.rho.cpu().numpy(), o.density_sum()) < (1e-12 if prec == "f64" else 1e-5)
+    # brute force on the first 200 sorted particles (float64 predicate): the f64 engine must reproduce it exactly
+    if prec == "f64":
+        xs = eng.field("X").cpu().numpy()
+        d2 = ((xs[:200, None, :] - xs[None, :, :]) ** 2)
+        r = np.sqrt((d2[..., 0] + d2[..., 1]) + d2[..., 2])
+        brute = (r < 3.0).sum(axis=1) - 1
+        assert np.array_equal(box.count.cpu().numpy()[:200], brute)
+
+
+def test_c5_million_particle_properties():
+    import torch
+    from tisphi_b200.c5 import UniformBox
+    box = UniformBox(1_000_000)
+    box.sweep()
+    eng = box.engine
+    gid = eng.field("GRID_IDS")
+    assert bool((gid[1:] >= gid[:-1]).all())                                           # sorted
+    assert torch.equal(torch.sort(eng.field("ID0").long())[0], torch.arange(box.n, device=gid.device))   # a permutation
+    cnt = box.count
+    assert int(cnt.sum()) % 2 == 0                                                      # symmetric relation: pairs counted twice
+    interior = 113.1                                                                    # (4/3) pi 3^3 - 1 expected neighbours
+    m = float(cnt.float().mean())
+    assert 0.85 * interior < m < interior, m                                            # faces of the box have fewer
+    first = box.rho.clone()
+    box.sweep()                                                                         # rebuilding a sorted set changes nothing
+    assert torch.equal(first, box.rho)

@@ -5,17 +5,23 @@
 // owns the l-th particle of that cell.  Because the flattened cell id is fastest-axis-major (ps:221-222), the
 // particles of the (BX+2) x (BY+2) x (ZB+2) cells a block needs form NR = (BX+2)(BY+2) contiguous spans ("runs") of
 // the sorted arrays: each run is brought into shared memory with ONE 1-D TMA bulk copy per payload array
-// (cp.async.bulk ... mbarrier::complete_tx), raw, with no transformation.
+// (cp.async.bulk ... mbarrier::complete_tx), raw, with no transformation.  Persistent blocks pull footprint segments
+// that hold work from per-step work lists with an atomic cursor.
 //
-// Neighbour predicate.  Evaluated ONCE per step (positions are frozen inside a step; they only change in
-// advect_pos) by k_tile_mask into one 32-bit word per (particle, stencil cell): bit b = the b-th particle of that
-// cell is a neighbour.  The predicate is the float32 expression of sph_dev.cuh::for_neighbors, which is exactly
-// symmetric, so a cell pair (A, B > A) is evaluated once by A's warp and the 32 x 32 bit matrix is transposed with
-// warp shuffles to give B's words.  Wall particles keep only their FLOW neighbours (all a wall sum ever reads,
-// base:647-669): dry walls end up with empty masks and cost nothing.
-//
-// The wall pass and the fluid pass of both one_steps then only visit set bits, four neighbours per round in stencil
-// order (cells x-major / z-fastest, j ascending), with the mask words streamed from global memory one cell ahead.
+// Kernels, in the order of a step:
+//   k_tile_worklist / k_wall_cells   which footprint segments / wall cells have work (compacted lists)
+//   k_tile_mask                      the neighbour predicate, ONCE per step (positions are frozen inside a step), into one
+//                                    32-bit word per (particle, stencil cell): packed float32 pairs (FADD2/FMUL2/FFMA2)
+//                                    over SoA tiles, every cell pair evaluated once + warp bit-matrix transpose, double-
+//                                    buffered tiles.  Wall particles keep only their FLOW neighbours (all a wall sum ever
+//                                    reads, base:647-669): dry walls end up with empty masks and cost nothing.
+//   k_tile_prep                      EOS, tile payloads, dry walls (+ advect_LF_half inside sph_step)          pointwise
+//   k_wall_gather                    wall pass (wc:90-103): one warp per wall cell in reach of flow, payloads gathered via L1
+//   k_tile_fluid                     fluid pass (wc:108-126): set bits only, four neighbours per round in stencil order
+//                                    (cells x-major / z-fastest, j ascending), mask words streamed one cell ahead;
+//                                    optionally records / replays neighbour round lists
+//   k_tile_shepard                   calc_CSPM_f alone (the stand-alone API call; inside a step the first wall / fluid
+//                                    pass forms the same sums)
 // Cells that cannot be represented (more than 32 particles in a stencil cell, or a tile that overflows) are flagged
 // together with their stencil neighbours and processed by the generic kernels of sweeps.cu.
 //
