@@ -439,8 +439,8 @@ def main():
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-depth", type=int, default=3, help="contexts the end-to-end jobs are pipelined over (1 = serial)")
-    ap.add_argument("--cpu-scale", type=float, default=0.25, help="coarsening of the CPU-baseline sample")
-    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--cpu-scale", type=float, default=0.5, help="coarsening of the CPU-baseline sample (0.5: 1.97 M particles)")
+    ap.add_argument("--cpu-steps", type=int, default=4, help="steps of the CPU-baseline sample (about 10 s on 16 threads)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--lists", type=int, default=None, help="1 / 0: neighbour round lists on / off (default: engine default)")
     args = ap.parse_args()

@@ -90,7 +90,8 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
     int64_t o_pw4 = 0;
     int64_t o_ps4 = 0, o_pk4 = 0, o_mask = 0, o_nflow = 0, o_cflag = 0, o_nflag = 0, o_cinfo = 0, o_wl = 0, o_soa = 0, o_cflow = 0;
     const int64_t soa_stride = align_up(n_max * 4 + 64), wl_stride = align_up((C + 1) * 4);
-    const bool lists = fast && p->fast >= 2 && p->ti != 1;     // SE has a single fluid pass per step: nothing to replay
+    // neighbour round lists: SE has a single fluid pass per step (nothing to replay); entries are addressed with 32 bits
+    const bool lists = fast && p->fast >= 2 && p->ti != 1 && n_max * (int64_t)LIST_ROUNDS < (1ll << 32);
     int64_t o_nlist = 0, o_lrounds = 0;
     if (fast) {
         o_ps4 = off; off += align_up(n_max * 16);
