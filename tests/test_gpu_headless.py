@@ -59,3 +59,47 @@ def test_run_simulation_entry_point(tmp_path):
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     res = json.loads(line)
     assert res["steps"] == 20 and res["scene"] == "test1_db_water" and res["bad_cells"] == 0
+
+
+def test_viewer_members_and_host_neighbour_helper():
+    """assign_value_color / v_maxmin / set_color / copy2vis (ps:380-407, base:721-789) and the host-side
+    for_all_neighbors helper against the engine's own neighbour counts."""
+    import torch
+    g = Golden("wc2d_small_lf")
+    sim = make_sim(g.scene, precision="f64", colorTitle=7, colorGroup=0, showBdyPts=False)
+    sim.solver.run_steps(5)
+    ps, pt = sim.ps, sim.ps.pt
+    ps.initialize_particle_system()
+    sim.solver.assign_value_color()
+    ps.v_maxmin(-1, -1, 0, 0)
+    ps.set_color()
+    ps.copy2vis(0.5)
+    flow = pt.mat_type == 1
+    p = pt.pressure.double()
+    assert torch.equal(pt.val[flow].double(), p[flow])                       # colorTitle 7 = pressure
+    assert ps.vmax[None] == float(p[flow].max()) and ps.vmin[None] == float(p[flow].min())
+    col = pt.color
+    assert col.shape == (ps.particle_num[None], 3) and float(col.min()) >= 0.0 and float(col.max()) <= 1.0
+    hi = int(torch.argmax(torch.where(flow, p, torch.full_like(p, -1e300))))
+    assert float(col[hi][0]) > float(col[hi][2])                              # highest pressure is drawn at the red end
+    assert torch.allclose(pt.pos2vis[flow].double(), (pt.x[flow] * 0.5).float().double())
+    # viewer members follow their particle through a sort
+    before = {int(i): float(v) for i, v in zip(pt.id0[:50].tolist(), pt.val[:50].tolist())}
+    sim.solver.run_steps(3)
+    after = {int(i): float(v) for i, v in zip(pt.id0.tolist(), pt.val.tolist())}
+    assert all(after[i] == v for i, v in before.items())
+    # host for_all_neighbors == device neighbour count, and the helper's cell of x_i is the engine's grid id
+    ps.initialize_particle_system()
+    counts = ps.neighbor_count().cpu().numpy()
+    gid = pt.grid_ids.cpu().numpy()
+    for i in (0, 17, ps.particle_num[None] // 2, ps.particle_num[None] - 1):
+        seen = []
+        ps.for_all_neighbors(i, lambda a, b, ret: ret.append(b), seen)
+        assert len(seen) == counts[i] and seen == sorted(seen) and i not in seen, i
+        idx = ps.pos_to_index(pt.x[i].cpu().numpy())
+        assert int(idx[0] * ps.grid_num[1] + idx[1]) == gid[i]
+    # hydrostatic init_pressure (base:263-271) on fluid particles only
+    sim.solver.init_pressure(1000.0)
+    y = pt.x[:, 1]
+    want = 1000.0 * 9.81 * (y[flow].max() - y[flow])
+    assert torch.allclose(pt.pressure[flow].double(), want.double(), rtol=1e-12, atol=1e-9)

@@ -120,3 +120,51 @@ def test_scene_files_are_the_baseline_configs():
     assert c4["Configuration"]["is2D"] is False and c4["Blocks"][0]["size"] == [1.6, 1.0, 0.8]
     for f in os.listdir(d):
         assert "precision" not in json.load(open(os.path.join(d, f)))["Configuration"], f
+
+
+# ------------------------------------------------------------------------------------------------ viewer helpers (host)
+def test_jet_colour_map_is_the_reference_tent_map():
+    import torch
+    from tisphi_b200.eng.colormap import color_map, ColorMap
+    x = torch.tensor([-0.5, 0.0, 0.25, 0.5, 0.75, 1.0, 1.5], dtype=torch.float64)
+    rgb = color_map(x).double().numpy()
+    assert rgb.shape == (7, 3) and rgb.min() >= 0.0 and rgb.max() <= 1.0
+    # colormap.py:20-27 by hand: clamp((w - |clamp(x) - c|) / w * h), jet = (1.5, .37, .37, c) with c = .75 / .5 / .25
+    def tent(v, c):
+        v = min(1.0, max(0.0, v))
+        return min(1.0, max(0.0, (0.37 - abs(v - c)) / 0.37 * 1.5))
+    for k, v in enumerate(x.tolist()):
+        want = [tent(v, 0.75), tent(v, 0.5), tent(v, 0.25)]
+        assert np.allclose(rgb[k], want, atol=1e-6), (v, rgb[k], want)
+    assert np.allclose(rgb[3], [0.0, 1.0, 0.0], atol=0.49) and rgb[3][1] == 1.0          # mid-range is green
+    assert rgb[1][2] > rgb[1][0] and rgb[5][0] > rgb[5][2]                               # blue end, red end
+    asym = ColorMap(1.0, .25, 1, .5)                                                       # bwrR: different widths left / right
+    assert abs(float(asym.map(torch.tensor([0.4]))[0]) - (0.25 - 0.1) / 0.25) < 1e-6
+    assert abs(float(asym.map(torch.tensor([0.9]))[0]) - (1 - 0.4) / 1) < 1e-6
+
+
+def test_cell_index_helpers_match_the_oracle_grid():
+    from oracle import oracle as orc
+    from tisphi_b200.eng.particle_system import pos_to_index, flatten_grid_index
+    scene = json.load(open(os.path.join(ROOT, "data", "scenes", "test1_db_water.json")))
+    o = orc.Oracle.from_scene(scene, serial=0)
+    o.grid_build()
+    D = o.D
+    idx = pos_to_index(o.x, D["vstart"], D["grid_size"])
+    gn = [int(g) for g in D["grid_num"]]
+    if len(gn) == 2 or gn[2] == 0:
+        gn = [gn[0], gn[1], 1]
+    idx[:, 2] = 0                                                                         # 2D scene: z plays no part
+    assert np.array_equal(flatten_grid_index(idx, gn), o.grid_ids)
+
+
+def test_value_range_follows_the_reference_precedence():
+    import torch
+    from tisphi_b200.eng.particle_system import value_range
+    val = torch.tensor([1.0, 5.0, 9.0, 100.0])
+    flow = torch.tensor([True, True, True, False])
+    assert value_range(val, flow, -1, -1, 0, 0) == (9.0, 1.0)                              # no given range
+    assert value_range(val, flow, 20.0, 0.5, 0, 0) == (9.0, 1.0)                           # given range wider: data wins
+    assert value_range(val, flow, 6.0, 2.0, 0, 0) == (6.0, 2.0)                            # given range narrower: capped
+    assert value_range(val, flow, 20.0, 0.5, 1, 1) == (20.0, 0.5)                          # fixed: always the given values
+    assert value_range(val, torch.zeros(4, dtype=torch.bool), -1, -1, 0, 0) == (-float("inf"), float("inf"))

@@ -41,6 +41,31 @@ _SYM = {"stress": "STRESS", "d_stress": "D_STRESS", "stress_tmp": "STRESS_TMP", 
 _FULL = {"CSPM_L": "CSPM_L", "v_grad": "V_GRAD"}
 _CONST = ("obj_id", "mat_id", "is_dynamic", "color", "x0")     # per-particle constants, keyed by id0
 _SYM_IDX = [0, 3, 5, 3, 1, 4, 5, 4, 2]                         # xx,yy,zz,xy,yz,zx -> row-major 3x3
+_DEAD = {"MLS_beta": (4,), "dist_B": (), "g_p": (), "drag_force": (3,)}   # pf:13-69, dead in the reference
+
+
+# ---- host-side restatements of the reference's device helpers (pure functions of arrays: also used by the tests)
+def pos_to_index(pos, vdomain_start, grid_size):
+    """ps:216-218: trunc((pos - vdomain_start) / grid_size) per axis (C-style cast)."""
+    q = (np.asarray(pos, dtype=np.float64) - np.asarray(vdomain_start, dtype=np.float64)) / float(grid_size)
+    return np.trunc(q).astype(np.int64)
+
+
+def flatten_grid_index(grid_index, grid_num):
+    """ps:220-222: x-major, z fastest."""
+    g = np.asarray(grid_index, dtype=np.int64)
+    return g[..., 0] * int(grid_num[1]) * int(grid_num[2]) + g[..., 1] * int(grid_num[2]) + g[..., 2]
+
+
+def value_range(val, flow, givenmax, givenmin, fixmax, fixmin):
+    """ps:387-397 v_maxmin: extrema of `val` over flow particles, optionally overridden / capped by the given values."""
+    import torch
+    sel = val[flow]
+    vmax = float(sel.max()) if sel.numel() else -float("inf")
+    vmin = float(sel.min()) if sel.numel() else float("inf")
+    out_max = vmax if (givenmax == -1 or (vmax < givenmax and not fixmax)) else givenmax
+    out_min = vmin if (givenmin == -1 or (vmin > givenmin and not fixmin)) else givenmin
+    return out_max, out_min
 
 
 class _ParticleFields:
@@ -67,9 +92,14 @@ class _ParticleFields:
             return s6[:, _SYM_IDX].reshape(-1, 3, 3)
         if name in _FULL:
             return eng.field(_FULL[name]).reshape(-1, 3, 3)
+        if name in ("val", "pos2vis") or (name == "color" and ps._vis.get("color") is not None):
+            return ps._vis_field(name)
         if name in _CONST:
             idx = eng.field("ID0").long()
             return ps._const_dev(name)[idx]
+        if name in _DEAD:                       # members the reference declares but never computes
+            shape = (eng.n,) + _DEAD[name]
+            return ps._torch.zeros(shape, dtype=eng.real, device=eng.device)
         raise AttributeError(f"Particle has no member {name!r} in this engine")
 
 
@@ -91,6 +121,8 @@ class ParticleSystem:
         self.mat_fluid_type, self.mat_soil_type, self.mat_rigid_type = 1, 2, 11
         self.bdy_none, self.bdy_collision, self.bdy_dummy, self.bdy_rep, self.bdy_dummy_rep = 0, 1, 2, 3, 4
         self.i_dump = _Scalar(0)
+        self.rigid_rest_cm = np.zeros(3)                         # rigid bodies are out of scope
+        self._vis = {"val": None, "pos2vis": None, "color": None}   # viewer members, keyed by id0 (they survive the sort)
 
         # discretisation (ps:32-39)
         self.particle_radius = self.cfg.get_cfg("particleRadius")
@@ -272,6 +304,7 @@ class ParticleSystem:
         for k in self._const:
             self._const[k] = []
         self._const_cache.clear()
+        self._vis = {"val": None, "pos2vis": None, "color": None}
         self.particle_num[None] = 0
 
     def set_id0(self):
@@ -337,12 +370,137 @@ class ParticleSystem:
     def is_rigid(self, t):
         return t == self.mat_rigid_type
 
-    # ------------------------------------------------------------------------------------------ export
-    def v_maxmin(self):
-        val = self.pt.v.norm(dim=1) if self.engine.n else self._torch.zeros(1)
-        self.vmax[None] = float(val.max())
-        self.vmin[None] = float(val.min())
+    # ------------------------------------------------------------------------------------------ device helpers on the host
+    def pos_to_index(self, pos):
+        return pos_to_index(pos, self.vdomain_start, self.grid_size)
 
+    def flatten_grid_index(self, grid_index):
+        return flatten_grid_index(grid_index, self.grid_num)
+
+    def get_flatten_grid_index(self, pos):
+        return self.flatten_grid_index(self.pos_to_index(pos))
+
+    def for_all_neighbors(self, i, task, ret):
+        """ps:259-269 for ONE particle on the host (debug / oracle helper; the sweeps do this on the device): calls
+        ``task(i, j, ret)`` for every j of the 3^dim cells around i with |x_i - x_j| < support_radius, in the
+        reference's order (cells x-major / z fastest, j ascending).  Needs a current grid."""
+        x = self.pt.x
+        xi = x[int(i)].cpu().numpy()
+        cell_end = self.grid_particle_num.cpu().numpy()
+        centre = self.pos_to_index(xi)
+        zs = (0,) if self.dim == 2 else (-1, 0, 1)
+        for ox in (-1, 0, 1):
+            for oy in (-1, 0, 1):
+                for oz in zs:
+                    c = centre + np.array([ox, oy, oz])
+                    if np.any(c < 0) or np.any(c[:self.dim] >= self.grid_num[:self.dim]):
+                        continue                                  # the reference reads out of range here (SURVEY H6)
+                    g = int(self.flatten_grid_index(c if self.dim == 3 else np.array([c[0], c[1], 0])))   # grid_num[2] == 1 in 2D
+                    j0 = int(cell_end[g - 1]) if g > 0 else 0
+                    j1 = int(cell_end[g])
+                    if j1 <= j0:
+                        continue
+                    xj = x[j0:j1].cpu().numpy()
+                    d = xi[None, :] - xj
+                    r = np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2])
+                    for k in np.nonzero(r < self.support_radius)[0]:
+                        j = j0 + int(k)
+                        if j != int(i):
+                            task(int(i), j, ret)
+
+    def add_particle(self, p, obj_id, x, v, density, pressure, material_id, material_type, is_dynamic, color):
+        """ps:274-287: one particle (appended; ``p`` must be the next free index, as in the reference's callers)."""
+        assert int(p) == self.particle_num[None], "particles are appended: p must equal particle_num"
+        self._add_particles(obj_id, 1, np.asarray(x, dtype=np.float64).reshape(1, 3), np.asarray(v, dtype=np.float64).reshape(1, 3),
+                            np.array([density], dtype=np.float64), np.array([pressure], dtype=np.float64),
+                            np.array([material_id], dtype=np.int32), np.array([material_type], dtype=np.int32),
+                            np.array([int(is_dynamic)], dtype=np.int32), np.asarray(color, dtype=np.float32).reshape(1, 3))
+
+    # ------------------------------------------------------------------------------------------ viewer members (ps:380-407)
+    def _vis_store(self, name, values):
+        """Viewer members are kept keyed by id0, so that they follow their particle through the sorts."""
+        n = self.engine.n
+        shape = (n,) + tuple(values.shape[1:])
+        buf = self._vis.get(name)
+        if buf is None or tuple(buf.shape) != shape or buf.dtype != values.dtype:
+            buf = self._torch.zeros(shape, dtype=values.dtype, device=self.engine.device)
+            if name == "color":
+                buf.copy_(self._const_dev("color").to(values.dtype))
+        buf[self.pt.id0.long()] = values
+        self._vis[name] = buf
+
+    def _vis_field(self, name):
+        buf = self._vis.get(name)
+        n = self.engine.n
+        if buf is None:
+            shape = (n,) if name == "val" else (n, 3)
+            return self._torch.zeros(shape, dtype=self._torch.float32 if name != "val" else self.engine.real, device=self.engine.device)
+        return buf[self.pt.id0.long()]
+
+    def _shown(self):
+        t = self.pt.mat_type
+        real = t > 0
+        return real | (t == self.mat_dummy_type) | (t == self.mat_rep_type) if self.show_bdy else real
+
+    def copy2vis(self, w2s_ratio):
+        """ps:380-385: positions scaled to the viewer's unit box, float32, for real (and, if shown, boundary) particles."""
+        x = self.pt.x
+        vis = self._vis_field("pos2vis").clone()
+        shown = self._shown()
+        vis[shown] = (x[shown] * float(w2s_ratio)).to(self._torch.float32)
+        self._vis_store("pos2vis", vis)
+
+    def v_maxmin(self, givenmax=-1, givenmin=-1, fixmax=0, fixmin=0):
+        """ps:387-397: range of pt.val over FLOW particles (pt.val is set by solver.assign_value_color)."""
+        t = self.pt.mat_type
+        flow = (t == self.mat_fluid_type) | (t == self.mat_soil_type)
+        self.vmax[None], self.vmin[None] = value_range(self.pt.val, flow, givenmax, givenmin, fixmax, fixmin)
+
+    def set_color(self):
+        """ps:399-407: pt.color = color_map((val - vmin) / (vmax - vmin)) for the particles of the colour group."""
+        from .colormap import color_map
+        t = self.pt.mat_type
+        flow = (t == self.mat_fluid_type) | (t == self.mat_soil_type)
+        real = t > 0
+        if self.color_group == 0:
+            sel = flow
+        elif self.color_group == 1:
+            sel = real
+        else:
+            sel = real | (t == self.mat_dummy_type) if self.show_bdy else real
+        rng = self.vmax[None] - self.vmin[None]
+        col = self.pt.color.to(self._torch.float32).clone()
+        if rng != 0:
+            col[sel] = color_map((self.pt.val[sel].double() - self.vmin[None]) / rng)
+        self._vis_store("color", col)
+
+    # ps:412-455: typed copies into caller-provided numpy arrays (``src_arr`` is a ps.pt member)
+    def copy_to_numpy(self, np_arr, src_arr):
+        np_arr[...] = src_arr.detach().cpu().numpy()
+
+    def copy_to_numpy_vec(self, np_arr, src_arr):
+        np_arr[...] = src_arr.detach().cpu().numpy()
+
+    def copy_to_numpy_mat(self, np_arr, src_arr):
+        np_arr[...] = src_arr.detach().cpu().numpy()
+
+    def copy_to_numpy_vecxyz(self, np_arr_x, np_arr_y, np_arr_z, src_arr):
+        a = src_arr.detach().cpu().numpy()
+        np_arr_x[...], np_arr_y[...], np_arr_z[...] = a[:, 0], a[:, 1], a[:, 2]
+
+    def copy_to_numpy_matxyz(self, np_arr_xx, np_arr_yy, np_arr_zz, np_arr_xy, np_arr_yz, np_arr_zx, src_arr):
+        a = src_arr.detach().cpu().numpy()
+        np_arr_xx[...], np_arr_yy[...], np_arr_zz[...] = a[:, 0, 0], a[:, 1, 1], a[:, 2, 2]
+        np_arr_xy[...], np_arr_yz[...], np_arr_zx[...] = a[:, 0, 1], a[:, 1, 2], a[:, 2, 0]
+
+    def copy_to_numpy_vecnorm(self, np_arr, src_arr):
+        np_arr[...] = src_arr.detach().double().norm(dim=1).cpu().numpy()
+
+    def copy_to_numpy_mathydro(self, np_arr, src_arr):
+        a = src_arr.detach().cpu().numpy()
+        np_arr[...] = (a[:, 0, 0] + a[:, 1, 1] + a[:, 2, 2]) / 3.0
+
+    # ------------------------------------------------------------------------------------------ export
     def dump(self):
         """ps:459-545: (positions, data) dicts of float64 / int64 numpy arrays in current (sorted) order."""
         pt = self.pt

@@ -149,5 +149,49 @@ class SPHBase:
     def enforce_boundary(self):
         return None
 
-    def assign_value_color(self, *args, **kw):
+    def assign_value_color(self):
+        """base:721-789: pt.val := the scalar selected by ``colorTitle`` for real (and, if shown, dummy) particles."""
+        ps, pt = self.ps, self.ps.pt
+        f = _COLOR_VALUES.get(int(ps.color_title))
+        if f is None:
+            return None
+        t = pt.mat_type
+        shown = (t > 0) | (t == ps.mat_dummy_type) if ps.show_bdy else (t > 0)
+        val = ps._vis_field("val").clone()
+        new = f(pt, ps).to(val.dtype)
+        val[shown] = new[shown]
+        ps._vis_store("val", val)
         return None
+
+    def init_pressure(self, density0):
+        """base:263-271: hydrostatic pressure below the highest fluid particle (not called by the reference's solvers)."""
+        pt = self.ps.pt
+        fluid = pt.mat_type == self.ps.mat_fluid_type
+        if not bool(fluid.any()):
+            return None
+        y = pt.x[:, 1]
+        ymax = y[fluid].max()
+        p = pt.pressure
+        p[fluid] = (-float(density0) * float(self.g[1]) * (ymax - y[fluid])).to(p.dtype)
+        return None
+
+
+def _norm(v):
+    return v.double().norm(dim=1)
+
+
+# colorTitle -> value (base:725-787); signs as in the reference (compression positive for 32, 52, 53, 57)
+_COLOR_VALUES = {
+    1: lambda pt, ps: pt.id0.double(), 2: lambda pt, ps: pt.density, 21: lambda pt, ps: pt.d_density,
+    3: lambda pt, ps: _norm(pt.v), 31: lambda pt, ps: pt.v[:, 0], 32: lambda pt, ps: -pt.v[:, 1], 33: lambda pt, ps: pt.v[:, 2],
+    34: lambda pt, ps: _norm(pt.d_vel), 35: lambda pt, ps: pt.d_vel[:, 0], 36: lambda pt, ps: pt.d_vel[:, 1], 37: lambda pt, ps: pt.d_vel[:, 2],
+    4: lambda pt, ps: _norm(pt.x), 41: lambda pt, ps: pt.x[:, 0], 42: lambda pt, ps: pt.x[:, 1], 43: lambda pt, ps: pt.x[:, 2],
+    44: lambda pt, ps: _norm(pt.x - pt.x0),
+    51: lambda pt, ps: pt.stress[:, 0, 0], 52: lambda pt, ps: -pt.stress[:, 1, 1], 53: lambda pt, ps: -pt.stress[:, 2, 2],
+    54: lambda pt, ps: pt.stress[:, 0, 1], 55: lambda pt, ps: pt.stress[:, 1, 2], 56: lambda pt, ps: pt.stress[:, 2, 0],
+    57: lambda pt, ps: -(pt.stress[:, 0, 0] + pt.stress[:, 1, 1] + pt.stress[:, 2, 2]) / 3.0,
+    61: lambda pt, ps: pt.strain_equ, 62: lambda pt, ps: pt.strain_equ_p, 7: lambda pt, ps: pt.pressure,
+    8: lambda pt, ps: pt.flag_retmap.double(), 100: lambda pt, ps: pt.grid_ids.double(),
+    101: lambda pt, ps: ps._torch.rand(ps.engine.n, device=ps.engine.device, dtype=ps._torch.float64),
+    102: lambda pt, ps: pt.CSPM_L[:, 0, 0], 103: lambda pt, ps: _norm(pt.v_tmp),
+}

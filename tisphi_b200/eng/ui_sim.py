@@ -155,13 +155,22 @@ def export_vtk(stamp, simpath, case):
 
 
 def export_frame(stamp, simpath, case):
-    """Stands in for window.save_image (ui:309, 319): positions and the scalar the viewer would colour by."""
+    """Stands in for window.save_image (ui:309, 319): what the viewer would draw -- positions, the scalar selected by
+    ``colorTitle`` (solver.assign_value_color), its range (ps.v_maxmin) and the jet colours (ps.set_color)."""
     pos, data = case.ps.dump()
-    title = choose_color_title(case.ps.color_title)
-    value = data.get(_COLOR_KEY.get(case.ps.color_title, "vel.norm"), data["vel.norm"])
+    extra = {}
+    if hasattr(case, "solver") and case.ps.color_title > 0:                  # assign_color, ui:286-290
+        cfg = case.cfg.get_cfg
+        case.solver.assign_value_color()
+        case.ps.v_maxmin(cfg("givenMax"), cfg("givenMin"), cfg("fixMax"), cfg("fixMin"))
+        case.ps.set_color()
+        value = case.ps.pt.val.detach().cpu().numpy()
+        extra = {"color": case.ps.pt.color.detach().cpu().numpy(), "vmax": case.ps.vmax[None], "vmin": case.ps.vmin[None]}
+    else:
+        value = data.get(_COLOR_KEY.get(case.ps.color_title, "vel.norm"), data["vel.norm"])
     fname = os.path.join(simpath, "%s.npz" % stamp)
-    np.savez_compressed(fname, x=pos["pos.x"], y=pos["pos.y"], z=pos["pos.z"], value=value, title=title,
-                        material=data["material"])
+    np.savez_compressed(fname, x=pos["pos.x"], y=pos["pos.y"], z=pos["pos.z"], value=value,
+                        title=choose_color_title(case.ps.color_title), material=data["material"], **extra)
     return fname
 
 
