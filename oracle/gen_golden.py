@@ -45,6 +45,23 @@ def _scene(base, cfg=None, block=None, materials=None):
     return sc
 
 
+def _indenter(water=False):
+    with open(os.path.join(REF, "data", "scenes", "test4_in_ver.json")) as f:
+        sc = json.load(f)
+    sc["Configuration"].update(particleRadius=0.0005, domainEnd=[0.05, 0.03, 0.05])
+    sc["Blocks"][0].update(size=[0.05, 0.02, 0.05])
+    sc["Blocks"][1].update(translation=[0.021, 0.02, 0.0], size=[0.008, 0.004, 0.05])
+    if water:
+        with open(os.path.join(REF, "data", "scenes", "test1_db_water.json")) as f:
+            w = json.load(f)
+        fluid = dict(w["Materials"][0], matId=0)
+        rigid = [m for m in sc["Materials"] if m["matType"] == 11][0]
+        sc["Materials"] = [fluid, dict(rigid, matId=1)]
+        sc["Configuration"].update(simulationMethod=1, xsph=False, timeStepSizeMin=w["Configuration"]["timeStepSizeMin"])
+        sc["Blocks"][1].update(velocity=[0.1, -0.25, 0.0])
+    return sc
+
+
 WATER3D = dict(is2D=False, particleRadius=0.01, domainStart=[0.0, 0.0, 0.0], domainEnd=[0.24, 0.2, 0.18],
                timeStepSizeMin=1e-6)
 
@@ -77,6 +94,11 @@ CASES = {
     "c2_test2_mui_lf": (lambda: _scene("test2_cc_sand.json", dict(simulationMethod=2)), [1, 2]),
     "c3_test2_dp_rk4_cspm": (lambda: _scene("test2_cc_sand.json",
                                             dict(simulationMethod=3, kernelCorrection=1, timeIntegration=4)), [1]),
+    # static rigid indenter with a prescribed velocity pressed into a DP soil bed (the shipped test4
+    # scene shrunken: bed 50 x 20 particles, indenter 8 x 4, v = (0, -0.25, 0), isDynamic 0), "LF", XSPH
+    "dp2d_indenter_lf": (lambda: _indenter(), [1, 2, 10, 30]),
+    # the same indenter pushed sideways through a water bed under WCSPH (type 11 in the wall loop of wc:90-106, 125-126)
+    "wc2d_indenter_lf": (lambda: _indenter(water=True), [1, 2, 10]),
     # tiny 3D dambreak with the C4 parameter set
     "wc3d_tiny_lf": (lambda: _scene("test1_db_water.json", dict(WATER3D), dict(size=[0.16, 0.12, 0.12])), [1, 2, 3]),
 }

@@ -11,8 +11,10 @@ from helpers import Golden, relmax, sym6_to_9, make_sim, engine_fields
 
 pytestmark = pytest.mark.gpu
 
-WC_CASES = ["wc2d_small_lf", "wc2d_small_se_cubic", "wc2d_small_rk4_cspm", "wc3d_tiny_lf", "c1_test1_wc_lf"]
-SOIL_CASES = ["mui2d_small_lf", "dp2d_small_rk4_cspm", "dp2d_small_lf", "c2_test2_mui_lf", "c3_test2_dp_rk4_cspm"]
+# the *_indenter_* fixtures hold a static rigid block (type 11) with a prescribed velocity
+WC_CASES = ["wc2d_small_lf", "wc2d_small_se_cubic", "wc2d_small_rk4_cspm", "wc3d_tiny_lf", "c1_test1_wc_lf", "wc2d_indenter_lf"]
+SOIL_CASES = ["mui2d_small_lf", "dp2d_small_rk4_cspm", "dp2d_small_lf", "c2_test2_mui_lf", "c3_test2_dp_rk4_cspm",
+              "dp2d_indenter_lf"]
 ALL_CASES = WC_CASES + SOIL_CASES
 
 F64_TOL = 1e-9
@@ -50,7 +52,7 @@ def test_f64_matches_reference_fixtures(name):
         racy |= RACY["mui"]
     if cfg["xsph"]:
         racy |= RACY["xsph"]
-    last = max(g.steps) if ("small_lf" in name and not cfg["xsph"]) or "tiny" in name else min(max(g.steps), 10)
+    last = max(g.steps) if (("small_lf" in name or "indenter" in name) and not cfg["xsph"]) or "tiny" in name else min(max(g.steps), 10)
     # with XSPH the serial reference moves particles in place: positions drift from the snapshot evaluation by
     # O(dt * |v| * 1e-4) per step, so only the first snapshots are compared tightly
     if cfg["xsph"]:

@@ -9,7 +9,7 @@ import pytest
 
 from helpers import Golden, ROOT
 
-CASES = ["c1_test1_wc_lf", "c2_test2_mui_lf", "c3_test2_dp_rk4_cspm", "wc3d_tiny_lf", "dp2d_small_lf"]
+CASES = ["c1_test1_wc_lf", "c2_test2_mui_lf", "c3_test2_dp_rk4_cspm", "wc3d_tiny_lf", "dp2d_small_lf", "dp2d_indenter_lf"]
 
 
 def test_library_exports_every_declared_symbol():

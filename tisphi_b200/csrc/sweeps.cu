@@ -149,8 +149,18 @@ template <typename T> __global__ void __launch_bounds__(256) k_wc_eos(Dev<T> c) 
 }
 // loop A, wall branch (wc:90-103).  p_j is read "in place" by the reference; serial semantics are reproduced
 // pointwise: fluid j < i already holds EOS(rho~_j) (pnew), fluid j > i still holds the previous pressure (press).
+// Static rigid particles (type 11, SURVEY 8 f2: an indenter with a prescribed velocity) are wall particles in loop A
+// and keep d_vel = 0 (wc:125-126, muI:131-132, dp:273-274) and the d_density = 0 they were created with; the
+// integrators treat them as real particles (base:79-170), so both are written here -- the derivative arrays are
+// scratch that does not travel through the sort.
+template <typename T> __device__ __forceinline__ void zero_rigid_derivatives(const Dev<T> &c, int i) {
+    c.d_rho[i] = 0;
+    Vec4<T> z; z.x = z.y = z.z = z.w = 0;
+    c.d_vel[i] = z;
+}
 template <typename T> __device__ __forceinline__ void body_wc_wall(const Dev<T> &c, int i) {
     if (!is_wall(c.type[i])) return;
+    if (is_rigid(c.type[i]) && !c.flagged_only) zero_rigid_derivatives(c, i);      // the tile path does it in k_tile_prep
     if (skip_unflagged(c, i)) return;
     T Sv0 = 0, Sv1 = 0, Sv2 = 0, Sp = 0;
     for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
@@ -221,6 +231,7 @@ template <typename T> __global__ void __launch_bounds__(128) k_soil_wall(Dev<T> 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n) return;
     if (!is_wall(c.type[i])) return;
+    if (is_rigid(c.type[i])) zero_rigid_derivatives(c, i);
     if (not_owned(c, i)) return;
     T Sv0 = 0, Sv1 = 0, Sv2 = 0, Sr = 0, Ss[6] = {0, 0, 0, 0, 0, 0};
     for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
@@ -562,13 +573,14 @@ template <typename T> __global__ void __launch_bounds__(128) k_advect_pos_xsph(D
     if (is_real(ti)) {
         const Vec4<T> vi = c.v4[i];
         T s0 = 0, s1 = 0, s2 = 0;
-        for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
-            if (c.type[j] == ti) {
-                const T w = kernel_W(c, r);
-                const Vec4<T> vj = c.v4[j];
-                s0 += Vj * (vj.x - vi.x) * w; s1 += Vj * (vj.y - vi.y) * w; s2 += Vj * (vj.z - vi.z) * w;
-            }
-        });
+        if (!is_rigid(ti))                                           // base:234: XSPH only for dynamic particles (rigid here = static)
+            for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
+                if (c.type[j] == ti) {
+                    const T w = kernel_W(c, r);
+                    const Vec4<T> vj = c.v4[j];
+                    s0 += Vj * (vj.x - vi.x) * w; s1 += Vj * (vj.y - vi.y) * w; s2 += Vj * (vj.z - vi.z) * w;
+                }
+            });
         o0 += c.dt * (double)(vi.x + (T)0.5 * s0); o1 += c.dt * (double)(vi.y + (T)0.5 * s1); o2 += c.dt * (double)(vi.z + (T)0.5 * s2);
     }
     xnew[3 * (size_t)i] = o0; xnew[3 * (size_t)i + 1] = o1; xnew[3 * (size_t)i + 2] = o2;

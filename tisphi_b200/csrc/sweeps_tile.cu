@@ -709,6 +709,11 @@ template <bool ADV> __global__ void __launch_bounds__(256) k_tile_prep(DevF c, i
         F4 pw; pw.x = po; pw.y = po; pw.z = 0.f; pw.w = 0.f;
         c.pw4[i] = pw;
     }
+    if (is_rigid(t)) {                                              // static rigid: d_vel = 0, d_density = 0 (wc:125-126)
+        c.d_rho[i] = 0.f;
+        F4 z; z.x = z.y = z.z = z.w = 0.f;
+        c.d_vel[i] = z;
+    }
     if (!fl && c.nzw[i] == 0u && !c.cellflag[c.gid[i]]) {           // dry: v~ = 2 v, rho~ = rho0, p = 0, f = 1
         const F4 v = c.v4[i];
         F4 wt; wt.x = 2.f * v.x; wt.y = 2.f * v.y; wt.z = 2.f * v.z; wt.w = c.rho0T;

@@ -231,11 +231,16 @@ class ParticleSystem:
     def init_block(self, block):
         mat = get_material(self, block["materialId"])
         mat_type = mat["matType"]
-        if mat_type > 10:
-            raise NotImplementedError("rigid blocks are out of scope of this engine (SURVEY 8f-2)")
+        is_dynamic = True
+        if mat_type > 10:                                   # ps:160-162
+            self.object_id_rigid.add(block["objectId"])
+            is_dynamic = bool(block["isDynamic"])
+            if is_dynamic:
+                raise NotImplementedError("dynamic rigid bodies (shape matching, base:467-518) are not built yet "
+                                          "(SURVEY 8 f2); static rigid blocks with a prescribed velocity are")
         add_cube(self, object_id=block["objectId"], lower_corner=np.array(block["translation"]),
                  cube_size=np.array(block["size"]), velocity=block["velocity"], density=mat["density0"],
-                 is_dynamic=True, color=np.array([ic / 255 for ic in mat["color"]], dtype=np.float32),
+                 is_dynamic=is_dynamic, color=np.array([ic / 255 for ic in mat["color"]], dtype=np.float32),
                  mat_id=block["materialId"], mat_type=mat_type)
 
     def init_body(self, body):

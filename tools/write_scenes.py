@@ -30,6 +30,7 @@ OUT = {
     "test1_db_water.json": lambda: Golden("c1_test1_wc_lf").scene,                 # C1
     "test2_cc_sand_muI.json": lambda: Golden("c2_test2_mui_lf").scene,             # C2
     "test2_cc_sand_dp_rk4_cspm.json": lambda: Golden("c3_test2_dp_rk4_cspm").scene,  # C3
+    "test4_in_ver_small.json": lambda: Golden("dp2d_indenter_lf").scene,            # shipped test4 shrunken: static rigid indenter (8 f2)
     "c4_db3d_water_13M.json": lambda: scenes.dambreak3d(scale=1.0),                # C4
     "c4_db3d_water_small.json": lambda: scenes.dambreak3d(scale=0.25),             # C4 coarsened x4 (CPU-baseline sample)
 }
