@@ -62,6 +62,19 @@ def _indenter(water=False):
     return sc
 
 
+def _plate():
+    with open(os.path.join(REF, "data", "scenes", "test5_in_hor.json")) as f:
+        sc = json.load(f)
+    sc["Configuration"].update(particleRadius=0.0005, domainEnd=[0.04, 0.025, 0.05])
+    b = sc["Blocks"]
+    b[0].update(translation=[0, 0, 0], size=[0.04, 0.012, 0.05])
+    b[1].update(translation=[0, 0.016, 0], size=[0.04, 0.004, 0.05])
+    b[2].update(translation=[0, 0.012, 0], size=[0.01, 0.004, 0.05])
+    b[3].update(translation=[0.012, 0.012, 0], size=[0.028, 0.004, 0.05])
+    b[4].update(translation=[0.01, 0.012, 0], size=[0.002, 0.004, 0.05])
+    return sc
+
+
 WATER3D = dict(is2D=False, particleRadius=0.01, domainStart=[0.0, 0.0, 0.0], domainEnd=[0.24, 0.2, 0.18],
                timeStepSizeMin=1e-6)
 
@@ -99,6 +112,9 @@ CASES = {
     "dp2d_indenter_lf": (lambda: _indenter(), [1, 2, 10, 30]),
     # the same indenter pushed sideways through a water bed under WCSPH (type 11 in the wall loop of wc:90-106, 125-126)
     "wc2d_indenter_lf": (lambda: _indenter(water=True), [1, 2, 10]),
+    # the shipped test5 scene shrunken: four soil blocks (an L-shaped bed with a gap) and a static rigid plate pushed
+    # sideways at 0.64 m/s (oracle-only fixture: several objects of one material + a horizontal indenter)
+    "dp2d_plate_lf": (lambda: _plate(), [1, 2, 10]),
     # tiny 3D dambreak with the C4 parameter set
     "wc3d_tiny_lf": (lambda: _scene("test1_db_water.json", dict(WATER3D), dict(size=[0.16, 0.12, 0.12])), [1, 2, 3]),
 }

@@ -1,4 +1,4 @@
-"""world_size-2/3 gloo runs of the slab-decomposition protocol (tisphi_b200/parallel.py) on CPU.
+"""world_size-2/3/4 gloo runs of the slab-decomposition protocol (tisphi_b200/parallel.py) on CPU.
 
 The driver is the product's; the engine behind it is the CPU oracle (tests/slab_oracle.py).  After every step the
 owned ranges of all ranks, concatenated in rank order, must equal a single-process oracle run BIT FOR BIT: same cell
@@ -79,6 +79,8 @@ def _worker(rank, world, port, name, nsteps, serial):
     ("wc3d_tiny_lf", 2, 3, 0),
     ("dp2d_small_lf", 2, 3, 0),
     ("mui2d_small_lf", 2, 3, 0),
+    ("c1_test1_wc_lf", 4, 2, 0),              # four slabs of the full test1 scene (92 columns)
+    ("dp2d_indenter_lf", 2, 3, 0),            # a static rigid indenter inside one slab, next to the face
 ])
 def test_slab_protocol_equals_single_process(name, world, nsteps, serial):
     mp.start_processes(_worker, args=(world, _free_port(), name, nsteps, serial), nprocs=world, join=True,
