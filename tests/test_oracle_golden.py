@@ -9,7 +9,9 @@ from oracle import oracle as orc
 CASES = ["wc2d_small_lf", "wc2d_small_se_cubic", "wc2d_small_rk4_cspm", "mui2d_small_lf", "dp2d_small_rk4_cspm",
          "dp2d_small_lf", "wc3d_tiny_lf", "c1_test1_wc_lf", "c2_test2_mui_lf", "c3_test2_dp_rk4_cspm",
          # static rigid indenter with a prescribed velocity (type 11 in the wall loops, d_vel = 0)
-         "dp2d_indenter_lf", "wc2d_indenter_lf"]
+         "dp2d_indenter_lf", "wc2d_indenter_lf",
+         # shipped test5 shrunken: four soil blocks + a static rigid plate pushed sideways
+         "dp2d_plate_lf"]
 
 # float64 restatement of the same serial algorithm: only summation-order / libm noise is allowed
 TOL = 1e-9
@@ -27,7 +29,7 @@ def test_oracle_matches_reference_run(name):
     assert o.n == g.meta["n"]
     assert o.P.dt == g.meta["dt"]
     assert [int(v) for v in o.D["grid_num"]] == g.meta["grid_num"]
-    last = max(g.steps) if name.endswith("small_lf") or "tiny" in name or "indenter" in name else min(max(g.steps), 10)
+    last = max(g.steps) if name.endswith("small_lf") or "tiny" in name or "indenter" in name or "plate" in name else min(max(g.steps), 10)
     for s in range(1, last + 1):
         if s in g.steps:
             # state right after the grid build + kernel correction of step s
