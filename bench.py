@@ -28,6 +28,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC, UNIT = "particle-updates/s", "particle-updates/s"
+# The reference's 3D WCSPH scheme diverges about 35 steps after rest at ANY resolution (its 3D Wendland normaliser is
+# 8x the textbook value, SURVEY H8: density 1.3 rho0 at step 30, 1e11 rho0 at step 36 in the float64 oracle).
+# A run longer than the stable horizon is therefore cut into legs of at most STABLE_STEPS steps, each started from the
+# restored initial state (a device-to-device re-upload inside the timed region, < 1 % of a leg).
+STABLE_STEPS = 20
+
+
+def run_in_legs(run_steps, restore, total):
+    done = 0
+    while done < total:
+        restore()
+        leg = min(STABLE_STEPS, total - done)
+        run_steps(leg)
+        done += leg
 
 
 def log(*a):
@@ -194,14 +208,26 @@ def run_ours(args):
     h_x, h_rho, h_typ = pin(ps.pt.x), pin(ps.pt.density), pin(ps.pt.mat_type)
     h_v = pin(ps.pt.v.double())
 
-    solver.run_steps(args.warmup)
+    replay = args.warmup + args.steps > STABLE_STEPS + 4           # the default 3 + 20 runs straight through
+    if replay:                                                      # device-resident copy of the initial state
+        d_x, d_rho, d_typ = ps.pt.x.clone().contiguous(), ps.pt.density.clone().contiguous(), ps.pt.mat_type.clone().contiguous()
+        d_v = ps.pt.v.double().contiguous()
+
+        def restore():
+            eng.call("sph_clear_particles")
+            eng.call("sph_add_particles", n, d_x.data_ptr(), d_v.data_ptr(), d_rho.data_ptr(), d_typ.data_ptr())
+
+    solver.run_steps(min(args.warmup, STABLE_STEPS) if replay else args.warmup)
     torch.cuda.synchronize()
     launches0 = eng.L.sph_launch_count(eng.h)
     eng.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         e0.record(eng.stream)
-        solver.run_steps(args.steps)
+        if replay:
+            run_in_legs(solver.run_steps, restore, args.steps)
+        else:
+            solver.run_steps(args.steps)
         e1.record(eng.stream)
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -301,7 +327,9 @@ def run_ours(args):
             "config": {"workload": f"C4 3D WCSPH dambreak (Wendland C2, dummy walls, LF): N={n} ({n_fluid} fluid + {n_wall} wall), "
                                    f"cells={ps.grid_num_total}, dt={solver.dt[None]!r}, scale={args.scale}",
                        "precision": "mixed: fp32 sweeps, fp64 positions+densities" if args.precision != "f64" else "f64",
-                       "l2": "state (>= 2 GB) larger than L2, no flush needed", "bad_cells": int(bad)},
+                       "l2": "state (>= 2 GB) larger than L2, no flush needed", "bad_cells": int(bad),
+                       "legs": (f"{-(-args.steps // STABLE_STEPS)} legs of <= {STABLE_STEPS} steps from the restored initial state "
+                                "(the reference's 3D scheme diverges ~35 steps after rest)") if replay else "one run from rest"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "real_particle_updates_per_s": n_fluid * args.steps / (ms * 1e-3)}
     print(json.dumps(line), flush=True)
@@ -336,7 +364,19 @@ def run_ours_multi(args, rank, local, world):
         dist.barrier()
         torch.cuda.synchronize()
 
-    sim.run_steps(args.warmup)
+    replay = args.warmup + args.steps > STABLE_STEPS + 4
+    if replay:                                                      # device-resident copy of this rank's initial state
+        d_x, d_rho, d_typ = ps.pt.x.clone().contiguous(), ps.pt.density.clone().contiguous(), ps.pt.mat_type.clone().contiguous()
+        d_v, d_id = ps.pt.v.double().contiguous(), ps.pt.id0.clone().contiguous()
+        n_init = len(d_rho)
+
+        def restore():
+            eng.call("sph_clear_particles")
+            eng.call("sph_add_particles", n_init, d_x.data_ptr(), d_v.data_ptr(), d_rho.data_ptr(), d_typ.data_ptr())
+            eng.field("ID0").copy_(d_id)
+            drv.reset()
+
+    sim.run_steps(min(args.warmup, STABLE_STEPS) if replay else args.warmup)
     barrier()
     launches0 = eng.L.sph_launch_count(eng.h)
     bytes0, ex0 = drv.bytes_sent, drv.exchanges
@@ -345,7 +385,10 @@ def run_ours_multi(args, rank, local, world):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         e0.record(eng.stream)
-        sim.run_steps(args.steps)
+        if replay:
+            run_in_legs(sim.run_steps, restore, args.steps)
+        else:
+            sim.run_steps(args.steps)
         e1.record(eng.stream)
         barrier()
     ms_t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")

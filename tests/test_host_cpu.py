@@ -104,3 +104,20 @@ def test_configer_keyerror_and_sections(tmp_path):
     with pytest.raises(KeyError):
         c.get_cfg("kernel")
     assert c.get_blocks() == [] and c.get_materials() == [] and c.get_bodies() == [] and c.get_motions() == []
+
+
+def test_bench_replays_long_runs_in_stable_legs():
+    """bench.py cuts runs longer than the reference scheme's stable horizon (3D WCSPH diverges ~35 steps after rest)
+    into legs from the restored initial state; every requested step is taken exactly once."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for total in (1, 20, 21, 50, 100):
+        log = []
+        bench.run_in_legs(lambda k: log.append(("run", k)), lambda: log.append(("restore", 0)), total)
+        runs = [k for what, k in log if what == "run"]
+        assert sum(runs) == total and max(runs) <= bench.STABLE_STEPS
+        assert [w for w, _ in log] == ["restore", "run"] * len(runs)          # every leg starts from the restored state
