@@ -33,6 +33,7 @@ METRIC, UNIT = "particle-updates/s", "particle-updates/s"
 # A run longer than the stable horizon is therefore cut into legs of at most STABLE_STEPS steps, each started from the
 # restored initial state (a device-to-device re-upload inside the timed region, < 1 % of a leg).
 STABLE_STEPS = 20
+STRAIGHT_STEPS = 30       # warm-up + timed steps up to here run straight from rest (rho_max < 1.35 rho0, no crowded cell yet)
 
 
 def run_in_legs(run_steps, restore, total):
@@ -208,7 +209,7 @@ def run_ours(args):
     h_x, h_rho, h_typ = pin(ps.pt.x), pin(ps.pt.density), pin(ps.pt.mat_type)
     h_v = pin(ps.pt.v.double())
 
-    replay = args.warmup + args.steps > STABLE_STEPS + 4           # the default 3 + 20 runs straight through
+    replay = args.warmup + args.steps > STRAIGHT_STEPS                # the default 3 + 20 runs straight through
     if replay:                                                      # device-resident copy of the initial state
         d_x, d_rho, d_typ = ps.pt.x.clone().contiguous(), ps.pt.density.clone().contiguous(), ps.pt.mat_type.clone().contiguous()
         d_v = ps.pt.v.double().contiguous()
@@ -364,7 +365,7 @@ def run_ours_multi(args, rank, local, world):
         dist.barrier()
         torch.cuda.synchronize()
 
-    replay = args.warmup + args.steps > STABLE_STEPS + 4
+    replay = args.warmup + args.steps > STRAIGHT_STEPS
     if replay:                                                      # device-resident copy of this rank's initial state
         d_x, d_rho, d_typ = ps.pt.x.clone().contiguous(), ps.pt.density.clone().contiguous(), ps.pt.mat_type.clone().contiguous()
         d_v, d_id = ps.pt.v.double().contiguous(), ps.pt.id0.clone().contiguous()
