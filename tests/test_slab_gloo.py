@@ -80,6 +80,7 @@ def _worker(rank, world, port, name, nsteps, serial):
     ("dp2d_small_lf", 2, 3, 0),
     ("mui2d_small_lf", 2, 3, 0),
     ("c1_test1_wc_lf", 4, 2, 0),              # four slabs of the full test1 scene (92 columns)
+    ("c1_test1_wc_lf", 8, 2, 0),              # eight slabs: the width the driver's scaling run goes to
     ("dp2d_indenter_lf", 2, 3, 0),            # a static rigid indenter inside one slab, next to the face
 ])
 def test_slab_protocol_equals_single_process(name, world, nsteps, serial):
