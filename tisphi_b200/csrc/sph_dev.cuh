@@ -81,8 +81,8 @@ template <typename T> struct Dev {
     int *nflag;               // number of flagged cells (device counter)
     unsigned char *cellinfo;  // per cell, written by the mask kernel: 1 has flow particles, 2 has wall particles,
                               // 4 has wall particles AND a stencil cell with flow particles (candidate for the wall pass)
-    int *worklist[4];         // footprint segments with work: 0 occupied (stand-alone Shepard pass), 1 flow (fluid pass),
-                              // 2 wall pass, 3 occupied with flow particles in reach (mask pass)
+    int *worklist[4];         // work lists: footprint segments 0 occupied (stand-alone Shepard pass), 1 flow (fluid pass),
+                              // 3 occupied with flow particles in reach (mask pass); 2 wall CELLS in reach of flow (wall pass)
     int *wcount;              // their lengths (4 ints), then the dynamic cursors of the persistent kernels
     T *psx, *psy, *psz, *psf; // SoA copy of the sweep coordinates + flow sign (+1 flow / -1 other): mask-kernel tiles
     unsigned char *cellflow;  // per cell: 1 when it holds a flow particle (written by the reorder kernel)

@@ -731,7 +731,7 @@ template <bool ADV> __global__ void __launch_bounds__(256) k_tile_prep(DevF c, i
 // SHEP (the first wall pass after the masks were built): f = 1 / sum V W (calc_CSPM_f) is formed in the same visit and
 // stored; later passes of the step reuse the stored f like the reference does (m_V changes with the stage density).
 // Masks of wall particles hold flow neighbours only.
-// Tile payloads: ps4 (coords, signed volume), vt4 (v~, rho~), pw4 (EOS pressure, previous pressure).
+// Payloads per neighbour: ps4 (coords, signed volume), vt4 (v~, rho~), pw4 (EOS pressure, previous pressure).
 template <int KERNEL>
 __device__ __forceinline__ void wall_pair(const KernConst &kc, float ex, float ey, float ez, const F4 pj, const F4 vj, float pjv,
                                           float gy, float &vw, float &pterm) {
@@ -741,7 +741,7 @@ __device__ __forceinline__ void wall_pair(const KernConst &kc, float ex, float e
 }
 
 // ------------------------------------------------------------------------------------------------ pass A: walls, gathered
-// The same wall pass without a tile: one warp per wall cell that has flow particles in reach (a compacted CELL list),
+// The wall pass without a tile (the first version staged 1x1x4-cell footprints like the fluid pass): one warp per wall cell that has flow particles in reach (a compacted CELL list),
 // lane = particle, the mask bits walked in the same order with the same arithmetic, but the neighbour payloads are
 // gathered from global memory through L1 (the lanes of a warp share most of their neighbours).  Only ~5 % of the
 // particles take part in this pass and each has few (flow-only) neighbours, so staging 54 cells x 3 payloads per four
