@@ -275,6 +275,7 @@ template <typename T> int step_once(SphCtx *c) {
     // init_real2tmp in the reorder kernel, advect_LF_half in the EOS / payload kernel of the cell-tile path, and
     // advect_SE|LF + advect_pos + advect_something in one kernel.
     const bool wc_fused = c->p.solver == SPH_SOLVER_WC && !c->p.xsph && (c->p.ti == 1 || c->p.ti == 2);
+    c->fuse_half = false;                                     // (a step that failed half way must not leave the flag behind)
     c->fuse_init = wc_fused;
     if ((r = grid_build<T>(c))) return r;
     c->fuse_init = false;
