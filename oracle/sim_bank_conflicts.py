@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""CPU model of the shared-memory gather traffic of k_tile_fluid (the fluid pass is bound by
+"""TEST / ANALYSIS INFRASTRUCTURE (lives under oracle/ because it runs the oracle; nothing in the product imports it).
+
+CPU model of the shared-memory gather traffic of k_tile_fluid (the fluid pass is bound by
 LDS.128 gathers, 47 % of whose wavefronts are bank-conflict replays) and of a conflict-aware neighbour order.
 
 An LDS.128 of a warp is served per quarter-warp (8 lanes x 16 B = the 32 banks once).  Two lanes of a quarter that
@@ -22,7 +24,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import oracle as orc          # noqa: E402  (analysis tool, not product code)
+from oracle import oracle as orc          # noqa: E402
 from tisphi_b200 import scenes            # noqa: E402
 
 BX, BY, ZB, SENT = 2, 2, 4, 3072

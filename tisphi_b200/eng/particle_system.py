@@ -386,7 +386,7 @@ class ParticleSystem:
         return self.flatten_grid_index(self.pos_to_index(pos))
 
     def for_all_neighbors(self, i, task, ret):
-        """ps:259-269 for ONE particle on the host (debug / oracle helper; the sweeps do this on the device): calls
+        """ps:259-269 for ONE particle on the host (a debugging helper; the sweeps do this on the device): calls
         ``task(i, j, ret)`` for every j of the 3^dim cells around i with |x_i - x_j| < support_radius, in the
         reference's order (cells x-major / z fastest, j ascending).  Needs a current grid."""
         x = self.pt.x
