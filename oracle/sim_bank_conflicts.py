@@ -23,7 +23,7 @@ import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+sys.path = [ROOT] + [q for q in sys.path if os.path.abspath(q or '.') != os.path.dirname(os.path.abspath(__file__))]
 from oracle import oracle as orc          # noqa: E402
 from tisphi_b200 import scenes            # noqa: E402
 
