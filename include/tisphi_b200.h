@@ -136,6 +136,9 @@ int sph_advect_pos(SphCtx *ctx);
 int sph_post_step(SphCtx *ctx);
 /* SPHBase.init_stress (base:249-260) */
 int sph_init_stress(SphCtx *ctx);
+/* the same with y_max given by the caller: a ctx that holds one slab of a scene must use the highest soil particle of
+ * the WHOLE scene, not of its own columns */
+int sph_init_stress_ymax(SphCtx *ctx, double y_max);
 /* SPHBase.step (base:41-51) repeated nsteps times, enqueued without host round trips */
 int sph_step(SphCtx *ctx, int nsteps);
 
@@ -194,6 +197,36 @@ int sph_pack_selected(SphCtx *ctx, int32_t which, int32_t nfields, const int32_t
  * the higher-x neighbour behind, so that the next stable sort reproduces the single-GPU global order. */
 int sph_replace_particles(SphCtx *ctx, int64_t keep_first, int64_t keep_count, const void *left_msg, int64_t n_left,
                           const void *right_msg, int64_t n_right);
+
+
+/* ---- the slab step without host round trips (tisphi_b200/csrc/slab.cu) ---------------------------------------------
+ * The calls above let a host program run the slab protocol itself (tisphi_b200/parallel.py::SlabDriver does, over
+ * torch.distributed).  The calls below move the whole protocol onto the device: after sph_slab_init + sph_slab_connect,
+ * sph_step(ctx, nsteps) runs SPHBase.step (base:41-51) on the slab -- migration, the one sort, every ghost refresh --
+ * with the particle count and the column table kept in device memory and every message STORED by the packing kernel
+ * straight into the neighbour's inbox (a peer mapping over NVLink), completed by a system-scope flag the receiver's
+ * stream waits on.  Results are bit-identical to the single-GPU run (the stable sort, see above).
+ *   inbox: device memory of sph_slab_inbox_bytes() bytes, 256-byte aligned, owned by the caller; with one process per
+ *   GPU it must be its own cudaMalloc allocation so that it can be exported (sph_ipc_*).  face_cap: the most particles
+ *   one message may carry (a boundary column + migrants); exceeding it sets an error bit, it never overruns. */
+int64_t sph_slab_inbox_bytes(SphCtx *ctx, int64_t face_cap);
+int sph_slab_init(SphCtx *ctx, int32_t rank, int32_t world, int32_t cx_begin, int32_t cx_end, int64_t face_cap, void *inbox,
+                  int64_t inbox_bytes);
+/* the neighbours' inboxes as device pointers valid on THIS device (NULL at the ends of the row of slabs) */
+int sph_slab_connect(SphCtx *ctx, void *left_inbox, void *right_inbox);
+/* While the slab steps, the host does not know the particle count.  This reads the device control block back:
+ * count (owned + ghosts), the index range of the owned particles, sticky error bits (timeout 1, ghost / boundary
+ * column sizes disagree 2, capacity 4, a particle moved more than one column 8, face capacity 16; != 0 returns -4).
+ * Synchronises the stream.  sph_num_particles / sph_read_state* use the count of the last sync. */
+int sph_slab_sync(SphCtx *ctx, int64_t *n, int64_t *own_first, int64_t *own_count, int32_t *err_bits);
+int64_t sph_slab_epoch(SphCtx *ctx);                 /* exchanges enqueued so far (every rank counts the same) */
+/* CUDA IPC plumbing for one process per GPU: allocate an exportable inbox, export it as a 64-byte handle, map a
+ * neighbour's handle (peer access is enabled lazily).  Handles travel through any host channel (torch.distributed). */
+void *sph_ipc_alloc(int64_t bytes);
+void sph_ipc_free(void *dev_ptr);
+int sph_ipc_get_handle(void *dev_ptr, void *handle64);
+void *sph_ipc_open(const void *handle64);
+void sph_ipc_close(void *dev_ptr);
 
 #ifdef __cplusplus
 }

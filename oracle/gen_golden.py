@@ -117,6 +117,16 @@ CASES = {
     "dp2d_plate_lf": (lambda: _plate(), [1, 2, 10]),
     # tiny 3D dambreak with the C4 parameter set
     "wc3d_tiny_lf": (lambda: _scene("test1_db_water.json", dict(WATER3D), dict(size=[0.16, 0.12, 0.12])), [1, 2, 3]),
+    # ---- round 2: the BASELINE configs over their full horizons (100 steps for C1-C3) ----
+    "c1_test1_wc_lf_h100": (lambda: _scene("test1_db_water.json"), [1, 10, 50, 100]),
+    "c2_test2_mui_lf_h100": (lambda: _scene("test2_cc_sand.json", dict(simulationMethod=2)), [1, 10, 50, 100]),
+    "c3_test2_dp_rk4_cspm_h30": (lambda: _scene("test2_cc_sand.json",
+                                                dict(simulationMethod=3, kernelCorrection=1, timeIntegration=4)),
+                                 [1, 10, 30]),
+    # 3D dambreak with the C4 parameter set, N = 20 772 (fluid 24 x 16 x 20)
+    "wc3d_20k_lf": (lambda: _scene("test1_db_water.json",
+                                   dict(WATER3D, particleRadius=0.005, domainEnd=[0.4, 0.24, 0.2]),
+                                   dict(size=[0.24, 0.16, 0.2])), [1, 10, 20]),
 }
 
 SCALARS = ["mat_type", "id0", "obj_id", "grid_ids", "m_V", "density", "mass", "pressure", "CSPM_f", "d_density",

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libtisphi_b200.so")
-SOURCES = ["api.cu", "grid.cu", "integrate.cu", "sweeps.cu", "sweeps_tile.cu", "halo.cu"]
+SOURCES = ["api.cu", "grid.cu", "integrate.cu", "sweeps.cu", "sweeps_tile.cu", "halo.cu", "slab.cu"]
 HEADERS = ["sph_dev.cuh", "sph_host.h", os.path.join("..", "..", "include", "tisphi_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

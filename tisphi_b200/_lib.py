@@ -22,11 +22,13 @@ SYMBOLS = ["sph_arena_bytes", "sph_create", "sph_destroy", "sph_last_error", "sp
            "sph_add_particles", "sph_num_particles", "sph_clear_particles", "sph_read_state", "sph_read_state_async",
            "sph_synchronize", "sph_grid_build",
            "sph_calc_kernel_corr", "sph_calc_kernel_corr_deferred", "sph_init_real2tmp", "sph_one_step", "sph_advect", "sph_advect_pos", "sph_post_step",
-           "sph_init_stress", "sph_step", "sph_neighbor_count", "sph_neighbor_count_masks", "sph_density_sum", "sph_read_bad_cells",
+           "sph_init_stress", "sph_init_stress_ymax", "sph_step", "sph_neighbor_count", "sph_neighbor_count_masks", "sph_density_sum", "sph_read_bad_cells",
            "sph_launch_count", "sph_num_phases", "sph_one_step_phase", "sph_set_owned_columns",
            "sph_column_starts", "sph_state_fields", "sph_message_bytes", "sph_pack_fields", "sph_unpack_fields",
            "sph_replace_particles", "sph_select_columns", "sph_select_counts", "sph_pack_selected", "sph_profile_enable", "sph_profile_num_kernels",
-           "sph_profile_name", "sph_profile_read", "sph_params_size"]
+           "sph_profile_name", "sph_profile_read", "sph_params_size",
+           "sph_slab_inbox_bytes", "sph_slab_init", "sph_slab_connect", "sph_slab_sync", "sph_slab_epoch",
+           "sph_ipc_alloc", "sph_ipc_free", "sph_ipc_get_handle", "sph_ipc_open", "sph_ipc_close"]
 
 
 class SphParams(C.Structure):
@@ -71,6 +73,7 @@ def load():
                "sph_post_step", "sph_init_stress"):
         getattr(L, fn).restype, getattr(L, fn).argtypes = C.c_int, [vp]
     L.sph_advect.restype, L.sph_advect.argtypes = C.c_int, [vp, C.c_int, C.c_int]
+    L.sph_init_stress_ymax.restype, L.sph_init_stress_ymax.argtypes = C.c_int, [vp, C.c_double]
     L.sph_step.restype, L.sph_step.argtypes = C.c_int, [vp, C.c_int]
     L.sph_neighbor_count.restype, L.sph_neighbor_count.argtypes = C.c_int, [vp, vp]
     L.sph_density_sum.restype, L.sph_density_sum.argtypes = C.c_int, [vp, vp]
@@ -94,6 +97,17 @@ def load():
     L.sph_profile_name.restype, L.sph_profile_name.argtypes = C.c_char_p, [C.c_int]
     L.sph_profile_read.restype, L.sph_profile_read.argtypes = C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     L.sph_params_size.restype, L.sph_params_size.argtypes = i64, []
+    L.sph_slab_inbox_bytes.restype, L.sph_slab_inbox_bytes.argtypes = i64, [vp, i64]
+    L.sph_slab_init.restype, L.sph_slab_init.argtypes = C.c_int, [vp, i32, i32, i32, i32, i64, vp, i64]
+    L.sph_slab_connect.restype, L.sph_slab_connect.argtypes = C.c_int, [vp, vp, vp]
+    L.sph_slab_sync.restype = C.c_int
+    L.sph_slab_sync.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
+    L.sph_slab_epoch.restype, L.sph_slab_epoch.argtypes = i64, [vp]
+    L.sph_ipc_alloc.restype, L.sph_ipc_alloc.argtypes = vp, [i64]
+    L.sph_ipc_free.restype, L.sph_ipc_free.argtypes = None, [vp]
+    L.sph_ipc_get_handle.restype, L.sph_ipc_get_handle.argtypes = C.c_int, [vp, vp]
+    L.sph_ipc_open.restype, L.sph_ipc_open.argtypes = vp, [vp]
+    L.sph_ipc_close.restype, L.sph_ipc_close.argtypes = None, [vp]
     if L.sph_params_size() != C.sizeof(SphParams):
         raise SphError('SphParams layout mismatch between tisphi_b200/_lib.py and include/tisphi_b200.h')
     _lib = L

@@ -84,6 +84,7 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
     int64_t o_perm = off; off += ib;
     int64_t o_tmp = off; off += ib;
     int64_t o_bad = off; off += 256;
+    int64_t o_ctl = off; off += 256;                                   // SlabCtl (slab.cu)
     const int64_t nt = ((C > n_max ? C : n_max) + 2047) / 2048 + 2;    // scan tiles: cells (grid build) or particles (selection)
     int64_t o_tiles = off; off += align_up(nt * 4);
     const int mask_words = p->dim == 3 ? 27 : 9;
@@ -116,7 +117,7 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
         c->off_psoa = o_soa; c->off_cellflow = o_cflow; c->soa_stride = soa_stride; c->wl_stride = wl_stride;
         c->off_nlist = o_nlist; c->off_lrounds = o_lrounds; c->use_list = lists; c->list_valid = false;
         c->off_gid_unsorted = o_gid; c->off_slot = o_slot; c->off_perm = o_perm; c->off_tmpidx = o_tmp;
-        c->off_bad = o_bad; c->off_scan_tiles = o_tiles;
+        c->off_bad = o_bad; c->off_scan_tiles = o_tiles; c->off_slabctl = o_ctl;
         c->real_bytes = rb; c->soil = soil; c->rk = rk; c->has_L = hasL; c->C = (int)C;
     }
     return off;
@@ -161,7 +162,7 @@ struct ProfState {
 const char *KNAMES[K_NUM] = {"cell_id", "scan", "scatter_index", "rank", "reorder", "cspm_f", "cspm_L", "wc_eos", "wc_wall",
                              "wc_fluid", "mui_soil1", "soil_wall", "mui_soil3", "dp_adapt", "dp_soil", "advect_pos", "post",
                              "post_sweep", "neighbor_count", "density_sum", "other", "init_real2tmp", "advect", "tile_mask",
-                             "tile_fluid", "tile_wall", "halo"};
+                             "tile_fluid", "tile_wall", "halo", "halo_wait", "c5_sweep"};
 }
 void sph_prof_begin(SphCtx *c, int id) {
     ProfState *ps = (ProfState *)c->prof_state;
@@ -189,6 +190,7 @@ template <typename T> Dev<T> make_dev(SphCtx *c, int which) {
     Dev<T> d;
     memset(&d, 0, sizeof(d));
     d.n = (int)c->n;
+    d.ndev = slab_ndev(c);
     d.dim = p.dim; d.kernel = p.kernel; d.kcorr = p.kcorr; d.solver = p.solver; d.xsph = p.xsph; d.wc_fresh = p.wc_fresh;
     for (int a = 0; a < 3; a++) { d.gn[a] = p.gn[a]; d.vstart[a] = p.vstart[a]; d.g[a] = (T)p.g[a]; }
     if (p.dim == 2) d.gn[2] = 1;
@@ -277,27 +279,27 @@ template <typename T> int step_once(SphCtx *c) {
     const bool wc_fused = c->p.solver == SPH_SOLVER_WC && !c->p.xsph && (c->p.ti == 1 || c->p.ti == 2);
     c->fuse_half = false;                                     // (a step that failed half way must not leave the flag behind)
     c->fuse_init = wc_fused;
-    if ((r = grid_build<T>(c))) return r;
+    if ((r = c->slab ? slab_redistribute<T>(c) : grid_build<T>(c))) return r;
     c->fuse_init = false;
     if ((r = calc_kernel_corr<T>(c, false))) return r;
     if (!wc_fused && (r = init_real2tmp<T>(c))) return r;
     switch (c->p.ti) {
     case 1:
-        if ((r = one_step<T>(c))) return r;
+        if ((r = one_step<T>(c, true))) return r;
         if (!wc_fused && (r = advect<T>(c, 0, 0))) return r;
         break;
     case 2:
-        if ((r = one_step<T>(c))) return r;
+        if ((r = one_step<T>(c, false))) return r;
         if (wc_fused && c->fast) c->fuse_half = true;          // consumed by the next one_step's first kernel
         else if ((r = advect<T>(c, 1, 0))) return r;
-        if ((r = one_step<T>(c))) return r;
+        if ((r = one_step<T>(c, true))) return r;
         if (!wc_fused && (r = advect<T>(c, 0, 0))) return r;
         break;
     case 4: {
         static const int m[4] = {1, 2, 2, 1};
         if ((r = advect<T>(c, 3, 0))) return r;
         for (int s = 0; s < 4; s++) {
-            if ((r = one_step<T>(c))) return r;
+            if ((r = one_step<T>(c, s == 3))) return r;
             if ((r = advect<T>(c, 4, m[s]))) return r;
             if (s < 3 && (r = advect<T>(c, 2, 0))) return r;
         }
@@ -309,6 +311,7 @@ template <typename T> int step_once(SphCtx *c) {
     }
     if (wc_fused) return finish_step<T>(c);
     if ((r = advect_pos<T>(c))) return r;
+    if ((r = slab_refresh_post(c))) return r;
     return post_step<T>(c);
 }
 template <typename T> int dispatch_step(SphCtx *c, int nsteps) {
@@ -355,6 +358,7 @@ void sph_destroy(SphCtx *c) {
         for (cudaEvent_t e : ps->pool) cudaEventDestroy(e);
         delete ps;
     }
+    slab_free(c);
     delete c;
 }
 const char *sph_last_error(SphCtx *c) { return c ? c->err : "null ctx"; }
@@ -368,6 +372,7 @@ int sph_set_params(SphCtx *c, const SphParams *p) {
     c->p = *p;
     c->r2thr64 = r2_threshold64(p->support);
     c->r2thr32 = r2_threshold32((float)p->support);
+    c->masks_valid = false;
     return 0;
 }
 
@@ -386,6 +391,8 @@ int sph_field_info(SphCtx *c, int field, int64_t *offset_bytes, int32_t *ncomp, 
 
 int sph_add_particles(SphCtx *c, int64_t n, const double *x, const double *v, const double *density, const int32_t *mat_type) {
     if (n <= 0) return 0;
+    if (slab_armed(c)) { snprintf(c->err, sizeof(c->err), "sph_add_particles on a stepping slab: sph_clear_particles first"); return -2; }
+    c->masks_valid = false;
     if (c->n + n > c->n_max) { snprintf(c->err, sizeof(c->err), "particle capacity %lld exceeded", (long long)c->n_max); return -2; }
     const int64_t first = c->n;
     char *X = c->arena + c->f[SPH_F_X].off[c->f[SPH_F_X].cur];
@@ -399,16 +406,31 @@ int sph_add_particles(SphCtx *c, int64_t n, const double *x, const double *v, co
     c->n += n;
     return DISPATCH(c, add_particles_finish, c, first, n);
 }
-int64_t sph_num_particles(SphCtx *c) { return c->n; }
+int64_t sph_num_particles(SphCtx *c) { return slab_exact_n(c); }
+// Only what a fresh upload does not overwrite has to be zero: the carried members of the live range (both ping-pong
+// buffers, so that members sph_add_particles does not set -- v_tmp, pressure, stress ... -- start from 0 like the
+// reference's zero-initialised fields) and the small counters; every other array is scratch rewritten before use.
 int sph_clear_particles(SphCtx *c) {
+    const int64_t live = c->slab ? c->n_max : c->n;
+    slab_disarm(c);
+    for (int f = 0; f < SPH_F_NUM; f++) {
+        FieldSlot &F = c->f[f];
+        if (!F.present || f == SPH_F_MASS || f == SPH_F_M_V || f == SPH_F_CELL_END || f == SPH_F_CELL_COUNT) continue;
+        const int64_t bytes = live * F.stride * elem_bytes(F.kind, c->real_bytes);
+        if (bytes == 0) continue;
+        SPH_CHECK(c, cudaMemsetAsync(c->arena + F.off[0], 0, (size_t)bytes, c->stream));
+        if (F.off[1] != F.off[0]) SPH_CHECK(c, cudaMemsetAsync(c->arena + F.off[1], 0, (size_t)bytes, c->stream));
+    }
+    SPH_CHECK(c, cudaMemsetAsync(c->arena + c->off_bad, 0, 512, c->stream));      // bad-cell counter, selection counts, SlabCtl
     c->n = 0;
-    SPH_CHECK(c, cudaMemsetAsync(c->arena, 0, (size_t)layout(&c->p, c->n_max, nullptr), c->stream));
+    c->masks_valid = false;
+    c->list_valid = false; c->shep_pending = c->shep_wall_pending = false; c->fuse_half = c->fuse_init = false;
     for (int f = 0; f < SPH_F_NUM; f++) c->f[f].cur = 0;
     return 0;
 }
 
 int sph_read_state_async(SphCtx *c, double *x, double *v, double *density, double *pressure, int32_t *id0) {
-    const int64_t n = c->n;
+    const int64_t n = slab_exact_n(c);
     if (x) SPH_CHECK(c, cudaMemcpyAsync(x, c->arena + c->f[SPH_F_X].off[c->f[SPH_F_X].cur], (size_t)n * 24, cudaMemcpyDefault, c->stream));
     if (density) SPH_CHECK(c, cudaMemcpyAsync(density, c->arena + c->f[SPH_F_DENSITY].off[c->f[SPH_F_DENSITY].cur], (size_t)n * 8, cudaMemcpyDefault, c->stream));
     if (id0) SPH_CHECK(c, cudaMemcpyAsync(id0, c->arena + c->f[SPH_F_ID0].off[c->f[SPH_F_ID0].cur], (size_t)n * 4, cudaMemcpyDefault, c->stream));
@@ -431,11 +453,12 @@ int sph_grid_build(SphCtx *c) { return DISPATCH(c, grid_build, c); }
 int sph_calc_kernel_corr(SphCtx *c) { return DISPATCH(c, calc_kernel_corr, c, true); }
 int sph_calc_kernel_corr_deferred(SphCtx *c) { return DISPATCH(c, calc_kernel_corr, c, false); }
 int sph_init_real2tmp(SphCtx *c) { return DISPATCH(c, init_real2tmp, c); }
-int sph_one_step(SphCtx *c) { return DISPATCH(c, one_step, c); }
+int sph_one_step(SphCtx *c) { return DISPATCH(c, one_step, c, false); }
 int sph_advect(SphCtx *c, int kind, int m) { return DISPATCH(c, advect, c, kind, m); }
 int sph_advect_pos(SphCtx *c) { return DISPATCH(c, advect_pos, c); }
 int sph_post_step(SphCtx *c) { return DISPATCH(c, post_step, c); }
-int sph_init_stress(SphCtx *c) { return DISPATCH(c, init_stress, c); }
+int sph_init_stress(SphCtx *c) { return DISPATCH(c, init_stress, c, nullptr); }
+int sph_init_stress_ymax(SphCtx *c, double ymax) { return DISPATCH(c, init_stress, c, &ymax); }
 int sph_step(SphCtx *c, int nsteps) { return DISPATCH(c, dispatch_step, c, nsteps); }
 int sph_neighbor_count(SphCtx *c, int32_t *out_dev) { return DISPATCH(c, neighbor_count, c, out_dev); }
 int sph_density_sum(SphCtx *c, void *out_dev) { return DISPATCH(c, density_sum, c, out_dev); }

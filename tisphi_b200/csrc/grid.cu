@@ -19,7 +19,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_cell_id(Dev<T> c, int *__restrict__ gid_out, int *__restrict__ slot) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool valid = i < c.n;
+    const bool valid = i < c.N();
     long long g = -1 - lane;                    // idle lanes: distinct keys that match nobody
     if (valid) {
         const double x[3] = {c.x[3 * (size_t)i], c.x[3 * (size_t)i + 1], c.x[3 * (size_t)i + 2]};
@@ -108,17 +108,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const int *__restri
 }
 
 // ------------------------------------------------------------------------------------------------ stable rank
-__global__ void __launch_bounds__(256) k_scatter_index(int n, const int *__restrict__ gid, const int *__restrict__ slot,
-                                                       const int *__restrict__ cell_end, int *__restrict__ tmpidx) {
+__global__ void __launch_bounds__(256) k_scatter_index(int n, const int *__restrict__ ndev, const int *__restrict__ gid,
+                                                       const int *__restrict__ slot, const int *__restrict__ cell_end,
+                                                       int *__restrict__ tmpidx) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ndev) n = *ndev;
     if (i >= n) return;
     int g = gid[i];
     int start = g > 0 ? cell_end[g - 1] : 0;
     tmpidx[start + slot[i]] = i;
 }
-__global__ void __launch_bounds__(256) k_rank(int n, const int *__restrict__ gid, const int *__restrict__ cell_end,
-                                              const int *__restrict__ tmpidx, int *__restrict__ perm, int *__restrict__ id_new) {
+__global__ void __launch_bounds__(256) k_rank(int n, const int *__restrict__ ndev, const int *__restrict__ gid,
+                                              const int *__restrict__ cell_end, const int *__restrict__ tmpidx,
+                                              int *__restrict__ perm, int *__restrict__ id_new) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ndev) n = *ndev;
     if (i >= n) return;
     int g = gid[i];
     int start = g > 0 ? cell_end[g - 1] : 0, end = cell_end[g];
@@ -135,7 +139,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_reorder(Dev<T> a, Dev<T> b, const int *__restrict__ perm,
                                                  const int *__restrict__ gid_unsorted, int soil, int init_tmp) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= a.n) return;
+    if (k >= a.N()) return;
     const int s = perm[k];
     const size_t k3 = 3 * (size_t)k, s3 = 3 * (size_t)s;
     const double x0 = a.x[s3], x1 = a.x[s3 + 1], x2 = a.x[s3 + 2];
@@ -233,6 +237,7 @@ template int select_columns<double>(SphCtx *, int, int64_t, int64_t, int, int);
 template <typename T> int grid_build(SphCtx *c) {
     const int n = (int)c->n;
     if (n == 0) return 0;
+    c->masks_valid = false;                       // masks, work lists and round lists index the previous order
     Dev<T> a = make_dev<T>(c, -1), b = make_dev<T>(c, 1);
     int *gid_u = (int *)(c->arena + c->off_gid_unsorted), *slot = (int *)(c->arena + c->off_slot);
     int *perm = (int *)(c->arena + c->off_perm), *tmpidx = (int *)(c->arena + c->off_tmpidx);
@@ -255,10 +260,10 @@ template <typename T> int grid_build(SphCtx *c) {
     k_scan_apply<<<nt, SCAN_THREADS, 0, st>>>(a.cell_cnt, c->C, tiles, a.cell_end);
     SPH_LAUNCH_CHECK(c);
     SPH_PROF(c, K_SCATTER);
-    k_scatter_index<<<blocks_for(n, 256), 256, 0, st>>>(n, gid_u, slot, a.cell_end, tmpidx);
+    k_scatter_index<<<blocks_for(n, 256), 256, 0, st>>>(n, a.ndev, gid_u, slot, a.cell_end, tmpidx);
     SPH_LAUNCH_CHECK(c);
     SPH_PROF(c, K_RANK);
-    k_rank<<<blocks_for(n, 256), 256, 0, st>>>(n, gid_u, a.cell_end, tmpidx, perm, id_new);
+    k_rank<<<blocks_for(n, 256), 256, 0, st>>>(n, a.ndev, gid_u, a.cell_end, tmpidx, perm, id_new);
     SPH_LAUNCH_CHECK(c);
     SPH_PROF(c, K_REORDER);
     const int init_tmp = (c->fuse_init && !c->soil) ? 1 : 0;

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) k_multi_gather(CopyBatch b, const int *__
 static inline int64_t align16(int64_t v) { return (v + 15) / 16 * 16; }
 
 // bytes per particle of a member and its buffer (current or alternate)
-static bool field_ref(SphCtx *c, int f, bool alt, char **ptr, int *elem_bytes) {
+bool field_ref(SphCtx *c, int f, bool alt, char **ptr, int *elem_bytes) {
     if (f < 0 || f >= SPH_F_NUM || f == SPH_F_MASS || f == SPH_F_M_V || f == SPH_F_CELL_END || f == SPH_F_CELL_COUNT) return false;
     const FieldSlot &F = c->f[f];
     if (!F.present) return false;
@@ -155,6 +155,7 @@ int sph_replace_particles(SphCtx *c, int64_t keep_first, int64_t keep_count, con
     }
     for (int k = 0; k < nf; k++) flip(c, fields[k]);
     c->n = total;
+    c->masks_valid = false;
     return 0;
 }
 

@@ -1,5 +1,6 @@
 // integrate.cu -- pointwise kernels: particle creation, init_real2tmp, SE / "LF" / RK4 updates, init_stress.
 // Replaces eng/solver_sph_base.py:67-180 (integrators), :249-260 (init_stress) and eng/particle_system.py:274-314.
+#include <string.h>
 #include "sph_host.h"
 
 namespace sph {
@@ -36,7 +37,7 @@ template <typename T> int add_particles_finish(SphCtx *c, int64_t first, int64_t
 // base:67-74
 template <typename T> __global__ void __launch_bounds__(256) k_init_real2tmp(Dev<T> c) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     const int t = c.type[i];
     if (is_real(t)) {
         const double r = c.rho[i];
@@ -45,7 +46,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_init_real2tmp(Dev
         v.w = (T)r;
         c.vt4[i] = v;
     }
-    if (is_soil(t)) {
+    if (is_soil(t) && c.stress) {              // (a WCSPH engine has no stress arrays: a soil block in a water scene is inert)
 #pragma unroll
         for (int q = 0; q < 6; q++) c.stress_t[6 * (size_t)i + q] = c.stress[6 * (size_t)i + q];
     }
@@ -62,9 +63,9 @@ template <typename T> int init_real2tmp(SphCtx *c) {
 //       3 init_RK (base:144-151), 4 update_RK(m) (base:153-160), 5 advect_RK (base:162-170)
 template <typename T> __global__ void __launch_bounds__(256) k_advect(Dev<T> c, int kind, T m) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     const int t = c.type[i];
-    const bool re = is_real(t), so = is_soil(t);
+    const bool re = is_real(t), so = is_soil(t) && c.stress != nullptr;
     if (!re && !so) return;
     const double dt = c.dt;
     const size_t i6 = 6 * (size_t)i;
@@ -151,26 +152,39 @@ __device__ __forceinline__ double dec_f64(unsigned long long u) {
 }
 template <typename T> __global__ void __launch_bounds__(256) k_ymax(Dev<T> c, unsigned long long *ymax) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     if (is_soil(c.type[i])) atomicMax(ymax, enc_f64(c.x[3 * (size_t)i + 1]));
 }
 template <typename T> __global__ void __launch_bounds__(256) k_init_stress(Dev<T> c, const unsigned long long *ymax, double K0, double gy) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     if (!is_soil(c.type[i])) return;
     const double ver = c.rho0 * gy * (dec_f64(*ymax) - c.x[3 * (size_t)i + 1]);
     T *s = c.stress + 6 * (size_t)i;
     s[0] = (T)(K0 * ver); s[1] = (T)ver; s[2] = (T)(K0 * ver);
 }
-template <typename T> int init_stress(SphCtx *c) {
+static unsigned long long enc_f64_host(double v) {
+    unsigned long long u;
+    memcpy(&u, &v, 8);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+// ymax_ext: the y of the highest soil particle of the WHOLE scene when this ctx only holds a slab of it (a rank-local
+// maximum would give every slab its own geostatic stress); null: the maximum over this ctx's particles (base:251-255)
+template <typename T> int init_stress(SphCtx *c, const double *ymax_ext) {
     if (c->n == 0) return 0;
     if (!c->soil) { snprintf(c->err, sizeof(c->err), "init_stress needs a soil solver"); return -2; }
     Dev<T> d = make_dev<T>(c);
     unsigned long long *ymax = (unsigned long long *)(c->arena + c->off_bad + 8);
-    SPH_CHECK(c, cudaMemsetAsync(ymax, 0, 8, c->stream));
-    SPH_PROF(c, K_OTHER);
-    k_ymax<T><<<blocks_for(c->n, 256), 256, 0, c->stream>>>(d, ymax);
-    SPH_LAUNCH_CHECK(c);
+    if (ymax_ext) {
+        const unsigned long long e = enc_f64_host(*ymax_ext);
+        SPH_CHECK(c, cudaMemcpyAsync(ymax, &e, 8, cudaMemcpyHostToDevice, c->stream));
+        SPH_CHECK(c, cudaStreamSynchronize(c->stream));
+    } else {
+        SPH_CHECK(c, cudaMemsetAsync(ymax, 0, 8, c->stream));
+        SPH_PROF(c, K_OTHER);
+        k_ymax<T><<<blocks_for(c->n, 256), 256, 0, c->stream>>>(d, ymax);
+        SPH_LAUNCH_CHECK(c);
+    }
     SPH_PROF(c, K_OTHER);
     k_init_stress<T><<<blocks_for(c->n, 256), 256, 0, c->stream>>>(d, ymax, 1.0 - sin(c->p.fric), c->p.g[1]);
     SPH_LAUNCH_CHECK(c);
@@ -183,7 +197,7 @@ template int init_real2tmp<float>(SphCtx *);
 template int init_real2tmp<double>(SphCtx *);
 template int advect<float>(SphCtx *, int, int);
 template int advect<double>(SphCtx *, int, int);
-template int init_stress<float>(SphCtx *);
-template int init_stress<double>(SphCtx *);
+template int init_stress<float>(SphCtx *, const double *);
+template int init_stress<double>(SphCtx *, const double *);
 
 }  // namespace sph

@@ -42,7 +42,10 @@ __device__ __forceinline__ float dist2(float dx, float dy, float dz) {
 // Device view of one engine instance.  Passed by value to every kernel.
 template <typename T> struct Dev {
     // sizes
-    int n;               // particles in the arrays (owned + ghosts)
+    int n;               // particles in the arrays (owned + ghosts); multi-GPU slabs: an upper bound, see ndev
+    const int *ndev;     // multi-GPU slabs: the particle count lives on the device (migration changes it without the host
+                         // ever reading it back); null on one GPU.  Kernels bound their loops with N().
+    __device__ __forceinline__ int N() const { return ndev ? *ndev : n; }
     int dim, kernel, kcorr, solver, xsph, wc_fresh;
     int gn[3];
     int C;

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include "sph_dev.cuh"
 
+namespace sph { struct SlabState; }
+
 struct FieldSlot {
     int64_t off[2];      // byte offsets of the two ping-pong buffers (off[1] == off[0] when not carried)
     int cur;             // which buffer is current
@@ -45,6 +47,9 @@ struct SphCtx {
     bool shep_pending;   // tile path: CSPM_f of flow particles is still to be formed by the next fluid pass
     bool fuse_init, fuse_half;   // sph_step only: init_real2tmp rides in the reorder kernel / advect_LF_half in k_tile_prep
     int own0, own1;      // owned x-columns [own0, own1) (multi-GPU slabs); the whole grid on one GPU
+    int64_t off_slabctl; // device-resident control block of the native slab step (slab.cu)
+    sph::SlabState *slab;   // native multi-GPU slab step (sph_slab_init); null on one GPU
+    bool masks_valid;    // the neighbour masks / work lists belong to the current sort (cleared by every re-sort / upload)
 };
 
 #define SPH_CHECK(ctx, call)                                                                          \
@@ -60,7 +65,7 @@ struct SphCtx {
 enum SphKernelId { K_CELL_ID = 0, K_SCAN, K_SCATTER, K_RANK, K_REORDER, K_CSPM_F, K_CSPM_L, K_WC_EOS, K_WC_WALL, K_WC_FLUID,
                    K_MUI_SOIL1, K_SOIL_WALL, K_MUI_SOIL3, K_DP_ADAPT, K_DP_SOIL, K_ADVECT_POS, K_POST, K_POST_SWEEP,
                    K_NEIGHBOR_COUNT, K_DENSITY_SUM, K_OTHER, K_INIT_TMP, K_ADVECT, K_TILE_MASK, K_TILE_FLUID, K_TILE_WALL,
-                   K_HALO, K_NUM };
+                   K_HALO, K_HALO_WAIT, K_C5, K_NUM };
 void sph_prof_begin(SphCtx *c, int id);
 void sph_prof_end(SphCtx *c);
 
@@ -90,7 +95,7 @@ template <typename T> int grid_build(SphCtx *c);
 template <typename T> int select_columns(SphCtx *c, int which, int64_t first, int64_t count, int lo, int hi);
 // sweeps.cu
 template <typename T> int calc_kernel_corr(SphCtx *c, bool standalone);
-template <typename T> int one_step(SphCtx *c);
+template <typename T> int one_step(SphCtx *c, bool last = false);
 template <typename T> int one_step_phase(SphCtx *c, int phase);
 template <typename T> int advect_pos(SphCtx *c);
 template <typename T> int post_step(SphCtx *c);
@@ -105,9 +110,21 @@ int tile_wc_fluid(SphCtx *c);
 // integrate.cu
 template <typename T> int init_real2tmp(SphCtx *c);
 template <typename T> int advect(SphCtx *c, int kind, int m);
-template <typename T> int init_stress(SphCtx *c);
+template <typename T> int init_stress(SphCtx *c, const double *ymax_ext = nullptr);
 template <typename T> int add_particles_finish(SphCtx *c, int64_t first, int64_t count);
 
 void flip(SphCtx *c, int field);
+// halo.cu: current (or alternate) buffer of a member that can travel in a message + bytes per particle
+bool field_ref(SphCtx *c, int f, bool alt, char **ptr, int *elem_bytes);
+// slab.cu (native multi-GPU slab step; no-ops when c->slab is null)
+template <typename T> int slab_redistribute(SphCtx *c);                       // migration + halo + ONE sort
+int slab_refresh(SphCtx *c, int phase, bool final_phase, bool last_one_step); // ghost columns after a phase of one_step
+int slab_refresh_post(SphCtx *c);                                             // ghost columns after advect_pos (mu(I) + XSPH)
+int slab_arm(SphCtx *c);
+void slab_disarm(SphCtx *c);
+bool slab_armed(const SphCtx *c);
+int64_t slab_exact_n(const SphCtx *c);    // particle count the host knows (as of the last sph_slab_sync while stepping)
+const int *slab_ndev(SphCtx *c);          // device-resident count while the native slab step runs, else null
+void slab_free(SphCtx *c);
 
 }  // namespace sph

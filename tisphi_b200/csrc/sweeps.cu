@@ -32,10 +32,10 @@ constexpr int FLAGGED_BLOCKS = 148 * 8;
     template <typename T> __global__ void __launch_bounds__(128) NAME(Dev<T> c) {                  \
         if (c.flagged_only) {                                                                      \
             if (*c.nflag == 0) return;                                                             \
-            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) BODY(c, i); \
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.N(); i += gridDim.x * blockDim.x) BODY(c, i); \
         } else {                                                                                   \
             const int i = blockIdx.x * blockDim.x + threadIdx.x;                                   \
-            if (i < c.n) BODY(c, i);                                                               \
+            if (i < c.N()) BODY(c, i);                                                               \
         }                                                                                          \
     }
 template <typename T> inline int sweep_blocks(const Dev<T> &d) { return d.flagged_only ? FLAGGED_BLOCKS : blocks_for(d.n, 128); }
@@ -55,7 +55,7 @@ template <typename T> __device__ __forceinline__ T det3(const T *m) {
 }
 template <typename T> __global__ void __launch_bounds__(128) k_cspm_L(Dev<T> c) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     if (not_owned(c, i)) return;
     T L[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     const int ti = c.type[i];
@@ -142,7 +142,7 @@ __device__ __forceinline__ double eos_wc(double rho, double rho0, double stiff, 
 // loop A, fluid branch: pointwise EOS into the NEW pressure buffer
 template <typename T> __global__ void __launch_bounds__(256) k_wc_eos(Dev<T> c) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     const int t = c.type[i];
     if (is_fluid(t)) c.pnew[i] = (T)eos_wc(c.rho_t[i], c.rho0, c.stiff, c.gamma_);
     else if (!is_wall(t)) c.pnew[i] = c.press[i];
@@ -229,7 +229,7 @@ template <typename T> __device__ __forceinline__ T dev_component(const T *t) {  
 // Adami wall extrapolation for soil solvers (muI:95-109, dp:220-231; tasks base:647-669)
 template <typename T> __global__ void __launch_bounds__(128) k_soil_wall(Dev<T> c) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     if (!is_wall(c.type[i])) return;
     if (is_rigid(c.type[i])) zero_rigid_derivatives(c, i);
     if (not_owned(c, i)) return;
@@ -310,7 +310,7 @@ __device__ __forceinline__ void soil_sweep(const Dev<T> &c, int i, T vg[9], T *d
 // ----------------------------------------------------------------------------------------------------- mu(I)
 template <typename T> __global__ void __launch_bounds__(128) k_mui_soil1(Dev<T> c) {          // muI:67-92
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     if (!is_soil(c.type[i])) return;
     if (not_owned(c, i)) return;
     T vg[9], dd, mom[3];
@@ -342,7 +342,7 @@ template <typename T> __global__ void __launch_bounds__(128) k_mui_soil1(Dev<T> 
 }
 template <typename T> __global__ void __launch_bounds__(128) k_mui_soil3(Dev<T> c) {          // muI:115-128
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     if (!is_soil(c.type[i])) return;
     if (not_owned(c, i)) return;
     T vg[9], dd, mom[3];
@@ -389,7 +389,7 @@ template <typename T> __device__ __forceinline__ int flag_dp(const Dev<T> &c, co
 }
 template <typename T> __global__ void __launch_bounds__(256) k_dp_adapt(Dev<T> c) {           // dp:215-217
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     if (!is_soil(c.type[i])) return;
     T s[9];
     sym_load(c.stress_t, (size_t)i, s);
@@ -448,7 +448,7 @@ __device__ __forceinline__ void bui2008(const Dev<T> &c, const T *st, const T *v
 }
 template <typename T> __global__ void __launch_bounds__(128) k_dp_soil(Dev<T> c) {            // dp:237-270
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     if (!is_soil(c.type[i])) return;
     if (not_owned(c, i)) return;
     T vg[9], dd, mom[3];
@@ -545,11 +545,13 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
     }
     return 0;
 }
-template <typename T> int one_step(SphCtx *c) {
+// `last`: the last one_step of a step (multi-GPU slabs skip the ghost refresh of derivatives nobody reads any more)
+template <typename T> int one_step(SphCtx *c, bool last) {
     const int np = c->p.solver == SPH_SOLVER_WC ? 2 : 3;
     for (int ph = 0; ph < np; ph++) {
         int r = one_step_phase<T>(c, ph);
         if (r) return r;
+        if ((r = slab_refresh(c, ph, ph == np - 1, last))) return r;
     }
     return 0;
 }
@@ -557,7 +559,7 @@ template <typename T> int one_step(SphCtx *c) {
 // ---------------------------------------------------------------------------------------- advect_pos (base:228-238)
 template <typename T> __global__ void __launch_bounds__(256) k_advect_pos(Dev<T> c) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     if (!is_real(c.type[i])) return;
     const Vec4<T> v = c.v4[i];
     double *x = c.x + 3 * (size_t)i;
@@ -566,7 +568,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_advect_pos(Dev<T>
 // XSPH on a snapshot: new positions go to the alternate x buffer
 template <typename T> __global__ void __launch_bounds__(128) k_advect_pos_xsph(Dev<T> c, double *__restrict__ xnew) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     const double *x = c.x + 3 * (size_t)i;
     double o0 = x[0], o1 = x[1], o2 = x[2];
     const int ti = c.type[i];
@@ -588,7 +590,7 @@ template <typename T> __global__ void __launch_bounds__(128) k_advect_pos_xsph(D
 // after positions moved on a stale grid: refresh the sweep coordinates relative to the cell each particle is STORED in
 template <typename T> __global__ void __launch_bounds__(256) k_refresh_xs(Dev<T> c) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     const double *x = c.x + 3 * (size_t)i;
     Vec4<T> xs = c.xs4[i];
     if (sizeof(T) == 8) { xs.x = (T)x[0]; xs.y = (T)x[1]; xs.z = (T)x[2]; }
@@ -630,12 +632,12 @@ template <typename T> __device__ __forceinline__ void chk_density(const Dev<T> &
 }
 template <typename T> __global__ void __launch_bounds__(256) k_post_wc(Dev<T> c) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     if (is_fluid(c.type[i])) chk_density(c, i);
 }
 template <typename T> __global__ void __launch_bounds__(256) k_post_dp(Dev<T> c) {            // dp:276-296
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     if (!is_soil(c.type[i])) return;
     chk_density(c, i);
     T s[9];
@@ -648,7 +650,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_post_dp(Dev<T> c)
 }
 template <typename T> __global__ void __launch_bounds__(256) k_post_mui_a(Dev<T> c) {         // muI:147-150
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     if (!is_soil(c.type[i])) return;
     chk_density(c, i);
     c.strain[i] += (T)c.dt * c.d_strain[i];
@@ -656,7 +658,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_post_mui_a(Dev<T>
 // muI:151-156 Shepard regularisation on a snapshot (stress_tmp), post-advect positions on the pre-move grid (H15)
 template <typename T> __global__ void __launch_bounds__(128) k_post_mui_b(Dev<T> c) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     const int ti = c.type[i];
     if (!is_soil(ti)) return;
     if (not_owned(c, i)) return;
@@ -705,7 +707,7 @@ template <typename T> int post_step(SphCtx *c) {
 // and k_post_wc, without writing and re-reading density, velocity and volume in between (sph_step only).
 template <typename T> __global__ void __launch_bounds__(256) k_wc_finish(Dev<T> c) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     const int t = c.type[i];
     if (!is_real(t)) return;
     Vec4<T> v = c.v4[i];
@@ -733,14 +735,14 @@ template <typename T> int finish_step(SphCtx *c) {
 // -------------------------------------------------------------------------------------------- stand-alone sweeps
 template <typename T> __global__ void __launch_bounds__(128) k_neighbor_count(Dev<T> c, int *__restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     int cnt = 0;
     for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) { cnt++; });
     out[i] = cnt;
 }
 template <typename T> __global__ void __launch_bounds__(128) k_density_sum(Dev<T> c, T *__restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     T s = 0;
     for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) { s += c.v4[j].w * kernel_W(c, r); });
     out[i] = s;
@@ -762,7 +764,7 @@ template <typename T> int density_sum(SphCtx *c, void *out) {
 
 #define INST(T)                                            \
     template int calc_kernel_corr<T>(SphCtx *, bool);            \
-    template int one_step<T>(SphCtx *);                    \
+    template int one_step<T>(SphCtx *, bool);                 \
     template int one_step_phase<T>(SphCtx *, int);                    \
     template int advect_pos<T>(SphCtx *);                  \
     template int post_step<T>(SphCtx *);                   \

@@ -670,7 +670,7 @@ template <int KERNEL, class FT> __global__ void __launch_bounds__(FT::BT) k_tile
 // particle first, so that the stage state is written once and not read back by a second kernel.
 template <bool ADV> __global__ void __launch_bounds__(256) k_tile_prep(DevF c, int shep) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     const int t = c.type[i];
     F4 xs = c.xs4[i];
     F4 vt;
@@ -1018,7 +1018,7 @@ template <int KERNEL, class FT, bool SHEP, int LIST> __global__ void __launch_bo
 // number of neighbours per FLOW particle of unflagged cells from the masks (parity probe of k_tile_mask); -1 elsewhere
 __global__ void __launch_bounds__(256) k_mask_count(DevF c, int nw, int *__restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= c.N()) return;
     int cnt = -1;
     if (c.ps4[i].w > 0.f && !c.cellflag[c.gid[i]]) {
         cnt = 0;
@@ -1120,6 +1120,7 @@ int tile_mask(SphCtx *c, bool shepard) {
     SPH_LAUNCH_CHECK(c);
     c->shep_pending = c->shep_wall_pending = !shepard;
     c->list_valid = false;
+    c->masks_valid = true;
     if (!shepard) return 0;
     if ((r = d3 ? build_worklist<F3M>(c, d, 0) : build_worklist<F2M>(c, d, 0))) return r;
     SPH_PROF(c, K_CSPM_F);
@@ -1138,7 +1139,13 @@ template <int KERNEL, bool D3> static void launch_wall_gather(SphCtx *c, const D
     else k_wall_gather<KERNEL, D3, false><<<grid, WG_WARPS * 32, 0, c->stream>>>(d);
 }
 // WCSPH one_step (wc:82-126) on the tile path; flagged cells are completed by the generic kernels (flagged_only).
+static int need_masks(SphCtx *c) {
+    if (c->masks_valid) return 0;
+    snprintf(c->err, sizeof(c->err), "the neighbour masks are stale: call sph_calc_kernel_corr after sph_grid_build / an upload and before sph_one_step");
+    return -3;
+}
 int tile_wc_prep_and_wall(SphCtx *c) {
+    if (need_masks(c)) return -3;
     DevF d = make_dev<float>(c);
     const int n = (int)c->n;
     const bool shep = c->shep_wall_pending;
@@ -1170,6 +1177,7 @@ template <int KERNEL, class FT> static void launch_fluid(SphCtx *c, const DevF &
     }
 }
 int tile_wc_fluid(SphCtx *c) {
+    if (need_masks(c)) return -3;
     DevF d = make_dev<float>(c);
     const bool shep = c->shep_pending;
     c->shep_pending = false;

@@ -291,6 +291,10 @@ class ParticleSystem:
         if cap is None:
             cap = int(1.5 * (len(mine) + ghosts)) + 4 * int(counts.max()) + 1024
         self.global_particle_num = len(x)
+        soil = typ == self.mat_soil_type
+        self.slab_soil_ymax = float(x[soil, 1].max()) if soil.any() else None      # base:251-255 over the WHOLE scene
+        # the most particles one slab message may carry: a boundary column + migrants (multi-GPU)
+        self.slab_face_cap = int(self.cfg.get_opt("slabFaceCapacity", 2 * int(counts.max()) + 4096))
         self.engine = _lib.Engine(self.params, max(int(cap), 1), device=self._device)
         if len(mine):
             self.engine.add_particles(x[mine], v[mine], rho[mine], typ[mine])

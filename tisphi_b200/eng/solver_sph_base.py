@@ -132,7 +132,11 @@ class SPHBase:
         raise NotImplementedError("per-particle hooks run inside the native post-step kernel")
 
     def init_stress(self, density0=None, fric=None):
-        self._eng.call("sph_init_stress")
+        ymax = getattr(self.ps, "slab_soil_ymax", None)     # one slab of a multi-GPU scene: the GLOBAL soil top
+        if ymax is not None:
+            self._eng.call("sph_init_stress_ymax", float(ymax))
+        else:
+            self._eng.call("sph_init_stress")
 
     def calc_kernel_corr(self):
         self._eng.call("sph_calc_kernel_corr")

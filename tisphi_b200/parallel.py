@@ -362,13 +362,57 @@ class CudaSlabEngine:
         self.e.call("sph_post_step")
 
 
+class NativeSlab:
+    """The slab protocol run by the library itself (tisphi_b200/csrc/slab.cu): device-resident counts and column table,
+    messages stored by the packing kernels straight into the neighbours' inboxes, no host round trip inside a step.
+
+    ``inbox_ptr`` is device memory of ``inbox_bytes(engine, face_cap)`` bytes owned by the caller (exportable over CUDA
+    IPC when the neighbours are other processes)."""
+
+    def __init__(self, engine, rank, world, columns, face_cap, inbox_ptr, inbox_bytes):
+        self.e, self.L = engine, engine.L
+        self.rank, self.world = rank, world
+        self.a, self.b = int(columns[0]), int(columns[1])
+        self.inbox_ptr = int(inbox_ptr)
+        engine.call("sph_slab_init", rank, world, self.a, self.b, int(face_cap), inbox_ptr, int(inbox_bytes))
+        self.own_first, self.own_count = 0, engine.n
+
+    @staticmethod
+    def inbox_bytes(engine, face_cap):
+        return int(engine.L.sph_slab_inbox_bytes(engine.h, int(face_cap)))
+
+    def connect(self, left_ptr, right_ptr):
+        self.e.call("sph_slab_connect", left_ptr, right_ptr)
+
+    def run_steps(self, n):
+        self.e.call("sph_step", int(n))
+
+    def sync(self):
+        """Reads the device control block back (count, owned range); raises if the step set an error bit."""
+        n, of, oc, err = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        self.e.call("sph_slab_sync", C.byref(n), C.byref(of), C.byref(oc), C.byref(err))
+        self.own_first, self.own_count = int(of.value), int(oc.value)
+        return int(n.value)
+
+    def reset(self):
+        """The particle set was replaced from outside (sph_clear_particles + sph_add_particles)."""
+        self.own_first, self.own_count = 0, self.e.n
+
+    @property
+    def exchanges(self):
+        return int(self.L.sph_slab_epoch(self.e.h))
+
+
 class SlabSimulation:
     """``Simulation`` for one rank of a slab-partitioned run (same scene JSON; torch.distributed must be initialised).
 
     Every rank builds the scene on the host, keeps the particles of its columns (id0 stays the GLOBAL creation index,
-    ps:208-211) and steps them with SlabDriver.  ``gather_state`` reassembles the global arrays for parity checks."""
+    ps:208-211) and steps them.  ``transport``: "p2p" = the native device-driven step of slab.cu with the inboxes
+    exchanged over CUDA IPC (one process per GPU of one box); "dist" = SlabDriver over torch.distributed send / recv
+    (NCCL or gloo).  ``owned`` / ``gather_state`` reassemble arrays for parity checks."""
 
-    def __init__(self, config, device, rank, world, group=None, wall_weight=0.15, columns=None, check=False):
+    def __init__(self, config, device, rank, world, group=None, wall_weight=0.15, columns=None, check=False,
+                 transport="p2p"):
         from .eng.simulation import Simulation
         self.rank, self.world = rank, world
         self.sim = Simulation(config, device=device, slab=dict(rank=rank, world=world, wall_weight=wall_weight,
@@ -376,14 +420,108 @@ class SlabSimulation:
         self.ps, self.solver = self.sim.ps, self.sim.solver
         cfg = config
         self.columns = self.ps.slab_columns[rank]
-        self.engine = CudaSlabEngine(self.ps.engine, cfg.get_cfg("timeIntegration"), bool(cfg.get_cfg("xsph")),
-                                     cfg.get_cfg("simulationMethod"))
-        self.driver = SlabDriver(self.engine, self.columns, rank, world, int(self.ps.grid_num[0]), group=group, check=check)
+        self.transport = transport
+        self._ipc = []
+        if transport == "p2p":
+            self.driver = self._connect_p2p(group)
+        else:
+            self.engine = CudaSlabEngine(self.ps.engine, cfg.get_cfg("timeIntegration"), bool(cfg.get_cfg("xsph")),
+                                         cfg.get_cfg("simulationMethod"))
+            self.driver = SlabDriver(self.engine, self.columns, rank, world, int(self.ps.grid_num[0]), group=group, check=check)
+
+    def _connect_p2p(self, group):
+        import torch.distributed as dist
+        eng = self.ps.engine
+        L = eng.L
+        nbytes = NativeSlab.inbox_bytes(eng, self.ps.slab_face_cap)
+        with eng.torch.cuda.device(eng.device):
+            inbox = L.sph_ipc_alloc(nbytes)
+            if not inbox:
+                raise MemoryError(f"cudaMalloc of the {nbytes}-byte slab inbox failed")
+            self._inbox = inbox
+            drv = NativeSlab(eng, self.rank, self.world, self.columns, self.ps.slab_face_cap, inbox, nbytes)
+            handle = (C.c_ubyte * 64)()
+            if L.sph_ipc_get_handle(inbox, handle) != 0:
+                raise RuntimeError("cudaIpcGetMemHandle failed for the slab inbox")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            ptrs = [None, None]
+            for side, nb in ((0, self.rank - 1), (1, self.rank + 1)):
+                if 0 <= nb < self.world:
+                    h = (C.c_ubyte * 64).from_buffer_copy(handles[nb])
+                    p = L.sph_ipc_open(h)
+                    if not p:
+                        raise RuntimeError(f"cudaIpcOpenMemHandle failed for the inbox of rank {nb} (no peer access between the GPUs?)")
+                    self._ipc.append(p)
+                    ptrs[side] = p
+            drv.connect(ptrs[0], ptrs[1])
+        dist.barrier(group=group)
+        return drv
+
+    def close(self):
+        L = self.ps.engine.L
+        with self.ps.engine.torch.cuda.device(self.ps.engine.device):
+            for p in self._ipc:
+                L.sph_ipc_close(p)
+            self._ipc = []
+            if getattr(self, "_inbox", None):
+                self.ps.engine.torch.cuda.synchronize(self.ps.engine.device)
+                L.sph_ipc_free(self._inbox)
+                self._inbox = None
 
     def run_steps(self, n):
         self.driver.run_steps(n)
 
+    def sync(self):
+        if self.transport == "p2p":
+            return self.driver.sync()
+        return self.ps.engine.n
+
     def owned(self, name):
         """torch view of a member restricted to the particles this rank owns (current order)."""
+        self.sync()
         d = self.driver
         return getattr(self.ps.pt, name)[d.own_first:d.own_first + d.own_count]
+
+
+class LocalSlabGroup:
+    """``world`` slabs of one scene as independent contexts (own arena, own stream) of ONE process on ONE device, connected
+    through plain device pointers: the native slab step on a single-GPU box (tests/test_gpu_slab.py).  The ranks are
+    stepped one step at a time in turn -- nothing ever blocks the host, every wait is a one-block kernel -- so each
+    stream's waits are answered by kernels the host enqueues right afterwards on the other streams."""
+
+    def __init__(self, config_factory, world, device="cuda:0", columns=None, wall_weight=0.15):
+        import torch
+        from .eng.simulation import Simulation
+        self.world = world
+        self.sims, self.drivers, self._inboxes = [], [], []
+        for r in range(world):
+            with torch.cuda.stream(torch.cuda.Stream(device=device)):
+                sim = Simulation(config_factory(), device=device, slab=dict(rank=r, world=world, wall_weight=wall_weight,
+                                                                          columns=columns))
+            self.sims.append(sim)
+        torch.cuda.synchronize(device)
+        for r, sim in enumerate(self.sims):
+            eng = sim.ps.engine
+            nbytes = NativeSlab.inbox_bytes(eng, sim.ps.slab_face_cap)
+            box = torch.zeros(nbytes + 256, dtype=torch.uint8, device=device)
+            off = (-box.data_ptr()) % 256
+            self._inboxes.append(box)
+            self.drivers.append(NativeSlab(eng, r, world, sim.ps.slab_columns[r], sim.ps.slab_face_cap, box.data_ptr() + off, nbytes))
+        for r, d in enumerate(self.drivers):
+            d.connect(self.drivers[r - 1].inbox_ptr if r > 0 else None, self.drivers[r + 1].inbox_ptr if r < world - 1 else None)
+        self.global_particle_num = self.sims[0].ps.global_particle_num
+
+    def run_steps(self, n):
+        for _ in range(n):
+            for d in self.drivers:
+                d.run_steps(1)
+
+    def gather(self, name):
+        """Member ``name`` of the owned particles of every rank, concatenated in rank order (= the global sorted order)."""
+        import torch
+        parts = []
+        for sim, d in zip(self.sims, self.drivers):
+            d.sync()
+            parts.append(getattr(sim.ps.pt, name)[d.own_first:d.own_first + d.own_count].clone())
+        return torch.cat(parts)
