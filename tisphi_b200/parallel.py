@@ -493,6 +493,16 @@ class LocalSlabGroup:
     def __init__(self, config_factory, world, device="cuda:0", columns=None, wall_weight=0.15):
         import torch
         from .eng.simulation import Simulation
+        torch.cuda.init()
+        mode = C.c_int(0)
+        try:                                     # CUmoduleLoadingMode: 1 eager, 2 lazy
+            C.CDLL("libcuda.so.1").cuModuleGetLoadingMode(C.byref(mode))
+        except OSError:
+            pass
+        if mode.value == 2:
+            raise RuntimeError("LocalSlabGroup needs CUDA_MODULE_LOADING=EAGER set before CUDA initialises: with lazy "
+                               "loading the first launch of a kernel synchronises with the spinning wait kernel of "
+                               "another slab of this process (one process per GPU is not affected)")
         self.world = world
         self.sims, self.drivers, self._inboxes = [], [], []
         for r in range(world):
