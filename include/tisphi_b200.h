@@ -151,6 +151,9 @@ int sph_neighbor_count_masks(SphCtx *ctx, int32_t *out_dev);
 
 /* number of particles whose cell fell outside the grid since the last call.  Synchronises. */
 int64_t sph_read_bad_cells(SphCtx *ctx);
+/* cells the cell-tile path left to the generic per-particle kernels at the last mask build (a stencil cell holds more
+ * than 32 particles, or a tile overflowed); 0 without the fast path.  Synchronises. */
+int64_t sph_read_flagged_cells(SphCtx *ctx);
 /* how many kernels the library has launched on this ctx since creation */
 int64_t sph_launch_count(SphCtx *ctx);
 /* sizeof(SphParams) as compiled, so that bindings can verify their mirror of the struct */

@@ -76,6 +76,8 @@ def lib():
                    "orc_density_sum_f32pos"):
             getattr(L, fn).argtypes = [C.c_void_p, C.c_void_p]
             getattr(L, fn).restype = None
+        L.orc_set_threads.argtypes, L.orc_set_threads.restype = [C.c_int], None
+        L.orc_max_threads.argtypes, L.orc_max_threads.restype = [], C.c_int
         L.orc_r2_threshold_f32.argtypes = [C.c_float]
         L.orc_r2_threshold_f32.restype = C.c_float
         L.orc_r2_threshold_f64.argtypes = [C.c_double]

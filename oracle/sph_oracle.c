@@ -27,6 +27,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 typedef struct {
     int dim, kernel, kcorr, ti, xsph, solver, serial, wc_fresh;
@@ -85,6 +88,21 @@ double *orc_field(Orc *o, int k) { return o->f[k]; }
 int32_t *orc_ifield(Orc *o, int k) { return o->ia[k]; }
 int64_t *orc_cell_end(Orc *o) { return o->cell_end; }
 int orc_field_ncomp(int k) { return F_NC[k]; }
+/* threads of the parallel loops (bench.py's CPU arm sets and reports them: torchrun exports OMP_NUM_THREADS=1) */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+int orc_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
 void orc_set_params(Orc *o, const OrcParams *p) { o->p = *p; }
 
 /* --------------------------------------------------------------------------------- grid (ps:216-257) */

@@ -475,6 +475,15 @@ int64_t sph_read_bad_cells(SphCtx *c) {
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
     return (int64_t)v;
 }
+// cells the cell-tile path handed to the generic kernels in the last mask build (a stencil cell with > 32 particles or a
+// tile that overflowed); 0 when the fast path is not allocated.  Synchronises.
+int64_t sph_read_flagged_cells(SphCtx *c) {
+    if (!c->fast) return 0;
+    int v = 0;
+    if (cudaMemcpyAsync(&v, c->arena + c->off_nflag, 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    return v;
+}
 int64_t sph_launch_count(SphCtx *c) { return c->launches; }
 int64_t sph_params_size(void) { return (int64_t)sizeof(SphParams); }
 
