@@ -7,6 +7,7 @@
 // relative order).  On the GPU the atomic slot order inside a cell is arbitrary, so the rank inside the cell is
 // recomputed deterministically as "number of particles of my cell with a smaller previous index".
 // The reference moves its whole 800-byte record twice; here only the carried members move, once, as SoA streams.
+#include <string.h>
 #include "sph_host.h"
 
 namespace sph {
@@ -15,20 +16,40 @@ namespace sph {
 // After the first step the arrays are already almost sorted, so the lanes of a warp mostly fall into one or two cells:
 // the histogram update is aggregated per warp (one atomicAdd per distinct cell) with match.any.  Slots inside a cell
 // are arbitrary anyway -- k_rank recomputes the stable order.
-template <typename T>
-__global__ void __launch_bounds__(256) k_cell_id(Dev<T> c, int *__restrict__ gid_out, int *__restrict__ slot) {
+// Multi-GPU slabs: element v of the sort's input is read where it lies (SLAB; see VSrc in sph_host.h)
+struct VLoc { const char *msg; int idx; };      // msg == nullptr: the member's current buffer
+__device__ __forceinline__ VLoc vlocate(const VSrc &s, int v) {
+    const int nl = s.ctl->src_nl, own = s.ctl->src_count;      // snapshot taken by k_slab_wait_set_n (the column table of
+    VLoc r;                                                    // the new order overwrites own_first / own_count meanwhile)
+    if (v < nl) { r.msg = inbox_msg((char *)s.inbox, 0, s.parity, s.msg_cap); r.idx = v; }
+    else if (v < nl + own) { r.msg = nullptr; r.idx = s.ctl->src_first + (v - nl); }
+    else { r.msg = inbox_msg((char *)s.inbox, 1, s.parity, s.msg_cap); r.idx = v - nl - own; }
+    return r;
+}
+template <typename E> __device__ __forceinline__ const E *vptr(const VSrc &s, const VLoc &l, int slot, const E *cur) {
+    return l.msg ? (const E *)(l.msg + s.sec[slot]) : cur;
+}
+template <typename T, bool SLAB>
+__global__ void __launch_bounds__(256) k_cell_id(Dev<T> c, int *__restrict__ gid_out, int *__restrict__ slot, VSrc vs, int cell0, int cell1) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool valid = i < c.N();
     long long g = -1 - lane;                    // idle lanes: distinct keys that match nobody
     if (valid) {
-        const double x[3] = {c.x[3 * (size_t)i], c.x[3 * (size_t)i + 1], c.x[3 * (size_t)i + 2]};
+        const double *xp = c.x;
+        size_t xi = (size_t)i;
+        if (SLAB) { const VLoc l = vlocate(vs, i); xp = vptr(vs, l, 0, c.x); xi = (size_t)l.idx; }
+        const double x[3] = {xp[3 * xi], xp[3 * xi + 1], xp[3 * xi + 2]};
         int cc[3];
         pos_to_cell(c, x, cc);
         g = (long long)cc[0] * c.gn[1] * c.gn[2] + (long long)cc[1] * c.gn[2] + cc[2];
         if (g < 0 || g >= c.C) {                // the reference has no check; we clamp and count
             atomicAdd(c.bad, 1ull);
             g = g < 0 ? 0 : c.C - 1;
+        }
+        if (SLAB && (g < cell0 || g >= cell1)) {            // outside the slab's columns and their ghosts: it moved too far
+            atomicOr(&const_cast<SlabCtl *>(vs.ctl)->err, 8);   // SLAB_ERR_FAR; the clamp only keeps the arrays consistent
+            g = g < cell0 ? cell0 : cell1 - 1;
         }
         gid_out[i] = (int)g;
     }
@@ -108,11 +129,34 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const int *__restri
 }
 
 // ------------------------------------------------------------------------------------------------ stable rank
+// Column cx starts at cell_end[cx * nyz - 1] (x-major cell ids, ps:221-222): own / ghost / boundary ranges of a slab and
+// the regions the next redistribution has to look at (one thread, right after the scan).
+__device__ void slab_coltable(const ColTab &t, const int *__restrict__ cell_end) {
+    SlabCtl *ctl = t.ctl;
+    const int n = ctl->n, a = t.a, b = t.b;
+    auto start = [&](int cx) { return cx <= 0 ? 0 : (cx >= t.gn0 ? n : cell_end[(long long)cx * t.nyz - 1]); };
+    const int ca1 = start(a - 1), ca = start(a), cb = start(b), cb1 = start(b + 1);
+    int err = 0;
+    if (ca1 != 0 || cb1 != n) err |= 8;                            // SLAB_ERR_FAR: something moved more than one column in a step
+    if ((!t.has0 && ca != 0) || (!t.has1 && cb != n)) err |= 8;
+    if (err) atomicOr(&ctl->err, err);
+    ctl->own_first = ca; ctl->own_count = cb - ca;
+    ctl->ghost_first[0] = ca1; ctl->ghost_count[0] = t.has0 ? ca - ca1 : 0;
+    ctl->ghost_first[1] = cb; ctl->ghost_count[1] = t.has1 ? cb1 - cb : 0;
+    ctl->send_first[0] = ca; ctl->send_count[0] = t.has0 ? start(a + 1) - ca : 0;
+    const int cbm1 = start(b - 1);
+    ctl->send_first[1] = cbm1; ctl->send_count[1] = t.has1 ? cb - cbm1 : 0;
+    // particles move less than a cell per step: only the two old columns at each face can hold leavers
+    const int l_end = start(min(a + 2, b)), r_beg = start(max(b - 2, a));
+    ctl->reg_first[0] = ca; ctl->reg_count[0] = t.has0 ? l_end - ca : 0;
+    ctl->reg_first[1] = r_beg; ctl->reg_count[1] = t.has1 ? cb - r_beg : 0;
+}
 __global__ void __launch_bounds__(256) k_scatter_index(int n, const int *__restrict__ ndev, const int *__restrict__ gid,
                                                        const int *__restrict__ slot, const int *__restrict__ cell_end,
-                                                       int *__restrict__ tmpidx) {
+                                                       int *__restrict__ tmpidx, ColTab ct) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (ndev) n = *ndev;
+    if (i == 0 && ct.ctl) slab_coltable(ct, cell_end);
     if (i >= n) return;
     int g = gid[i];
     int start = g > 0 ? cell_end[g - 1] : 0;
@@ -135,14 +179,27 @@ __global__ void __launch_bounds__(256) k_rank(int n, const int *__restrict__ nde
 // ------------------------------------------------------------------------------------------------ reorder
 // One thread per DESTINATION slot: writes are fully coalesced; reads follow perm, which is near-identity between
 // consecutive steps (particles move much less than a cell per step), so they are near-coalesced too.
-template <typename T>
+template <typename T, bool SLAB>
 __global__ void __launch_bounds__(256) k_reorder(Dev<T> a, Dev<T> b, const int *__restrict__ perm,
-                                                 const int *__restrict__ gid_unsorted, int soil, int init_tmp) {
+                                                 const int *__restrict__ gid_unsorted, int soil, int init_tmp, VSrc vs) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.N()) return;
     const int s = perm[k];
-    const size_t k3 = 3 * (size_t)k, s3 = 3 * (size_t)s;
-    const double x0 = a.x[s3], x1 = a.x[s3 + 1], x2 = a.x[s3 + 2];
+    // where element s of the input lives: the current buffers, or (slabs) a section of an inbox message
+    int si = s;
+    const double *px = a.x, *prho = a.rho;
+    const Vec4<T> *pxs = a.xs4, *pv = a.v4, *pvt = a.vt4;
+    const T *ppress = a.press, *pstress = a.stress, *pstrain = a.strain, *pstrain_p = a.strain_p;
+    const int *ptype = a.type, *pid0 = a.id0, *pflag = a.flag;
+    if (SLAB) {
+        const VLoc l = vlocate(vs, s);
+        si = l.idx;
+        px = vptr(vs, l, 0, a.x); pxs = vptr(vs, l, 1, a.xs4); pv = vptr(vs, l, 2, a.v4); pvt = vptr(vs, l, 3, a.vt4);
+        prho = vptr(vs, l, 4, a.rho); ppress = vptr(vs, l, 5, a.press); ptype = vptr(vs, l, 6, a.type); pid0 = vptr(vs, l, 7, a.id0);
+        if (soil) { pstress = vptr(vs, l, 8, a.stress); pstrain = vptr(vs, l, 9, a.strain); pstrain_p = vptr(vs, l, 10, a.strain_p); pflag = vptr(vs, l, 11, a.flag); }
+    }
+    const size_t k3 = 3 * (size_t)k, s3 = 3 * (size_t)si;
+    const double x0 = px[s3], x1 = px[s3 + 1], x2 = px[s3 + 2];
     b.x[k3] = x0; b.x[k3 + 1] = x1; b.x[k3 + 2] = x2;
     const int g = gid_unsorted[s];
     a.gid[k] = g;                                   // grid_ids has a single (sorted) buffer
@@ -156,34 +213,34 @@ __global__ void __launch_bounds__(256) k_reorder(Dev<T> a, Dev<T> b, const int *
         xs.y = (T)__dsub_rn(x1, cell_origin(a.vstart[1], a.gs, cc[1]));
         xs.z = (T)__dsub_rn(x2, cell_origin(a.vstart[2], a.gs, cc[2]));
     }
-    xs.w = a.xs4[s].w;                              // m_V travels with the particle
+    xs.w = pxs[si].w;                               // m_V travels with the particle
     b.xs4[k] = xs;
-    const int ty = a.type[s];
+    const int ty = ptype[si];
     if (a.ps4) {                                    // cell-tile payloads: AoS for the passes, SoA for the mask kernel
         const bool fl = is_flow(ty);
         Vec4<T> ps = xs; ps.w = fl ? xs.w : -xs.w; a.ps4[k] = ps;
         a.psx[k] = xs.x; a.psy[k] = xs.y; a.psz[k] = xs.z; a.psf[k] = fl ? (T)1 : (T)-1;
         if (fl) a.cellflow[g] = 1;
     }
-    const Vec4<T> v = a.v4[s];
-    const double rho = a.rho[s];
+    const Vec4<T> v = pv[si];
+    const double rho = prho[si];
     b.v4[k] = v;
     if (init_tmp && is_real(ty)) {                  // init_real2tmp (base:67-74) of the WCSPH step: tmp := real
         Vec4<T> vt = v; vt.w = (T)rho;
         b.vt4[k] = vt;
         a.rho_t[k] = rho;                           // density_tmp is not carried: one buffer, sorted order
-    } else b.vt4[k] = a.vt4[s];
+    } else b.vt4[k] = pvt[si];
     b.rho[k] = rho;
-    b.press[k] = a.press[s];
+    b.press[k] = ppress[si];
     b.type[k] = ty;
-    b.id0[k] = a.id0[s];
+    b.id0[k] = pid0[si];
     if (soil) {
-        const size_t k6 = 6 * (size_t)k, s6 = 6 * (size_t)s;
+        const size_t k6 = 6 * (size_t)k, s6 = 6 * (size_t)si;
 #pragma unroll
-        for (int q = 0; q < 6; q++) b.stress[k6 + q] = a.stress[s6 + q];
-        b.strain[k] = a.strain[s];
-        b.strain_p[k] = a.strain_p[s];
-        b.flag[k] = a.flag[s];
+        for (int q = 0; q < 6; q++) b.stress[k6 + q] = pstress[s6 + q];
+        b.strain[k] = pstrain[si];
+        b.strain_p[k] = pstrain_p[si];
+        b.flag[k] = pflag[si];
     }
 }
 
@@ -244,23 +301,33 @@ template <typename T> int grid_build(SphCtx *c) {
     int *tiles = (int *)(c->arena + c->off_scan_tiles);
     int *id_new = (int *)(c->arena + c->f[SPH_F_ID_NEW].off[0]);
     cudaStream_t st = c->stream;
-    SPH_CHECK(c, cudaMemsetAsync(a.cell_cnt, 0, sizeof(int) * (size_t)c->C, st));
-    if (c->fast) SPH_CHECK(c, cudaMemsetAsync(a.cellflow, 0, (size_t)c->C, st));
+    // the sort of a slab redistribution: input = virtual concatenation, cells of the slab's columns only, column table
+    const bool slab = c->slab_sort;
+    VSrc vs;
+    ColTab ct;
+    memset(&vs, 0, sizeof(vs));
+    memset(&ct, 0, sizeof(ct));
+    int cell0 = 0, cell1 = c->C;
+    if (slab) slab_sort_args(c, &vs, &ct, &cell0, &cell1);
+    const int nc = cell1 - cell0;
+    SPH_CHECK(c, cudaMemsetAsync(a.cell_cnt + cell0, 0, sizeof(int) * (size_t)nc, st));
+    if (c->fast) SPH_CHECK(c, cudaMemsetAsync(a.cellflow + cell0, 0, (size_t)nc, st));
     SPH_PROF(c, K_CELL_ID);
-    k_cell_id<T><<<blocks_for(n, 256), 256, 0, st>>>(a, gid_u, slot);
+    if (slab) k_cell_id<T, true><<<blocks_for(n, 256), 256, 0, st>>>(a, gid_u, slot, vs, cell0, cell1);
+    else k_cell_id<T, false><<<blocks_for(n, 256), 256, 0, st>>>(a, gid_u, slot, vs, cell0, cell1);
     SPH_LAUNCH_CHECK(c);
-    const int nt = (c->C + SCAN_TILE - 1) / SCAN_TILE;
+    const int nt = (nc + SCAN_TILE - 1) / SCAN_TILE;
     SPH_PROF(c, K_SCAN);
-    k_scan_reduce<<<nt, SCAN_THREADS, 0, st>>>(a.cell_cnt, c->C, tiles);
+    k_scan_reduce<<<nt, SCAN_THREADS, 0, st>>>(a.cell_cnt + cell0, nc, tiles);
     SPH_LAUNCH_CHECK(c);
     SPH_PROF(c, K_SCAN);
     k_scan_tiles<<<1, 1024, 0, st>>>(tiles, nt);
     SPH_LAUNCH_CHECK(c);
     SPH_PROF(c, K_SCAN);
-    k_scan_apply<<<nt, SCAN_THREADS, 0, st>>>(a.cell_cnt, c->C, tiles, a.cell_end);
+    k_scan_apply<<<nt, SCAN_THREADS, 0, st>>>(a.cell_cnt + cell0, nc, tiles, a.cell_end + cell0);
     SPH_LAUNCH_CHECK(c);
     SPH_PROF(c, K_SCATTER);
-    k_scatter_index<<<blocks_for(n, 256), 256, 0, st>>>(n, a.ndev, gid_u, slot, a.cell_end, tmpidx);
+    k_scatter_index<<<blocks_for(n, 256), 256, 0, st>>>(n, a.ndev, gid_u, slot, a.cell_end, tmpidx, ct);
     SPH_LAUNCH_CHECK(c);
     SPH_PROF(c, K_RANK);
     k_rank<<<blocks_for(n, 256), 256, 0, st>>>(n, a.ndev, gid_u, a.cell_end, tmpidx, perm, id_new);
@@ -268,7 +335,8 @@ template <typename T> int grid_build(SphCtx *c) {
     SPH_PROF(c, K_REORDER);
     const int init_tmp = (c->fuse_init && !c->soil) ? 1 : 0;
     c->fuse_init = false;
-    k_reorder<T><<<blocks_for(n, 256), 256, 0, st>>>(a, b, perm, gid_u, c->soil ? 1 : 0, init_tmp);
+    if (slab) k_reorder<T, true><<<blocks_for(n, 256), 256, 0, st>>>(a, b, perm, gid_u, c->soil ? 1 : 0, init_tmp, vs);
+    else k_reorder<T, false><<<blocks_for(n, 256), 256, 0, st>>>(a, b, perm, gid_u, c->soil ? 1 : 0, init_tmp, vs);
     SPH_LAUNCH_CHECK(c);
     static const int carried[] = {SPH_F_X, SPH_F_XS, SPH_F_V, SPH_F_V_TMP, SPH_F_DENSITY, SPH_F_PRESSURE, SPH_F_MAT_TYPE, SPH_F_ID0};
     for (int f : carried) flip(c, f);

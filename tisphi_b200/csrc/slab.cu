@@ -23,23 +23,7 @@ namespace sph {
 
 constexpr int SLAB_MAXF = 16;
 constexpr long long SLAB_WAIT_NS = 30ll * 1000 * 1000 * 1000;   // a neighbour may still be building its scene
-constexpr int SLAB_HDR = 256;                                   // bytes in front of the message buffers of an inbox
 enum { SLAB_ERR_TIMEOUT = 1, SLAB_ERR_COUNT = 2, SLAB_ERR_CAPACITY = 4, SLAB_ERR_FAR = 8, SLAB_ERR_FACE = 16 };
-
-struct SlabCtl {                 // device-resident; ctl->n is what Dev::ndev points to
-    int n;
-    int own_first, own_count;
-    int ghost_first[2], ghost_count[2];     // [0]: ghost column a - 1, [1]: ghost column b
-    int send_first[2], send_count[2];       // [0]: my column a (the left neighbour's ghosts), [1]: my column b - 1
-    int reg_first[2], reg_count[2];         // where the next redistribution looks for particles that leave / are on a face
-    int sel_count[2];
-    int err;
-    unsigned done[2];                       // completion counters of the push kernels, per side
-};
-struct InboxHdr {
-    unsigned long long flag[2];             // [side the message came from]: epoch of the newest complete message
-    int count[2][2];                        // [side][epoch parity]: particles in that message
-};
 
 struct SlabField { char *cur, *alt; int wpe; long long secw; };   // member buffers, 4-byte words per particle, section offset (words)
 struct SlabMsg { SlabField f[SLAB_MAXF]; int n; };
@@ -53,7 +37,8 @@ struct SlabState {
     bool armed;
     int64_t n_exact, own_first, own_count;
     int err;
-    int64_t pushed_bytes_bound;
+    unsigned long long sort_epoch;          // the migration exchange the pending sort reads
+    SlabMsg sort_msg;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -68,9 +53,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
-}
-__device__ __forceinline__ char *inbox_msg(char *inbox, int side, unsigned parity, long long msg_cap) {
-    return inbox + SLAB_HDR + (long long)(side * 2 + (int)parity) * msg_cap;
 }
 // every thread of a push kernel calls this after its stores: the LAST block of the side publishes count and epoch
 __device__ __forceinline__ void push_finish(SlabCtl *ctl, char *peer_inbox, int side, unsigned long long epoch, int count) {
@@ -226,15 +208,29 @@ __global__ void __launch_bounds__(256) k_slab_push_range(SlabMsg msg, SlabCtl *c
     }
     push_finish(ctl, peer, side, epoch, count);
 }
-// one block, one thread per side: wait (bounded) until both neighbours' messages of this epoch are complete
-__global__ void k_slab_wait(SlabCtl *ctl, char *inbox, int has0, int has1, unsigned long long epoch) {
-    const int side = threadIdx.x;
-    if (side > 1 || !(side == 0 ? has0 : has1)) return;
+// bounded wait until the message of `epoch` from `side` is complete (one thread); false on timeout
+__device__ __forceinline__ bool wait_flag(SlabCtl *ctl, const char *inbox, int side, unsigned long long epoch) {
     const InboxHdr *h = (const InboxHdr *)inbox;
     const unsigned long long t0 = globaltimer_ns();
     while (ld_acquire_sys(&h->flag[side]) < epoch) {
-        if ((long long)(globaltimer_ns() - t0) > SLAB_WAIT_NS) { atomicOr(&ctl->err, SLAB_ERR_TIMEOUT); break; }
-        __nanosleep(200);
+        if ((long long)(globaltimer_ns() - t0) > SLAB_WAIT_NS) { atomicOr(&ctl->err, SLAB_ERR_TIMEOUT); return false; }
+        __nanosleep(100);
+    }
+    return true;
+}
+// one block, one thread per side: wait until both neighbours' migration messages are complete, then the particle
+// count of the sort's input: arrivals from L + own range + arrivals from R
+__global__ void k_slab_wait_set_n(SlabCtl *ctl, char *inbox, int has0, int has1, unsigned long long epoch, int n_max) {
+    const int side = threadIdx.x;
+    if (side <= 1 && (side == 0 ? has0 : has1)) wait_flag(ctl, inbox, side, epoch);
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        const InboxHdr *h = (const InboxHdr *)inbox;
+        const int nl = has0 ? h->count[0][epoch & 1ull] : 0, nr = has1 ? h->count[1][epoch & 1ull] : 0;
+        long long n = (long long)nl + ctl->own_count + nr;
+        if (n > n_max) { ctl->err |= SLAB_ERR_CAPACITY; n = n_max; }     // (the sort then drops the tail; the step is flagged)
+        ctl->n = (int)n;
+        ctl->src_nl = nl; ctl->src_first = ctl->own_first; ctl->src_count = ctl->own_count;
     }
 }
 // inbox -> the listed members of my ghost columns
@@ -242,6 +238,8 @@ __global__ void __launch_bounds__(256) k_slab_unpack_range(SlabMsg msg, SlabCtl 
                                                            unsigned long long epoch) {
     const int side = blockIdx.y;
     if (!(side == 0 ? has0 : has1)) return;
+    if (threadIdx.x == 0) wait_flag(ctl, inbox, side, epoch);     // every block waits for the message itself (acquire)
+    __syncthreads();
     const InboxHdr *h = (const InboxHdr *)inbox;
     const int first = ctl->ghost_first[side];
     int count = ctl->ghost_count[side];
@@ -260,64 +258,6 @@ __global__ void __launch_bounds__(256) k_slab_unpack_range(SlabMsg msg, SlabCtl 
         for (long long t = t00; t < nw; t += stride) d[t] = s[t];
     }
 }
-// particle set := [from L][own range][from R] in the ALTERNATE buffers of every state member (blockIdx.y: 0 L, 1 R, 2 own)
-__global__ void __launch_bounds__(256) k_slab_assemble(SlabMsg msg, const SlabCtl *ctl, char *inbox, int has0, int has1, long long msg_cap,
-                                                       unsigned long long epoch, int n_max) {
-    const InboxHdr *h = (const InboxHdr *)inbox;
-    const int nl = has0 ? h->count[0][epoch & 1ull] : 0, nr = has1 ? h->count[1][epoch & 1ull] : 0;
-    const int own_first = ctl->own_first;
-    int own = ctl->own_count;
-    const int part = blockIdx.y;
-    long long dst0;
-    int count;
-    const uint32_t *inb = nullptr;
-    if (part == 0) { dst0 = 0; count = nl; inb = (const uint32_t *)inbox_msg(inbox, 0, (unsigned)(epoch & 1ull), msg_cap); }
-    else if (part == 1) { dst0 = (long long)nl + own; count = nr; inb = (const uint32_t *)inbox_msg(inbox, 1, (unsigned)(epoch & 1ull), msg_cap); }
-    else { dst0 = nl; count = own; }
-    if (dst0 + count > n_max) count = (int)max(0ll, (long long)n_max - dst0);        // capacity error is raised by k_slab_set_n
-    const long long stride = (long long)gridDim.x * blockDim.x, t00 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (int k = 0; k < msg.n; k++) {
-        const int wpe = msg.f[k].wpe;
-        uint32_t *d = (uint32_t *)msg.f[k].alt + dst0 * wpe;
-        const uint32_t *s = part == 2 ? (const uint32_t *)msg.f[k].cur + (long long)own_first * wpe : inb + msg.f[k].secw;
-        const long long nw = (long long)count * wpe;
-        if (part == 2 && (((uintptr_t)d | (uintptr_t)s) & 15) == 0) {          // the big copy: 16 bytes per thread when aligned
-            const long long nq = nw >> 2;
-            for (long long t = t00; t < nq; t += stride) ((uint4 *)d)[t] = ((const uint4 *)s)[t];
-            for (long long t = (nq << 2) + t00; t < nw; t += stride) d[t] = s[t];
-        } else
-            for (long long t = t00; t < nw; t += stride) d[t] = s[t];
-    }
-}
-__global__ void k_slab_set_n(SlabCtl *ctl, const char *inbox, int has0, int has1, unsigned long long epoch, int n_max) {
-    const InboxHdr *h = (const InboxHdr *)inbox;
-    const int nl = has0 ? h->count[0][epoch & 1ull] : 0, nr = has1 ? h->count[1][epoch & 1ull] : 0;
-    long long n = (long long)nl + ctl->own_count + nr;
-    if (n > n_max) { ctl->err |= SLAB_ERR_CAPACITY; n = n_max; }
-    ctl->n = (int)n;
-}
-// after the sort: the column table.  Column cx starts at cell_end[cx * nyz - 1] (x-major cell ids, ps:221-222).
-__global__ void k_slab_coltable(SlabCtl *ctl, const int *cell_end, int a, int b, int gn0, int nyz, int has0, int has1) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int n = ctl->n;
-    auto start = [&](int cx) { return cx <= 0 ? 0 : (cx >= gn0 ? n : cell_end[(long long)cx * nyz - 1]); };
-    const int ca1 = start(a - 1), ca = start(a), cb = start(b), cb1 = start(b + 1);
-    int err = 0;
-    if (ca1 != 0 || cb1 != n) err |= SLAB_ERR_FAR;                 // something moved more than one column in a step
-    if ((!has0 && ca != 0) || (!has1 && cb != n)) err |= SLAB_ERR_FAR;
-    if (err) atomicOr(&ctl->err, err);
-    ctl->own_first = ca; ctl->own_count = cb - ca;
-    ctl->ghost_first[0] = ca1; ctl->ghost_count[0] = has0 ? ca - ca1 : 0;
-    ctl->ghost_first[1] = cb; ctl->ghost_count[1] = has1 ? cb1 - cb : 0;
-    ctl->send_first[0] = ca; ctl->send_count[0] = has0 ? start(a + 1) - ca : 0;
-    const int cbm1 = start(b - 1);
-    ctl->send_first[1] = cbm1; ctl->send_count[1] = has1 ? cb - cbm1 : 0;
-    // particles move less than a cell per step: only the two old columns at each face can hold leavers
-    const int l_end = start(min(a + 2, b)), r_beg = start(max(b - 2, a));
-    ctl->reg_first[0] = ca; ctl->reg_count[0] = has0 ? l_end - ca : 0;
-    ctl->reg_first[1] = r_beg; ctl->reg_count[1] = has1 ? cb - r_beg : 0;
-}
-
 // ---------------------------------------------------------------------------------------------- host side
 static inline long long align16(long long v) { return (v + 15) / 16 * 16; }
 
@@ -380,11 +320,10 @@ static int slab_exchange(SphCtx *c, const int *fields, int nf) {
     SPH_PROF(c, K_HALO);
     k_slab_push_range<<<dim3(grid, 2), 256, 0, c->stream>>>(m, ctl, S->peer[0], S->peer[1], S->msg_cap, ep);
     SPH_LAUNCH_CHECK(c);
+    // the copy out of the inbox starts with the wait for the message (every block spins on the flag; the grid is kept
+    // small so that waiting blocks never fill the device: slabs of ONE device -- the test harness -- share it)
     SPH_PROF(c, K_HALO_WAIT);
-    k_slab_wait<<<1, 32, 0, c->stream>>>(ctl, S->inbox, S->has[0], S->has[1], ep);
-    SPH_LAUNCH_CHECK(c);
-    SPH_PROF(c, K_HALO);
-    k_slab_unpack_range<<<dim3(grid, 2), 256, 0, c->stream>>>(m, ctl, S->inbox, S->has[0], S->has[1], S->msg_cap, ep);
+    k_slab_unpack_range<<<dim3(grid < 96 ? grid : 96, 2), 256, 0, c->stream>>>(m, ctl, S->inbox, S->has[0], S->has[1], S->msg_cap, ep);
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
@@ -445,21 +384,28 @@ template <typename T> int slab_redistribute(SphCtx *c) {
     k_slab_push_selected<<<dim3(copy_grid(wsum * S->face_cap / 2), 2), 256, 0, st>>>(m, ctl, S->peer[0], S->peer[1], idx0, idx1, S->msg_cap, ep);
     SPH_LAUNCH_CHECK(c);
     SPH_PROF(c, K_HALO_WAIT);
-    k_slab_wait<<<1, 32, 0, st>>>(ctl, S->inbox, S->has[0], S->has[1], ep);
+    k_slab_wait_set_n<<<1, 32, 0, st>>>(ctl, S->inbox, S->has[0], S->has[1], ep, (int)c->n_max);
     SPH_LAUNCH_CHECK(c);
-    SPH_PROF(c, K_HALO);
-    k_slab_assemble<<<dim3(copy_grid(wsum * c->n_max / 4), 3), 256, 0, st>>>(m, ctl, S->inbox, S->has[0], S->has[1], S->msg_cap, ep, (int)c->n_max);
-    SPH_LAUNCH_CHECK(c);
-    SPH_PROF(c, K_HALO);
-    k_slab_set_n<<<1, 1, 0, st>>>(ctl, S->inbox, S->has[0], S->has[1], ep, (int)c->n_max);
-    SPH_LAUNCH_CHECK(c);
-    for (int k = 0; k < nf; k++) flip(c, fields[k]);
-    if ((r = grid_build<T>(c))) return r;
+    // ONE sort of [from L | own | from R], read where it lies (grid.cu, VSrc); the column table comes out of it
+    S->sort_epoch = ep;
+    S->sort_msg = m;
+    c->slab_sort = true;
+    r = grid_build<T>(c);
+    c->slab_sort = false;
+    return r;
+}
+void slab_sort_args(SphCtx *c, VSrc *vs, ColTab *ct, int *cell0, int *cell1) {
+    SlabState *S = c->slab;
     const int nyz = c->p.gn[1] * (c->p.dim == 3 ? c->p.gn[2] : 1);
-    SPH_PROF(c, K_HALO);
-    k_slab_coltable<<<1, 32, 0, st>>>(ctl, (const int *)(c->arena + c->f[SPH_F_CELL_END].off[0]), S->a, S->b, c->p.gn[0], nyz, S->has[0], S->has[1]);
-    SPH_LAUNCH_CHECK(c);
-    return 0;
+    vs->ctl = ctl_of(c); vs->inbox = S->inbox; vs->has0 = S->has[0]; vs->has1 = S->has[1];
+    vs->parity = (unsigned)(S->sort_epoch & 1ull); vs->msg_cap = S->msg_cap;
+    for (int k = 0; k < S->sort_msg.n && k < 12; k++) vs->sec[k] = S->sort_msg.f[k].secw * 4;
+    ct->ctl = ctl_of(c); ct->a = S->a; ct->b = S->b; ct->gn0 = c->p.gn[0]; ct->nyz = nyz; ct->has0 = S->has[0]; ct->has1 = S->has[1];
+    // Cells of the slab's columns, its ghost columns and the columns a tile footprint of an owned cell can reach (up to
+    // 4 columns wide + 1 halo): no particle lives beyond the ghost columns, so their cell_end is 0 below / n above --
+    // exactly what scanning them yields; everything further out is never read.
+    const int lo = S->a - 5 > 0 ? S->a - 5 : 0, hi = S->b + 5 < c->p.gn[0] ? S->b + 5 : c->p.gn[0];
+    *cell0 = lo * nyz; *cell1 = hi * nyz;
 }
 template int slab_redistribute<float>(SphCtx *);
 template int slab_redistribute<double>(SphCtx *);
@@ -496,6 +442,9 @@ int sph_slab_init(SphCtx *c, int32_t rank, int32_t world, int32_t cx_begin, int3
     S->face_cap = face_cap; S->msg_cap = (need - SLAB_HDR) / 4;
     S->inbox = (char *)inbox;
     SPH_CHECK(c, cudaMemsetAsync(inbox, 0, SLAB_HDR, c->stream));
+    // the slab sort only scans the cells near its columns: everything else must read as "no particle" from the start
+    SPH_CHECK(c, cudaMemsetAsync(c->arena + c->f[SPH_F_CELL_END].off[0], 0, sizeof(int) * (size_t)(c->C + 1), c->stream));
+    SPH_CHECK(c, cudaMemsetAsync(c->arena + c->f[SPH_F_CELL_COUNT].off[0], 0, sizeof(int) * (size_t)(c->C + 1), c->stream));
     SPH_CHECK(c, cudaStreamSynchronize(c->stream));
     c->slab = S;
     c->masks_valid = false;

@@ -5,7 +5,42 @@
 #include <stdio.h>
 #include "sph_dev.cuh"
 
-namespace sph { struct SlabState; }
+namespace sph {
+struct SlabState;
+// ---- native multi-GPU slab step (slab.cu); the sort (grid.cu) reads these too -------------------------------------
+constexpr int SLAB_HDR = 256;                 // bytes in front of the message buffers of an inbox
+struct SlabCtl {                 // device-resident; ctl->n is what Dev::ndev points to
+    int n;
+    int own_first, own_count;
+    int ghost_first[2], ghost_count[2];     // [0]: ghost column a - 1, [1]: ghost column b
+    int send_first[2], send_count[2];       // [0]: my column a (the left neighbour's ghosts), [1]: my column b - 1
+    int reg_first[2], reg_count[2];         // where the next redistribution looks for particles that leave / are on a face
+    int sel_count[2];
+    int err;
+    unsigned done[2];                       // completion counters of the push kernels, per side
+    int src_nl, src_first, src_count;       // input of the pending sort: arrivals from L, then the OLD own range, then arrivals from R
+};
+struct InboxHdr {
+    unsigned long long flag[2];             // [side the message came from]: epoch of the newest complete message
+    int count[2][2];                        // [side][epoch parity]: particles in that message
+};
+// What the slab sort reads: the VIRTUAL concatenation [arrivals from L | own range | arrivals from R] -- arrivals stay in
+// the inbox, own particles in their current buffers; nothing is copied together before the reorder kernel gathers.
+// sec[k]: byte offset of the k-th carried member's section inside a message (order of sph_state_fields).
+struct VSrc {
+    const SlabCtl *ctl;
+    const char *inbox;
+    int has0, has1;
+    unsigned parity;
+    long long msg_cap;
+    long long sec[12];
+};
+// after the scan: the column table of the slab (own / ghost / boundary ranges), written by one thread of k_scatter_index
+struct ColTab { SlabCtl *ctl; int a, b, gn0, nyz, has0, has1; };
+__host__ __device__ __forceinline__ char *inbox_msg(char *inbox, int side, unsigned parity, long long msg_cap) {
+    return inbox + SLAB_HDR + (long long)(side * 2 + (int)parity) * msg_cap;
+}
+}
 
 struct FieldSlot {
     int64_t off[2];      // byte offsets of the two ping-pong buffers (off[1] == off[0] when not carried)
@@ -49,6 +84,7 @@ struct SphCtx {
     int own0, own1;      // owned x-columns [own0, own1) (multi-GPU slabs); the whole grid on one GPU
     int64_t off_slabctl; // device-resident control block of the native slab step (slab.cu)
     sph::SlabState *slab;   // native multi-GPU slab step (sph_slab_init); null on one GPU
+    bool slab_sort;      // grid_build is the sort of a slab redistribution: virtual concatenation, column table, cell sub-range
     bool masks_valid;    // the neighbour masks / work lists belong to the current sort (cleared by every re-sort / upload)
 };
 
@@ -121,6 +157,7 @@ template <typename T> int slab_redistribute(SphCtx *c);                       //
 int slab_refresh(SphCtx *c, int phase, bool final_phase, bool last_one_step); // ghost columns after a phase of one_step
 int slab_refresh_post(SphCtx *c);                                             // ghost columns after advect_pos (mu(I) + XSPH)
 int slab_arm(SphCtx *c);
+void slab_sort_args(SphCtx *c, VSrc *vs, ColTab *ct, int *cell0, int *cell1);   // grid.cu asks while c->slab_sort is set
 void slab_disarm(SphCtx *c);
 bool slab_armed(const SphCtx *c);
 int64_t slab_exact_n(const SphCtx *c);    // particle count the host knows (as of the last sph_slab_sync while stepping)
