@@ -145,6 +145,10 @@ int sph_step(SphCtx *ctx, int nsteps);
 /* stand-alone sweeps on the current grid (BASELINE config C5; parity of the neighbour predicate, ps:259-269) */
 int sph_neighbor_count(SphCtx *ctx, int32_t *out_dev);          /* n int32  */
 int sph_density_sum(SphCtx *ctx, void *out_dev);                /* n real: sum_j mass_j W_ij (wc:30-31) */
+/* both in ONE walk of the neighbours (BASELINE config C5).  With the cell-tile path allocated (fast != 0, MIXED) the
+ * walk follows the per-step neighbour bit masks (built here if they are not current): count = popcount, density over
+ * the set bits with shared-memory tiles; wall particles and crowded cells go through the generic walk. */
+int sph_density_sweep(SphCtx *ctx, int32_t *count_dev, void *rho_dev);
 /* cell-tile path only, after sph_calc_kernel_corr: the count read back from the per-step neighbour bit masks for
  * flow particles of representable cells, -1 for every other particle (parity probe of the mask kernel) */
 int sph_neighbor_count_masks(SphCtx *ctx, int32_t *out_dev);

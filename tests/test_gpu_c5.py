@@ -23,10 +23,12 @@ def oracle_box(x, n_side, f32):
     return o
 
 
-@pytest.mark.parametrize("prec", ["f64", "f32"])
-def test_c5_small_box_matches_oracle(prec):
+@pytest.mark.parametrize("prec,fast", [("f64", 0), ("f32", 1), ("f32", 0)])
+def test_c5_small_box_matches_oracle(prec, fast):
+    """fast = 1: count and density follow the neighbour bit masks on shared-memory tiles (sph_density_sweep on the cell-tile
+    path); fast = 0 / float64: the generic per-particle walk.  Same counts, bit for bit."""
     from tisphi_b200.c5 import UniformBox
-    box = UniformBox(27_000, precision=prec)
+    box = UniformBox(27_000, precision=prec, fast=fast)
     box.sweep()
     o = oracle_box(box.x, box.n_side, prec == "f32")
     eng = box.engine

@@ -1,0 +1,123 @@
+"""bench.py --workload c5: BASELINE config C5, the synthetic 3D uniform box.
+
+One "update" = one particle through grid build (cell id, histogram, scan, stable counting sort, reorder) + neighbour
+count + density sum -- the bare for_all_neighbors iteration of the reference (eng/particle_system.py:216-269) with the
+density task of eng/solver_sph_wc.py:30-31.  N > 1: the same box slab-partitioned along x (strong scaling), every sweep
+preceded by the migration / halo exchange of the native slab step (csrc/slab.cu).
+"""
+import json
+import os
+import time
+
+import numpy as np
+
+METRIC, UNIT = "particle-updates/s", "particle-updates/s"
+
+
+def _cpu_baseline(n_target, threads, log):
+    """oracle (float64, OpenMP): grid build + neighbour count + density sum on a bounded box."""
+    from oracle import oracle as orc
+    from .c5 import box_positions, box_params
+    L = orc.lib()
+    L.orc_set_threads(threads)
+    x, n_side = box_positions(n_target)
+    Pe = box_params(n_side)
+    P = orc.OrcParams()
+    P.dim, P.kernel, P.kcorr, P.ti, P.xsph, P.solver, P.serial, P.wc_fresh = 3, 1, 0, 1, 0, 1, 0, 0
+    for a in range(3):
+        P.gn[a], P.vstart[a], P.g[a] = Pe.gn[a], Pe.vstart[a], 0.0
+    P.h, P.support, P.grid_size, P.m_V0, P.eps = Pe.h, Pe.support, Pe.grid_size, Pe.m_V0, 1e-8
+    P.dt, P.rho0, P.visc, P.stiff, P.gamma_, P.vsound = Pe.dt, Pe.rho0, Pe.visc, Pe.stiff, Pe.gamma_, Pe.vsound
+    o = orc.Oracle(P, x, np.zeros_like(x), np.ones(len(x)), np.ones(len(x), dtype=np.int32))
+    o.grid_build(); o.neighbor_count(); o.density_sum()          # warm-up
+    reps, t0 = 2, time.perf_counter()
+    for _ in range(reps):
+        o.grid_build(); o.neighbor_count(); o.density_sum()
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": len(x) / dt, "unit": UNIT, "cores": int(L.orc_max_threads()), "kind": "port",
+            "sample": f"uniform box N={len(x)}, {reps} sweeps (sort + count + density as separate oracle calls), float64, "
+                      f"OpenMP omp_get_max_threads()={int(L.orc_max_threads())}, {dt:.2f} s per sweep"}
+
+
+def run(args, local, log, ClockSampler, measured_peaks, host_threads=None):
+    import torch
+    from .c5 import UniformBox
+    n_target = int(args.size or 1e7)
+    t0 = time.time()
+    box = UniformBox(n_target, device=f"cuda:{local}")
+    eng, n = box.engine, box.n
+    cells = box.params.gn[0] * box.params.gn[1] * box.params.gn[2]
+    log(f"box built: N={n} ({box.n_side}^3), cells={cells}, {time.time() - t0:.1f}s")
+    for _ in range(max(3, args.warmup)):
+        box.sweep()
+    torch.cuda.synchronize()
+    launches0 = eng.L.sph_launch_count(eng.h)
+    eng.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record(eng.stream)
+        for _ in range(args.steps):
+            box.sweep()
+        e1.record(eng.stream)
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    prof = eng.profile_read()
+    eng.profile(False)
+    launches = eng.L.sph_launch_count(eng.h) - launches0
+    value = n * args.steps / (ms * 1e-3)
+    cnt = box.count
+    peak, peak_kind = measured_peaks()
+    kernel_ms = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    # per-kernel algorithmic bytes: the grid-build kernels are the HBM-bound ones
+    ab = {"cell_id": 32 * n, "scan": 12 * cells, "scatter_index": 12 * n, "rank": 12 * n, "reorder": 220 * n,
+          "tile_mask": 16 * n, "c5_sweep": 20 * n + 8 * n}
+    kernel_gbs = {k: round(ab[k] / (v * 1e-3) / 1e9, 1) for k, v in kernel_ms.items() if k in ab and v > 0}
+    grid_ms = sum(kernel_ms.get(k, 0.0) for k in ("cell_id", "scan", "scatter_index", "rank", "reorder"))
+    grid_bytes = 92 * n + 12 * cells
+    dom = next(iter(kernel_ms))
+    achieved = ab[dom] / (kernel_ms[dom] * 1e-3) / 1e9 if dom in ab else None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None, "traffic": None, "peak_kind": peak_kind,
+                "kernel_ms_per_sweep": kernel_ms, "kernel_gbs": kernel_gbs,
+                "grid_build": {"ms": round(grid_ms, 4), "algorithmic_bytes": grid_bytes, "gbs": round(grid_bytes / (grid_ms * 1e-3) / 1e9, 1),
+                               "frac_of_hbm": round(grid_bytes / (grid_ms * 1e-3) / 1e9 / peak, 4)},
+                "whole_sweep_algorithmic_gbs": (72 * n + 12 * cells) * args.steps / (ms * 1e-3) / 1e9,
+                "note": "the mask and sweep kernels are fp32-pipe / shared-memory bound (SURVEY 8d); the grid-build kernels are the HBM-bound part"}
+
+    # end to end: positions from pinned host memory -> sweep -> counts and densities back to the host
+    h_x = torch.from_numpy(box.x).pin_memory()
+    h_v = torch.zeros((n, 3), dtype=torch.float64).pin_memory()
+    h_rho = torch.ones(n, dtype=torch.float64).pin_memory()
+    h_typ = torch.ones(n, dtype=torch.int32).pin_memory()
+    o_cnt = torch.empty(n, dtype=torch.int32).pin_memory()
+    o_rho = torch.empty(n, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        eng.call("sph_clear_particles")
+        eng.call("sph_add_particles", n, h_x.data_ptr(), h_v.data_ptr(), h_rho.data_ptr(), h_typ.data_ptr())
+        box.sweep()
+        with torch.cuda.stream(eng.stream):
+            o_cnt.copy_(box.count, non_blocking=True)
+            o_rho.copy_(box.rho, non_blocking=True)
+        eng.call("sph_synchronize")
+
+    e2e_step()
+    k = max(1, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    assert int(o_cnt.max()) == int(cnt.max())
+    cpu = None if args.no_cpu else _cpu_baseline(min(n_target, 2_000_000), host_threads() if host_threads else os.cpu_count(), log)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"C5 synthetic 3D uniform box: N={n} ({box.n_side}^3 jittered lattice, seed 1234), cells={cells}; "
+                                   "one step = grid build + neighbour count + density sum",
+                       "mean_neighbours": float(cnt.float().mean()), "max_neighbours": int(cnt.max()),
+                       "flagged_cells": int(eng.L.sph_read_flagged_cells(eng.h)), "l2": "state larger than L2, no flush needed"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": n * k / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 60, "d2h_bytes_per_step": n * 8, "steps": k,
+                    "ms_per_step": e2e_s / k * 1e3},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)

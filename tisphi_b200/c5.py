@@ -5,7 +5,7 @@ jitter (numpy default_rng(1234)), kappa * kh = 3 => support = cell edge = 3 d, t
 mass.  One "update" of this workload = grid build (cell ids, counting sort, reorder) + neighbour count (int32) +
 density sum  sum_j m_j W_ij  per particle -- the bare ``for_all_neighbors`` iteration of the reference
 (eng/particle_system.py:216-269) with the density task of eng/solver_sph_wc.py:30-31, through the C ABI
-(sph_grid_build, sph_neighbor_count, sph_density_sum).
+(sph_grid_build, sph_density_sweep: count and density in one walk of the neighbours).
 """
 import math
 
@@ -22,12 +22,12 @@ def box_positions(n_target, seed=1234, d=1.0):
     return x, n_side
 
 
-def box_params(n_side, precision="f32", d=1.0):
+def box_params(n_side, precision="f32", d=1.0, fast=1):
     """SphParams of the box: h = 1.5 d, support = grid_size = 3 d, one cell of padding on every side."""
     P = _lib.SphParams()
     P.dim, P.kernel, P.kcorr, P.ti, P.xsph, P.solver = 3, 1, 0, 1, 0, _lib.SOLVER_WC
     P.precision = _lib.PREC_MIXED if precision in ("f32", "mixed") else _lib.PREC_F64
-    P.wc_fresh, P.fast = 0, 0                                   # no WCSPH step is taken: no cell-tile scratch
+    P.wc_fresh, P.fast = 0, int(fast)                           # fast: the sweep walks the per-step neighbour bit masks
     gs = 3.0 * d
     cells = int(math.ceil(n_side * d / gs)) + 2
     for a in range(3):
@@ -42,12 +42,12 @@ def box_params(n_side, precision="f32", d=1.0):
 class UniformBox:
     """Engine + particles of one C5 instance on one device."""
 
-    def __init__(self, n_target, device="cuda:0", precision="f32", seed=1234):
+    def __init__(self, n_target, device="cuda:0", precision="f32", seed=1234, fast=1):
         import torch
         self.torch = torch
         self.x, self.n_side = box_positions(n_target, seed)
         self.n = len(self.x)
-        self.params = box_params(self.n_side, precision)
+        self.params = box_params(self.n_side, precision, fast=fast)
         self.engine = _lib.Engine(self.params, self.n, device=device)
         self.engine.add_particles(self.x, np.zeros_like(self.x), np.ones(self.n), np.ones(self.n, dtype=np.int32))
         self.count = torch.empty(self.n, dtype=torch.int32, device=self.engine.device)
@@ -57,8 +57,7 @@ class UniformBox:
         """grid build + neighbour count + density sum, enqueued on the engine's stream."""
         e = self.engine
         e.call("sph_grid_build")
-        e.call("sph_neighbor_count", self.count.data_ptr())
-        e.call("sph_density_sum", self.rho.data_ptr())
+        e.call("sph_density_sweep", self.count.data_ptr(), self.rho.data_ptr())
 
     def algorithmic_bytes(self):
         cells = self.params.gn[0] * self.params.gn[1] * self.params.gn[2]

@@ -449,7 +449,8 @@ int sph_read_state(SphCtx *c, double *x, double *v, double *density, double *pre
     return r ? r : sph_synchronize(c);
 }
 
-int sph_grid_build(SphCtx *c) { return DISPATCH(c, grid_build, c); }
+// on a native slab (sph_slab_init) the build starts with the migration / halo exchange and sorts [from L | own | from R]
+int sph_grid_build(SphCtx *c) { return c->slab ? DISPATCH(c, slab_redistribute, c) : DISPATCH(c, grid_build, c); }
 int sph_calc_kernel_corr(SphCtx *c) { return DISPATCH(c, calc_kernel_corr, c, true); }
 int sph_calc_kernel_corr_deferred(SphCtx *c) { return DISPATCH(c, calc_kernel_corr, c, false); }
 int sph_init_real2tmp(SphCtx *c) { return DISPATCH(c, init_real2tmp, c); }
@@ -462,6 +463,7 @@ int sph_init_stress_ymax(SphCtx *c, double ymax) { return DISPATCH(c, init_stres
 int sph_step(SphCtx *c, int nsteps) { return DISPATCH(c, dispatch_step, c, nsteps); }
 int sph_neighbor_count(SphCtx *c, int32_t *out_dev) { return DISPATCH(c, neighbor_count, c, out_dev); }
 int sph_density_sum(SphCtx *c, void *out_dev) { return DISPATCH(c, density_sum, c, out_dev); }
+int sph_density_sweep(SphCtx *c, int32_t *count_dev, void *rho_dev) { return DISPATCH(c, density_sweep, c, count_dev, rho_dev); }
 int sph_neighbor_count_masks(SphCtx *c, int32_t *out_dev) {
     if (!c->fast) { snprintf(c->err, sizeof(c->err), "neighbour masks exist only on the cell-tile path (MIXED precision WCSPH)"); return -2; }
     if (c->n == 0) return 0;

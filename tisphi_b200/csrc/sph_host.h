@@ -138,9 +138,11 @@ template <typename T> int post_step(SphCtx *c);
 template <typename T> int finish_step(SphCtx *c);      // advect_SE/LF + advect_pos + advect_something of WCSPH in one kernel
 template <typename T> int neighbor_count(SphCtx *c, int32_t *out);
 template <typename T> int density_sum(SphCtx *c, void *out);
+template <typename T> int density_sweep(SphCtx *c, int32_t *count_out, void *rho_out);
 // sweeps_tile.cu (float only)
 int tile_mask(SphCtx *c, bool shepard);
 int tile_mask_count(SphCtx *c, int32_t *out);
+int tile_density_sweep(SphCtx *c, int32_t *count_out, float *rho_out);
 int tile_wc_prep_and_wall(SphCtx *c);
 int tile_wc_fluid(SphCtx *c);
 // integrate.cu

@@ -747,6 +747,35 @@ template <typename T> __global__ void __launch_bounds__(128) k_density_sum(Dev<T
     for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) { s += c.v4[j].w * kernel_W(c, r); });
     out[i] = s;
 }
+// count and density in one walk (BASELINE config C5).  rest_only: the cell-tile kernel already wrote the flow particles of
+// unflagged cells; this kernel completes wall particles (their masks hold flow neighbours only) and flagged cells.
+template <typename T> __global__ void __launch_bounds__(128) k_density_count(Dev<T> c, int *__restrict__ cnt_out, T *__restrict__ rho_out, int rest_only) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.N(); i += gridDim.x * blockDim.x) {
+        if (not_owned(c, i)) continue;                        // ghost columns of a slab belong to the neighbour rank
+        if (rest_only && is_flow(c.type[i]) && !c.cellflag[c.gid[i]]) continue;
+        int cnt = 0;
+        T s = 0;
+        for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) { cnt++; s += c.v4[j].w * kernel_W(c, r); });
+        cnt_out[i] = cnt;
+        rho_out[i] = s;
+    }
+}
+template <typename T> int density_sweep(SphCtx *c, int32_t *count_out, void *rho_out) {
+    if (c->n == 0) return 0;
+    int rest_only = 0;
+    if (c->fast && sizeof(T) == 4) {
+        if (!c->masks_valid) { int r = tile_mask(c, false); if (r) return r; }
+        int r = tile_density_sweep(c, count_out, (float *)rho_out);
+        if (r) return r;
+        rest_only = 1;
+    }
+    Dev<T> d = make_dev<T>(c);
+    SPH_PROF(c, K_DENSITY_SUM);
+    const int blocks = rest_only ? 148 * 16 : blocks_for(c->n, 128);
+    k_density_count<T><<<blocks, 128, 0, c->stream>>>(d, count_out, (T *)rho_out, rest_only);
+    SPH_LAUNCH_CHECK(c);
+    return 0;
+}
 template <typename T> int neighbor_count(SphCtx *c, int32_t *out) {
     if (c->n == 0) return 0;
     SPH_PROF(c, K_NEIGHBOR_COUNT);
@@ -770,7 +799,8 @@ template <typename T> int density_sum(SphCtx *c, void *out) {
     template int post_step<T>(SphCtx *);                   \
     template int finish_step<T>(SphCtx *);                   \
     template int neighbor_count<T>(SphCtx *, int32_t *);   \
-    template int density_sum<T>(SphCtx *, void *);
+    template int density_sum<T>(SphCtx *, void *);           \
+    template int density_sweep<T>(SphCtx *, int32_t *, void *);
 INST(float)
 INST(double)
 

@@ -346,15 +346,17 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0,
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-// Two more candidates against one particle: bits B and B + 1 of the chunk word are set when dist2(d) < thr.
-// The packed FP32 pipe is the busiest unit of this kernel (six packed operations per two candidates), so the compare
-// stays off it: one FSETP and one predicated OR with an immediate per candidate, both on the ALU pipe.
-template <int B> __device__ __forceinline__ unsigned push2(unsigned cm, u64 dx, u64 dy, u64 dz, float thr) {
+// Two more candidates against one particle, pushed into the chunk word from the bottom (the caller walks a chunk from its
+// last pair to its first, so candidate k of the chunk ends up at bit k).  The predicate dist2(d) < thr is read off the
+// SIGN of the packed difference r2 - thr: for finite operands the rounded difference is negative exactly when r2 < thr
+// (a nonzero exact difference never rounds to zero, and r2 == thr gives +0), so the bit is the same as FSETP.LT's --
+// but it costs one packed subtraction on the FMA pipe per two candidates and ONE funnel shift per candidate on the
+// half-rate ALU pipe, where the compare + predicated OR took two.
+__device__ __forceinline__ unsigned push2(unsigned cm, u64 dx, u64 dy, u64 dz, u64 thr2) {
     float lo, hi;
-    up2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), lo, hi);                 // == dist2(dx, dy, dz) in each half
-    asm("{\n.reg .pred p, q;\nsetp.lt.f32 p, %1, %3;\nsetp.lt.f32 q, %2, %3;\n@p or.b32 %0, %0, %4;\n@q or.b32 %0, %0, %5;\n}"
-        : "+r"(cm) : "f"(lo), "f"(hi), "f"(thr), "n"(1u << B), "n"(2u << B));
-    return cm;
+    up2(sub2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), thr2), lo, hi);     // dist2(dx, dy, dz) - thr in each half
+    cm = __funnelshift_l(__float_as_uint(hi), cm, 1);
+    return __funnelshift_l(__float_as_uint(lo), cm, 1);
 }
 __device__ __forceinline__ u64 chunk_bits(unsigned cm, int t0) { return (u64)cm << t0; }
 
@@ -483,7 +485,7 @@ __device__ __forceinline__ void mask_body(const DevF &c, const TileGeom &g, Mask
     // the cells before it that lie in a ghost column.  A pair of cells without any flow particle has empty words
     // (walls keep flow neighbours only).  Empty words are never stored: readers only follow the bits of nzw.
     unsigned todo = __ballot_sync(0xffffffffu, te.y > 0 && (lane >= FT::CENTRE || !bowned) && (flowA != 0 || bflowc));
-    const float thr = c.r2thr;
+    const u64 thr2 = pk2(c.r2thr, c.r2thr);
     // (mask words are addressed inside the cell blocks: mask_row)
     unsigned *mrow = mask_row(c.mask, w.is, FT::NW, mine ? lane : 0);
     unsigned nz = 0;
@@ -509,10 +511,10 @@ __device__ __forceinline__ void mask_body(const DevF &c, const TileGeom &g, Mask
                 const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(X + a4 + t0), x1 = *reinterpret_cast<const ulonglong2 *>(X + a4 + t0 + 4);
                 const ulonglong2 y0 = *reinterpret_cast<const ulonglong2 *>(Y + a4 + t0), y1 = *reinterpret_cast<const ulonglong2 *>(Y + a4 + t0 + 4);
                 const ulonglong2 z0 = *reinterpret_cast<const ulonglong2 *>(Z + a4 + t0), z1 = *reinterpret_cast<const ulonglong2 *>(Z + a4 + t0 + 4);
-                unsigned cm = push2<0>(0u, sub2(Ex, x0.x), sub2(Ey, y0.x), sub2(Ez, z0.x), thr);
-                cm = push2<2>(cm, sub2(Ex, x0.y), sub2(Ey, y0.y), sub2(Ez, z0.y), thr);
-                cm = push2<4>(cm, sub2(Ex, x1.x), sub2(Ey, y1.x), sub2(Ez, z1.x), thr);
-                cm = push2<6>(cm, sub2(Ex, x1.y), sub2(Ey, y1.y), sub2(Ez, z1.y), thr);
+                unsigned cm = push2(0u, sub2(Ex, x1.y), sub2(Ey, y1.y), sub2(Ez, z1.y), thr2);
+                cm = push2(cm, sub2(Ex, x1.x), sub2(Ey, y1.x), sub2(Ez, z1.x), thr2);
+                cm = push2(cm, sub2(Ex, x0.y), sub2(Ey, y0.y), sub2(Ez, z0.y), thr2);
+                cm = push2(cm, sub2(Ex, x0.x), sub2(Ey, y0.x), sub2(Ez, z0.x), thr2);
                 m64 |= chunk_bits(cm, t0);
             }
         } else {                                                   // B precedes A and is a ghost column: d' = (x_j + s) - x_i
@@ -522,10 +524,10 @@ __device__ __forceinline__ void mask_body(const DevF &c, const TileGeom &g, Mask
                 const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(X + a4 + t0), x1 = *reinterpret_cast<const ulonglong2 *>(X + a4 + t0 + 4);
                 const ulonglong2 y0 = *reinterpret_cast<const ulonglong2 *>(Y + a4 + t0), y1 = *reinterpret_cast<const ulonglong2 *>(Y + a4 + t0 + 4);
                 const ulonglong2 z0 = *reinterpret_cast<const ulonglong2 *>(Z + a4 + t0), z1 = *reinterpret_cast<const ulonglong2 *>(Z + a4 + t0 + 4);
-                unsigned cm = push2<0>(0u, sub2(add2(x0.x, Sx), Px), sub2(add2(y0.x, Sy), Py), sub2(add2(z0.x, Sz), Pz), thr);
-                cm = push2<2>(cm, sub2(add2(x0.y, Sx), Px), sub2(add2(y0.y, Sy), Py), sub2(add2(z0.y, Sz), Pz), thr);
-                cm = push2<4>(cm, sub2(add2(x1.x, Sx), Px), sub2(add2(y1.x, Sy), Py), sub2(add2(z1.x, Sz), Pz), thr);
-                cm = push2<6>(cm, sub2(add2(x1.y, Sx), Px), sub2(add2(y1.y, Sy), Py), sub2(add2(z1.y, Sz), Pz), thr);
+                unsigned cm = push2(0u, sub2(add2(x1.y, Sx), Px), sub2(add2(y1.y, Sy), Py), sub2(add2(z1.y, Sz), Pz), thr2);
+                cm = push2(cm, sub2(add2(x1.x, Sx), Px), sub2(add2(y1.x, Sy), Py), sub2(add2(z1.x, Sz), Pz), thr2);
+                cm = push2(cm, sub2(add2(x0.y, Sx), Px), sub2(add2(y0.y, Sy), Py), sub2(add2(z0.y, Sz), Pz), thr2);
+                cm = push2(cm, sub2(add2(x0.x, Sx), Px), sub2(add2(y0.x, Sy), Py), sub2(add2(z0.x, Sz), Pz), thr2);
                 m64 |= chunk_bits(cm, t0);
             }
         }
@@ -661,6 +663,65 @@ template <int KERNEL, class FT> __global__ void __launch_bounds__(FT::BT) k_tile
     TileShared<FT, 1> &sh = *reinterpret_cast<TileShared<FT, 1> *>(smem_raw);
     tile_init<FT, 1>(sh);
     TILE_PERSISTENT_LOOP(sh, c.worklist[0], c.wcount + 0, c.wcount + 5, (shepard_body<KERNEL, FT>(c, g, sh, blk, parity)))
+}
+
+// ------------------------------------------------------------------------------------------------ count + density sweep
+// BASELINE config C5: the bare for_all_neighbors iteration (ps:259-269) with the density task (wc:30-31) -- per FLOW
+// particle of an unflagged cell the neighbour count (popcount of its mask words: exact) and sum_j mass_j W_ij over the
+// set bits, in ONE walk of the masks.  Payloads: ps4 (coordinates) and v4 (.w = mass).  Everything else (wall particles,
+// whose masks hold flow neighbours only, and flagged cells) is left to the generic kernel.
+template <int KERNEL, class FT>
+__device__ __forceinline__ bool density_body(const DevF &c, const TileGeom &g, TileShared<FT, 2> &sh, int blk, unsigned parity,
+                                             int *__restrict__ count_out, float *__restrict__ rho_out) {
+    WarpCell w = warp_cell<FT>(c, g, blk);
+    const int lane = threadIdx.x & 31;
+    if (w.nc > 0 && c.cellflag[w.gcell]) w.nc = 0;
+    const int i = w.is + lane;
+    const bool work = lane < w.nc && c.ps4[i].w > 0.f;
+    const unsigned nz = work ? c.nzw[i] : 0u;
+    if (!__syncthreads_or(work)) return false;
+    cursor_prefetch(mask_row(c.mask, w.is, FT::NW, work ? lane : 0), (unsigned)w.nc, nz);
+    if (!tile_setup<FT, 2>(c, g, sh, w, parity, c.ps4, c.v4)) return true;
+    build_ctab<FT, 2>(c, sh, w, lane);
+    if (!__any_sync(0xffffffffu, work)) return true;
+    const F4 *A = sh.P[0], *B = sh.P[1];
+    const F4 *ct = sh.ctab + (threadIdx.x >> 5) * FT::NW;
+    const F4 pi = A[sh.cb[stencil_cb<FT>(w, 0, 0, 0)] + (work ? lane : 0)];
+    const KernConst kc = kern_const(c);
+    const unsigned n = (unsigned)w.nc;
+    const unsigned *mrow = mask_row(c.mask, w.is, FT::NW, work ? lane : 0);
+    Cursor k;
+    cursor_init(k, mrow, n, nz);
+    float s0 = 0.f, s1 = 0.f;
+    int cnt = 0;
+    while (true) {
+        const unsigned before = k.nz;
+        cursor_jump(k, mrow, n, ct, pi);
+        if (before != k.nz) cnt += __popc(k.m);                 // a new cell's word was taken: its bits are neighbours
+        if (!__any_sync(0xffffffffu, k.m != 0)) break;
+        int i0, i1, i2, i3;
+        cursor_take2<FT::SENT>(k, i0, i1);
+        const float e0x = k.ex, e0y = k.ey, e0z = k.ez;
+        const unsigned before2 = k.nz;
+        cursor_jump(k, mrow, n, ct, pi);
+        if (before2 != k.nz) cnt += __popc(k.m);
+        cursor_take2<FT::SENT>(k, i2, i3);
+        const F4 p0 = A[i0], p1 = A[i1], p2 = A[i2], p3 = A[i3];
+        const float m0 = B[i0].w, m1 = B[i1].w, m2 = B[i2].w, m3 = B[i3].w;     // sentinel: mass 0
+        s0 = fmaf(m0, fastW<KERNEL>(kc, dist2(e0x - p0.x, e0y - p0.y, e0z - p0.z)), s0);
+        s1 = fmaf(m1, fastW<KERNEL>(kc, dist2(e0x - p1.x, e0y - p1.y, e0z - p1.z)), s1);
+        s0 = fmaf(m2, fastW<KERNEL>(kc, dist2(k.ex - p2.x, k.ey - p2.y, k.ez - p2.z)), s0);
+        s1 = fmaf(m3, fastW<KERNEL>(kc, dist2(k.ex - p3.x, k.ey - p3.y, k.ez - p3.z)), s1);
+    }
+    if (work) { count_out[i] = cnt; rho_out[i] = s0 + s1; }
+    return true;
+}
+template <int KERNEL, class FT>
+__global__ void __launch_bounds__(FT::BT, 2) k_tile_density(DevF c, TileGeom g, int *__restrict__ count_out, float *__restrict__ rho_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileShared<FT, 2> &sh = *reinterpret_cast<TileShared<FT, 2> *>(smem_raw);
+    tile_init<FT, 2>(sh);
+    TILE_PERSISTENT_LOOP(sh, c.worklist[1], c.wcount + 1, c.wcount + 6, (density_body<KERNEL, FT>(c, g, sh, blk, parity, count_out, rho_out)))
 }
 
 // ------------------------------------------------------------------------------------------------ prep (pointwise)
@@ -1047,6 +1108,7 @@ template <int KERNEL, class FT> static int set_fluid_attrs(SphCtx *c) {
     if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 1>, smem_of<FT, 2>());
     if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, true, 1>, smem_of<FT, 2>());
     if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 2>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_density<KERNEL, FT>, smem_of<FT, 2>());
     return r;
 }
 template <int KERNEL> static int set_attrs(SphCtx *c) {
@@ -1188,6 +1250,24 @@ int tile_wc_fluid(SphCtx *c) {
         if (c->p.kernel == 0) launch_fluid<0, F3M>(c, d, shep, list); else launch_fluid<1, F3M>(c, d, shep, list);
     } else {
         if (c->p.kernel == 0) launch_fluid<0, F2M>(c, d, shep, list); else launch_fluid<1, F2M>(c, d, shep, list);
+    }
+    SPH_LAUNCH_CHECK(c);
+    return 0;
+}
+// count + density of the flow particles of unflagged cells (masks must be current)
+template <int KERNEL, class FT> static void launch_density(SphCtx *c, const DevF &d, int *count_out, float *rho_out) {
+    const TileGeom g_ = make_geom<FT>(d.gn);
+    cudaMemsetAsync(d.wcount + 6, 0, 4, c->stream);
+    k_tile_density<KERNEL, FT><<<pgrid(k_tile_density<KERNEL, FT>, FT::BT, smem_of<FT, 2>(), nblocks<FT>(g_)), FT::BT, smem_of<FT, 2>(), c->stream>>>(d, g_, count_out, rho_out);
+}
+int tile_density_sweep(SphCtx *c, int32_t *count_out, float *rho_out) {
+    if (need_masks(c)) return -3;
+    DevF d = make_dev<float>(c);
+    SPH_PROF(c, K_C5);
+    if (c->p.dim == 3) {
+        if (c->p.kernel == 0) launch_density<0, F3M>(c, d, count_out, rho_out); else launch_density<1, F3M>(c, d, count_out, rho_out);
+    } else {
+        if (c->p.kernel == 0) launch_density<0, F2M>(c, d, count_out, rho_out); else launch_density<1, F2M>(c, d, count_out, rho_out);
     }
     SPH_LAUNCH_CHECK(c);
     return 0;

@@ -20,7 +20,9 @@ try:
     for t in c.get("rank_timeline_ms_per_step") or []:
         print({k: v for k, v in t.items() if k != "kernel_ms"})
     print("limiter", c.get("limiter"))
-    print("rank0 kernels", (c.get("rank_timeline_ms_per_step") or [{}])[0].get("kernel_ms"))
+    for r, t in enumerate(c.get("rank_timeline_ms_per_step") or []):
+        if r in (0, 1, len(c["rank_timeline_ms_per_step"]) // 2, len(c["rank_timeline_ms_per_step"]) - 1):
+            print("rank", r, "kernels", t.get("kernel_ms"))
 except Exception as e:
     print("no bench line:", e)
 PY
