@@ -30,6 +30,19 @@ def relmax(a, b):
     return 0.0 if num == 0.0 else (num / den if den > 0 else np.inf)
 
 
+def relelem(a, b, floor_frac=1e-3):
+    """ELEMENT-WISE relative difference max_k |a_k - b_k| / max(|b_k|, floor) with the absolute floor
+    floor = floor_frac * max|b|: entries much smaller than the field's scale are held to the floor, every other entry
+    to its own magnitude (the max-norm of relmax leaves small entries unconstrained)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    scale = np.max(np.abs(b))
+    if scale == 0.0:
+        return 0.0 if np.max(np.abs(a)) == 0.0 else np.inf
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor_frac * scale)))
+
+
 def sym6_to_9(s6):
     """(n,6) xx,yy,zz,xy,yz,zx -> (n,9) row-major full tensor."""
     xx, yy, zz, xy, yz, zx = [s6[:, k] for k in range(6)]
