@@ -670,6 +670,7 @@ def main():
     ap.add_argument("--transport", default="p2p", choices=["p2p", "dist"])
     ap.add_argument("--wall-weight", type=float, default=0.15, help="work of a wall particle relative to a fluid particle (column partition)")
     ap.add_argument("--size", type=float, default=None, help="c5: particles (default 1e7); c3: refinement of the test2 geometry")
+    ap.add_argument("--soil", default="dp", choices=["dp", "mui"], help="c3 workload: Drucker-Prager + CSPM + RK4 (C3) or mu(I) + LF (C2)")
     ap.add_argument("--lists", type=int, default=None, help="1 / 0: neighbour round lists on / off (default: engine default)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -25,14 +25,14 @@ from helpers import Golden, relmax, relelem, make_sim, engine_fields
 
 pytestmark = pytest.mark.gpu
 
-# (max-norm tolerance, element-wise tolerance) per field
-F64_WC = {"x": (1e-9, 1e-8), "v": (1e-8, 1e-6), "density": (1e-10, 1e-10), "pressure": (1e-8, 1e-6), "d_vel": (1e-8, 1e-5),
-          "d_density": (1e-8, 1e-5)}
-MIXED_WC_100 = {"x": (1e-6, 1e-5), "density": (1e-6, 1e-6), "v": (1e-3, 2e-2), "pressure": (2e-2, 5e-1)}
-# DP + CSPM + RK4 with XSPH: bounded by the in-place vs snapshot XSPH of the reference (module docstring)
-F64_DP_30 = {"x": (1e-8, 1e-6), "v": (1e-6, 1e-4), "density": (1e-10, 1e-10), "stress": (1e-6, 1e-4), "d_vel": (1e-6, 1e-4),
-             "d_stress": (1e-4, 1e-2), "strain_equ": (1e-6, 1e-5)}
-MIXED_DP_30 = {"x": (1e-6, 1e-5), "density": (1e-6, 1e-6), "v": (5e-3, 5e-1), "stress": (5e-3, 5e-1)}
+# (max-norm tolerance, element-wise tolerance) per field; about 10x what the B200 run measured (profiles/r2_horizon_parity.log)
+F64_WC = {"x": (1e-12, 1e-10), "v": (1e-11, 1e-8), "density": (1e-13, 1e-13), "pressure": (1e-10, 1e-7), "d_vel": (1e-10, 1e-7),
+          "d_density": (1e-10, 1e-7)}
+MIXED_WC_100 = {"x": (1e-9, 1e-6), "density": (1e-8, 1e-8), "v": (1e-5, 1e-2), "pressure": (1e-5, 1e-2)}
+# DP + CSPM + RK4 with XSPH: the float64 figures are the in-place vs snapshot XSPH of the reference (module docstring)
+F64_DP_30 = {"x": (1e-9, 1e-6), "v": (1e-7, 1e-5), "density": (1e-12, 1e-12), "stress": (1e-7, 1e-6), "d_vel": (1e-7, 1e-5),
+             "d_stress": (1e-5, 1e-3), "strain_equ": (1e-6, 1e-6)}
+MIXED_DP_30 = {"x": (1e-9, 1e-6), "density": (1e-8, 1e-8), "v": (1e-4, 2e-2), "stress": (5e-4, 1e-2)}
 F64_MUI_100 = {"x": (1e-6, 1e-4), "v": (1e-4, 1e-2), "density": (1e-8, 1e-8), "stress_tmp": (1e-3, 1e-1)}
 MIXED_MUI_100 = {"x": (1e-5, 1e-4), "density": (1e-6, 1e-6), "v": (2e-2, 1.0), "stress_tmp": (5e-2, 1.0)}
 
@@ -121,19 +121,17 @@ def test_dump_matches_reference_keys():
 def test_c4_coarse_vs_oracle(prec):
     """BASELINE config C4 (the benchmarked 3D dambreak) coarsened x8, against the float64 oracle at steps 1, 10 and 20
     (the reference's 3D scheme diverges after ~35 steps).  float64: bit-exact integers, floats to
-    1e-7; mixed precision: the stated one-step 1e-5 and a 20-step tolerance."""
+    1e-10; mixed precision: the stated one-step 1e-5, 5e-5 at 10 steps, 2e-4 at 20 steps."""
     from oracle import oracle as orc
     from tisphi_b200 import scenes
     scene = scenes.dambreak3d(scale=0.125, precision=prec)
     sim = make_sim(scene, precision=prec)
     o = orc.Oracle.from_scene(scene, serial=0)
     assert sim.ps.particle_num[None] == o.n
-    tol = {1: {"density": 1e-9, "pressure": 1e-9, "d_vel": 1e-9, "v": 1e-9, "x": 1e-9},
-           10: {"density": 1e-9, "pressure": 1e-7, "d_vel": 1e-7, "v": 1e-7, "x": 1e-9},
-           20: {"density": 1e-9, "pressure": 1e-7, "d_vel": 1e-7, "v": 1e-7, "x": 1e-9}} if prec == "f64" else \
-          {1: {"density": 1e-5, "pressure": 1e-5, "d_vel": 1e-5, "v": 1e-5, "x": 1e-7},
-           10: {"density": 1e-6, "pressure": 1e-3, "d_vel": 1e-3, "v": 1e-3, "x": 1e-6},
-           20: {"density": 1e-5, "pressure": 2e-2, "d_vel": 2e-2, "v": 1e-2, "x": 1e-6}}
+    tol = {s: {"density": 1e-11, "pressure": 1e-10, "d_vel": 1e-10, "v": 1e-10, "x": 1e-12} for s in (1, 10, 20)} if prec == "f64" else \
+          {1: {"density": 1e-8, "pressure": 1e-5, "d_vel": 1e-5, "v": 1e-5, "x": 1e-10},
+           10: {"density": 1e-7, "pressure": 5e-5, "d_vel": 5e-5, "v": 5e-5, "x": 1e-9},
+           20: {"density": 5e-6, "pressure": 2e-4, "d_vel": 2e-4, "v": 2e-4, "x": 1e-8}}
     done = 0
     for s in (1, 10, 20):
         sim.solver.run_steps(s - done)

@@ -191,6 +191,7 @@ template <typename T> Dev<T> make_dev(SphCtx *c, int which) {
     memset(&d, 0, sizeof(d));
     d.n = (int)c->n;
     d.ndev = slab_ndev(c);
+    d.list_cap = c->nb_cap;
     d.dim = p.dim; d.kernel = p.kernel; d.kcorr = p.kcorr; d.solver = p.solver; d.xsph = p.xsph; d.wc_fresh = p.wc_fresh;
     for (int a = 0; a < 3; a++) { d.gn[a] = p.gn[a]; d.vstart[a] = p.vstart[a]; d.g[a] = (T)p.g[a]; }
     if (p.dim == 2) d.gn[2] = 1;
@@ -346,6 +347,9 @@ SphCtx *sph_create(const SphParams *p, int64_t n_max, void *arena, int64_t arena
     c->stream = (cudaStream_t)stream;
     layout(p, n_max, c);
     c->own0 = 0; c->own1 = p->gn[0];
+    // 2D: a particle has ~28 neighbours among 81 candidates; 64 list entries cover compressed states (overflow falls back)
+    c->nb_cap = (p->fast == 3 && p->dim == 2 && n_max < (1ll << 27)) ? 64 : 0;
+    c->cell_tiles = p->fast == 4;
     c->r2thr64 = r2_threshold64(p->support);
     c->r2thr32 = r2_threshold32((float)p->support);
     if (cudaMemsetAsync(arena, 0, (size_t)layout(p, n_max, nullptr), c->stream) != cudaSuccess) { delete c; return nullptr; }

@@ -84,6 +84,8 @@ struct SphCtx {
     int own0, own1;      // owned x-columns [own0, own1) (multi-GPU slabs); the whole grid on one GPU
     int64_t off_slabctl; // device-resident control block of the native slab step (slab.cu)
     sph::SlabState *slab;   // native multi-GPU slab step (sph_slab_init); null on one GPU
+    bool cell_tiles;     // generic sweeps are launched per cell segment with the neighbourhood staged in shared memory
+    int nb_cap;          // generic sweeps: entries of the per-thread neighbour list in shared memory (0: direct form)
     bool slab_sort;      // grid_build is the sort of a slab redistribution: virtual concatenation, column table, cell sub-range
     bool masks_valid;    // the neighbour masks / work lists belong to the current sort (cleared by every re-sort / upload)
 };
@@ -123,6 +125,9 @@ namespace sph {
 constexpr int LIST_ROUNDS = 56;     // rounds (of four neighbour slots) a particle's list can hold
 
 template <typename T> Dev<T> make_dev(SphCtx *c, int which = -1);   // which = -1: current buffers, 1: alternates
+
+// dynamic shared memory of a generic sweep launched with 128 threads (sph_dev.cuh::for_neighbors, listed form)
+#define NB_SMEM(ctx) ((size_t)(ctx)->nb_cap * 128 * sizeof(unsigned))
 
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 

@@ -11,6 +11,11 @@
 
 namespace sph {
 
+// the same sweeps launched per cell segment with the neighbourhood staged in shared memory (defined below)
+enum { ST_TYPE = 1, ST_VT = 2, ST_STRESS = 4, ST_V = 8, ST_PRESS = 16, ST_PNEW = 32 };
+enum { CK_CSPM_F = 0, CK_CSPM_L, CK_WC_WALL, CK_WC_FLUID, CK_SOIL_WALL, CK_MUI1, CK_MUI3, CK_DP_SOIL, CK_XSPH, CK_POST_MUI_B };
+template <typename T, int KIND> static bool launch_cell_sweep(SphCtx *c, const Dev<T> &d, int prof_id);
+
 // --------------------------------------------------------------------------------------------- kernel correction
 // flagged-only mode: the cell-tile kernels handled every particle except those of flagged cells
 template <typename T> __device__ __forceinline__ bool not_owned(const Dev<T> &c, int i) {
@@ -53,9 +58,7 @@ SPH_PARTICLE_KERNEL(k_cspm_f, body_cspm_f)
 template <typename T> __device__ __forceinline__ T det3(const T *m) {
     return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
 }
-template <typename T> __global__ void __launch_bounds__(128) k_cspm_L(Dev<T> c) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N()) return;
+template <typename T> __device__ __forceinline__ void body_cspm_L(const Dev<T> &c, int i) {
     if (not_owned(c, i)) return;
     T L[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     const int ti = c.type[i];
@@ -92,6 +95,10 @@ template <typename T> __global__ void __launch_bounds__(128) k_cspm_L(Dev<T> c) 
 #pragma unroll
     for (int a = 0; a < 9; a++) c.cspm_L[9 * (size_t)i + a] = L[a];
 }
+template <typename T> __global__ void __launch_bounds__(128) k_cspm_L(Dev<T> c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c.N()) body_cspm_L(c, i);
+}
 
 // standalone: every CSPM_f is final on return (the API call).  Otherwise (inside sph_step) the tile path leaves the
 // Shepard sums of unflagged cells to the wall pass and the first fluid pass, which visit the same neighbours anyway.
@@ -103,12 +110,14 @@ template <typename T> int calc_kernel_corr(SphCtx *c, bool standalone) {
         if (r) return r;
         d.flagged_only = 1;
     }
-    SPH_PROF(c, K_CSPM_F);
-    k_cspm_f<T><<<sweep_blocks(d), 128, 0, c->stream>>>(d);
-    SPH_LAUNCH_CHECK(c);
-    if (c->p.kcorr == 1) {
+    if (d.flagged_only || !launch_cell_sweep<T, CK_CSPM_F>(c, d, K_CSPM_F)) {
+        SPH_PROF(c, K_CSPM_F);
+        k_cspm_f<T><<<sweep_blocks(d), 128, NB_SMEM(c), c->stream>>>(d);
+        SPH_LAUNCH_CHECK(c);
+    }
+    if (c->p.kcorr == 1 && !launch_cell_sweep<T, CK_CSPM_L>(c, d, K_CSPM_L)) {
         SPH_PROF(c, K_CSPM_L);
-        k_cspm_L<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(d);
+        k_cspm_L<T><<<blocks_for(c->n, 128), 128, NB_SMEM(c), c->stream>>>(d);
         SPH_LAUNCH_CHECK(c);
     }
     return 0;
@@ -227,9 +236,7 @@ template <typename T> __device__ __forceinline__ T dev_component(const T *t) {  
     return sqrt(s * (T)2 / (T)3);
 }
 // Adami wall extrapolation for soil solvers (muI:95-109, dp:220-231; tasks base:647-669)
-template <typename T> __global__ void __launch_bounds__(128) k_soil_wall(Dev<T> c) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N()) return;
+template <typename T> __device__ __forceinline__ void body_soil_wall(const Dev<T> &c, int i) {
     if (!is_wall(c.type[i])) return;
     if (is_rigid(c.type[i])) zero_rigid_derivatives(c, i);
     if (not_owned(c, i)) return;
@@ -260,6 +267,10 @@ template <typename T> __global__ void __launch_bounds__(128) k_soil_wall(Dev<T> 
 #pragma unroll
     for (int q = 0; q < 6; q++) c.stress_t[6 * (size_t)i + q] = Ss[q] * f;
 }
+template <typename T> __global__ void __launch_bounds__(128) k_soil_wall(Dev<T> c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c.N()) body_soil_wall(c, i);
+}
 
 // accumulators of one soil sweep: velocity gradient, continuity sum, momentum sum
 template <typename T, bool VG, bool MOM>
@@ -268,10 +279,10 @@ __device__ __forceinline__ void soil_sweep(const Dev<T> &c, int i, T vg[9], T *d
     const T rhoi = vi.w;
     T L[9], si[9];
     load_L(c, i, L);
+    T inv_r2i = 0;
     if (MOM) {
         sym_load(c.stress_t, (size_t)i, si);
-        const T ir = (T)1 / (rhoi * rhoi);
-        (void)ir;
+        inv_r2i = (T)1 / (rhoi * rhoi);
     }
     T acc = 0;
 #pragma unroll
@@ -291,16 +302,28 @@ __device__ __forceinline__ void soil_sweep(const Dev<T> &c, int i, T vg[9], T *d
             acc += Vj * (-u[0]) * gc[0] + Vj * (-u[1]) * gc[1] + Vj * (-u[2]) * gc[2];
         }
         if (MOM) {      // muI:38-46 / dp:156-165: V_j rho~_j (sigma~_j / rho~_j^2 + sigma~_i / rho~_i^2) . gradW^c
-            T sj[9];
-            sym_load(c.stress_t, (size_t)j, sj);
             const T rhoj = vj.w, cf = Vj * rhoj;
-            const T r2j = rhoj * rhoj, r2i = rhoi * rhoi;
+            if (sizeof(T) == 4) {
+                // float32 sweeps: the 18 IEEE divisions of the expression above are two reciprocals (the particle's own
+                // outside the loop) and the symmetric tensor is combined in its 6 components -- same terms, regrouped
+                const T *q = c.stress_t + 6 * (size_t)j;
+                const T cj = cf * ((T)1 / (rhoj * rhoj)), ci = cf * inv_r2i;
+                const T mxx = cj * q[0] + ci * si[0], myy = cj * q[1] + ci * si[4], mzz = cj * q[2] + ci * si[8];
+                const T mxy = cj * q[3] + ci * si[1], myz = cj * q[4] + ci * si[5], mzx = cj * q[5] + ci * si[2];
+                mom[0] += mxx * gc[0] + mxy * gc[1] + mzx * gc[2];
+                mom[1] += mxy * gc[0] + myy * gc[1] + myz * gc[2];
+                mom[2] += mzx * gc[0] + myz * gc[1] + mzz * gc[2];
+            } else {
+                T sj[9];
+                sym_load(c.stress_t, (size_t)j, sj);
+                const T r2j = rhoj * rhoj, r2i = rhoi * rhoi;
 #pragma unroll
-            for (int a = 0; a < 3; a++) {
-                T t = 0;
+                for (int a = 0; a < 3; a++) {
+                    T t = 0;
 #pragma unroll
-                for (int b = 0; b < 3; b++) t += (cf * (sj[3 * a + b] / r2j + si[3 * a + b] / r2i)) * gc[b];
-                mom[a] += t;
+                    for (int b = 0; b < 3; b++) t += (cf * (sj[3 * a + b] / r2j + si[3 * a + b] / r2i)) * gc[b];
+                    mom[a] += t;
+                }
             }
         }
     });
@@ -308,9 +331,7 @@ __device__ __forceinline__ void soil_sweep(const Dev<T> &c, int i, T vg[9], T *d
 }
 
 // ----------------------------------------------------------------------------------------------------- mu(I)
-template <typename T> __global__ void __launch_bounds__(128) k_mui_soil1(Dev<T> c) {          // muI:67-92
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N()) return;
+template <typename T> __device__ __forceinline__ void body_mui_soil1(const Dev<T> &c, int i) {          // muI:67-92
     if (!is_soil(c.type[i])) return;
     if (not_owned(c, i)) return;
     T vg[9], dd, mom[3];
@@ -340,9 +361,11 @@ template <typename T> __global__ void __launch_bounds__(128) k_mui_soil1(Dev<T> 
     sr[0] -= tr / (T)3; sr[4] -= tr / (T)3; sr[8] -= tr / (T)3;
     c.d_strain[i] = dev_component(sr);
 }
-template <typename T> __global__ void __launch_bounds__(128) k_mui_soil3(Dev<T> c) {          // muI:115-128
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N()) return;
+template <typename T> __global__ void __launch_bounds__(128) k_mui_soil1(Dev<T> c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c.N()) body_mui_soil1(c, i);
+}
+template <typename T> __device__ __forceinline__ void body_mui_soil3(const Dev<T> &c, int i) {          // muI:115-128
     if (!is_soil(c.type[i])) return;
     if (not_owned(c, i)) return;
     T vg[9], dd, mom[3];
@@ -352,6 +375,10 @@ template <typename T> __global__ void __launch_bounds__(128) k_mui_soil3(Dev<T> 
     Vec4<T> dv;
     dv.x = mom[0] + c.g[0] + dc * vi.x; dv.y = mom[1] + c.g[1] + dc * vi.y; dv.z = mom[2] + c.g[2] + dc * vi.z; dv.w = 0;
     c.d_vel[i] = dv;
+}
+template <typename T> __global__ void __launch_bounds__(128) k_mui_soil3(Dev<T> c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c.N()) body_mui_soil3(c, i);
 }
 
 // -------------------------------------------------------------------------------------------- Drucker-Prager
@@ -446,9 +473,7 @@ __device__ __forceinline__ void bui2008(const Dev<T> &c, const T *st, const T *v
         *dsep = dev_component(ep);
     }
 }
-template <typename T> __global__ void __launch_bounds__(128) k_dp_soil(Dev<T> c) {            // dp:237-270
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N()) return;
+template <typename T> __device__ __forceinline__ void body_dp_soil(const Dev<T> &c, int i) {            // dp:237-270
     if (!is_soil(c.type[i])) return;
     if (not_owned(c, i)) return;
     T vg[9], dd, mom[3];
@@ -468,6 +493,10 @@ template <typename T> __global__ void __launch_bounds__(128) k_dp_soil(Dev<T> c)
     dv.x = mom[0] + c.g[0] + dc * vi.x; dv.y = mom[1] + c.g[1] + dc * vi.y; dv.z = mom[2] + c.g[2] + dc * vi.z; dv.w = 0;
     c.d_vel[i] = dv;
 }
+template <typename T> __global__ void __launch_bounds__(128) k_dp_soil(Dev<T> c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c.N()) body_dp_soil(c, i);
+}
 
 // one top-level loop of <Solver>.one_step (phases documented in include/tisphi_b200.h: sph_one_step_phase)
 template <typename T> int one_step_phase(SphCtx *c, int phase) {
@@ -486,7 +515,7 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
             Dev<T> d = make_dev<T>(c);
             d.flagged_only = 1;
             SPH_PROF(c, K_WC_WALL);
-            k_wc_wall<T><<<sweep_blocks(d), 128, 0, st>>>(d);
+            k_wc_wall<T><<<sweep_blocks(d), 128, NB_SMEM(c), st>>>(d);
             SPH_LAUNCH_CHECK(c);
             flip(c, SPH_F_PRESSURE);
         } else {
@@ -495,7 +524,7 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
             Dev<T> d = make_dev<T>(c);
             d.flagged_only = 1;
             SPH_PROF(c, K_WC_FLUID);
-            k_wc_fluid<T><<<sweep_blocks(d), 128, 0, st>>>(d);
+            k_wc_fluid<T><<<sweep_blocks(d), 128, NB_SMEM(c), st>>>(d);
             SPH_LAUNCH_CHECK(c);
         }
     } else if (solver == SPH_SOLVER_WC) {
@@ -504,26 +533,31 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
             SPH_PROF(c, K_WC_EOS);
             k_wc_eos<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
             SPH_LAUNCH_CHECK(c);
-            SPH_PROF(c, K_WC_WALL);
-            k_wc_wall<T><<<sweep_blocks(d), 128, 0, st>>>(d);
-            SPH_LAUNCH_CHECK(c);
+            if (!launch_cell_sweep<T, CK_WC_WALL>(c, d, K_WC_WALL)) {
+                SPH_PROF(c, K_WC_WALL);
+                k_wc_wall<T><<<sweep_blocks(d), 128, NB_SMEM(c), st>>>(d);
+                SPH_LAUNCH_CHECK(c);
+            }
             flip(c, SPH_F_PRESSURE);               // pnew becomes pt.pressure
-        } else {
+        } else if (!launch_cell_sweep<T, CK_WC_FLUID>(c, d, K_WC_FLUID)) {
             SPH_PROF(c, K_WC_FLUID);
-            k_wc_fluid<T><<<sweep_blocks(d), 128, 0, st>>>(d);
+            k_wc_fluid<T><<<sweep_blocks(d), 128, NB_SMEM(c), st>>>(d);
             SPH_LAUNCH_CHECK(c);
         }
     } else if (solver == SPH_SOLVER_MUI) {
         Dev<T> d = make_dev<T>(c);
         if (phase == 0) {
+            if (launch_cell_sweep<T, CK_MUI1>(c, d, K_MUI_SOIL1)) return 0;
             SPH_PROF(c, K_MUI_SOIL1);
-            k_mui_soil1<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+            k_mui_soil1<T><<<blocks_for(n, 128), 128, NB_SMEM(c), st>>>(d);
         } else if (phase == 1) {
+            if (launch_cell_sweep<T, CK_SOIL_WALL>(c, d, K_SOIL_WALL)) return 0;
             SPH_PROF(c, K_SOIL_WALL);
-            k_soil_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+            k_soil_wall<T><<<blocks_for(n, 128), 128, NB_SMEM(c), st>>>(d);
         } else {
+            if (launch_cell_sweep<T, CK_MUI3>(c, d, K_MUI_SOIL3)) return 0;
             SPH_PROF(c, K_MUI_SOIL3);
-            k_mui_soil3<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+            k_mui_soil3<T><<<blocks_for(n, 128), 128, NB_SMEM(c), st>>>(d);
         }
         SPH_LAUNCH_CHECK(c);
     } else if (solver == SPH_SOLVER_DP) {
@@ -532,11 +566,13 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
             SPH_PROF(c, K_DP_ADAPT);
             k_dp_adapt<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
         } else if (phase == 1) {
+            if (launch_cell_sweep<T, CK_SOIL_WALL>(c, d, K_SOIL_WALL)) return 0;
             SPH_PROF(c, K_SOIL_WALL);
-            k_soil_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+            k_soil_wall<T><<<blocks_for(n, 128), 128, NB_SMEM(c), st>>>(d);
         } else {
+            if (launch_cell_sweep<T, CK_DP_SOIL>(c, d, K_DP_SOIL)) return 0;
             SPH_PROF(c, K_DP_SOIL);
-            k_dp_soil<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+            k_dp_soil<T><<<blocks_for(n, 128), 128, NB_SMEM(c), st>>>(d);
         }
         SPH_LAUNCH_CHECK(c);
     } else {
@@ -566,9 +602,8 @@ template <typename T> __global__ void __launch_bounds__(256) k_advect_pos(Dev<T>
     x[0] += c.dt * (double)v.x; x[1] += c.dt * (double)v.y; x[2] += c.dt * (double)v.z;
 }
 // XSPH on a snapshot: new positions go to the alternate x buffer
-template <typename T> __global__ void __launch_bounds__(128) k_advect_pos_xsph(Dev<T> c, double *__restrict__ xnew) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N()) return;
+template <typename T> __device__ __forceinline__ void body_advect_pos_xsph(const Dev<T> &c, int i) {
+    double *xnew = c.xnew;
     const double *x = c.x + 3 * (size_t)i;
     double o0 = x[0], o1 = x[1], o2 = x[2];
     const int ti = c.type[i];
@@ -586,6 +621,10 @@ template <typename T> __global__ void __launch_bounds__(128) k_advect_pos_xsph(D
         o0 += c.dt * (double)(vi.x + (T)0.5 * s0); o1 += c.dt * (double)(vi.y + (T)0.5 * s1); o2 += c.dt * (double)(vi.z + (T)0.5 * s2);
     }
     xnew[3 * (size_t)i] = o0; xnew[3 * (size_t)i + 1] = o1; xnew[3 * (size_t)i + 2] = o2;
+}
+template <typename T> __global__ void __launch_bounds__(128) k_advect_pos_xsph(Dev<T> c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c.N()) body_advect_pos_xsph(c, i);
 }
 // after positions moved on a stale grid: refresh the sweep coordinates relative to the cell each particle is STORED in
 template <typename T> __global__ void __launch_bounds__(256) k_refresh_xs(Dev<T> c) {
@@ -612,10 +651,12 @@ template <typename T> int advect_pos(SphCtx *c) {
         k_advect_pos<T><<<blocks_for(n, 256), 256, 0, c->stream>>>(d);
         SPH_LAUNCH_CHECK(c);
     } else {
-        double *xnew = (double *)(c->arena + c->f[SPH_F_X].off[1 - c->f[SPH_F_X].cur]);
-        SPH_PROF(c, K_ADVECT_POS);
-        k_advect_pos_xsph<T><<<blocks_for(n, 128), 128, 0, c->stream>>>(d, xnew);
-        SPH_LAUNCH_CHECK(c);
+        d.xnew = (double *)(c->arena + c->f[SPH_F_X].off[1 - c->f[SPH_F_X].cur]);
+        if (!launch_cell_sweep<T, CK_XSPH>(c, d, K_ADVECT_POS)) {
+            SPH_PROF(c, K_ADVECT_POS);
+            k_advect_pos_xsph<T><<<blocks_for(n, 128), 128, NB_SMEM(c), c->stream>>>(d);
+            SPH_LAUNCH_CHECK(c);
+        }
         flip(c, SPH_F_X);
     }
     return 0;
@@ -656,9 +697,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_post_mui_a(Dev<T>
     c.strain[i] += (T)c.dt * c.d_strain[i];
 }
 // muI:151-156 Shepard regularisation on a snapshot (stress_tmp), post-advect positions on the pre-move grid (H15)
-template <typename T> __global__ void __launch_bounds__(128) k_post_mui_b(Dev<T> c) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N()) return;
+template <typename T> __device__ __forceinline__ void body_post_mui_b(const Dev<T> &c, int i) {
     const int ti = c.type[i];
     if (!is_soil(ti)) return;
     if (not_owned(c, i)) return;
@@ -674,6 +713,10 @@ template <typename T> __global__ void __launch_bounds__(128) k_post_mui_b(Dev<T>
     const T f = c.cspm_f[i];
 #pragma unroll
     for (int q = 0; q < 6; q++) c.stress[6 * (size_t)i + q] = acc[q] * f;
+}
+template <typename T> __global__ void __launch_bounds__(128) k_post_mui_b(Dev<T> c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c.N()) body_post_mui_b(c, i);
 }
 template <typename T> int post_step(SphCtx *c) {
     if (c->n == 0) return 0;
@@ -695,9 +738,11 @@ template <typename T> int post_step(SphCtx *c) {
         SPH_PROF(c, K_POST);
         k_refresh_xs<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
-        SPH_PROF(c, K_POST_SWEEP);
-        k_post_mui_b<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
-        SPH_LAUNCH_CHECK(c);
+        if (!launch_cell_sweep<T, CK_POST_MUI_B>(c, d, K_POST_SWEEP)) {
+            SPH_PROF(c, K_POST_SWEEP);
+            k_post_mui_b<T><<<blocks_for(n, 128), 128, NB_SMEM(c), st>>>(d);
+            SPH_LAUNCH_CHECK(c);
+        }
     }
     return 0;
 }
@@ -730,6 +775,166 @@ template <typename T> int finish_step(SphCtx *c) {
     k_wc_finish<T><<<blocks_for(c->n, 256), 256, 0, c->stream>>>(make_dev<T>(c));
     SPH_LAUNCH_CHECK(c);
     return 0;
+}
+
+// ------------------------------------------------------------------------------ the same sweeps, one block per cell segment
+// Every sweep above walks the 3^dim cells around each particle with dependent global loads (an L1 hit per candidate and
+// one or more gathers per neighbour): they run at ~0.15 instructions per clock, bound by load latency.  Here a block owns
+// CSeg::ZS consecutive cells of one grid column and first copies the particles its stencils can reach -- 3 (2D) or 9 (3D)
+// CONTIGUOUS spans of the sorted arrays, cell ids being fastest-axis-major (ps:221-222) -- into shared memory, positions
+// always and the members the sweep's task reads (STAGE mask).  The per-particle bodies are the SAME functions; their
+// neighbour walk (sph_dev.cuh::for_neighbors_tile) takes candidates and payloads from the tile in the same order, so the
+// results are bit-identical to the per-particle kernels (which remain the fallback for tiles that do not fit).
+template <bool D3> struct CSeg {
+    static constexpr int ZS = D3 ? 4 : 12, NRY = D3 ? 3 : 1, NR = 3 * NRY, CBW = ZS + 3, CAP = D3 ? 1536 : 512, BT = 128;
+};
+template <int KIND> struct CKind;
+// STAGE: members the task reads of its neighbours.  GHOSTS: the body also has work for particles of a slab's ghost columns
+// (static rigid particles get their derivatives zeroed there; XSPH moves every particle), so those columns are not skipped.
+template <> struct CKind<CK_CSPM_F> { static constexpr int STAGE = ST_TYPE; static constexpr bool GHOSTS = false; };
+template <> struct CKind<CK_CSPM_L> { static constexpr int STAGE = ST_TYPE; static constexpr bool GHOSTS = false; };
+template <> struct CKind<CK_WC_WALL> { static constexpr int STAGE = ST_TYPE | ST_VT | ST_PRESS | ST_PNEW; static constexpr bool GHOSTS = true; };
+template <> struct CKind<CK_WC_FLUID> { static constexpr int STAGE = ST_TYPE | ST_VT | ST_PRESS; static constexpr bool GHOSTS = false; };
+template <> struct CKind<CK_SOIL_WALL> { static constexpr int STAGE = ST_TYPE | ST_VT | ST_STRESS; static constexpr bool GHOSTS = true; };
+template <> struct CKind<CK_MUI1> { static constexpr int STAGE = ST_VT; static constexpr bool GHOSTS = false; };
+template <> struct CKind<CK_MUI3> { static constexpr int STAGE = ST_VT | ST_STRESS; static constexpr bool GHOSTS = false; };
+template <> struct CKind<CK_DP_SOIL> { static constexpr int STAGE = ST_VT | ST_STRESS; static constexpr bool GHOSTS = false; };
+template <> struct CKind<CK_XSPH> { static constexpr int STAGE = ST_TYPE | ST_V; static constexpr bool GHOSTS = true; };
+template <> struct CKind<CK_POST_MUI_B> { static constexpr int STAGE = ST_TYPE | ST_STRESS; static constexpr bool GHOSTS = false; };
+template <typename T, int KIND> __device__ __forceinline__ void cell_body(const Dev<T> &c, int i) {
+    if (KIND == CK_CSPM_F) body_cspm_f(c, i);
+    else if (KIND == CK_CSPM_L) { if (!not_owned(c, i)) body_cspm_L(c, i); }
+    else if (KIND == CK_WC_WALL) body_wc_wall(c, i);
+    else if (KIND == CK_WC_FLUID) body_wc_fluid(c, i);
+    else if (KIND == CK_SOIL_WALL) body_soil_wall(c, i);
+    else if (KIND == CK_MUI1) body_mui_soil1(c, i);
+    else if (KIND == CK_MUI3) body_mui_soil3(c, i);
+    else if (KIND == CK_DP_SOIL) body_dp_soil(c, i);
+    else if (KIND == CK_XSPH) body_advect_pos_xsph(c, i);
+    else body_post_mui_b(c, i);
+}
+template <typename T, bool D3> __host__ __device__ constexpr size_t cell_smem(int stage) {
+    size_t per = sizeof(Vec4<T>);                                        // positions, always
+    if (stage & ST_VT) per += sizeof(Vec4<T>);
+    if (stage & ST_V) per += sizeof(Vec4<T>);
+    if (stage & ST_STRESS) per += 6 * sizeof(T);
+    if (stage & ST_PRESS) per += sizeof(T);
+    if (stage & ST_PNEW) per += sizeof(T);
+    if (stage & ST_TYPE) per += sizeof(int);
+    return sizeof(CellTile) + 16 + per * CSeg<D3>::CAP;
+}
+template <typename T, bool D3, int KIND> __global__ void __launch_bounds__(128) k_cell_sweep(Dev<T> cin, int nseg) {
+    typedef CSeg<D3> S;
+    constexpr int STAGE = CKind<KIND>::STAGE;
+    extern __shared__ __align__(16) unsigned char cell_smem_raw[];
+    CellTile &t = *reinterpret_cast<CellTile *>(cell_smem_raw);
+    Dev<T> c = cin;                                       // mutable view: the tiled neighbour walk rebases payload pointers
+    c.list_cap = 0;                                       // (the listed form's shared-memory list is not part of this launch)
+    const int tid = threadIdx.x;
+    const int nF = D3 ? c.gn[2] : c.gn[1], n1 = D3 ? c.gn[1] : 1, n0 = c.gn[0];
+    const int seg = blockIdx.x % nseg, col = blockIdx.x / nseg;
+    const int cy = col % n1, cx = col / n1;
+    if (!CKind<KIND>::GHOSTS && (cx < c.own0 || cx >= c.own1)) return;      // ghost columns of a slab: the neighbour rank's work
+    const int f0 = seg * S::ZS, f1 = min(f0 + S::ZS, nF);
+    const int base = (cx * n1 + cy) * nF;
+    const int own_lo = (base + f0) > 0 ? c.cell_end[base + f0 - 1] : 0, own_hi = c.cell_end[base + f1 - 1];
+    if (own_lo == own_hi) return;                         // empty segment
+    if (tid < 32) {                                       // spans and cell boundaries of the runs (one warp)
+        const int f_lo = max(f0 - 1, 0), f_hi = min(f0 + S::ZS, nF - 1);
+        int len = 0, st = 0, gb = 0;
+        bool valid = false;
+        if (tid < S::NR) {
+            const int m0 = cx + tid / S::NRY - 1, m1 = D3 ? cy + tid % S::NRY - 1 : 0;
+            valid = m0 >= 0 && m0 < n0 && m1 >= 0 && m1 < n1;
+            if (valid) {
+                gb = (m0 * n1 + m1) * nF;
+                st = (gb + f_lo) > 0 ? c.cell_end[gb + f_lo - 1] : 0;
+                len = c.cell_end[gb + f_hi] - st;
+            }
+        }
+        int inc = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= o) inc += u;
+        }
+        const int roff = inc - len;
+        if (tid < S::NR) {
+            t.gdelta[tid] = st - roff;
+            t.roff[tid] = roff;
+            for (int k = 0; k < S::CBW; k++) {
+                const int f = f0 - 1 + k;
+                int v;
+                if (!valid || f < f_lo) v = roff;
+                else if (f > f_hi) v = roff + len;
+                else v = roff + ((gb + f) > 0 ? c.cell_end[gb + f - 1] : 0) - st;
+                t.cb[tid * S::CBW + k] = v;
+            }
+        }
+        if (tid == S::NR - 1) { t.roff[S::NR] = inc; t.total = inc; t.ok = inc <= S::CAP; t.f0 = f0; t.cbw = S::CBW; t.d3 = D3 ? 1 : 0; }
+    }
+    __syncthreads();
+    if (!t.ok) {                                          // the neighbourhood does not fit: per-particle walk from global memory
+        for (int p = own_lo + tid; p < own_hi; p += S::BT) cell_body<T, KIND>(c, p);
+        return;
+    }
+    // carve the staged arrays out of the dynamic shared memory behind the header
+    unsigned char *mem = cell_smem_raw + ((sizeof(CellTile) + 15) / 16) * 16;
+    Vec4<T> *s_xs = (Vec4<T> *)mem; mem += sizeof(Vec4<T>) * S::CAP;
+    Vec4<T> *s_vt = nullptr, *s_v4 = nullptr;
+    T *s_st = nullptr, *s_press = nullptr, *s_pnew = nullptr;
+    int *s_ty = nullptr;
+    if (STAGE & ST_VT) { s_vt = (Vec4<T> *)mem; mem += sizeof(Vec4<T>) * S::CAP; }
+    if (STAGE & ST_V) { s_v4 = (Vec4<T> *)mem; mem += sizeof(Vec4<T>) * S::CAP; }
+    if (STAGE & ST_STRESS) { s_st = (T *)mem; mem += 6 * sizeof(T) * S::CAP; }
+    if (STAGE & ST_PRESS) { s_press = (T *)mem; mem += sizeof(T) * S::CAP; }
+    if (STAGE & ST_PNEW) { s_pnew = (T *)mem; mem += sizeof(T) * S::CAP; }
+    if (STAGE & ST_TYPE) { s_ty = (int *)mem; mem += sizeof(int) * S::CAP; }
+    const int total = t.total;
+    for (int q = tid; q < total; q += S::BT) {
+        int r = 0;
+#pragma unroll
+        for (int k = 1; k < S::NR; k++) r += (q >= t.roff[k]) ? 1 : 0;
+        const size_t j = (size_t)(q + t.gdelta[r]);
+        s_xs[q] = c.xs4[j];
+        if (STAGE & ST_VT) s_vt[q] = c.vt4[j];
+        if (STAGE & ST_V) s_v4[q] = c.v4[j];
+        if (STAGE & ST_STRESS) {
+#pragma unroll
+            for (int a = 0; a < 6; a++) s_st[6 * q + a] = c.stress_t[6 * j + a];
+        }
+        if (STAGE & ST_PRESS) s_press[q] = c.press[j];
+        if (STAGE & ST_PNEW) s_pnew[q] = c.pnew[j];
+        if (STAGE & ST_TYPE) s_ty[q] = c.type[j];
+    }
+    if (tid == 0) { t.xs = s_xs; t.vt = s_vt; t.v4 = s_v4; t.st = s_st; t.press = s_press; t.pnew = s_pnew; t.ty = s_ty; }
+    __syncthreads();
+    c.tile = &t;
+    for (int p = own_lo + tid; p < own_hi; p += S::BT) cell_body<T, KIND>(c, p);
+}
+// launches one sweep per cell segment when the engine was created with fast != 0 (any precision, any solver);
+// returns false when the caller has to launch the per-particle kernel instead
+template <typename T, int KIND> static bool launch_cell_sweep(SphCtx *c, const Dev<T> &d, int prof_id) {
+    if (!c->cell_tiles) return false;
+    const bool d3 = c->p.dim == 3;
+    const int nF = d3 ? c->p.gn[2] : c->p.gn[1], ncol = d3 ? c->p.gn[0] * c->p.gn[1] : c->p.gn[0];
+    const int zs = d3 ? CSeg<true>::ZS : CSeg<false>::ZS, nseg = (nF + zs - 1) / zs;
+    const long long blocks = (long long)ncol * nseg;
+    if (blocks > 0x7fffffffll) return false;
+    const size_t smem = d3 ? cell_smem<T, true>(CKind<KIND>::STAGE) : cell_smem<T, false>(CKind<KIND>::STAGE);
+    static bool attr_done[2][2] = {};
+    if (!attr_done[sizeof(T) == 8][d3]) {                  // (per instantiation: KIND and T are template parameters)
+        cudaError_t e = d3 ? cudaFuncSetAttribute(k_cell_sweep<T, true, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(k_cell_sweep<T, false, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { cudaGetLastError(); return false; }
+        attr_done[sizeof(T) == 8][d3] = true;
+    }
+    SPH_PROF(c, prof_id);
+    if (d3) k_cell_sweep<T, true, KIND><<<(int)blocks, 128, smem, c->stream>>>(d, nseg);
+    else k_cell_sweep<T, false, KIND><<<(int)blocks, 128, smem, c->stream>>>(d, nseg);
+    c->launches++;
+    if (c->prof_on) sph_prof_end(c);
+    return cudaGetLastError() == cudaSuccess;
 }
 
 // -------------------------------------------------------------------------------------------- stand-alone sweeps
@@ -772,21 +977,21 @@ template <typename T> int density_sweep(SphCtx *c, int32_t *count_out, void *rho
     Dev<T> d = make_dev<T>(c);
     SPH_PROF(c, K_DENSITY_SUM);
     const int blocks = rest_only ? 148 * 16 : blocks_for(c->n, 128);
-    k_density_count<T><<<blocks, 128, 0, c->stream>>>(d, count_out, (T *)rho_out, rest_only);
+    k_density_count<T><<<blocks, 128, NB_SMEM(c), c->stream>>>(d, count_out, (T *)rho_out, rest_only);
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
 template <typename T> int neighbor_count(SphCtx *c, int32_t *out) {
     if (c->n == 0) return 0;
     SPH_PROF(c, K_NEIGHBOR_COUNT);
-    k_neighbor_count<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(make_dev<T>(c), out);
+    k_neighbor_count<T><<<blocks_for(c->n, 128), 128, NB_SMEM(c), c->stream>>>(make_dev<T>(c), out);
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
 template <typename T> int density_sum(SphCtx *c, void *out) {
     if (c->n == 0) return 0;
     SPH_PROF(c, K_DENSITY_SUM);
-    k_density_sum<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(make_dev<T>(c), (T *)out);
+    k_density_sum<T><<<blocks_for(c->n, 128), 128, NB_SMEM(c), c->stream>>>(make_dev<T>(c), (T *)out);
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
