@@ -1,0 +1,5 @@
+"""Re-export of tisphi_b200.eng.solver_sph_dp under the reference's module path (see eng/__init__.py)."""
+from tisphi_b200.eng.solver_sph_dp import *  # noqa: F401,F403
+from tisphi_b200.eng import solver_sph_dp as _impl
+
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith("__")})

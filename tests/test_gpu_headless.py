@@ -34,7 +34,8 @@ def test_headless_run_exports_and_stops(tmp_path):
     assert np.array_equal(vtu["points"], f["x"]) and np.array_equal(vtu["density"], f["density"])
 
 
-@pytest.mark.parametrize("name,prec", [("wc2d_small_lf", "f64"), ("wc2d_small_lf", "f32"), ("dp2d_small_lf", "f64")])
+@pytest.mark.parametrize("name,prec", [("wc2d_small_lf", "f64"), ("wc2d_small_lf", "f32"), ("dp2d_small_lf", "f64"),
+                                       ("mui2d_small_lf", "f64"), ("mui2d_small_lf", "f32")])    # mu(I): wall v_tmp is carried state (H27)
 def test_checkpoint_resume_is_bit_exact(tmp_path, name, prec):
     from tisphi_b200.eng import ui_sim as U
     g = Golden(name)

@@ -101,17 +101,20 @@ def test_f64_matches_oracle_jacobi_long(name):
                 assert err < tol, f"{name}: step {s} field {f}: rel err {err:.3e}"
 
 
-@pytest.mark.parametrize("name", ["wc2d_small_lf", "wc3d_tiny_lf"])
-def test_native_step_loop_equals_python_orchestration(name):
-    """sph_step (whole step enqueued natively) must be bit-identical to SPHBase.step() driven from Python."""
+@pytest.mark.parametrize("name", ["wc2d_small_lf", "wc3d_tiny_lf", "wc2d_small_rk4_cspm", "dp2d_small_rk4_cspm", "mui2d_small_lf"])
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_native_step_loop_equals_python_orchestration(name, prec):
+    """sph_step (whole step enqueued natively: fused pointwise stages -- init_real2tmp in the reorder, the RK4 stage kernels
+    in one pass -- and the per-step neighbour lists) must be bit-identical to SPHBase.step() driven from Python."""
     g = Golden(name)
-    a = make_sim(g.scene, precision="f64")
-    b = make_sim(g.scene, precision="f64")
+    a = make_sim(g.scene, precision=prec)
+    b = make_sim(g.scene, precision=prec)
     for _ in range(3):
         a.solver.step()
     b.solver.run_steps(3)
     fa, fb = engine_fields(a), engine_fields(b)
-    for k in ("id0", "x", "v", "density", "pressure", "d_vel"):
+    keys = ["id0", "x", "v", "density", "pressure", "d_vel"] + (["stress", "d_stress", "strain_equ"] if "stress" in fa else [])
+    for k in keys:
         assert np.array_equal(fa[k], fb[k]), k
 
 

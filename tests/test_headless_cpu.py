@@ -56,6 +56,27 @@ def test_stop_rules_pause_the_run():
     assert not any(p for s, e, p, d in run_rules(U.RunControl(cfg_with(stepsPerRenderUpdate=10, stopEveryStep=5), dt=1e-4), 20))
 
 
+def test_resumed_run_does_not_fire_spent_rules_again():
+    """A run that stopped at stopAtStep / stopEveryStep and is resumed from a checkpoint of that step continues; an
+    exportEveryTime schedule picks up at the next multiple instead of exporting every frame until it has caught up."""
+    def resumed(step, **over):
+        ctl = U.RunControl(cfg_with(stepsPerRenderUpdate=10, **over), dt=1e-4)
+        ctl.fast_forward(step)
+        out = []
+        for k in range(1, 13):
+            s = step + 10 * k
+            export, paused, done = ctl.after_frame(s)
+            out.append((s, export, paused, done))
+            if paused or done:
+                break
+        return out
+    assert resumed(30, stopAtStep=30, exitAtStep=100)[-1][0] == 100             # not stopped again at 40
+    assert resumed(40, stopEveryStep=40)[-1][::2] == (80, True)                  # the NEXT multiple
+    assert resumed(30, stopAtTime=0.003, exitAtStep=60)[-1][0] == 60
+    log = resumed(50, exportEveryTime=0.002, exportCSV=True, exitAtStep=170)
+    assert [s for s, e, p, d in log if e is not None] == [60, 80, 100, 120, 140, 160]
+
+
 def test_no_exports_without_a_format_or_a_schedule():
     assert not U.RunControl(cfg_with(exportEveryRender=2), dt=1e-4).exports
     assert not U.RunControl(cfg_with(exportCSV=True), dt=1e-4).exports

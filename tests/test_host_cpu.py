@@ -121,3 +121,17 @@ def test_bench_replays_long_runs_in_stable_legs():
         runs = [k for what, k in log if what == "run"]
         assert sum(runs) == total and max(runs) <= bench.STABLE_STEPS
         assert [w for w, _ in log] == ["restore", "run"] * len(runs)          # every leg starts from the restored state
+
+
+def test_reference_module_paths_resolve_to_the_engine():
+    """the reference imports ``eng.simulation`` / ``eng.ui_sim`` (run_simulation.py:3-4); the top-level ``eng``
+    package re-exports this repository's classes under those paths."""
+    import importlib
+    import tisphi_b200.eng as impl
+    for mod, names in {"simulation": ["Simulation", "SimConfiger"], "ui_sim": ["ui_sim"], "particle_system": ["ParticleSystem"],
+                       "solver_sph_base": ["SPHBase"], "solver_sph_wc": ["WCSPHSolver"], "solver_sph_muI": ["MUISPHSolver"],
+                       "solver_sph_dp": ["DPSPHSolver"], "configer_builder": ["SimConfiger"], "particle_func": ["add_cube"]}.items():
+        shim = importlib.import_module("eng." + mod)
+        real = importlib.import_module("tisphi_b200.eng." + mod)
+        for n in names:
+            assert getattr(shim, n) is getattr(real, n), (mod, n)

@@ -12,8 +12,8 @@ CASES = ["wc2d_small_lf", "wc2d_small_se_cubic", "wc2d_small_rk4_cspm", "mui2d_s
          "dp2d_indenter_lf", "wc2d_indenter_lf",
          # shipped test5 shrunken: four soil blocks + a static rigid plate pushed sideways
          "dp2d_plate_lf",
-         # round 2: the BASELINE configs over their full horizons (C1: 100 steps, C3: 30 steps; ~1 h of emulator each)
-         "c1_test1_wc_lf_h100", "c3_test2_dp_rk4_cspm_h30"]
+         # round 2: the BASELINE configs over their full horizons (C1, C2: 100 steps, C3: 30 steps; ~1 h of emulator each)
+         "c1_test1_wc_lf_h100", "c2_test2_mui_lf_h100", "c3_test2_dp_rk4_cspm_h30"]
 
 # float64 restatement of the same serial algorithm: only summation-order / libm noise is allowed
 TOL = 1e-9

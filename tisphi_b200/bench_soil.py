@@ -21,8 +21,6 @@ def soil_scene(refine, soil="dp", precision="f32"):
         sc = json.load(f)
     sc["Configuration"]["particleRadius"] = sc["Configuration"]["particleRadius"] / refine
     sc["Configuration"]["precision"] = precision
-    if os.environ.get("SPH_SWEEP_MODE"):
-        sc["Configuration"]["sweepMode"] = int(os.environ["SPH_SWEEP_MODE"])
     return sc
 
 

@@ -85,6 +85,12 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
     int64_t o_tmp = off; off += ib;
     int64_t o_bad = off; off += 256;
     int64_t o_ctl = off; off += 256;                                   // SlabCtl (slab.cu)
+    // Per-step neighbour lists of the generic sweeps (every solver / precision that does not run the cell-tile WCSPH
+    // path).  2D: ~28 neighbours among 81 candidates, 64 entries cover compressed states; 3D would need ~160 entries
+    // (640 B per particle), so there the sweeps keep walking the cells.  Particles that do not fit walk, too.
+    const int nl_cap = (p->fast && !fast && p->dim == 2 && n_max < (1ll << 27)) ? 64 : 0;
+    int64_t o_nl = 0, o_nc = 0;
+    if (nl_cap) { o_nl = off; off += align_up(n_max * 4 * (int64_t)nl_cap); o_nc = off; off += align_up(n_max * 4); }
     const int64_t nt = ((C > n_max ? C : n_max) + 2047) / 2048 + 2;    // scan tiles: cells (grid build) or particles (selection)
     int64_t o_tiles = off; off += align_up(nt * 4);
     const int mask_words = p->dim == 3 ? 27 : 9;
@@ -118,6 +124,7 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
         c->off_nlist = o_nlist; c->off_lrounds = o_lrounds; c->use_list = lists; c->list_valid = false;
         c->off_gid_unsorted = o_gid; c->off_slot = o_slot; c->off_perm = o_perm; c->off_tmpidx = o_tmp;
         c->off_bad = o_bad; c->off_scan_tiles = o_tiles; c->off_slabctl = o_ctl;
+        c->off_gnl = o_nl; c->off_gnl_count = o_nc; c->gnl_cap = nl_cap; c->gnl_valid = false;
         c->real_bytes = rb; c->soil = soil; c->rk = rk; c->has_L = hasL; c->C = (int)C;
     }
     return off;
@@ -162,7 +169,7 @@ struct ProfState {
 const char *KNAMES[K_NUM] = {"cell_id", "scan", "scatter_index", "rank", "reorder", "cspm_f", "cspm_L", "wc_eos", "wc_wall",
                              "wc_fluid", "mui_soil1", "soil_wall", "mui_soil3", "dp_adapt", "dp_soil", "advect_pos", "post",
                              "post_sweep", "neighbor_count", "density_sum", "other", "init_real2tmp", "advect", "tile_mask",
-                             "tile_fluid", "tile_wall", "halo", "halo_wait", "c5_sweep"};
+                             "tile_fluid", "tile_wall", "halo", "halo_wait", "c5_sweep", "nlist_build"};
 }
 void sph_prof_begin(SphCtx *c, int id) {
     ProfState *ps = (ProfState *)c->prof_state;
@@ -191,7 +198,10 @@ template <typename T> Dev<T> make_dev(SphCtx *c, int which) {
     memset(&d, 0, sizeof(d));
     d.n = (int)c->n;
     d.ndev = slab_ndev(c);
-    d.list_cap = c->nb_cap;
+    if (c->gnl_valid) {
+        d.gnl = (const unsigned *)(c->arena + c->off_gnl); d.gnl_count = (const int *)(c->arena + c->off_gnl_count);
+        d.gnl_stride = (int)c->n_max; d.gnl_cap = c->gnl_cap;
+    }
     d.dim = p.dim; d.kernel = p.kernel; d.kcorr = p.kcorr; d.solver = p.solver; d.xsph = p.xsph; d.wc_fresh = p.wc_fresh;
     for (int a = 0; a < 3; a++) { d.gn[a] = p.gn[a]; d.vstart[a] = p.vstart[a]; d.g[a] = (T)p.g[a]; }
     if (p.dim == 2) d.gn[2] = 1;
@@ -298,13 +308,10 @@ template <typename T> int step_once(SphCtx *c) {
         break;
     case 4: {
         static const int m[4] = {1, 2, 2, 1};
-        if ((r = advect<T>(c, 3, 0))) return r;
-        for (int s = 0; s < 4; s++) {
+        for (int s = 0; s < 4; s++) {          // init_RK / update_RK / advect_RK_4 / advect_RK fused per stage (integrate.cu)
             if ((r = one_step<T>(c, s == 3))) return r;
-            if ((r = advect<T>(c, 4, m[s]))) return r;
-            if (s < 3 && (r = advect<T>(c, 2, 0))) return r;
+            if ((r = rk_stage<T>(c, m[s], s == 0, s == 3))) return r;
         }
-        if ((r = advect<T>(c, 5, 0))) return r;
     } break;
     default:
         snprintf(c->err, sizeof(c->err), "timeIntegration %d is not runnable (3 is broken in the reference, base:126-130)", c->p.ti);
@@ -347,9 +354,6 @@ SphCtx *sph_create(const SphParams *p, int64_t n_max, void *arena, int64_t arena
     c->stream = (cudaStream_t)stream;
     layout(p, n_max, c);
     c->own0 = 0; c->own1 = p->gn[0];
-    // 2D: a particle has ~28 neighbours among 81 candidates; 64 list entries cover compressed states (overflow falls back)
-    c->nb_cap = (p->fast == 3 && p->dim == 2 && n_max < (1ll << 27)) ? 64 : 0;
-    c->cell_tiles = p->fast == 4;
     c->r2thr64 = r2_threshold64(p->support);
     c->r2thr32 = r2_threshold32((float)p->support);
     if (cudaMemsetAsync(arena, 0, (size_t)layout(p, n_max, nullptr), c->stream) != cudaSuccess) { delete c; return nullptr; }
@@ -376,7 +380,7 @@ int sph_set_params(SphCtx *c, const SphParams *p) {
     c->p = *p;
     c->r2thr64 = r2_threshold64(p->support);
     c->r2thr32 = r2_threshold32((float)p->support);
-    c->masks_valid = false;
+    c->masks_valid = false; c->gnl_valid = false;
     return 0;
 }
 
@@ -396,7 +400,7 @@ int sph_field_info(SphCtx *c, int field, int64_t *offset_bytes, int32_t *ncomp, 
 int sph_add_particles(SphCtx *c, int64_t n, const double *x, const double *v, const double *density, const int32_t *mat_type) {
     if (n <= 0) return 0;
     if (slab_armed(c)) { snprintf(c->err, sizeof(c->err), "sph_add_particles on a stepping slab: sph_clear_particles first"); return -2; }
-    c->masks_valid = false;
+    c->masks_valid = false; c->gnl_valid = false;
     if (c->n + n > c->n_max) { snprintf(c->err, sizeof(c->err), "particle capacity %lld exceeded", (long long)c->n_max); return -2; }
     const int64_t first = c->n;
     char *X = c->arena + c->f[SPH_F_X].off[c->f[SPH_F_X].cur];
@@ -427,7 +431,7 @@ int sph_clear_particles(SphCtx *c) {
     }
     SPH_CHECK(c, cudaMemsetAsync(c->arena + c->off_bad, 0, 512, c->stream));      // bad-cell counter, selection counts, SlabCtl
     c->n = 0;
-    c->masks_valid = false;
+    c->masks_valid = false; c->gnl_valid = false;
     c->list_valid = false; c->shep_pending = c->shep_wall_pending = false; c->fuse_half = c->fuse_init = false;
     for (int f = 0; f < SPH_F_NUM; f++) c->f[f].cur = 0;
     return 0;

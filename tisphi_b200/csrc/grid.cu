@@ -294,7 +294,7 @@ template int select_columns<double>(SphCtx *, int, int64_t, int64_t, int, int);
 template <typename T> int grid_build(SphCtx *c) {
     const int n = (int)c->n;
     if (n == 0) return 0;
-    c->masks_valid = false;                       // masks, work lists and round lists index the previous order
+    c->masks_valid = false; c->gnl_valid = false;                       // masks, work lists and round lists index the previous order
     Dev<T> a = make_dev<T>(c, -1), b = make_dev<T>(c, 1);
     int *gid_u = (int *)(c->arena + c->off_gid_unsorted), *slot = (int *)(c->arena + c->off_slot);
     int *perm = (int *)(c->arena + c->off_perm), *tmpidx = (int *)(c->arena + c->off_tmpidx);

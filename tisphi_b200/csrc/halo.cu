@@ -155,7 +155,7 @@ int sph_replace_particles(SphCtx *c, int64_t keep_first, int64_t keep_count, con
     }
     for (int k = 0; k < nf; k++) flip(c, fields[k]);
     c->n = total;
-    c->masks_valid = false;
+    c->masks_valid = false; c->gnl_valid = false;
     return 0;
 }
 

@@ -132,6 +132,68 @@ template <typename T> __global__ void __launch_bounds__(256) k_advect(Dev<T> c, 
         break;
     }
 }
+// RK4 inside sph_step: the pointwise kernels between two one_steps in ONE pass over the particle -- update_RK(m)
+// (base:153-160; the first stage also is init_RK, base:144-151: 0 + m D == m D) followed by advect_RK_4 (base:134-142)
+// or, after the last stage, advect_RK (base:162-170).  The same operations in the same order per particle as
+// k_advect kinds 3, 4, 2 / 5, without writing the accumulators and reading them back between launches.
+template <typename T> __global__ void __launch_bounds__(256) k_rk_stage(Dev<T> c, T m, int first, int last) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N()) return;
+    const int t = c.type[i];
+    const bool re = is_real(t), so = is_soil(t) && c.stress != nullptr;
+    if (!re && !so) return;
+    const double dt = c.dt;
+    const size_t i6 = 6 * (size_t)i;
+    if (re) {
+        const Vec4<T> dv = c.d_vel[i];
+        const T dr = c.d_rho[i];
+        T ar = first ? (T)0 : c.d_rho_rk[i];
+        Vec4<T> a;
+        if (first) { a.x = a.y = a.z = a.w = 0; } else a = c.d_vel_rk[i];
+        ar += dr * m;
+        a.x += dv.x * m; a.y += dv.y * m; a.z += dv.z * m;
+        c.d_rho_rk[i] = ar;
+        c.d_vel_rk[i] = a;
+        Vec4<T> v = c.v4[i];
+        Vec4<T> xs = c.xs4[i];
+        if (!last) {
+            Vec4<T> vt;
+            const double r = 0.5 * dt * (double)dr + c.rho[i];
+            c.rho_t[i] = r;
+            xs.w = (T)((double)v.w / r); c.xs4[i] = xs;
+            const T hdt = (T)(0.5 * dt);
+            vt.x = hdt * dv.x + v.x; vt.y = hdt * dv.y + v.y; vt.z = hdt * dv.z + v.z; vt.w = (T)r;
+            c.vt4[i] = vt;
+        } else {
+            const double r = c.rho[i] + dt / 6.0 * (double)ar;
+            c.rho[i] = r;
+            xs.w = (T)((double)v.w / r); c.xs4[i] = xs;
+            const T s = (T)(dt / 6.0);
+            v.x += s * a.x; v.y += s * a.y; v.z += s * a.z;
+            c.v4[i] = v;
+        }
+    }
+    if (so) {
+        for (int q = 0; q < 6; q++) {
+            const T ds = c.d_stress[i6 + q];
+            T as = first ? (T)0 : c.d_stress_rk[i6 + q];
+            as += ds * m;
+            c.d_stress_rk[i6 + q] = as;
+            if (!last) c.stress_t[i6 + q] = (T)(0.5 * dt) * ds + c.stress[i6 + q];
+            else c.stress[i6 + q] += (T)(dt / 6.0) * as;
+        }
+    }
+}
+template <typename T> int rk_stage(SphCtx *c, int m, bool first, bool last) {
+    if (c->n == 0) return 0;
+    SPH_PROF(c, K_ADVECT);
+    k_rk_stage<T><<<blocks_for(c->n, 256), 256, 0, c->stream>>>(make_dev<T>(c), (T)m, first ? 1 : 0, last ? 1 : 0);
+    SPH_LAUNCH_CHECK(c);
+    return 0;
+}
+template int rk_stage<float>(SphCtx *, int, bool, bool);
+template int rk_stage<double>(SphCtx *, int, bool, bool);
+
 template <typename T> int advect(SphCtx *c, int kind, int m) {
     if (c->n == 0) return 0;
     if (kind >= 3 && !c->rk) { snprintf(c->err, sizeof(c->err), "RK buffers exist only when timeIntegration == 4"); return -2; }

@@ -447,7 +447,7 @@ int sph_slab_init(SphCtx *c, int32_t rank, int32_t world, int32_t cx_begin, int3
     SPH_CHECK(c, cudaMemsetAsync(c->arena + c->f[SPH_F_CELL_COUNT].off[0], 0, sizeof(int) * (size_t)(c->C + 1), c->stream));
     SPH_CHECK(c, cudaStreamSynchronize(c->stream));
     c->slab = S;
-    c->masks_valid = false;
+    c->masks_valid = false; c->gnl_valid = false;
     return 0;
 }
 // left / right: the neighbours' inboxes as device pointers valid on THIS device (peer mappings; null at the ends)

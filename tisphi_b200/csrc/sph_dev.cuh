@@ -39,19 +39,6 @@ __device__ __forceinline__ float dist2(float dx, float dy, float dz) {
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
 
-// Cell-segment tile of the generic sweeps (sweeps.cu::k_cell_sweep): a block owns up to ZS consecutive cells of one
-// grid column; the particles of the 3 (2D) / 9 (3D) neighbouring columns' cells in reach are contiguous spans ("runs") of
-// the sorted arrays (ps:221-222) and are staged in shared memory once per block.  cb: tile index of the first particle of
-// each (run, cell); global index = tile index + gdelta[run].  Staged member arrays are generic pointers into shared
-// memory (null = not staged: that member is read from global memory).
-struct CellTile {
-    int cb[9 * 16];
-    int gdelta[9], roff[10];
-    int total, ok;
-    int f0, cbw, d3;
-    void *xs, *vt, *st, *ty, *v4, *press, *pnew;
-};
-
 // Device view of one engine instance.  Passed by value to every kernel.
 template <typename T> struct Dev {
     // sizes
@@ -109,10 +96,13 @@ template <typename T> struct Dev {
     uint2 *nlist;
     int *lrounds;
     int flagged_only;         // generic kernels: process only particles of flagged cells
-    CellTile *tile;           // generic kernels launched per cell segment: the block's staged neighbourhood (else null)
     double *xnew;             // XSPH: the alternate position buffer the advected positions go to
-    int list_cap;             // generic kernels: > 0 = for_neighbors first COLLECTS a particle's neighbours into a per-thread
-                              // list of this many entries in dynamic shared memory, then runs the task over the list
+    // per-step neighbour lists of the generic sweeps (sweeps.cu::k_build_nlist): positions are frozen between the grid build
+    // and advect_pos, so the candidate walk is done ONCE per step and every sweep in between replays its result.
+    // Entry k of particle i: gnl[k * gnl_stride + i] = (stencil cell << 27) | j; gnl_count[i] < 0: did not fit (walk again).
+    const unsigned *gnl;      // null: no valid list (every sweep walks the cells)
+    const int *gnl_count;
+    int gnl_stride, gnl_cap;
 };
 
 // ------------------------------------------------------------------------------------------------ cells
@@ -177,18 +167,16 @@ template <typename T> __device__ __forceinline__ T kernel_dW_over_r(const Dev<T>
 // it: it evaluates a cell pair once and transposes the bit matrix).   body(j, dx, dy, dz, r, V_j)
 //
 // Two forms with IDENTICAL results (same neighbours, same order, same arithmetic):
-//   direct  the task runs inside the candidate loops.  Only ~1/3 (2D) or ~1/7 (3D) of the candidates pass the test, and
-//           the lanes of a warp pass it for different candidates, so the (long) task body executes for almost every
-//           candidate with most lanes idle.
-//   listed  (Dev::list_cap > 0) the candidate loops only RECORD the neighbours ((stencil cell, index) in one word) in a
-//           per-thread list in dynamic shared memory (word k of thread t at list[k * blockDim.x + t]: conflict-free);
-//           the task then runs over the list, where every lane has work until its own list ends.  A particle with more
-//           neighbours than the list holds is redone with the direct form.
-extern __shared__ unsigned sph_nb_list[];
-constexpr unsigned NB_IDX_BITS = 27, NB_IDX_MASK = (1u << NB_IDX_BITS) - 1u;      // listed form: n_max < 2^27
+//   walk    the candidate loops over the 3^dim cells (LIST_BUILD: they only record (stencil cell, j) words, the task is
+//           not called -- sweeps.cu::k_build_nlist);
+//   replay  (Dev::gnl != null and the particle's list fits) the task runs over the recorded words: no candidate tests,
+//           and every lane of a warp has work until its own list ends instead of idling through the ~2/3 (2D) of the
+//           candidates that fail the test.
+constexpr unsigned NB_IDX_BITS = 27, NB_IDX_MASK = (1u << NB_IDX_BITS) - 1u;      // lists need n_max < 2^27
 
-template <typename T, bool LISTED, typename F>
-__device__ __forceinline__ void for_neighbors_impl(const Dev<T> &c, int i, F &&body) {
+// returns the number of neighbours (LIST_BUILD) or 0
+template <typename T, bool LIST_BUILD, typename F>
+__device__ __forceinline__ int for_neighbors_walk(const Dev<T> &c, int i, unsigned *out, int ostride, int ocap, F &&body) {
     int cc[3], sc[3] = {0, 0, 0};
     const double xi[3] = {c.x[3 * (size_t)i], c.x[3 * (size_t)i + 1], c.x[3 * (size_t)i + 2]};
     pos_to_cell(c, xi, cc);
@@ -196,8 +184,6 @@ __device__ __forceinline__ void for_neighbors_impl(const Dev<T> &c, int i, F &&b
     if (sizeof(T) == 4) unflatten(c, gi, sc);                 // the cell xs4[i] is local to
     const Vec4<T> pi = c.xs4[i];
     const int z0 = (c.dim == 2) ? 0 : -1, z1 = (c.dim == 2) ? 0 : 1;
-    unsigned *list = sph_nb_list + threadIdx.x;
-    const int lstride = blockDim.x;
     int cnt = 0;
     for (int ox = -1; ox <= 1; ox++) {
         int cx = cc[0] + ox;
@@ -215,7 +201,7 @@ __device__ __forceinline__ void for_neighbors_impl(const Dev<T> &c, int i, F &&b
                 int jb = g > 0 ? c.cell_end[g - 1] : 0, je = c.cell_end[g];
                 const bool rev = sizeof(T) == 4 && g < gi;    // the neighbour's cell precedes mine: evaluate from its side
                 const T ex = pi.x - sx, ey = pi.y - sy, ez = pi.z - sz;
-                const unsigned code = (unsigned)((ox + 1) * 9 + (oy + 1) * 3 + (oz + 1)) << NB_IDX_BITS;
+                const unsigned code = (unsigned)((cx - sc[0] + 1) * 9 + (cy - sc[1] + 1) * 3 + (cz - sc[2] + 1)) << NB_IDX_BITS;
                 for (int j = jb; j < je; j++) {
                     if (j == i) continue;
                     Vec4<T> pj = c.xs4[j];
@@ -224,8 +210,8 @@ __device__ __forceinline__ void for_neighbors_impl(const Dev<T> &c, int i, F &&b
                     else { dx = -((pj.x + sx) - pi.x); dy = -((pj.y + sy) - pi.y); dz = -((pj.z + sz) - pi.z); }
                     T r2 = dist2(dx, dy, dz);
                     if (r2 < c.r2thr) {
-                        if (LISTED) {
-                            if (cnt < c.list_cap) list[cnt * lstride] = code | (unsigned)j;
+                        if (LIST_BUILD) {
+                            if (cnt < ocap) out[(size_t)cnt * ostride] = code | (unsigned)j;
                             cnt++;
                         } else body(j, dx, dy, dz, sqrt_rn(r2), pj.w);
                     }
@@ -233,94 +219,32 @@ __device__ __forceinline__ void for_neighbors_impl(const Dev<T> &c, int i, F &&b
             }
         }
     }
-    if (!LISTED) return;
-    if (cnt > c.list_cap) {                                   // does not fit: the direct form gives the same result
-        for_neighbors_impl<T, false>(c, i, body);
+    return cnt;
+}
+template <typename T, typename F> __device__ __forceinline__ void for_neighbors(const Dev<T> &c, int i, F &&body) {
+    const int cnt = c.gnl ? c.gnl_count[i] : -1;
+    if (cnt < 0) {
+        for_neighbors_walk<T, false>(c, i, nullptr, 0, 0, body);
         return;
     }
-    for (int k = 0; k < cnt; k++) {
-        const unsigned e = list[k * lstride];
-        const int j = (int)(e & NB_IDX_MASK), code = (int)(e >> NB_IDX_BITS);
-        const int ox = code / 9 - 1, oy = (code / 3) % 3 - 1, oz = code % 3 - 1;
-        const int cx = cc[0] + ox, cy = cc[1] + oy, cz = cc[2] + oz;
-        const T sx = (T)(cx - sc[0]) * c.gsT, sy = (T)(cy - sc[1]) * c.gsT, sz = (T)(cz - sc[2]) * c.gsT;
-        const bool rev = sizeof(T) == 4 && flatten(c, cx, cy, cz) < gi;
+    // replay: the list was built from the stored cell of i (positions have not changed since), shifts relative to it
+    int sc[3] = {0, 0, 0};
+    const int gi = sizeof(T) == 4 ? c.gid[i] : 0;
+    if (sizeof(T) == 4) unflatten(c, gi, sc);
+    const Vec4<T> pi = c.xs4[i];
+    const unsigned *e = c.gnl + i;
+    for (int k = 0; k < cnt; k++, e += c.gnl_stride) {
+        const unsigned w = *e;
+        const int j = (int)(w & NB_IDX_MASK), code = (int)(w >> NB_IDX_BITS);
+        const int ox = code / 9 - 1, oy = (code / 3) % 3 - 1, oz = code % 3 - 1;     // neighbour cell - stored cell, per axis
+        const T sx = (T)ox * c.gsT, sy = (T)oy * c.gsT, sz = (T)oz * c.gsT;
+        const bool rev = sizeof(T) == 4 && (ox < 0 || (ox == 0 && (oy < 0 || (oy == 0 && oz < 0))));
         const Vec4<T> pj = c.xs4[j];
         T dx, dy, dz;
         if (!rev) { dx = (pi.x - sx) - pj.x; dy = (pi.y - sy) - pj.y; dz = (pi.z - sz) - pj.z; }
         else { dx = -((pj.x + sx) - pi.x); dy = -((pj.y + sy) - pi.y); dz = -((pj.z + sz) - pi.z); }
         body(j, dx, dy, dz, sqrt_rn(dist2(dx, dy, dz)), pj.w);
     }
-}
-//   tiled   (Dev::tile != null, kernels launched per cell segment) the candidates AND the neighbour payloads come from the
-//           block's shared-memory tile: the walk rebases the payload pointers of the (mutable, kernel-local) Dev view run
-//           by run, so that the task bodies -- which index members by the GLOBAL particle index -- read shared memory
-//           without knowing it.  A particle whose current position left the cell it is stored in (sweeps on a stale grid,
-//           SURVEY H15) takes the direct form.
-template <typename T, typename F>
-__device__ __forceinline__ void for_neighbors_tile(const Dev<T> &c0, int i, F &&body) {
-    Dev<T> &c = const_cast<Dev<T> &>(c0);               // the kernel's own local copy (sweeps.cu::k_cell_sweep)
-    CellTile &t = *c.tile;
-    int cc[3], sc[3];
-    const double xi[3] = {c.x[3 * (size_t)i], c.x[3 * (size_t)i + 1], c.x[3 * (size_t)i + 2]};
-    pos_to_cell(c, xi, cc);
-    const int gi = c.gid[i];
-    unflatten(c, gi, sc);
-    if (cc[0] != sc[0] || cc[1] != sc[1] || cc[2] != sc[2]) {
-        CellTile *keep = c.tile;
-        c.tile = nullptr;
-        for_neighbors_impl<T, false>(c, i, body);
-        c.tile = keep;
-        return;
-    }
-    const bool d3 = t.d3 != 0;
-    const int wz = (d3 ? sc[2] : sc[1]) - t.f0 + 1;       // the centre cell's slot among the run's cell boundaries
-    Vec4<T> *const g_vt = c.vt4, *const g_v4 = c.v4;
-    T *const g_st = c.stress_t, *const g_press = c.press, *const g_pnew = c.pnew;
-    int *const g_ty = c.type;
-    const Vec4<T> pi = c.xs4[i];
-    const Vec4<T> *XS = (const Vec4<T> *)t.xs;
-    const int z0 = d3 ? -1 : 0, z1 = d3 ? 1 : 0;
-    for (int ox = -1; ox <= 1; ox++) {
-        const T sx = sizeof(T) == 4 ? (T)ox * c.gsT : (T)0;
-        for (int oy = -1; oy <= 1; oy++) {
-            const T sy = sizeof(T) == 4 ? (T)oy * c.gsT : (T)0;
-            const int r = d3 ? (ox + 1) * 3 + (oy + 1) : (ox + 1);
-            if (d3 || oy == -1) {                         // a new run: rebase the staged members
-                const int gd = t.gdelta[r];
-                if (t.vt) c.vt4 = (Vec4<T> *)t.vt - gd;
-                if (t.v4) c.v4 = (Vec4<T> *)t.v4 - gd;
-                if (t.st) c.stress_t = (T *)t.st - 6 * (long long)gd;
-                if (t.press) c.press = (T *)t.press - gd;
-                if (t.pnew) c.pnew = (T *)t.pnew - gd;
-                if (t.ty) c.type = (int *)t.ty - gd;
-            }
-            const int gd = t.gdelta[r];
-            for (int oz = z0; oz <= z1; oz++) {
-                const T sz = sizeof(T) == 4 ? (T)oz * c.gsT : (T)0;
-                const int k = r * t.cbw + wz + (d3 ? oz : oy);
-                const int jb = t.cb[k], je = t.cb[k + 1];
-                const bool rev = sizeof(T) == 4 && (ox < 0 || (ox == 0 && (oy < 0 || (oy == 0 && oz < 0))));
-                const T ex = pi.x - sx, ey = pi.y - sy, ez = pi.z - sz;
-                for (int jt = jb; jt < je; jt++) {
-                    const int j = jt + gd;
-                    if (j == i) continue;
-                    const Vec4<T> pj = XS[jt];
-                    T dx, dy, dz;
-                    if (!rev) { dx = ex - pj.x; dy = ey - pj.y; dz = ez - pj.z; }
-                    else { dx = -((pj.x + sx) - pi.x); dy = -((pj.y + sy) - pi.y); dz = -((pj.z + sz) - pi.z); }
-                    const T r2 = dist2(dx, dy, dz);
-                    if (r2 < c.r2thr) body(j, dx, dy, dz, sqrt_rn(r2), pj.w);
-                }
-            }
-        }
-    }
-    c.vt4 = g_vt; c.v4 = g_v4; c.stress_t = g_st; c.press = g_press; c.pnew = g_pnew; c.type = g_ty;
-}
-template <typename T, typename F> __device__ __forceinline__ void for_neighbors(const Dev<T> &c, int i, F &&body) {
-    if (c.tile) for_neighbors_tile<T>(c, i, body);
-    else if (c.list_cap > 0) for_neighbors_impl<T, true>(c, i, body);
-    else for_neighbors_impl<T, false>(c, i, body);
 }
 
 // symmetric 3x3 stored as xx,yy,zz,xy,yz,zx  <-> full row-major

@@ -84,8 +84,9 @@ struct SphCtx {
     int own0, own1;      // owned x-columns [own0, own1) (multi-GPU slabs); the whole grid on one GPU
     int64_t off_slabctl; // device-resident control block of the native slab step (slab.cu)
     sph::SlabState *slab;   // native multi-GPU slab step (sph_slab_init); null on one GPU
-    bool cell_tiles;     // generic sweeps are launched per cell segment with the neighbourhood staged in shared memory
-    int nb_cap;          // generic sweeps: entries of the per-thread neighbour list in shared memory (0: direct form)
+    int64_t off_gnl, off_gnl_count;  // per-step neighbour lists of the generic sweeps (0: not allocated)
+    int gnl_cap;
+    bool gnl_valid;      // built for the current sort and positions
     bool slab_sort;      // grid_build is the sort of a slab redistribution: virtual concatenation, column table, cell sub-range
     bool masks_valid;    // the neighbour masks / work lists belong to the current sort (cleared by every re-sort / upload)
 };
@@ -103,7 +104,7 @@ struct SphCtx {
 enum SphKernelId { K_CELL_ID = 0, K_SCAN, K_SCATTER, K_RANK, K_REORDER, K_CSPM_F, K_CSPM_L, K_WC_EOS, K_WC_WALL, K_WC_FLUID,
                    K_MUI_SOIL1, K_SOIL_WALL, K_MUI_SOIL3, K_DP_ADAPT, K_DP_SOIL, K_ADVECT_POS, K_POST, K_POST_SWEEP,
                    K_NEIGHBOR_COUNT, K_DENSITY_SUM, K_OTHER, K_INIT_TMP, K_ADVECT, K_TILE_MASK, K_TILE_FLUID, K_TILE_WALL,
-                   K_HALO, K_HALO_WAIT, K_C5, K_NUM };
+                   K_HALO, K_HALO_WAIT, K_C5, K_NLIST, K_NUM };
 void sph_prof_begin(SphCtx *c, int id);
 void sph_prof_end(SphCtx *c);
 
@@ -125,9 +126,6 @@ namespace sph {
 constexpr int LIST_ROUNDS = 56;     // rounds (of four neighbour slots) a particle's list can hold
 
 template <typename T> Dev<T> make_dev(SphCtx *c, int which = -1);   // which = -1: current buffers, 1: alternates
-
-// dynamic shared memory of a generic sweep launched with 128 threads (sph_dev.cuh::for_neighbors, listed form)
-#define NB_SMEM(ctx) ((size_t)(ctx)->nb_cap * 128 * sizeof(unsigned))
 
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
@@ -153,6 +151,7 @@ int tile_wc_fluid(SphCtx *c);
 // integrate.cu
 template <typename T> int init_real2tmp(SphCtx *c);
 template <typename T> int advect(SphCtx *c, int kind, int m);
+template <typename T> int rk_stage(SphCtx *c, int m, bool first, bool last);   // sph_step only: fused RK4 pointwise stages
 template <typename T> int init_stress(SphCtx *c, const double *ymax_ext = nullptr);
 template <typename T> int add_particles_finish(SphCtx *c, int64_t first, int64_t count);
 

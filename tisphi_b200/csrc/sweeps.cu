@@ -11,11 +11,6 @@
 
 namespace sph {
 
-// the same sweeps launched per cell segment with the neighbourhood staged in shared memory (defined below)
-enum { ST_TYPE = 1, ST_VT = 2, ST_STRESS = 4, ST_V = 8, ST_PRESS = 16, ST_PNEW = 32 };
-enum { CK_CSPM_F = 0, CK_CSPM_L, CK_WC_WALL, CK_WC_FLUID, CK_SOIL_WALL, CK_MUI1, CK_MUI3, CK_DP_SOIL, CK_XSPH, CK_POST_MUI_B };
-template <typename T, int KIND> static bool launch_cell_sweep(SphCtx *c, const Dev<T> &d, int prof_id);
-
 // --------------------------------------------------------------------------------------------- kernel correction
 // flagged-only mode: the cell-tile kernels handled every particle except those of flagged cells
 template <typename T> __device__ __forceinline__ bool not_owned(const Dev<T> &c, int i) {
@@ -100,24 +95,54 @@ template <typename T> __global__ void __launch_bounds__(128) k_cspm_L(Dev<T> c) 
     if (i < c.N()) body_cspm_L(c, i);
 }
 
+// The candidate walk of every particle, ONCE per step (positions are frozen from the grid build to advect_pos): the
+// sweeps that follow replay the recorded neighbours (sph_dev.cuh::for_neighbors).  A particle whose list does not fit,
+// or whose position is no longer in the cell it is stored in, is marked -1 and walks the cells in every sweep.
+template <typename T> __global__ void __launch_bounds__(128) k_build_nlist(Dev<T> c, unsigned *__restrict__ nlist, int *__restrict__ ncount,
+                                                                          int stride, int cap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N()) return;
+    int cc[3], sc[3];
+    const double xi[3] = {c.x[3 * (size_t)i], c.x[3 * (size_t)i + 1], c.x[3 * (size_t)i + 2]};
+    pos_to_cell(c, xi, cc);
+    unflatten(c, c.gid[i], sc);
+    int cnt = -1;
+    if (cc[0] == sc[0] && cc[1] == sc[1] && cc[2] == sc[2]) {
+        auto none = [](int, T, T, T, T, T) {};
+        cnt = for_neighbors_walk<T, true>(c, i, nlist + i, stride, cap, none);
+        if (cnt > cap) cnt = -1;
+    }
+    ncount[i] = cnt;
+}
+template <typename T> static int build_nlist(SphCtx *c) {
+    c->gnl_valid = false;
+    if (!c->off_gnl || c->n == 0) return 0;
+    Dev<T> d = make_dev<T>(c);
+    SPH_PROF(c, K_NLIST);
+    k_build_nlist<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(d, (unsigned *)(c->arena + c->off_gnl), (int *)(c->arena + c->off_gnl_count),
+                                                                   (int)c->n_max, c->gnl_cap);
+    SPH_LAUNCH_CHECK(c);
+    c->gnl_valid = true;
+    return 0;
+}
+
 // standalone: every CSPM_f is final on return (the API call).  Otherwise (inside sph_step) the tile path leaves the
 // Shepard sums of unflagged cells to the wall pass and the first fluid pass, which visit the same neighbours anyway.
 template <typename T> int calc_kernel_corr(SphCtx *c, bool standalone) {
     if (c->n == 0) return 0;
+    if (!c->fast) { int r = build_nlist<T>(c); if (r) return r; }      // the generic sweeps of this step replay it
     Dev<T> d = make_dev<T>(c);
     if (c->fast) {                       // tile path: masks (+ CSPM_f); the generic kernel completes flagged cells
         int r = tile_mask(c, standalone);
         if (r) return r;
         d.flagged_only = 1;
     }
-    if (d.flagged_only || !launch_cell_sweep<T, CK_CSPM_F>(c, d, K_CSPM_F)) {
-        SPH_PROF(c, K_CSPM_F);
-        k_cspm_f<T><<<sweep_blocks(d), 128, NB_SMEM(c), c->stream>>>(d);
-        SPH_LAUNCH_CHECK(c);
-    }
-    if (c->p.kcorr == 1 && !launch_cell_sweep<T, CK_CSPM_L>(c, d, K_CSPM_L)) {
+    SPH_PROF(c, K_CSPM_F);
+    k_cspm_f<T><<<sweep_blocks(d), 128, 0, c->stream>>>(d);
+    SPH_LAUNCH_CHECK(c);
+    if (c->p.kcorr == 1) {
         SPH_PROF(c, K_CSPM_L);
-        k_cspm_L<T><<<blocks_for(c->n, 128), 128, NB_SMEM(c), c->stream>>>(d);
+        k_cspm_L<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(d);
         SPH_LAUNCH_CHECK(c);
     }
     return 0;
@@ -279,10 +304,12 @@ __device__ __forceinline__ void soil_sweep(const Dev<T> &c, int i, T vg[9], T *d
     const T rhoi = vi.w;
     T L[9], si[9];
     load_L(c, i, L);
-    T inv_r2i = 0;
+    T sir[9];                                         // sigma~_i / rho~_i^2, the j-independent quotients of the momentum sum
     if (MOM) {
         sym_load(c.stress_t, (size_t)i, si);
-        inv_r2i = (T)1 / (rhoi * rhoi);
+        const T r2i = rhoi * rhoi;
+#pragma unroll
+        for (int a = 0; a < 9; a++) sir[a] = si[a] / r2i;
     }
     T acc = 0;
 #pragma unroll
@@ -304,15 +331,18 @@ __device__ __forceinline__ void soil_sweep(const Dev<T> &c, int i, T vg[9], T *d
         if (MOM) {      // muI:38-46 / dp:156-165: V_j rho~_j (sigma~_j / rho~_j^2 + sigma~_i / rho~_i^2) . gradW^c
             const T rhoj = vj.w, cf = Vj * rhoj;
             if (sizeof(T) == 4) {
-                // float32 sweeps: the 18 IEEE divisions of the expression above are two reciprocals (the particle's own
-                // outside the loop) and the symmetric tensor is combined in its 6 components -- same terms, regrouped
+                // float32 sweeps: the expression above divides 18 times per neighbour; 9 of the quotients (sigma~_i /
+                // rho~_i^2) do not depend on j and 3 of the other 9 are duplicates of a symmetric tensor.  Same quotients,
+                // same products, same sums -- bit-identical to evaluating it as written -- with 6 divisions per neighbour.
                 const T *q = c.stress_t + 6 * (size_t)j;
-                const T cj = cf * ((T)1 / (rhoj * rhoj)), ci = cf * inv_r2i;
-                const T mxx = cj * q[0] + ci * si[0], myy = cj * q[1] + ci * si[4], mzz = cj * q[2] + ci * si[8];
-                const T mxy = cj * q[3] + ci * si[1], myz = cj * q[4] + ci * si[5], mzx = cj * q[5] + ci * si[2];
-                mom[0] += mxx * gc[0] + mxy * gc[1] + mzx * gc[2];
-                mom[1] += mxy * gc[0] + myy * gc[1] + myz * gc[2];
-                mom[2] += mzx * gc[0] + myz * gc[1] + mzz * gc[2];
+                const T r2j = rhoj * rhoj;
+                const T mxx = cf * (q[0] / r2j + sir[0]), myy = cf * (q[1] / r2j + sir[4]), mzz = cf * (q[2] / r2j + sir[8]);
+                const T mxy = cf * (q[3] / r2j + sir[1]), myz = cf * (q[4] / r2j + sir[5]), mzx = cf * (q[5] / r2j + sir[2]);
+                T t0 = 0, t1 = 0, t2 = 0;
+                t0 += mxx * gc[0]; t0 += mxy * gc[1]; t0 += mzx * gc[2];
+                t1 += mxy * gc[0]; t1 += myy * gc[1]; t1 += myz * gc[2];
+                t2 += mzx * gc[0]; t2 += myz * gc[1]; t2 += mzz * gc[2];
+                mom[0] += t0; mom[1] += t1; mom[2] += t2;
             } else {
                 T sj[9];
                 sym_load(c.stress_t, (size_t)j, sj);
@@ -515,7 +545,7 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
             Dev<T> d = make_dev<T>(c);
             d.flagged_only = 1;
             SPH_PROF(c, K_WC_WALL);
-            k_wc_wall<T><<<sweep_blocks(d), 128, NB_SMEM(c), st>>>(d);
+            k_wc_wall<T><<<sweep_blocks(d), 128, 0, st>>>(d);
             SPH_LAUNCH_CHECK(c);
             flip(c, SPH_F_PRESSURE);
         } else {
@@ -524,7 +554,7 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
             Dev<T> d = make_dev<T>(c);
             d.flagged_only = 1;
             SPH_PROF(c, K_WC_FLUID);
-            k_wc_fluid<T><<<sweep_blocks(d), 128, NB_SMEM(c), st>>>(d);
+            k_wc_fluid<T><<<sweep_blocks(d), 128, 0, st>>>(d);
             SPH_LAUNCH_CHECK(c);
         }
     } else if (solver == SPH_SOLVER_WC) {
@@ -533,31 +563,26 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
             SPH_PROF(c, K_WC_EOS);
             k_wc_eos<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
             SPH_LAUNCH_CHECK(c);
-            if (!launch_cell_sweep<T, CK_WC_WALL>(c, d, K_WC_WALL)) {
-                SPH_PROF(c, K_WC_WALL);
-                k_wc_wall<T><<<sweep_blocks(d), 128, NB_SMEM(c), st>>>(d);
-                SPH_LAUNCH_CHECK(c);
-            }
+            SPH_PROF(c, K_WC_WALL);
+            k_wc_wall<T><<<sweep_blocks(d), 128, 0, st>>>(d);
+            SPH_LAUNCH_CHECK(c);
             flip(c, SPH_F_PRESSURE);               // pnew becomes pt.pressure
-        } else if (!launch_cell_sweep<T, CK_WC_FLUID>(c, d, K_WC_FLUID)) {
+        } else {
             SPH_PROF(c, K_WC_FLUID);
-            k_wc_fluid<T><<<sweep_blocks(d), 128, NB_SMEM(c), st>>>(d);
+            k_wc_fluid<T><<<sweep_blocks(d), 128, 0, st>>>(d);
             SPH_LAUNCH_CHECK(c);
         }
     } else if (solver == SPH_SOLVER_MUI) {
         Dev<T> d = make_dev<T>(c);
         if (phase == 0) {
-            if (launch_cell_sweep<T, CK_MUI1>(c, d, K_MUI_SOIL1)) return 0;
             SPH_PROF(c, K_MUI_SOIL1);
-            k_mui_soil1<T><<<blocks_for(n, 128), 128, NB_SMEM(c), st>>>(d);
+            k_mui_soil1<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         } else if (phase == 1) {
-            if (launch_cell_sweep<T, CK_SOIL_WALL>(c, d, K_SOIL_WALL)) return 0;
             SPH_PROF(c, K_SOIL_WALL);
-            k_soil_wall<T><<<blocks_for(n, 128), 128, NB_SMEM(c), st>>>(d);
+            k_soil_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         } else {
-            if (launch_cell_sweep<T, CK_MUI3>(c, d, K_MUI_SOIL3)) return 0;
             SPH_PROF(c, K_MUI_SOIL3);
-            k_mui_soil3<T><<<blocks_for(n, 128), 128, NB_SMEM(c), st>>>(d);
+            k_mui_soil3<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         }
         SPH_LAUNCH_CHECK(c);
     } else if (solver == SPH_SOLVER_DP) {
@@ -566,13 +591,11 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
             SPH_PROF(c, K_DP_ADAPT);
             k_dp_adapt<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
         } else if (phase == 1) {
-            if (launch_cell_sweep<T, CK_SOIL_WALL>(c, d, K_SOIL_WALL)) return 0;
             SPH_PROF(c, K_SOIL_WALL);
-            k_soil_wall<T><<<blocks_for(n, 128), 128, NB_SMEM(c), st>>>(d);
+            k_soil_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         } else {
-            if (launch_cell_sweep<T, CK_DP_SOIL>(c, d, K_DP_SOIL)) return 0;
             SPH_PROF(c, K_DP_SOIL);
-            k_dp_soil<T><<<blocks_for(n, 128), 128, NB_SMEM(c), st>>>(d);
+            k_dp_soil<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         }
         SPH_LAUNCH_CHECK(c);
     } else {
@@ -644,6 +667,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_refresh_xs(Dev<T>
 }
 template <typename T> int advect_pos(SphCtx *c) {
     if (c->n == 0) return 0;
+    c->gnl_valid = false;                     // positions move: what follows (mu(I) regularisation, H15) walks the cells
     const int n = (int)c->n;
     Dev<T> d = make_dev<T>(c);
     if (!c->p.xsph) {
@@ -652,11 +676,9 @@ template <typename T> int advect_pos(SphCtx *c) {
         SPH_LAUNCH_CHECK(c);
     } else {
         d.xnew = (double *)(c->arena + c->f[SPH_F_X].off[1 - c->f[SPH_F_X].cur]);
-        if (!launch_cell_sweep<T, CK_XSPH>(c, d, K_ADVECT_POS)) {
-            SPH_PROF(c, K_ADVECT_POS);
-            k_advect_pos_xsph<T><<<blocks_for(n, 128), 128, NB_SMEM(c), c->stream>>>(d);
-            SPH_LAUNCH_CHECK(c);
-        }
+        SPH_PROF(c, K_ADVECT_POS);
+        k_advect_pos_xsph<T><<<blocks_for(n, 128), 128, 0, c->stream>>>(d);
+        SPH_LAUNCH_CHECK(c);
         flip(c, SPH_F_X);
     }
     return 0;
@@ -738,11 +760,9 @@ template <typename T> int post_step(SphCtx *c) {
         SPH_PROF(c, K_POST);
         k_refresh_xs<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
         SPH_LAUNCH_CHECK(c);
-        if (!launch_cell_sweep<T, CK_POST_MUI_B>(c, d, K_POST_SWEEP)) {
-            SPH_PROF(c, K_POST_SWEEP);
-            k_post_mui_b<T><<<blocks_for(n, 128), 128, NB_SMEM(c), st>>>(d);
-            SPH_LAUNCH_CHECK(c);
-        }
+        SPH_PROF(c, K_POST_SWEEP);
+        k_post_mui_b<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+        SPH_LAUNCH_CHECK(c);
     }
     return 0;
 }
@@ -771,170 +791,11 @@ template <typename T> __global__ void __launch_bounds__(256) k_wc_finish(Dev<T> 
 }
 template <typename T> int finish_step(SphCtx *c) {
     if (c->n == 0) return 0;
+    c->gnl_valid = false;
     SPH_PROF(c, K_ADVECT);
     k_wc_finish<T><<<blocks_for(c->n, 256), 256, 0, c->stream>>>(make_dev<T>(c));
     SPH_LAUNCH_CHECK(c);
     return 0;
-}
-
-// ------------------------------------------------------------------------------ the same sweeps, one block per cell segment
-// Every sweep above walks the 3^dim cells around each particle with dependent global loads (an L1 hit per candidate and
-// one or more gathers per neighbour): they run at ~0.15 instructions per clock, bound by load latency.  Here a block owns
-// CSeg::ZS consecutive cells of one grid column and first copies the particles its stencils can reach -- 3 (2D) or 9 (3D)
-// CONTIGUOUS spans of the sorted arrays, cell ids being fastest-axis-major (ps:221-222) -- into shared memory, positions
-// always and the members the sweep's task reads (STAGE mask).  The per-particle bodies are the SAME functions; their
-// neighbour walk (sph_dev.cuh::for_neighbors_tile) takes candidates and payloads from the tile in the same order, so the
-// results are bit-identical to the per-particle kernels (which remain the fallback for tiles that do not fit).
-template <bool D3> struct CSeg {
-    static constexpr int ZS = D3 ? 4 : 12, NRY = D3 ? 3 : 1, NR = 3 * NRY, CBW = ZS + 3, CAP = D3 ? 1536 : 512, BT = 128;
-};
-template <int KIND> struct CKind;
-// STAGE: members the task reads of its neighbours.  GHOSTS: the body also has work for particles of a slab's ghost columns
-// (static rigid particles get their derivatives zeroed there; XSPH moves every particle), so those columns are not skipped.
-template <> struct CKind<CK_CSPM_F> { static constexpr int STAGE = ST_TYPE; static constexpr bool GHOSTS = false; };
-template <> struct CKind<CK_CSPM_L> { static constexpr int STAGE = ST_TYPE; static constexpr bool GHOSTS = false; };
-template <> struct CKind<CK_WC_WALL> { static constexpr int STAGE = ST_TYPE | ST_VT | ST_PRESS | ST_PNEW; static constexpr bool GHOSTS = true; };
-template <> struct CKind<CK_WC_FLUID> { static constexpr int STAGE = ST_TYPE | ST_VT | ST_PRESS; static constexpr bool GHOSTS = false; };
-template <> struct CKind<CK_SOIL_WALL> { static constexpr int STAGE = ST_TYPE | ST_VT | ST_STRESS; static constexpr bool GHOSTS = true; };
-template <> struct CKind<CK_MUI1> { static constexpr int STAGE = ST_VT; static constexpr bool GHOSTS = false; };
-template <> struct CKind<CK_MUI3> { static constexpr int STAGE = ST_VT | ST_STRESS; static constexpr bool GHOSTS = false; };
-template <> struct CKind<CK_DP_SOIL> { static constexpr int STAGE = ST_VT | ST_STRESS; static constexpr bool GHOSTS = false; };
-template <> struct CKind<CK_XSPH> { static constexpr int STAGE = ST_TYPE | ST_V; static constexpr bool GHOSTS = true; };
-template <> struct CKind<CK_POST_MUI_B> { static constexpr int STAGE = ST_TYPE | ST_STRESS; static constexpr bool GHOSTS = false; };
-template <typename T, int KIND> __device__ __forceinline__ void cell_body(const Dev<T> &c, int i) {
-    if (KIND == CK_CSPM_F) body_cspm_f(c, i);
-    else if (KIND == CK_CSPM_L) { if (!not_owned(c, i)) body_cspm_L(c, i); }
-    else if (KIND == CK_WC_WALL) body_wc_wall(c, i);
-    else if (KIND == CK_WC_FLUID) body_wc_fluid(c, i);
-    else if (KIND == CK_SOIL_WALL) body_soil_wall(c, i);
-    else if (KIND == CK_MUI1) body_mui_soil1(c, i);
-    else if (KIND == CK_MUI3) body_mui_soil3(c, i);
-    else if (KIND == CK_DP_SOIL) body_dp_soil(c, i);
-    else if (KIND == CK_XSPH) body_advect_pos_xsph(c, i);
-    else body_post_mui_b(c, i);
-}
-template <typename T, bool D3> __host__ __device__ constexpr size_t cell_smem(int stage) {
-    size_t per = sizeof(Vec4<T>);                                        // positions, always
-    if (stage & ST_VT) per += sizeof(Vec4<T>);
-    if (stage & ST_V) per += sizeof(Vec4<T>);
-    if (stage & ST_STRESS) per += 6 * sizeof(T);
-    if (stage & ST_PRESS) per += sizeof(T);
-    if (stage & ST_PNEW) per += sizeof(T);
-    if (stage & ST_TYPE) per += sizeof(int);
-    return sizeof(CellTile) + 16 + per * CSeg<D3>::CAP;
-}
-template <typename T, bool D3, int KIND> __global__ void __launch_bounds__(128) k_cell_sweep(Dev<T> cin, int nseg) {
-    typedef CSeg<D3> S;
-    constexpr int STAGE = CKind<KIND>::STAGE;
-    extern __shared__ __align__(16) unsigned char cell_smem_raw[];
-    CellTile &t = *reinterpret_cast<CellTile *>(cell_smem_raw);
-    Dev<T> c = cin;                                       // mutable view: the tiled neighbour walk rebases payload pointers
-    c.list_cap = 0;                                       // (the listed form's shared-memory list is not part of this launch)
-    const int tid = threadIdx.x;
-    const int nF = D3 ? c.gn[2] : c.gn[1], n1 = D3 ? c.gn[1] : 1, n0 = c.gn[0];
-    const int seg = blockIdx.x % nseg, col = blockIdx.x / nseg;
-    const int cy = col % n1, cx = col / n1;
-    if (!CKind<KIND>::GHOSTS && (cx < c.own0 || cx >= c.own1)) return;      // ghost columns of a slab: the neighbour rank's work
-    const int f0 = seg * S::ZS, f1 = min(f0 + S::ZS, nF);
-    const int base = (cx * n1 + cy) * nF;
-    const int own_lo = (base + f0) > 0 ? c.cell_end[base + f0 - 1] : 0, own_hi = c.cell_end[base + f1 - 1];
-    if (own_lo == own_hi) return;                         // empty segment
-    if (tid < 32) {                                       // spans and cell boundaries of the runs (one warp)
-        const int f_lo = max(f0 - 1, 0), f_hi = min(f0 + S::ZS, nF - 1);
-        int len = 0, st = 0, gb = 0;
-        bool valid = false;
-        if (tid < S::NR) {
-            const int m0 = cx + tid / S::NRY - 1, m1 = D3 ? cy + tid % S::NRY - 1 : 0;
-            valid = m0 >= 0 && m0 < n0 && m1 >= 0 && m1 < n1;
-            if (valid) {
-                gb = (m0 * n1 + m1) * nF;
-                st = (gb + f_lo) > 0 ? c.cell_end[gb + f_lo - 1] : 0;
-                len = c.cell_end[gb + f_hi] - st;
-            }
-        }
-        int inc = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (tid >= o) inc += u;
-        }
-        const int roff = inc - len;
-        if (tid < S::NR) {
-            t.gdelta[tid] = st - roff;
-            t.roff[tid] = roff;
-            for (int k = 0; k < S::CBW; k++) {
-                const int f = f0 - 1 + k;
-                int v;
-                if (!valid || f < f_lo) v = roff;
-                else if (f > f_hi) v = roff + len;
-                else v = roff + ((gb + f) > 0 ? c.cell_end[gb + f - 1] : 0) - st;
-                t.cb[tid * S::CBW + k] = v;
-            }
-        }
-        if (tid == S::NR - 1) { t.roff[S::NR] = inc; t.total = inc; t.ok = inc <= S::CAP; t.f0 = f0; t.cbw = S::CBW; t.d3 = D3 ? 1 : 0; }
-    }
-    __syncthreads();
-    if (!t.ok) {                                          // the neighbourhood does not fit: per-particle walk from global memory
-        for (int p = own_lo + tid; p < own_hi; p += S::BT) cell_body<T, KIND>(c, p);
-        return;
-    }
-    // carve the staged arrays out of the dynamic shared memory behind the header
-    unsigned char *mem = cell_smem_raw + ((sizeof(CellTile) + 15) / 16) * 16;
-    Vec4<T> *s_xs = (Vec4<T> *)mem; mem += sizeof(Vec4<T>) * S::CAP;
-    Vec4<T> *s_vt = nullptr, *s_v4 = nullptr;
-    T *s_st = nullptr, *s_press = nullptr, *s_pnew = nullptr;
-    int *s_ty = nullptr;
-    if (STAGE & ST_VT) { s_vt = (Vec4<T> *)mem; mem += sizeof(Vec4<T>) * S::CAP; }
-    if (STAGE & ST_V) { s_v4 = (Vec4<T> *)mem; mem += sizeof(Vec4<T>) * S::CAP; }
-    if (STAGE & ST_STRESS) { s_st = (T *)mem; mem += 6 * sizeof(T) * S::CAP; }
-    if (STAGE & ST_PRESS) { s_press = (T *)mem; mem += sizeof(T) * S::CAP; }
-    if (STAGE & ST_PNEW) { s_pnew = (T *)mem; mem += sizeof(T) * S::CAP; }
-    if (STAGE & ST_TYPE) { s_ty = (int *)mem; mem += sizeof(int) * S::CAP; }
-    const int total = t.total;
-    for (int q = tid; q < total; q += S::BT) {
-        int r = 0;
-#pragma unroll
-        for (int k = 1; k < S::NR; k++) r += (q >= t.roff[k]) ? 1 : 0;
-        const size_t j = (size_t)(q + t.gdelta[r]);
-        s_xs[q] = c.xs4[j];
-        if (STAGE & ST_VT) s_vt[q] = c.vt4[j];
-        if (STAGE & ST_V) s_v4[q] = c.v4[j];
-        if (STAGE & ST_STRESS) {
-#pragma unroll
-            for (int a = 0; a < 6; a++) s_st[6 * q + a] = c.stress_t[6 * j + a];
-        }
-        if (STAGE & ST_PRESS) s_press[q] = c.press[j];
-        if (STAGE & ST_PNEW) s_pnew[q] = c.pnew[j];
-        if (STAGE & ST_TYPE) s_ty[q] = c.type[j];
-    }
-    if (tid == 0) { t.xs = s_xs; t.vt = s_vt; t.v4 = s_v4; t.st = s_st; t.press = s_press; t.pnew = s_pnew; t.ty = s_ty; }
-    __syncthreads();
-    c.tile = &t;
-    for (int p = own_lo + tid; p < own_hi; p += S::BT) cell_body<T, KIND>(c, p);
-}
-// launches one sweep per cell segment when the engine was created with fast != 0 (any precision, any solver);
-// returns false when the caller has to launch the per-particle kernel instead
-template <typename T, int KIND> static bool launch_cell_sweep(SphCtx *c, const Dev<T> &d, int prof_id) {
-    if (!c->cell_tiles) return false;
-    const bool d3 = c->p.dim == 3;
-    const int nF = d3 ? c->p.gn[2] : c->p.gn[1], ncol = d3 ? c->p.gn[0] * c->p.gn[1] : c->p.gn[0];
-    const int zs = d3 ? CSeg<true>::ZS : CSeg<false>::ZS, nseg = (nF + zs - 1) / zs;
-    const long long blocks = (long long)ncol * nseg;
-    if (blocks > 0x7fffffffll) return false;
-    const size_t smem = d3 ? cell_smem<T, true>(CKind<KIND>::STAGE) : cell_smem<T, false>(CKind<KIND>::STAGE);
-    static bool attr_done[2][2] = {};
-    if (!attr_done[sizeof(T) == 8][d3]) {                  // (per instantiation: KIND and T are template parameters)
-        cudaError_t e = d3 ? cudaFuncSetAttribute(k_cell_sweep<T, true, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                           : cudaFuncSetAttribute(k_cell_sweep<T, false, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { cudaGetLastError(); return false; }
-        attr_done[sizeof(T) == 8][d3] = true;
-    }
-    SPH_PROF(c, prof_id);
-    if (d3) k_cell_sweep<T, true, KIND><<<(int)blocks, 128, smem, c->stream>>>(d, nseg);
-    else k_cell_sweep<T, false, KIND><<<(int)blocks, 128, smem, c->stream>>>(d, nseg);
-    c->launches++;
-    if (c->prof_on) sph_prof_end(c);
-    return cudaGetLastError() == cudaSuccess;
 }
 
 // -------------------------------------------------------------------------------------------- stand-alone sweeps
@@ -977,21 +838,21 @@ template <typename T> int density_sweep(SphCtx *c, int32_t *count_out, void *rho
     Dev<T> d = make_dev<T>(c);
     SPH_PROF(c, K_DENSITY_SUM);
     const int blocks = rest_only ? 148 * 16 : blocks_for(c->n, 128);
-    k_density_count<T><<<blocks, 128, NB_SMEM(c), c->stream>>>(d, count_out, (T *)rho_out, rest_only);
+    k_density_count<T><<<blocks, 128, 0, c->stream>>>(d, count_out, (T *)rho_out, rest_only);
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
 template <typename T> int neighbor_count(SphCtx *c, int32_t *out) {
     if (c->n == 0) return 0;
     SPH_PROF(c, K_NEIGHBOR_COUNT);
-    k_neighbor_count<T><<<blocks_for(c->n, 128), 128, NB_SMEM(c), c->stream>>>(make_dev<T>(c), out);
+    k_neighbor_count<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(make_dev<T>(c), out);
     SPH_LAUNCH_CHECK(c);
     return 0;
 }
 template <typename T> int density_sum(SphCtx *c, void *out) {
     if (c->n == 0) return 0;
     SPH_PROF(c, K_DENSITY_SUM);
-    k_density_sum<T><<<blocks_for(c->n, 128), 128, NB_SMEM(c), c->stream>>>(make_dev<T>(c), (T *)out);
+    k_density_sum<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(make_dev<T>(c), (T *)out);
     SPH_LAUNCH_CHECK(c);
     return 0;
 }

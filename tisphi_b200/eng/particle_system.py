@@ -198,7 +198,6 @@ class ParticleSystem:
         # (one); they also take 448 B per particle.  Default: on for timeIntegration 4 only.
         lists = self.cfg.get_opt("neighbourLists", P.ti == 4)
         P.fast = 0 if not self.cfg.get_opt("fastSweeps", True) else (2 if lists else 1)
-        P.fast = int(self.cfg.get_opt("sweepMode", P.fast))     # experiments: 3 listed / 4 cell-segment form of the generic sweeps
         grav = self.cfg.get_cfg("gravitation")
         for a in range(3):
             P.gn[a] = int(self.grid_num[a])

@@ -81,6 +81,22 @@ class RunControl:
                (cur_time >= self.exit_at_time and self.exit_at_time > 0)             # ui:236
         return export, paused, done
 
+    def fast_forward(self, count_step):
+        """A run resumed from a checkpoint taken at ``count_step``: the rules that already fired up to (and including) that
+        step are spent -- one-shot stops are cleared, the periodic thresholds move past the restored step / time -- so
+        that a run that had stopped at one of them continues instead of stopping again at once."""
+        cur_time = self.dt * count_step
+        if self.stop_at_step > 0 and count_step >= self.stop_at_step:
+            self.stop_at_step = 0
+        if self.stop_at_time > 0 and cur_time >= self.stop_at_time:
+            self.stop_at_time = 0
+        if self.stop_every_step > 0:
+            while self.stop_at_step_tmp <= count_step:
+                self.stop_at_step_tmp += self.stop_every_step
+        if self.save_every_time > 0:
+            while self.save_every_time <= cur_time:
+                self.save_every_time += self.save_every_time_tmp
+
 
 def stamp_of(export):
     kind, value = export
@@ -208,7 +224,9 @@ def save_info(simpath, text):
 
 
 # ------------------------------------------------------------------------------------------------------ checkpoints
-_CKPT_FIELDS = ("x", "v", "density", "pressure", "mat_type", "id0")
+# every member that travels through the sort (sph_state_fields): v_tmp / density_tmp of WALL particles are carried state
+# in mu(I) (the soil loop of a one_step reads the wall velocities extrapolated by the PREVIOUS one_step)
+_CKPT_FIELDS = ("x", "v", "density", "pressure", "mat_type", "id0", "v_tmp", "density_tmp")
 _CKPT_SOIL = ("strain_equ", "strain_equ_p", "flag_retmap")
 
 
@@ -263,6 +281,8 @@ def ui_sim(case, max_steps=None, out_dir=None, checkpoint_every=0, resume=None, 
         os.makedirs(simpath, exist_ok=True)
     log("UI %dD starts to serve! (headless)" % case.ps.dim)                          # ui:88-91
     count_step = load_checkpoint(resume, case) if resume else 0
+    if resume:
+        ctl.fast_forward(count_step)
     files, info_saved, reason = [], False, "max_steps"
 
     def do_export(export):
@@ -274,8 +294,9 @@ def ui_sim(case, max_steps=None, out_dir=None, checkpoint_every=0, resume=None, 
         if ctl.save_csv:
             files.append(export_csv(stamp, simpath, case))
 
-    # the reference evaluates its rules once before the first step too (count_step == 0 exports the initial state)
-    first = True
+    # the reference evaluates its rules once before the first step too (count_step == 0 exports the initial state);
+    # a resumed run has been through the rules of its restored step already
+    first = not resume
     while True:
         if not first:
             nstep = ctl.substeps if max_steps is None else min(ctl.substeps, max_steps - count_step)
