@@ -88,6 +88,8 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
     // Per-step neighbour lists of the generic sweeps (every solver / precision that does not run the cell-tile WCSPH
     // path).  2D: ~28 neighbours among 81 candidates, 64 entries cover compressed states; 3D would need ~160 entries
     // (640 B per particle), so there the sweeps keep walking the cells.  Particles that do not fit walk, too.
+    int64_t o_sor = 0;
+    if (soil) { o_sor = off; off += align_up(n_max * 6 * (int64_t)rb); }
     const int nl_cap = (p->fast && !fast && p->dim == 2 && n_max < (1ll << 27)) ? 64 : 0;
     int64_t o_nl = 0, o_nc = 0;
     if (nl_cap) { o_nl = off; off += align_up(n_max * 4 * (int64_t)nl_cap); o_nc = off; off += align_up(n_max * 4); }
@@ -124,7 +126,7 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
         c->off_nlist = o_nlist; c->off_lrounds = o_lrounds; c->use_list = lists; c->list_valid = false;
         c->off_gid_unsorted = o_gid; c->off_slot = o_slot; c->off_perm = o_perm; c->off_tmpidx = o_tmp;
         c->off_bad = o_bad; c->off_scan_tiles = o_tiles; c->off_slabctl = o_ctl;
-        c->off_gnl = o_nl; c->off_gnl_count = o_nc; c->gnl_cap = nl_cap; c->gnl_valid = false;
+        c->off_sor = o_sor; c->off_gnl = o_nl; c->off_gnl_count = o_nc; c->gnl_cap = nl_cap; c->gnl_valid = false;
         c->real_bytes = rb; c->soil = soil; c->rk = rk; c->has_L = hasL; c->C = (int)C;
     }
     return off;
@@ -240,6 +242,7 @@ template <typename T> Dev<T> make_dev(SphCtx *c, int which) {
     d.flag = (int *)ptr(SPH_F_FLAG_RETMAP, alt);
     d.stress = (T *)ptr(SPH_F_STRESS, alt);
     d.stress_t = (T *)ptr(SPH_F_STRESS_TMP, false);
+    d.sor = c->off_sor ? (T *)(c->arena + c->off_sor) : nullptr;
     d.strain = (T *)ptr(SPH_F_STRAIN_EQU, alt);
     d.strain_p = (T *)ptr(SPH_F_STRAIN_EQU_P, alt);
     d.cspm_f = (T *)ptr(SPH_F_CSPM_F, false);

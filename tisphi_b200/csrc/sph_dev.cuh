@@ -68,6 +68,7 @@ template <typename T> struct Dev {
     T *press, *pnew;
     int *type, *id0, *gid, *flag;
     T *stress, *stress_t, *strain, *strain_p;     // x6
+    T *sor;                                       // x6 scratch: stress_tmp / density_tmp^2, the per-neighbour quotients of the momentum sum
     T *cspm_f, *cspm_L;
     T *d_rho; Vec4<T> *d_vel; T *d_stress, *v_grad, *d_strain, *d_strain_p;
     T *d_rho_rk; Vec4<T> *d_vel_rk; T *d_stress_rk;
@@ -167,15 +168,16 @@ template <typename T> __device__ __forceinline__ T kernel_dW_over_r(const Dev<T>
 // it: it evaluates a cell pair once and transposes the bit matrix).   body(j, dx, dy, dz, r, V_j)
 //
 // Two forms with IDENTICAL results (same neighbours, same order, same arithmetic):
-//   walk    the candidate loops over the 3^dim cells (LIST_BUILD: they only record (stencil cell, j) words, the task is
-//           not called -- sweeps.cu::k_build_nlist);
+//   walk    the candidate loops over the 3^dim cells.  MODE 0: the task runs inside them; 1: they only record (stencil
+//           cell, j) words; 2: both -- the first sweep after the grid build, the kernel correction, builds the step's lists
+//           on its way (sweeps.cu::k_corr_nlist);
 //   replay  (Dev::gnl != null and the particle's list fits) the task runs over the recorded words: no candidate tests,
 //           and every lane of a warp has work until its own list ends instead of idling through the ~2/3 (2D) of the
 //           candidates that fail the test.
 constexpr unsigned NB_IDX_BITS = 27, NB_IDX_MASK = (1u << NB_IDX_BITS) - 1u;      // lists need n_max < 2^27
 
-// returns the number of neighbours (LIST_BUILD) or 0
-template <typename T, bool LIST_BUILD, typename F>
+// returns the number of neighbours (MODE 1, 2) or 0
+template <typename T, int MODE, typename F>
 __device__ __forceinline__ int for_neighbors_walk(const Dev<T> &c, int i, unsigned *out, int ostride, int ocap, F &&body) {
     int cc[3], sc[3] = {0, 0, 0};
     const double xi[3] = {c.x[3 * (size_t)i], c.x[3 * (size_t)i + 1], c.x[3 * (size_t)i + 2]};
@@ -210,10 +212,11 @@ __device__ __forceinline__ int for_neighbors_walk(const Dev<T> &c, int i, unsign
                     else { dx = -((pj.x + sx) - pi.x); dy = -((pj.y + sy) - pi.y); dz = -((pj.z + sz) - pi.z); }
                     T r2 = dist2(dx, dy, dz);
                     if (r2 < c.r2thr) {
-                        if (LIST_BUILD) {
+                        if (MODE != 0) {
                             if (cnt < ocap) out[(size_t)cnt * ostride] = code | (unsigned)j;
                             cnt++;
-                        } else body(j, dx, dy, dz, sqrt_rn(r2), pj.w);
+                        }
+                        if (MODE != 1) body(j, dx, dy, dz, sqrt_rn(r2), pj.w);
                     }
                 }
             }
@@ -224,7 +227,7 @@ __device__ __forceinline__ int for_neighbors_walk(const Dev<T> &c, int i, unsign
 template <typename T, typename F> __device__ __forceinline__ void for_neighbors(const Dev<T> &c, int i, F &&body) {
     const int cnt = c.gnl ? c.gnl_count[i] : -1;
     if (cnt < 0) {
-        for_neighbors_walk<T, false>(c, i, nullptr, 0, 0, body);
+        for_neighbors_walk<T, 0>(c, i, nullptr, 0, 0, body);
         return;
     }
     // replay: the list was built from the stored cell of i (positions have not changed since), shifts relative to it

@@ -84,6 +84,7 @@ struct SphCtx {
     int own0, own1;      // owned x-columns [own0, own1) (multi-GPU slabs); the whole grid on one GPU
     int64_t off_slabctl; // device-resident control block of the native slab step (slab.cu)
     sph::SlabState *slab;   // native multi-GPU slab step (sph_slab_init); null on one GPU
+    int64_t off_sor;     // soil: stress_tmp / density_tmp^2 of every particle, written right before a momentum sweep
     int64_t off_gnl, off_gnl_count;  // per-step neighbour lists of the generic sweeps (0: not allocated)
     int gnl_cap;
     bool gnl_valid;      // built for the current sort and positions

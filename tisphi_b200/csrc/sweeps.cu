@@ -53,22 +53,18 @@ SPH_PARTICLE_KERNEL(k_cspm_f, body_cspm_f)
 template <typename T> __device__ __forceinline__ T det3(const T *m) {
     return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
 }
-template <typename T> __device__ __forceinline__ void body_cspm_L(const Dev<T> &c, int i) {
-    if (not_owned(c, i)) return;
+// calc_CSPM_L (base:400-423): M += V_j (x_j - x_i) (x) gradW_ij over same-type neighbours, then L = M^-1 (2x2 block in 2D)
+template <typename T> __device__ __forceinline__ void cspm_L_add(const Dev<T> &c, T M[9], T dx, T dy, T dz, T r, T Vj) {
+    const T s = kernel_dW_over_r(c, r);
+    const T d[3] = {dx, dy, dz};
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) M[3 * a + b] += Vj * (-d[a]) * (s * d[b]);
+}
+template <typename T> __device__ __forceinline__ void cspm_L_store(const Dev<T> &c, int i, bool flow, const T M[9]) {
     T L[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    const int ti = c.type[i];
-    if (is_flow(ti)) {
-        T M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
-            if (c.type[j] == ti) {
-                const T s = kernel_dW_over_r(c, r);
-                const T d[3] = {dx, dy, dz};
-#pragma unroll
-                for (int a = 0; a < 3; a++)
-#pragma unroll
-                    for (int b = 0; b < 3; b++) M[3 * a + b] += Vj * (-d[a]) * (s * d[b]);
-            }
-        });
+    if (flow) {
         if (c.dim == 2) {
             const T det = M[0] * M[4] - M[1] * M[3];
             if (fabs(det) > c.eps) {
@@ -90,47 +86,68 @@ template <typename T> __device__ __forceinline__ void body_cspm_L(const Dev<T> &
 #pragma unroll
     for (int a = 0; a < 9; a++) c.cspm_L[9 * (size_t)i + a] = L[a];
 }
+template <typename T> __device__ __forceinline__ void body_cspm_L(const Dev<T> &c, int i) {
+    if (not_owned(c, i)) return;
+    T M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const int ti = c.type[i];
+    const bool flow = is_flow(ti);
+    if (flow)
+        for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
+            if (c.type[j] == ti) cspm_L_add(c, M, dx, dy, dz, r, Vj);
+        });
+    cspm_L_store(c, i, flow, M);
+}
 template <typename T> __global__ void __launch_bounds__(128) k_cspm_L(Dev<T> c) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < c.N()) body_cspm_L(c, i);
 }
 
-// The candidate walk of every particle, ONCE per step (positions are frozen from the grid build to advect_pos): the
-// sweeps that follow replay the recorded neighbours (sph_dev.cuh::for_neighbors).  A particle whose list does not fit,
-// or whose position is no longer in the cell it is stored in, is marked -1 and walks the cells in every sweep.
-template <typename T> __global__ void __launch_bounds__(128) k_build_nlist(Dev<T> c, unsigned *__restrict__ nlist, int *__restrict__ ncount,
-                                                                          int stride, int cap) {
+// The candidate walk of every particle, ONCE per step (positions are frozen from the grid build to advect_pos): it
+// records the neighbours for the sweeps that follow (sph_dev.cuh::for_neighbors replays them) and, being the first sweep
+// after the grid build anyway, forms the kernel correction on its way -- calc_CSPM_f (base:386-398) and, with CSPM,
+// calc_CSPM_L (base:400-423): the same tasks in the same order as k_cspm_f / k_cspm_L.  A particle whose list does not
+// fit, or whose position is no longer in the cell it is stored in, is marked -1 and walks the cells in every sweep.
+template <typename T> __global__ void __launch_bounds__(128) k_corr_nlist(Dev<T> c, unsigned *__restrict__ nlist, int *__restrict__ ncount,
+                                                                         int stride, int cap) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.N()) return;
     int cc[3], sc[3];
     const double xi[3] = {c.x[3 * (size_t)i], c.x[3 * (size_t)i + 1], c.x[3 * (size_t)i + 2]};
     pos_to_cell(c, xi, cc);
     unflatten(c, c.gid[i], sc);
+    const bool stored = cc[0] == sc[0] && cc[1] == sc[1] && cc[2] == sc[2];
+    const int ti = c.type[i];
+    const bool mine = !not_owned(c, i), want_L = c.kcorr == 1 && mine, flowL = want_L && is_flow(ti);
+    T S = 0, M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    auto task = [&](int j, T dx, T dy, T dz, T r, T Vj) {
+        const int tj = c.type[j];
+        if (mine && is_flow(tj)) S += Vj * kernel_W(c, r);
+        if (flowL && tj == ti) cspm_L_add(c, M, dx, dy, dz, r, Vj);
+    };
     int cnt = -1;
-    if (cc[0] == sc[0] && cc[1] == sc[1] && cc[2] == sc[2]) {
-        auto none = [](int, T, T, T, T, T) {};
-        cnt = for_neighbors_walk<T, true>(c, i, nlist + i, stride, cap, none);
+    if (stored) {
+        cnt = for_neighbors_walk<T, 2>(c, i, nlist + i, stride, cap, task);
         if (cnt > cap) cnt = -1;
-    }
+    } else for_neighbors_walk<T, 0>(c, i, nullptr, 0, 0, task);
     ncount[i] = cnt;
-}
-template <typename T> static int build_nlist(SphCtx *c) {
-    c->gnl_valid = false;
-    if (!c->off_gnl || c->n == 0) return 0;
-    Dev<T> d = make_dev<T>(c);
-    SPH_PROF(c, K_NLIST);
-    k_build_nlist<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(d, (unsigned *)(c->arena + c->off_gnl), (int *)(c->arena + c->off_gnl_count),
-                                                                   (int)c->n_max, c->gnl_cap);
-    SPH_LAUNCH_CHECK(c);
-    c->gnl_valid = true;
-    return 0;
+    if (mine) c.cspm_f[i] = (S != (T)0) ? (T)1 / S : (T)1;
+    if (want_L) cspm_L_store(c, i, flowL, M);
 }
 
 // standalone: every CSPM_f is final on return (the API call).  Otherwise (inside sph_step) the tile path leaves the
 // Shepard sums of unflagged cells to the wall pass and the first fluid pass, which visit the same neighbours anyway.
 template <typename T> int calc_kernel_corr(SphCtx *c, bool standalone) {
     if (c->n == 0) return 0;
-    if (!c->fast) { int r = build_nlist<T>(c); if (r) return r; }      // the generic sweeps of this step replay it
+    c->gnl_valid = false;
+    if (!c->fast && c->off_gnl) {        // generic sweeps with per-step lists: correction and lists in one walk
+        Dev<T> d = make_dev<T>(c);
+        SPH_PROF(c, K_NLIST);
+        k_corr_nlist<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(d, (unsigned *)(c->arena + c->off_gnl), (int *)(c->arena + c->off_gnl_count),
+                                                                      (int)c->n_max, c->gnl_cap);
+        SPH_LAUNCH_CHECK(c);
+        c->gnl_valid = true;
+        return 0;
+    }
     Dev<T> d = make_dev<T>(c);
     if (c->fast) {                       // tile path: masks (+ CSPM_f); the generic kernel completes flagged cells
         int r = tile_mask(c, standalone);
@@ -297,6 +314,16 @@ template <typename T> __global__ void __launch_bounds__(128) k_soil_wall(Dev<T> 
     if (i < c.N()) body_soil_wall(c, i);
 }
 
+// stress_tmp / density_tmp^2 of every particle (walls and ghosts included), the neighbour payload of the momentum sum
+template <typename T> __global__ void __launch_bounds__(256) k_soil_sor(Dev<T> c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N()) return;
+    const T rho = c.vt4[i].w, r2 = rho * rho;
+    const T *s = c.stress_t + 6 * (size_t)i;
+    T *o = c.sor + 6 * (size_t)i;
+#pragma unroll
+    for (int q = 0; q < 6; q++) o[q] = s[q] / r2;
+}
 // accumulators of one soil sweep: velocity gradient, continuity sum, momentum sum
 template <typename T, bool VG, bool MOM>
 __device__ __forceinline__ void soil_sweep(const Dev<T> &c, int i, T vg[9], T *dd, T mom[3]) {
@@ -329,32 +356,20 @@ __device__ __forceinline__ void soil_sweep(const Dev<T> &c, int i, T vg[9], T *d
             acc += Vj * (-u[0]) * gc[0] + Vj * (-u[1]) * gc[1] + Vj * (-u[2]) * gc[2];
         }
         if (MOM) {      // muI:38-46 / dp:156-165: V_j rho~_j (sigma~_j / rho~_j^2 + sigma~_i / rho~_i^2) . gradW^c
-            const T rhoj = vj.w, cf = Vj * rhoj;
-            if (sizeof(T) == 4) {
-                // float32 sweeps: the expression above divides 18 times per neighbour; 9 of the quotients (sigma~_i /
-                // rho~_i^2) do not depend on j and 3 of the other 9 are duplicates of a symmetric tensor.  Same quotients,
-                // same products, same sums -- bit-identical to evaluating it as written -- with 6 divisions per neighbour.
-                const T *q = c.stress_t + 6 * (size_t)j;
-                const T r2j = rhoj * rhoj;
-                const T mxx = cf * (q[0] / r2j + sir[0]), myy = cf * (q[1] / r2j + sir[4]), mzz = cf * (q[2] / r2j + sir[8]);
-                const T mxy = cf * (q[3] / r2j + sir[1]), myz = cf * (q[4] / r2j + sir[5]), mzx = cf * (q[5] / r2j + sir[2]);
-                T t0 = 0, t1 = 0, t2 = 0;
-                t0 += mxx * gc[0]; t0 += mxy * gc[1]; t0 += mzx * gc[2];
-                t1 += mxy * gc[0]; t1 += myy * gc[1]; t1 += myz * gc[2];
-                t2 += mzx * gc[0]; t2 += myz * gc[1]; t2 += mzz * gc[2];
-                mom[0] += t0; mom[1] += t1; mom[2] += t2;
-            } else {
-                T sj[9];
-                sym_load(c.stress_t, (size_t)j, sj);
-                const T r2j = rhoj * rhoj, r2i = rhoi * rhoi;
-#pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    T t = 0;
-#pragma unroll
-                    for (int b = 0; b < 3; b++) t += (cf * (sj[3 * a + b] / r2j + si[3 * a + b] / r2i)) * gc[b];
-                    mom[a] += t;
-                }
-            }
+            // The expression divides 18 times per neighbour.  The quotients sigma~_j / rho~_j^2 are a property of particle j
+            // alone: k_soil_sor forms them once per particle right before this sweep (the 6 components of the symmetric
+            // tensor), the particle's own are formed before the loop.  Same quotients, same products, same order of sums:
+            // bit-identical to the expression as written.  (A reciprocal-and-multiply form is cheaper still but multiplies
+            // the 30-step velocity error of BASELINE config C3 by 20 -- the sum cancels to ~1e-4 of its terms.)
+            const T cf = Vj * vj.w;
+            const T *q = c.sor + 6 * (size_t)j;
+            const T mxx = cf * (q[0] + sir[0]), myy = cf * (q[1] + sir[4]), mzz = cf * (q[2] + sir[8]);
+            const T mxy = cf * (q[3] + sir[1]), myz = cf * (q[4] + sir[5]), mzx = cf * (q[5] + sir[2]);
+            T t0 = 0, t1 = 0, t2 = 0;
+            t0 += mxx * gc[0]; t0 += mxy * gc[1]; t0 += mzx * gc[2];
+            t1 += mxy * gc[0]; t1 += myy * gc[1]; t1 += myz * gc[2];
+            t2 += mzx * gc[0]; t2 += myz * gc[1]; t2 += mzz * gc[2];
+            mom[0] += t0; mom[1] += t1; mom[2] += t2;
         }
     });
     *dd = acc;
@@ -581,6 +596,9 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
             SPH_PROF(c, K_SOIL_WALL);
             k_soil_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         } else {
+            SPH_PROF(c, K_OTHER);
+            k_soil_sor<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
+            SPH_LAUNCH_CHECK(c);
             SPH_PROF(c, K_MUI_SOIL3);
             k_mui_soil3<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         }
@@ -594,6 +612,9 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
             SPH_PROF(c, K_SOIL_WALL);
             k_soil_wall<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         } else {
+            SPH_PROF(c, K_OTHER);
+            k_soil_sor<T><<<blocks_for(n, 256), 256, 0, st>>>(d);
+            SPH_LAUNCH_CHECK(c);
             SPH_PROF(c, K_DP_SOIL);
             k_dp_soil<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
         }
@@ -667,9 +688,9 @@ template <typename T> __global__ void __launch_bounds__(256) k_refresh_xs(Dev<T>
 }
 template <typename T> int advect_pos(SphCtx *c) {
     if (c->n == 0) return 0;
-    c->gnl_valid = false;                     // positions move: what follows (mu(I) regularisation, H15) walks the cells
     const int n = (int)c->n;
-    Dev<T> d = make_dev<T>(c);
+    Dev<T> d = make_dev<T>(c);                  // (XSPH reads the pre-move positions: it still replays the step's lists)
+    c->gnl_valid = false;                     // positions move: what follows (mu(I) regularisation, H15) walks the cells
     if (!c->p.xsph) {
         SPH_PROF(c, K_ADVECT_POS);
         k_advect_pos<T><<<blocks_for(n, 256), 256, 0, c->stream>>>(d);
