@@ -47,6 +47,11 @@ typedef struct SphParams {
     double h, support, grid_size, vstart[3], m_V0, g[3], dt, eps;
     double rho0, visc, stiff, gamma_;                                   /* wc:12-15 */
     double coh, fric, E, poi, dila, vsound, mu, alpha, kc, G, K, eps_f; /* muI:12-24, dp:12-29 */
+    /* boundary treatment (ps:18, 25): 0 none, 1 enforced collision, 2 dummy particles, 3 repulsive particles,
+     * 4 dummy + repulsive.  Modes 3 / 4 add calc_repulsive_force (base:675-689) of type -2 neighbours to the momentum
+     * sums (wc:119-121, muI:121-123); mode 1 makes sph_enforce_boundary clamp flow particles into the domain box. */
+    int32_t boundary, pad_;
+    double radius, dstart[3], dend[3];                                  /* particleRadius, domainStart, domainEnd */
 } SphParams;
 
 /* Particle members (names of eng/particle_func.py:13-69).  KIND: 0 = float64, 1 = engine real (float64 or float32
@@ -134,6 +139,10 @@ int sph_advect(SphCtx *ctx, int kind, int m);
 int sph_advect_pos(SphCtx *ctx);
 /* SPHBase.advect_something (base:244-247 -> wc:129-132 | muI:134-156 | dp:276-296) */
 int sph_post_step(SphCtx *ctx);
+/* SPHBase.enforce_boundary (base:525-601): with boundary == 1 every flow particle outside the domain box (no lid) is put
+ * back on its face and loses (1 + 0.3) of its normal velocity; a no-op in the other modes (dynamic rigid bodies: see
+ * sph_solve_rigid_body) */
+int sph_enforce_boundary(SphCtx *ctx);
 /* SPHBase.init_stress (base:249-260) */
 int sph_init_stress(SphCtx *ctx);
 /* the same with y_max given by the caller: a ctx that holds one slab of a scene must use the highest soil particle of

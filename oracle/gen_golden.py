@@ -117,6 +117,16 @@ CASES = {
     "dp2d_plate_lf": (lambda: _plate(), [1, 2, 10]),
     # tiny 3D dambreak with the C4 parameter set
     "wc3d_tiny_lf": (lambda: _scene("test1_db_water.json", dict(WATER3D), dict(size=[0.16, 0.12, 0.12])), [1, 2, 3]),
+    # ---- round 2, SURVEY 8 f3: the other boundary modes (1 enforced collision, 3 repulsive particles, 4 dummy + repulsive)
+    "wc2d_rep_lf": (lambda: _scene("test1_db_water.json", dict(domainEnd=[1.0, 0.6, 0.5], boundary=3),
+                                   dict(size=[0.4, 0.3, 0.1])), [1, 2, 10]),
+    "wc2d_dummyrep_lf": (lambda: _scene("test1_db_water.json", dict(domainEnd=[1.0, 0.6, 0.5], boundary=4),
+                                        dict(size=[0.4, 0.3, 0.1])), [1, 2, 10]),
+    "wc2d_collision_lf": (lambda: _scene("test1_db_water.json", dict(domainEnd=[1.0, 0.6, 0.5], boundary=1),
+                                         dict(size=[0.4, 0.3, 0.1])), [1, 2, 10, 40]),
+    "mui2d_dummyrep_lf": (lambda: _scene("test2_cc_sand.json",
+                                         dict(domainEnd=[0.2, 0.08, 0.05], simulationMethod=2, boundary=4),
+                                         dict(size=[0.08, 0.05, 0.05])), [1, 2, 10]),
     # ---- round 2: the BASELINE configs over their full horizons (100 steps for C1-C3) ----
     "c1_test1_wc_lf_h100": (lambda: _scene("test1_db_water.json"), [1, 10, 50, 100]),
     "c2_test2_mui_lf_h100": (lambda: _scene("test2_cc_sand.json", dict(simulationMethod=2)), [1, 10, 50, 100]),

@@ -42,7 +42,9 @@ class OrcParams(C.Structure):
                [("h", C.c_double), ("support", C.c_double), ("grid_size", C.c_double), ("vstart", C.c_double * 3),
                 ("m_V0", C.c_double), ("g", C.c_double * 3), ("dt", C.c_double), ("eps", C.c_double)] + \
                [(k, C.c_double) for k in ("rho0", "visc", "stiff", "gamma_", "coh", "fric", "E", "poi", "dila",
-                                          "vsound", "mu", "alpha", "kc", "G", "K", "eps_f")]
+                                          "vsound", "mu", "alpha", "kc", "G", "K", "eps_f")] + \
+               [("boundary", C.c_int), ("pad_", C.c_int), ("radius", C.c_double), ("dstart", C.c_double * 3),
+                ("dend", C.c_double * 3)]
 
 
 _lib = None
@@ -61,7 +63,7 @@ def lib():
         L.orc_cell_end.restype = C.POINTER(C.c_int64)
         L.orc_cell_end.argtypes = [C.c_void_p]
         for fn in ("orc_destroy", "orc_calc_kernel_corr", "orc_init_real2tmp", "orc_one_step", "orc_init_stress",
-                   "orc_advect_pos", "orc_post_step"):
+                   "orc_advect_pos", "orc_post_step", "orc_enforce_boundary"):
             getattr(L, fn).argtypes = [C.c_void_p]
             getattr(L, fn).restype = None
         L.orc_set_params.argtypes = [C.c_void_p, C.POINTER(OrcParams)]
@@ -133,6 +135,20 @@ def dummy_boxes(dim, ds, de, vs, ve):
             (np.array([de[0], ds[1], ds[2]]), np.array([ve[0], de[1], de[2]]))]
 
 
+def rep_boxes(dim, ds, de, radius):
+    """pf:346-374: one layer of repulsive particles ON the domain faces (no lid), half a radius thick."""
+    t = radius / 2
+    if dim == 3:
+        return [(np.array([ds[0] - t, ds[1] + t, ds[2] - t]), np.array([ds[0] + t, de[1] - t, de[2] - t])),
+                (np.array([ds[0] - t, ds[1] + t, de[2] - t]), np.array([de[0] - t, de[1] - t, de[2] + t])),
+                (np.array([de[0] - t, ds[1] + t, ds[2] + t]), np.array([de[0] + t, de[1] - t, de[2] + t])),
+                (np.array([ds[0] + t, ds[1] + t, ds[2] - t]), np.array([de[0] + t, de[1] - t, ds[2] + t])),
+                (ds - t, np.array([de[0], ds[1], de[2]]) + t)]
+    return [(np.array([ds[0] - t, ds[1] + t, ds[2]]), np.array([ds[0] + t, de[1] - t, de[2]])),
+            (np.array([ds[0] - t, ds[1] - t, ds[2]]), np.array([de[0] + t, ds[1] + t, de[2]])),
+            (np.array([de[0] - t, ds[1] + t, ds[2]]), np.array([de[0] + t, de[1] - t, de[2]]))]
+
+
 def build_particles(scene):
     """Particle set in creation order (blocks in JSON order, then dummy boxes): ps:135-174, pf:308-313."""
     cfg = scene["Configuration"]
@@ -157,7 +173,13 @@ def build_particles(scene):
             vs_.append(np.zeros_like(p))
             rho.append(np.zeros(len(p)))              # walls: density 0 -> mass 0 (pf:206, ps:282)
             typ.append(np.full(len(p), -1, dtype=np.int32))
-    assert cfg["boundary"] in (0, 2), "oracle covers boundary modes 0 and 2 only"
+    if cfg["boundary"] in (3, 4):                     # ps:147-148: spacing = particle radius, type -2
+        for lo, hi in rep_boxes(dim, D["domain_start"], D["domain_end"], cfg["particleRadius"]):
+            p = cube_positions(lo, hi - lo, dim, cfg["particleRadius"])
+            xs.append(p)
+            vs_.append(np.zeros_like(p))
+            rho.append(np.zeros(len(p)))
+            typ.append(np.full(len(p), -2, dtype=np.int32))
     return D, np.concatenate(xs), np.concatenate(vs_), np.concatenate(rho), np.concatenate(typ)
 
 
@@ -178,6 +200,9 @@ def make_params(scene, serial=1, wc_fresh=0):
         P.vstart[a] = float(D["vstart"][a])
         P.g[a] = float(cfg["gravitation"][a])
     P.h, P.support, P.grid_size, P.m_V0, P.eps = D["h"], D["support"], D["grid_size"], D["m_V0"], 1e-8
+    P.boundary, P.radius = int(cfg["boundary"]), float(cfg["particleRadius"])
+    for a in range(3):
+        P.dstart[a], P.dend[a] = float(D["domain_start"][a]), float(D["domain_end"][a])
     fluids = [m for m in scene.get("Materials", []) if m["matType"] == 1]
     soils = [m for m in scene.get("Materials", []) if m["matType"] == 2]
     dt_min = cfg["timeStepSizeMin"]

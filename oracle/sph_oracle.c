@@ -37,6 +37,9 @@ typedef struct {
     double h, support, grid_size, vstart[3], m_V0, g[3], dt, eps;
     double rho0, visc, stiff, gamma_;                                  /* WCSPH material (wc:12-15)      */
     double coh, fric, E, poi, dila, vsound, mu, alpha, kc, G, K, eps_f; /* soil (muI:12-24, dp:12-29)     */
+    /* boundary treatment (ps:18, 25): 0 none, 1 enforced collision, 2 dummy, 3 repulsive, 4 dummy + repulsive */
+    int boundary, pad_;
+    double radius, dstart[3], dend[3];                                 /* particleRadius, domainStart / domainEnd */
 } OrcParams;
 
 enum { F_X, F_V, F_M_V, F_DENSITY, F_MASS, F_PRESSURE, F_STRESS, F_CSPM_F, F_CSPM_L, F_D_DENSITY, F_D_VEL,
@@ -375,6 +378,20 @@ static inline double eos_wc(const OrcParams *p, double rho) {
 /* phase: -1 = the whole one_step; 0, 1, (2) = one top-level loop only (used by the slab-decomposition tests, which
  * refresh ghost columns between the loops exactly as tisphi_b200/parallel.py does on the GPUs) */
 #define PHASE(k) if (phase == -1 || phase == (k))
+/* calc_repulsive_force (base:675-689) of rep particle j on i, d = x_i - x_j, added to acc */
+static inline void rep_force(const OrcParams *p, const double d[3], double r, double acc[3]) {
+    const double r_judge = 2.0 * p->radius;
+    const double chi = (r > 0.0 && r < r_judge) ? 1.0 - r / r_judge : 0.0;
+    const double gamma = r / (0.75 * p->h);
+    double f = 0.0;
+    if (gamma > 0 && gamma <= 2.0 / 3.0) f = 2.0 / 3.0;
+    else if (gamma > 2.0 / 3.0 && gamma <= 1) f = 2 * gamma - 1.5 * gamma * gamma;
+    else if (gamma > 1 && gamma < 2) f = 0.5 * (2 - gamma) * (2 - gamma);
+    const double k = 0.01 * p->vsound * p->vsound * chi * f / (r * r);
+    for (int a = 0; a < 3; a++) acc[a] += k * d[a];
+}
+static inline int has_rep(const OrcParams *p) { return p->boundary == 3 || p->boundary == 4; }
+
 static void one_step_wc(Orc *o, int phase) {
     const OrcParams *p = &o->p;
     int64_t n = o->n;
@@ -437,6 +454,7 @@ static void one_step_wc(Orc *o, int phase) {
             double pres = -p->rho0 * V * (pi / (rhoi * rhoi) + pr[j] / (rhoj * rhoj));
             for (int a = 0; a < 3; a++) dv[a] += visc * g[a] + pres * g[a];
         });
+        if (has_rep(p)) FOR_NEIGHBORS(o, i, { if (TYPE(o, j) == -2) rep_force(p, d, r, dv); });      /* wc:119-121 */
         o->f[F_D_DENSITY][i] = dd * rhoi;
         for (int a = 0; a < 3; a++) o->f[F_D_VEL][3 * i + a] = dv[a] + p->g[a];
     }
@@ -516,6 +534,7 @@ static void one_step_mui(Orc *o, int phase) {
         if (!is_soil(TYPE(o, i))) continue;
         double dv[3], Fd[3];
         soil_momentum(o, i, dv);
+        if (has_rep(p)) FOR_NEIGHBORS(o, i, { if (TYPE(o, j) == -2) rep_force(p, d, r, dv); });      /* muI:121-123 */
         viscous_damping(p, o->f[F_DENSITY_TMP][i], &o->f[F_V_TMP][3 * i], Fd);
         for (int a = 0; a < 3; a++) o->f[F_D_VEL][3 * i + a] = dv[a] + p->g[a] + Fd[a];
     }
@@ -615,6 +634,7 @@ static void one_step_dp(Orc *o, int phase) {
         o->f[F_D_DENSITY][i] = dd * o->f[F_DENSITY_TMP][i];
         bui2008(p, &o->f[F_STRESS_TMP][9 * i], vg, &o->f[F_D_STRESS][9 * i], &o->f[F_D_STRAIN_EQU][i], &o->f[F_D_STRAIN_EQU_P][i]);
         soil_momentum(o, i, dv);
+        if (has_rep(p)) FOR_NEIGHBORS(o, i, { if (TYPE(o, j) == -2) rep_force(p, d, r, dv); });      /* muI:121-123 */
         viscous_damping(p, o->f[F_DENSITY_TMP][i], &o->f[F_V_TMP][3 * i], Fd);
         for (int a = 0; a < 3; a++) o->f[F_D_VEL][3 * i + a] = dv[a] + p->g[a] + Fd[a];
     }
@@ -740,6 +760,32 @@ void orc_post_step(Orc *o) {
 }
 
 /* ---------------------------------------------------------------------------- SPHBase.step (base:41-61) */
+/* enforce_boundary (base:525-601): flow particles when boundary == 1 (dynamic rigid particles always -- none here) are
+ * put back inside the domain box, no lid, and lose (1 + c_f) of their normal velocity. */
+void orc_enforce_boundary(Orc *o) {
+    const OrcParams *p = &o->p;
+    if (p->boundary != 1) return;
+    const double rr = p->radius - p->eps;
+    for (int64_t i = 0; i < o->n; i++) {
+        if (!is_flow(TYPE(o, i))) continue;
+        double *x = X(o, i), *v = &o->f[F_V][3 * i], nrm[3] = {0, 0, 0};
+        const double pos[3] = {x[0], x[1], x[2]};
+        if (pos[0] > p->dend[0] - rr) { nrm[0] += 1.0; x[0] = p->dend[0] - rr; }
+        if (pos[0] <= p->dstart[0] + rr) { nrm[0] += -1.0; x[0] = p->dstart[0] + rr; }
+        if (pos[1] <= p->dstart[1] + rr) { nrm[1] += -1.0; x[1] = p->dstart[1] + rr; }
+        if (p->dim == 3) {
+            if (pos[2] > p->dend[2] - rr) { nrm[2] += 1.0; x[2] = p->dend[2] - rr; }
+            if (pos[2] <= p->dstart[2] + rr) { nrm[2] += -1.0; x[2] = p->dstart[2] + rr; }
+        }
+        const double len = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+        if (len > p->eps) {                                /* simulate_collisions, c_f = 0.3 (base:598-601) */
+            const double u[3] = {nrm[0] / len, nrm[1] / len, nrm[2] / len};
+            const double vn = v[0] * u[0] + v[1] * u[1] + v[2] * u[2];
+            for (int a = 0; a < 3; a++) v[a] -= (1.0 + 0.3) * vn * u[a];
+        }
+    }
+}
+
 int64_t orc_step(Orc *o) {
     int64_t bad = orc_grid_build(o);
     orc_calc_kernel_corr(o);
@@ -757,6 +803,7 @@ int64_t orc_step(Orc *o) {
     }
     orc_advect_pos(o);
     orc_post_step(o);
+    orc_enforce_boundary(o);
     return bad;
 }
 

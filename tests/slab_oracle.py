@@ -154,3 +154,6 @@ class OracleSlabEngine:
 
     def post_step(self):
         self.o.L.orc_post_step(self.o.h)
+
+    def enforce_boundary(self):
+        self.o.L.orc_enforce_boundary(self.o.h)

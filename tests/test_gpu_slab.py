@@ -82,6 +82,8 @@ SOIL_CASES = [
     ("dp2d_small_lf", "f32", {}),
     ("dp2d_plate_lf", "f64", {}),            # several soil blocks of different height: init_stress needs the GLOBAL soil top
     ("wc2d_indenter_lf", "f32", {}),         # static rigid block
+    ("wc2d_dummyrep_lf", "f64", {}),         # repulsive particles (boundary 4): generic sweeps with the type-dependent force
+    ("wc2d_collision_lf", "f32", {}),        # enforced collision (boundary 1): no wall particles at all
 ]
 
 

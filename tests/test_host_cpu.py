@@ -36,7 +36,7 @@ def test_params_struct_matches_header_size():
     P.precision = 0
     b = L.sph_arena_bytes(ctypes.byref(P), 1000)
     assert 0 < a < b < 10_000_000
-    assert ctypes.sizeof(_lib.SphParams) == L.sph_params_size() == 12 * 4 + 28 * 8
+    assert ctypes.sizeof(_lib.SphParams) == L.sph_params_size() == 14 * 4 + 35 * 8         # + boundary, pad, radius, dstart[3], dend[3]
 
 
 def test_engine_fails_loudly_without_cuda():

@@ -12,6 +12,8 @@ CASES = ["wc2d_small_lf", "wc2d_small_se_cubic", "wc2d_small_rk4_cspm", "mui2d_s
          "dp2d_indenter_lf", "wc2d_indenter_lf",
          # shipped test5 shrunken: four soil blocks + a static rigid plate pushed sideways
          "dp2d_plate_lf",
+         # boundary modes 3 (repulsive particles), 4 (dummy + repulsive), 1 (enforced collision)
+         "wc2d_rep_lf", "wc2d_dummyrep_lf", "wc2d_collision_lf", "mui2d_dummyrep_lf",
          # round 2: the BASELINE configs over their full horizons (C1, C2: 100 steps, C3: 30 steps; ~1 h of emulator each)
          "c1_test1_wc_lf_h100", "c2_test2_mui_lf_h100", "c3_test2_dp_rk4_cspm_h30"]
 
@@ -31,7 +33,7 @@ def test_oracle_matches_reference_run(name):
     assert o.n == g.meta["n"]
     assert o.P.dt == g.meta["dt"]
     assert [int(v) for v in o.D["grid_num"]] == g.meta["grid_num"]
-    last = max(g.steps) if name.endswith("small_lf") or "tiny" in name or "indenter" in name or "plate" in name or "_h" in name else min(max(g.steps), 10)
+    last = max(g.steps) if name.endswith("small_lf") or "tiny" in name or "indenter" in name or "plate" in name or "_h" in name or "rep" in name or "collision" in name else min(max(g.steps), 10)
     for s in range(1, last + 1):
         if s in g.steps:
             # state right after the grid build + kernel correction of step s

@@ -57,7 +57,9 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
     const bool soil = p->solver != SPH_SOLVER_WC, rk = p->ti == 4, hasL = p->kcorr == 1;
     const int64_t C = n_cells(p);
     // cell-tile fast path scratch: MIXED precision WCSPH without CSPM_L
-    const bool fast = p->fast && p->precision == SPH_PREC_MIXED && p->solver == SPH_SOLVER_WC && p->kcorr == 0;
+    // (the payload sign of the tile passes tells flow from non-flow only: repulsive particles, boundary 3 / 4, need the type)
+    const bool fast = p->fast && p->precision == SPH_PREC_MIXED && p->solver == SPH_SOLVER_WC && p->kcorr == 0 &&
+                      p->boundary != 3 && p->boundary != 4;
     int64_t off = 0;
     for (int f = 0; f < SPH_F_NUM; f++) {
         const FieldSpec &s = SPEC[f];
@@ -220,6 +222,9 @@ template <typename T> Dev<T> make_dev(SphCtx *c, int which) {
     d.coh = (T)p.coh; d.mu = (T)p.mu; d.E = (T)p.E; d.alpha = (T)p.alpha; d.kc = (T)p.kc; d.G = (T)p.G; d.K = (T)p.K;
     d.eps_f = (T)p.eps_f; d.sin_dila = (T)sin(p.dila);
     d.damp_c = (T)(-5e-5 * sqrt(p.E) / p.h);
+    d.boundary = p.boundary; d.radius_d = p.radius;
+    for (int a = 0; a < 3; a++) { d.dstart[a] = p.dstart[a]; d.dend[a] = p.dend[a]; }
+    d.rep_k = (T)(0.01 * p.vsound * p.vsound); d.rep_judge = (T)(2.0 * p.radius); d.rep_ginv = (T)(1.0 / (0.75 * p.h));
     auto ptr = [&](int f, bool alt) -> char * {
         const FieldSlot &F = c->f[f];
         if (!F.present) return nullptr;
@@ -320,10 +325,14 @@ template <typename T> int step_once(SphCtx *c) {
         snprintf(c->err, sizeof(c->err), "timeIntegration %d is not runnable (3 is broken in the reference, base:126-130)", c->p.ti);
         return -2;
     }
-    if (wc_fused) return finish_step<T>(c);
-    if ((r = advect_pos<T>(c))) return r;
-    if ((r = slab_refresh_post(c))) return r;
-    return post_step<T>(c);
+    if (wc_fused) r = finish_step<T>(c);
+    else {
+        if ((r = advect_pos<T>(c))) return r;
+        if ((r = slab_refresh_post(c))) return r;
+        r = post_step<T>(c);
+    }
+    if (r) return r;
+    return enforce_boundary<T>(c);                             // (solve_rigid_body: no dynamic rigid bodies)
 }
 template <typename T> int dispatch_step(SphCtx *c, int nsteps) {
     for (int s = 0; s < nsteps; s++) {
@@ -376,7 +385,7 @@ const char *sph_last_error(SphCtx *c) { return c ? c->err : "null ctx"; }
 
 int sph_set_params(SphCtx *c, const SphParams *p) {
     if (p->dim != c->p.dim || p->precision != c->p.precision || p->solver != c->p.solver || p->ti != c->p.ti ||
-        p->kcorr != c->p.kcorr || n_cells(p) != c->C || p->fast != c->p.fast) {
+        p->kcorr != c->p.kcorr || n_cells(p) != c->C || p->fast != c->p.fast || p->boundary != c->p.boundary) {
         snprintf(c->err, sizeof(c->err), "sph_set_params cannot change sizes, solver, precision or buffers");
         return -2;
     }
@@ -469,6 +478,7 @@ int sph_one_step(SphCtx *c) { return DISPATCH(c, one_step, c, false); }
 int sph_advect(SphCtx *c, int kind, int m) { return DISPATCH(c, advect, c, kind, m); }
 int sph_advect_pos(SphCtx *c) { return DISPATCH(c, advect_pos, c); }
 int sph_post_step(SphCtx *c) { return DISPATCH(c, post_step, c); }
+int sph_enforce_boundary(SphCtx *c) { return DISPATCH(c, enforce_boundary, c); }
 int sph_init_stress(SphCtx *c) { return DISPATCH(c, init_stress, c, nullptr); }
 int sph_init_stress_ymax(SphCtx *c, double ymax) { return DISPATCH(c, init_stress, c, &ymax); }
 int sph_step(SphCtx *c, int nsteps) { return DISPATCH(c, dispatch_step, c, nsteps); }

@@ -20,6 +20,8 @@ __host__ __device__ __forceinline__ bool is_bdy(int t) { return t == -1 || t == 
 __host__ __device__ __forceinline__ bool is_rigid(int t) { return t == 11; }
 __host__ __device__ __forceinline__ bool is_wall(int t) { return is_bdy(t) || is_rigid(t); }
 
+__host__ __device__ __forceinline__ bool is_rep(int t) { return t == -2; }
+
 // rounding-exact helpers: the neighbour predicate must not be FMA-contracted
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
@@ -58,6 +60,9 @@ template <typename T> struct Dev {
     T g[3], m_V0;
     T visc_coef, rho0T, h2_001;                   // 2(dim+2) nu ; rho0 ; 0.01 h^2
     double rho0, stiff, gamma_, vsound;
+    int boundary;        // 0 none, 1 enforced collision, 2 dummy, 3 repulsive, 4 dummy + repulsive
+    double dstart[3], dend[3], radius_d;
+    T rep_k, rep_judge, rep_ginv;                 // 0.01 vsound^2 ; particle diameter ; 1 / (0.75 h)   (base:675-689)
     T coh, mu, E, alpha, kc, G, K, eps_f, sin_dila, damp_c;   // damp_c = -5e-5 * sqrt(E)/h  (base:713-715)
     // arrays (sorted order)
     double *x;           // n x 3

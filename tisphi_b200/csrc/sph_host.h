@@ -139,6 +139,7 @@ template <typename T> int one_step(SphCtx *c, bool last = false);
 template <typename T> int one_step_phase(SphCtx *c, int phase);
 template <typename T> int advect_pos(SphCtx *c);
 template <typename T> int post_step(SphCtx *c);
+template <typename T> int enforce_boundary(SphCtx *c);
 template <typename T> int finish_step(SphCtx *c);      // advect_SE/LF + advect_pos + advect_something of WCSPH in one kernel
 template <typename T> int neighbor_count(SphCtx *c, int32_t *out);
 template <typename T> int density_sum(SphCtx *c, void *out);

@@ -237,6 +237,18 @@ template <typename T> __device__ __forceinline__ void body_wc_wall(const Dev<T> 
     if (c.pk4) { Vec4<T> pk = vt; pk.w = pc / (c.rho0T * c.rho0T); c.pk4[i] = pk; }
 }
 SPH_PARTICLE_KERNEL(k_wc_wall, body_wc_wall)
+// calc_repulsive_force (base:675-689) of a repulsive particle at d = x_i - x_j, |d| = r
+template <typename T> __device__ __forceinline__ void rep_force(const Dev<T> &c, T dx, T dy, T dz, T r, T &a0, T &a1, T &a2) {
+    const T chi = (r > (T)0 && r < c.rep_judge) ? (T)1 - r / c.rep_judge : (T)0;
+    const T gamma = r * c.rep_ginv;
+    T f = 0;
+    if (gamma > (T)0 && gamma <= (T)(2.0 / 3.0)) f = (T)(2.0 / 3.0);
+    else if (gamma > (T)(2.0 / 3.0) && gamma <= (T)1) f = (T)2 * gamma - (T)1.5 * gamma * gamma;
+    else if (gamma > (T)1 && gamma < (T)2) f = (T)0.5 * ((T)2 - gamma) * ((T)2 - gamma);
+    const T k = c.rep_k * chi * f / (r * r);
+    a0 += k * dx; a1 += k * dy; a2 += k * dz;
+}
+template <typename T> __device__ __forceinline__ bool has_rep(const Dev<T> &c) { return c.boundary == 3 || c.boundary == 4; }
 // loop B (wc:108-126): continuity (corrected gradient) + viscosity + pressure (plain gradient, H22)
 template <typename T> __device__ __forceinline__ void body_wc_fluid(const Dev<T> &c, int i) {
     if (!is_fluid(c.type[i])) return;
@@ -264,6 +276,8 @@ template <typename T> __device__ __forceinline__ void body_wc_fluid(const Dev<T>
         const T pres = -c.rho0T * Vj * (pri + c.press[j] / (rhoj * rhoj));
         a0 += visc * g[0] + pres * g[0]; a1 += visc * g[1] + pres * g[1]; a2 += visc * g[2] + pres * g[2];
     });
+    if (has_rep(c))                                              // wc:119-121: a second walk, after the first, like the reference
+        for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) { if (is_rep(c.type[j])) rep_force(c, dx, dy, dz, r, a0, a1, a2); });
     c.d_rho[i] = dd * rhoi;
     Vec4<T> dv; dv.x = a0 + c.g[0]; dv.y = a1 + c.g[1]; dv.z = a2 + c.g[2]; dv.w = 0;
     c.d_vel[i] = dv;
@@ -415,6 +429,8 @@ template <typename T> __device__ __forceinline__ void body_mui_soil3(const Dev<T
     if (not_owned(c, i)) return;
     T vg[9], dd, mom[3];
     soil_sweep<T, false, true>(c, i, vg, &dd, mom);
+    if (has_rep(c))                                              // muI:121-123
+        for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) { if (is_rep(c.type[j])) rep_force(c, dx, dy, dz, r, mom[0], mom[1], mom[2]); });
     const Vec4<T> vi = c.vt4[i];
     const T dc = c.damp_c / sqrt(vi.w);                            // -5e-5 sqrt(E / (rho~ h^2)) (base:713-715)
     Vec4<T> dv;
@@ -788,6 +804,40 @@ template <typename T> int post_step(SphCtx *c) {
     return 0;
 }
 
+// enforce_boundary (base:525-601), boundary mode 1: flow particles are put back inside the domain box (no lid) and lose
+// (1 + c_f) of their normal velocity (simulate_collisions, c_f = 0.3)
+template <typename T> __global__ void __launch_bounds__(256) k_enforce_boundary(Dev<T> c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N()) return;
+    if (!is_flow(c.type[i])) return;
+    double *x = c.x + 3 * (size_t)i;
+    const double rr = c.radius_d - 1e-8;
+    const double p0 = x[0], p1 = x[1], p2 = x[2];
+    T n0 = 0, n1 = 0, n2 = 0;
+    if (p0 > c.dend[0] - rr) { n0 += (T)1; x[0] = c.dend[0] - rr; }
+    if (p0 <= c.dstart[0] + rr) { n0 += (T)-1; x[0] = c.dstart[0] + rr; }
+    if (p1 <= c.dstart[1] + rr) { n1 += (T)-1; x[1] = c.dstart[1] + rr; }
+    if (c.dim == 3) {
+        if (p2 > c.dend[2] - rr) { n2 += (T)1; x[2] = c.dend[2] - rr; }
+        if (p2 <= c.dstart[2] + rr) { n2 += (T)-1; x[2] = c.dstart[2] + rr; }
+    }
+    const T len = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
+    if (len > c.eps) {
+        const T u0 = n0 / len, u1 = n1 / len, u2 = n2 / len;
+        Vec4<T> v = c.v4[i];
+        const T vn = v.x * u0 + v.y * u1 + v.z * u2;
+        v.x -= ((T)1 + (T)0.3) * vn * u0; v.y -= ((T)1 + (T)0.3) * vn * u1; v.z -= ((T)1 + (T)0.3) * vn * u2;
+        c.v4[i] = v;
+    }
+}
+template <typename T> int enforce_boundary(SphCtx *c) {
+    if (c->n == 0 || c->p.boundary != 1) return 0;
+    SPH_PROF(c, K_OTHER);
+    k_enforce_boundary<T><<<blocks_for(c->n, 256), 256, 0, c->stream>>>(make_dev<T>(c));
+    SPH_LAUNCH_CHECK(c);
+    return 0;
+}
+
 // advect_SE / advect_LF (base:79-87, 106-114) + advect_pos without XSPH (base:228-238) + WCSPH advect_something
 // (wc:129-132) of one particle in one kernel: the same operations in the same order as k_advect(kind 0), k_advect_pos
 // and k_post_wc, without writing and re-reading density, velocity and volume in between (sph_step only).
@@ -884,6 +934,7 @@ template <typename T> int density_sum(SphCtx *c, void *out) {
     template int one_step_phase<T>(SphCtx *, int);                    \
     template int advect_pos<T>(SphCtx *);                  \
     template int post_step<T>(SphCtx *);                   \
+    template int enforce_boundary<T>(SphCtx *);            \
     template int finish_step<T>(SphCtx *);                   \
     template int neighbor_count<T>(SphCtx *, int32_t *);   \
     template int density_sum<T>(SphCtx *, void *);           \

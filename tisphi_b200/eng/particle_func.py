@@ -5,7 +5,7 @@ Mirror of the scene builders of the reference's eng/particle_func.py (function n
   set_material / get_material pf:218-244, chk_block_in_domain pf:246-251, count_boundary / add_boundary pf:302-313,
   calc_dummy_boundary pf:316-343.
 The particle SET (positions, creation order) must be bit-identical to the reference's: it is the precondition of
-every parity test.  Repulsive wall boxes (boundary modes 3/4) and mesh bodies are out of scope.
+every parity test.  calc_rep_boundary pf:346-374.  Mesh bodies are out of scope (they need trimesh).
 """
 import numpy as np
 
@@ -115,7 +115,19 @@ def calc_dummy_boundary(dim, domain_start, domain_end, vdomain_start, vdomain_en
 
 
 def calc_rep_boundary(dim, domain_start, domain_end, pt_radius):
-    raise NotImplementedError("repulsive boundary particles (boundary modes 3/4) are out of scope of this engine")
+    """Boxes of the repulsive particles (pf:346-374): ONE layer on every domain face, no lid, half a radius thick on
+    either side of the face; they are filled with a spacing of one particle radius (ps:147-148)."""
+    ds, de = (np.asarray(a, dtype=np.float64) for a in (domain_start, domain_end))
+    t = pt_radius / 2
+    if dim == 3:
+        return [[np.array([ds[0] - t, ds[1] + t, ds[2] - t]), np.array([ds[0] + t, de[1] - t, de[2] - t])],
+                [np.array([ds[0] - t, ds[1] + t, de[2] - t]), np.array([de[0] - t, de[1] - t, de[2] + t])],
+                [np.array([de[0] - t, ds[1] + t, ds[2] + t]), np.array([de[0] + t, de[1] - t, de[2] + t])],
+                [np.array([ds[0] + t, ds[1] + t, ds[2] - t]), np.array([de[0] + t, de[1] - t, ds[2] + t])],
+                [ds - t, np.array([de[0], ds[1], de[2]]) + t]]
+    return [[np.array([ds[0] - t, ds[1] + t, ds[2]]), np.array([ds[0] + t, de[1] - t, de[2]])],
+            [np.array([ds[0] - t, ds[1] - t, ds[2]]), np.array([de[0] + t, ds[1] + t, de[2]])],
+            [np.array([de[0] - t, ds[1] + t, ds[2]]), np.array([de[0] + t, de[1] - t, de[2]])]]
 
 
 def load_body(body, vox_len):

@@ -11,7 +11,7 @@ import numpy as np
 
 from .. import _lib
 from .configer_builder import SimConfiger
-from .particle_func import (add_boundary, add_cube, calc_cube_particle_num, calc_dummy_boundary, chk_block_in_domain,
+from .particle_func import (add_boundary, add_cube, calc_cube_particle_num, calc_dummy_boundary, calc_rep_boundary, chk_block_in_domain,
                             count_boundary, get_material, set_material)
 
 
@@ -175,9 +175,12 @@ class ParticleSystem:
                                                       self.vdomain_end)
             dummy_particle_num = count_boundary(self.dummy_boundary, self.dim, self.particle_diameter)
             print("Dummy particle number: %d" % dummy_particle_num)
-        if self.flag_boundary in (self.bdy_rep, self.bdy_dummy_rep, self.bdy_collision):
-            raise NotImplementedError("boundary modes 1, 3 and 4 are out of scope of this engine (SURVEY 2.1)")
-        self.particle_max_num = block_particle_num + dummy_particle_num
+        rep_particle_num = 0
+        if self.flag_boundary in (self.bdy_rep, self.bdy_dummy_rep):                 # ps:100-105
+            self.rep_boundary = calc_rep_boundary(self.dim, self.domain_start, self.domain_end, self.particle_radius)
+            rep_particle_num = count_boundary(self.rep_boundary, self.dim, self.particle_radius)
+            print("Repulsive particle number: %d" % rep_particle_num)
+        self.particle_max_num = block_particle_num + dummy_particle_num + rep_particle_num
         print(f"Particle total num: {self.particle_max_num}")
 
         # engine (replaces the Taichi struct fields pt / pt_buf, the grid counters and the prefix-sum executor)
@@ -204,6 +207,9 @@ class ParticleSystem:
             P.vstart[a] = float(self.vdomain_start[a])
             P.g[a] = float(grav[a])
         P.h, P.support, P.grid_size, P.m_V0, P.eps = self.smoothing_len, self.support_radius, self.grid_size, self.m_V0, 1e-8
+        P.boundary, P.radius = int(self.flag_boundary), float(self.particle_radius)
+        for a in range(3):
+            P.dstart[a], P.dend[a] = float(self.domain_start[a]), float(self.domain_end[a])
         self.params = P
         self.pt = _ParticleFields(self)
         self.pt_buf = self.pt            # the ping-pong buffers are internal to the engine
@@ -227,6 +233,8 @@ class ParticleSystem:
             self.init_block(block)
         if self.flag_boundary in (self.bdy_dummy, self.bdy_dummy_rep):
             add_boundary(self, self.dummy_boundary, self.mat_dummy_type, color=[153, 153, 255])
+        if self.flag_boundary in (self.bdy_rep, self.bdy_dummy_rep):                 # ps:147-148
+            add_boundary(self, self.rep_boundary, self.mat_rep_type, offset=self.particle_radius, color=[170, 17, 255])
 
     def init_block(self, block):
         mat = get_material(self, block["materialId"])

@@ -151,7 +151,8 @@ class SPHBase:
         return None
 
     def enforce_boundary(self):
-        return None
+        """base:525-601: with ``boundary == 1`` flow particles are clamped into the domain box and reflected."""
+        self._eng.call("sph_enforce_boundary")
 
     def assign_value_color(self):
         """base:721-789: pt.val := the scalar selected by ``colorTitle`` for real (and, if shown, dummy) particles."""

@@ -66,6 +66,7 @@ class SlabDriver:
     message_bytes(fields, count), new_buffer(nbytes), pack(fields, first, count, buf), unpack(fields, first, count, buf),
     replace(keep_first, keep_count, left_buf, n_left, right_buf, n_right), set_owned_columns(a, b),
     calc_kernel_corr(), init_real2tmp(), num_phases(), one_step_phase(p), advect(kind, m), advect_pos(), post_step(),
+    enforce_boundary(),
     new_counts() -> int64 tensor[2] on the transport device.
     """
 
@@ -244,6 +245,7 @@ class SlabDriver:
         if e.post_fields:
             self.refresh_ghosts(e.post_fields)
         e.post_step()
+        e.enforce_boundary()                    # base:51 (pointwise; a no-op unless boundary == 1)
 
     def run_steps(self, n):
         for _ in range(n):
@@ -360,6 +362,9 @@ class CudaSlabEngine:
 
     def post_step(self):
         self.e.call("sph_post_step")
+
+    def enforce_boundary(self):
+        self.e.call("sph_enforce_boundary")
 
 
 class NativeSlab:
