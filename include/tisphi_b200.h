@@ -143,6 +143,19 @@ int sph_post_step(SphCtx *ctx);
  * back on its face and loses (1 + 0.3) of its normal velocity; a no-op in the other modes (dynamic rigid bodies: see
  * sph_solve_rigid_body) */
 int sph_enforce_boundary(SphCtx *ctx);
+/* ---- DYNAMIC rigid bodies (type 11 blocks with isDynamic), soil solvers only -- under WCSPH the reference
+ * itself cannot run them (wc:129-132 calls a kernel from kernel scope).  The caller provides two device tables indexed by
+ * the CREATION index id0 (they must stay alive): the body index of each particle (0 .. n_bodies-1; -1: not part of a
+ * dynamic rigid body) and its rest position x0 (n_ids x 3 float64).  The sweeps then give those particles d_vel = g minus
+ * the reaction of every momentum term they take part in (muI:45-46, 111-112; dp:164-165, 233-234), XSPH moves them like
+ * any dynamic particle (base:234), sph_enforce_boundary clamps them into the domain box, and
+ *   sph_init_rigid_body   stores each body's rest centre of mass (SPHBase.init_rigid_body, base:467-470);
+ *   sph_solve_rigid_body  shape matching (solve_constraints, base:478-499): x_i := cm + R (x0_i - rest_cm) with R the
+ *                         rotation of the polar decomposition of sum m (x - cm)(x0 - rest_cm)^T. */
+int sph_set_rigid_bodies(SphCtx *ctx, int64_t n_ids, const int32_t *body_of_id0_dev, const double *x0_of_id0_dev, int32_t n_bodies);
+int sph_init_rigid_body(SphCtx *ctx);
+int sph_solve_rigid_body(SphCtx *ctx);
+int sph_rigid_rest_cm(SphCtx *ctx, double *out_host);        /* n_bodies x 3 (ps.rigid_rest_cm); synchronises */
 /* SPHBase.init_stress (base:249-260) */
 int sph_init_stress(SphCtx *ctx);
 /* the same with y_max given by the caller: a ctx that holds one slab of a scene must use the highest soil particle of

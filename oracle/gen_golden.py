@@ -62,6 +62,18 @@ def _indenter(water=False):
     return sc
 
 
+def _dynrigid(method=3, wall=False):
+    """The shrunken test4 scene with the rigid block DYNAMIC: it falls onto / is thrown into the soil bed,
+    feels the reaction of the momentum sums (dp:164-165, muI:45-46), is shape-matched back to a rigid transform every
+    step (base:472-499) and, with ``wall``, starts against the left domain face (collision clamp, base:525-601)."""
+    sc = _indenter()
+    sc["Configuration"].update(simulationMethod=method)
+    sc["Blocks"][1].update(isDynamic=1, velocity=[0.3, -0.25, 0.0])
+    if wall:
+        sc["Blocks"][1].update(translation=[0.0, 0.0205, 0.0], velocity=[-0.5, -0.1, 0.0])
+    return sc
+
+
 def _plate():
     with open(os.path.join(REF, "data", "scenes", "test5_in_hor.json")) as f:
         sc = json.load(f)
@@ -117,6 +129,10 @@ CASES = {
     "dp2d_plate_lf": (lambda: _plate(), [1, 2, 10]),
     # tiny 3D dambreak with the C4 parameter set
     "wc3d_tiny_lf": (lambda: _scene("test1_db_water.json", dict(WATER3D), dict(size=[0.16, 0.12, 0.12])), [1, 2, 3]),
+    # ---- round 2, SURVEY 8 f2: DYNAMIC rigid body (shape matching + collision clamp) under the two soil solvers
+    "dp2d_dynrigid_lf": (lambda: _dynrigid(3), [1, 2, 10, 30]),
+    "mui2d_dynrigid_lf": (lambda: _dynrigid(2), [1, 2, 10]),
+    "dp2d_dynrigid_wall_lf": (lambda: _dynrigid(3, wall=True), [1, 2, 10]),
     # ---- round 2, SURVEY 8 f3: the other boundary modes (1 enforced collision, 3 repulsive particles, 4 dummy + repulsive)
     "wc2d_rep_lf": (lambda: _scene("test1_db_water.json", dict(domainEnd=[1.0, 0.6, 0.5], boundary=3),
                                    dict(size=[0.4, 0.3, 0.1])), [1, 2, 10]),

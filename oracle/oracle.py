@@ -21,9 +21,9 @@ LIB = os.path.join(BUILD, "libsph_oracle.so")
 
 FIELDS = ["x", "v", "m_V", "density", "mass", "pressure", "stress", "CSPM_f", "CSPM_L", "d_density", "d_vel",
           "d_stress", "v_grad", "strain_equ", "d_strain_equ", "strain_equ_p", "d_strain_equ_p", "density_tmp",
-          "v_tmp", "stress_tmp", "d_density_RK", "d_vel_RK", "d_stress_RK"]
-NCOMP = [3, 3, 1, 1, 1, 1, 9, 1, 9, 1, 3, 9, 9, 1, 1, 1, 1, 1, 3, 9, 1, 3, 9]
-IFIELDS = ["mat_type", "id0", "grid_ids", "flag_retmap"]
+          "v_tmp", "stress_tmp", "d_density_RK", "d_vel_RK", "d_stress_RK", "x0"]
+NCOMP = [3, 3, 1, 1, 1, 1, 9, 1, 9, 1, 3, 9, 9, 1, 1, 1, 1, 1, 3, 9, 1, 3, 9, 3]
+IFIELDS = ["mat_type", "id0", "grid_ids", "flag_retmap", "obj_id", "is_dynamic"]
 
 
 def build(force=False):
@@ -63,7 +63,7 @@ def lib():
         L.orc_cell_end.restype = C.POINTER(C.c_int64)
         L.orc_cell_end.argtypes = [C.c_void_p]
         for fn in ("orc_destroy", "orc_calc_kernel_corr", "orc_init_real2tmp", "orc_one_step", "orc_init_stress",
-                   "orc_advect_pos", "orc_post_step", "orc_enforce_boundary"):
+                   "orc_advect_pos", "orc_post_step", "orc_enforce_boundary", "orc_init_rigid_body", "orc_solve_rigid_body"):
             getattr(L, fn).argtypes = [C.c_void_p]
             getattr(L, fn).restype = None
         L.orc_set_params.argtypes = [C.c_void_p, C.POINTER(OrcParams)]
@@ -156,6 +156,7 @@ def build_particles(scene):
     dim, d = D["dim"], D["d"]
     mats = {m["matId"]: m for m in scene.get("Materials", [])}
     xs, vs_, rho, typ = [], [], [], []
+    obj, dyn = [], []                                 # object id and is_dynamic per particle (ps:150-174)
     for b in scene.get("Blocks", []):
         for a in range(dim):                          # pf:246-251
             assert b["translation"][a] - D["domain_start"][a] >= 0.0 and \
@@ -166,6 +167,8 @@ def build_particles(scene):
         vs_.append(np.tile(np.array(b["velocity"], dtype=np.float64), (len(p), 1)))
         rho.append(np.full(len(p), float(m["density0"])))
         typ.append(np.full(len(p), int(m["matType"]), dtype=np.int32))
+        obj.append(np.full(len(p), int(b["objectId"]), dtype=np.int32))
+        dyn.append(np.full(len(p), int(b["isDynamic"]) if m["matType"] > 10 else 1, dtype=np.int32))
     if cfg["boundary"] in (2, 4):
         for lo, hi in dummy_boxes(dim, D["domain_start"], D["domain_end"], D["vstart"], D["vend"]):
             p = cube_positions(lo, hi - lo, dim, d)
@@ -173,6 +176,8 @@ def build_particles(scene):
             vs_.append(np.zeros_like(p))
             rho.append(np.zeros(len(p)))              # walls: density 0 -> mass 0 (pf:206, ps:282)
             typ.append(np.full(len(p), -1, dtype=np.int32))
+            obj.append(np.full(len(p), -1, dtype=np.int32))       # add_boundary: object id = the type (pf:308-313)
+            dyn.append(np.ones(len(p), dtype=np.int32))
     if cfg["boundary"] in (3, 4):                     # ps:147-148: spacing = particle radius, type -2
         for lo, hi in rep_boxes(dim, D["domain_start"], D["domain_end"], cfg["particleRadius"]):
             p = cube_positions(lo, hi - lo, dim, cfg["particleRadius"])
@@ -180,6 +185,9 @@ def build_particles(scene):
             vs_.append(np.zeros_like(p))
             rho.append(np.zeros(len(p)))
             typ.append(np.full(len(p), -2, dtype=np.int32))
+            obj.append(np.full(len(p), -2, dtype=np.int32))
+            dyn.append(np.ones(len(p), dtype=np.int32))
+    build_particles.last_obj_dyn = (np.concatenate(obj), np.concatenate(dyn))
     return D, np.concatenate(xs), np.concatenate(vs_), np.concatenate(rho), np.concatenate(typ)
 
 
@@ -232,7 +240,7 @@ def make_params(scene, serial=1, wc_fresh=0):
 
 
 class Oracle:
-    def __init__(self, params, x, v, density, mat_type):
+    def __init__(self, params, x, v, density, mat_type, obj_id=None, is_dynamic=None):
         self.L = lib()
         self.P = params
         self.n = len(x)
@@ -245,6 +253,10 @@ class Oracle:
         self.mass[:] = params.m_V0 * np.asarray(density)
         self.mat_type[:] = mat_type
         self.id0[:] = np.arange(self.n)                                   # ps:208-211
+        self.x0[:] = x
+        self.obj_id[:] = 0 if obj_id is None else obj_id
+        self.is_dynamic[:] = 1 if is_dynamic is None else is_dynamic
+        self.L.orc_init_rigid_body(self.h)                                # base:28
         if params.solver == 3:
             self.L.orc_init_stress(self.h)                                # dp:35
 
@@ -252,7 +264,8 @@ class Oracle:
     def from_scene(cls, scene, serial=1, wc_fresh=0):
         P, D = make_params(scene, serial, wc_fresh)
         D2, x, v, rho, typ = build_particles(scene)
-        o = cls(P, x, v, rho, typ)
+        obj, dyn = build_particles.last_obj_dyn
+        o = cls(P, x, v, rho, typ, obj, dyn)
         o.D = D
         return o
 

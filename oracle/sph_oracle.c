@@ -44,9 +44,10 @@ typedef struct {
 
 enum { F_X, F_V, F_M_V, F_DENSITY, F_MASS, F_PRESSURE, F_STRESS, F_CSPM_F, F_CSPM_L, F_D_DENSITY, F_D_VEL,
        F_D_STRESS, F_V_GRAD, F_STRAIN_EQU, F_D_STRAIN_EQU, F_STRAIN_EQU_P, F_D_STRAIN_EQU_P, F_DENSITY_TMP,
-       F_V_TMP, F_STRESS_TMP, F_D_DENSITY_RK, F_D_VEL_RK, F_D_STRESS_RK, F_NUM };
-static const int F_NC[F_NUM] = {3, 3, 1, 1, 1, 1, 9, 1, 9, 1, 3, 9, 9, 1, 1, 1, 1, 1, 3, 9, 1, 3, 9};
-enum { I_MAT_TYPE, I_ID0, I_GRID_IDS, I_FLAG_RETMAP, I_NUM };
+       F_V_TMP, F_STRESS_TMP, F_D_DENSITY_RK, F_D_VEL_RK, F_D_STRESS_RK, F_X0, F_NUM };
+static const int F_NC[F_NUM] = {3, 3, 1, 1, 1, 1, 9, 1, 9, 1, 3, 9, 9, 1, 1, 1, 1, 1, 3, 9, 1, 3, 9, 3};
+enum { I_MAT_TYPE, I_ID0, I_GRID_IDS, I_FLAG_RETMAP, I_OBJ_ID, I_IS_DYNAMIC, I_NUM };
+#define MAX_OBJ 64
 
 typedef struct {
     OrcParams p;
@@ -57,6 +58,8 @@ typedef struct {
     int64_t *cell_tmp;
     double *scratch;        /* 9*n doubles */
     int32_t *iscratch;
+    double rest_cm[MAX_OBJ][3];   /* ps.rigid_rest_cm (ps:118), per object id */
+    int dyn_obj[MAX_OBJ], n_dyn;  /* object ids of the DYNAMIC rigid bodies */
 } Orc;
 
 #define X(o, i) (&(o)->f[F_X][3 * (i)])
@@ -67,6 +70,7 @@ static inline int is_flow(int t) { return t == 1 || t == 2; }
 static inline int is_real(int t) { return t > 0; }
 static inline int is_bdy(int t) { return t == -1 || t == -2; }
 static inline int is_rigid(int t) { return t == 11; }
+#define RIGID_DYN(o, i) (TYPE(o, i) == 11 && (o)->ia[I_IS_DYNAMIC][i] != 0)      /* ps:356-362 */
 
 /* ------------------------------------------------------------------------------------------------ API */
 Orc *orc_create(const OrcParams *p, int64_t n) {
@@ -461,20 +465,24 @@ static void one_step_wc(Orc *o, int phase) {
 }
 
 /* ------------------------------------------------------------------- soil momentum (muI:38-46, dp:156-165) */
-static void soil_momentum(const Orc *o, int64_t i, double out[3]) {
+/* react != 0: the same term is subtracted from d_vel of a DYNAMIC rigid neighbour (muI:45-46, dp:164-165; the caller
+ * runs the loop in index order then, like the serial reference) */
+static void soil_momentum(Orc *o, int64_t i, double out[3], int react) {
     const double *si = &o->f[F_STRESS_TMP][9 * i];
     double rhoi = o->f[F_DENSITY_TMP][i];
     out[0] = out[1] = out[2] = 0.0;
     FOR_NEIGHBORS(o, i, {
-        double g[3];
+        double g[3], t3[3];
         gradWc(o, i, d, r, g);
         const double *sj = &o->f[F_STRESS_TMP][9 * j];
         double rhoj = o->f[F_DENSITY_TMP][j], c = o->f[F_M_V][j] * rhoj;
         for (int a = 0; a < 3; a++) {
             double s = 0.0;
             for (int b = 0; b < 3; b++) s += (c * (sj[3 * a + b] / (rhoj * rhoj) + si[3 * a + b] / (rhoi * rhoi))) * g[b];
+            t3[a] = s;
             out[a] += s;
         }
+        if (react && RIGID_DYN(o, j)) for (int a = 0; a < 3; a++) o->f[F_D_VEL][3 * j + a] -= t3[a];
     });
 }
 static inline void viscous_damping(const OrcParams *p, double rho, const double *v, double out[3]) {   /* base:713-715 */
@@ -527,13 +535,14 @@ static void one_step_mui(Orc *o, int phase) {
         double rt = Sr * f;
         o->f[F_DENSITY_TMP][i] = rt > p->rho0 ? rt : p->rho0;
         for (int a = 0; a < 9; a++) o->f[F_STRESS_TMP][9 * i + a] = Ss[a] * f;
+        if (RIGID_DYN(o, i)) for (int a = 0; a < 3; a++) o->f[F_D_VEL][3 * i + a] = p->g[a];      /* muI:111-112 */
     }
     PHASE(2)
-#pragma omp parallel for schedule(dynamic, 256)
+#pragma omp parallel for schedule(dynamic, 256) if (o->n_dyn == 0)
     for (int64_t i = 0; i < n; i++) {                    /* loop 3 (muI:115-128) */
         if (!is_soil(TYPE(o, i))) continue;
         double dv[3], Fd[3];
-        soil_momentum(o, i, dv);
+        soil_momentum(o, i, dv, o->n_dyn > 0);
         if (has_rep(p)) FOR_NEIGHBORS(o, i, { if (TYPE(o, j) == -2) rep_force(p, d, r, dv); });      /* muI:121-123 */
         viscous_damping(p, o->f[F_DENSITY_TMP][i], &o->f[F_V_TMP][3 * i], Fd);
         for (int a = 0; a < 3; a++) o->f[F_D_VEL][3 * i + a] = dv[a] + p->g[a] + Fd[a];
@@ -623,9 +632,10 @@ static void one_step_dp(Orc *o, int phase) {
         for (int a = 0; a < 3; a++) o->f[F_V_TMP][3 * i + a] = 2 * o->f[F_V][3 * i + a] - Sv[a] * f;
         o->f[F_DENSITY_TMP][i] = p->rho0;
         for (int a = 0; a < 9; a++) o->f[F_STRESS_TMP][9 * i + a] = Ss[a] * f;
+        if (RIGID_DYN(o, i)) for (int a = 0; a < 3; a++) o->f[F_D_VEL][3 * i + a] = p->g[a];      /* dp:233-234 */
     }
     PHASE(2)
-#pragma omp parallel for schedule(dynamic, 256)
+#pragma omp parallel for schedule(dynamic, 256) if (o->n_dyn == 0)
     for (int64_t i = 0; i < n; i++) {                    /* loop 3 (dp:237-270) */
         if (!is_soil(TYPE(o, i))) continue;
         double vg[9], dd, dv[3], Fd[3];
@@ -633,8 +643,7 @@ static void one_step_dp(Orc *o, int phase) {
         memcpy(&o->f[F_V_GRAD][9 * i], vg, 72);
         o->f[F_D_DENSITY][i] = dd * o->f[F_DENSITY_TMP][i];
         bui2008(p, &o->f[F_STRESS_TMP][9 * i], vg, &o->f[F_D_STRESS][9 * i], &o->f[F_D_STRAIN_EQU][i], &o->f[F_D_STRAIN_EQU_P][i]);
-        soil_momentum(o, i, dv);
-        if (has_rep(p)) FOR_NEIGHBORS(o, i, { if (TYPE(o, j) == -2) rep_force(p, d, r, dv); });      /* muI:121-123 */
+        soil_momentum(o, i, dv, o->n_dyn > 0);
         viscous_damping(p, o->f[F_DENSITY_TMP][i], &o->f[F_V_TMP][3 * i], Fd);
         for (int a = 0; a < 3; a++) o->f[F_D_VEL][3 * i + a] = dv[a] + p->g[a] + Fd[a];
     }
@@ -673,6 +682,7 @@ void orc_advect_pos(Orc *o) {
             if (!is_real(TYPE(o, i))) continue;
             double s[3] = {0, 0, 0};
             const double *vi = &o->f[F_V][3 * i];
+            if (o->ia[I_IS_DYNAMIC][i])                       /* base:234: XSPH only moves dynamic particles */
             FOR_NEIGHBORS(o, i, {
                 if (TYPE(o, j) == TYPE(o, i)) {
                     double w = W(p, r), V = o->f[F_M_V][j];
@@ -690,6 +700,7 @@ void orc_advect_pos(Orc *o) {
         if (!is_real(TYPE(o, i))) continue;
         double s[3] = {0, 0, 0};
         const double *vi = &o->f[F_V][3 * i];
+        if (o->ia[I_IS_DYNAMIC][i])
         FOR_NEIGHBORS(o, i, {
             if (TYPE(o, j) == TYPE(o, i)) {
                 double w = W(p, r), V = o->f[F_M_V][j];
@@ -760,14 +771,123 @@ void orc_post_step(Orc *o) {
 }
 
 /* ---------------------------------------------------------------------------- SPHBase.step (base:41-61) */
-/* enforce_boundary (base:525-601): flow particles when boundary == 1 (dynamic rigid particles always -- none here) are
- * put back inside the domain box, no lid, and lose (1 + c_f) of their normal velocity. */
+/* ------------------------------------------------------------------- dynamic rigid bodies (base:467-518) */
+static void rigid_cm(const Orc *o, int obj, double cm[3]) {                 /* calc_cm, base:501-510 */
+    double sm = 0.0;
+    cm[0] = cm[1] = cm[2] = 0.0;
+    for (int64_t i = 0; i < o->n; i++)
+        if (RIGID_DYN(o, i) && o->ia[I_OBJ_ID][i] == obj) {
+            const double m = o->f[F_MASS][i];
+            for (int a = 0; a < 3; a++) cm[a] += m * X(o, i)[a];
+            sm += m;
+        }
+    for (int a = 0; a < 3; a++) cm[a] /= sm;
+}
+/* init_rigid_body (base:467-470), called by the solver constructors (base:28): rest centre of mass per dynamic object */
+void orc_init_rigid_body(Orc *o) {
+    o->n_dyn = 0;
+    for (int obj = 0; obj < MAX_OBJ; obj++) {
+        int has = 0;
+        for (int64_t i = 0; i < o->n && !has; i++) has = RIGID_DYN(o, i) && o->ia[I_OBJ_ID][i] == obj;
+        if (!has) continue;
+        o->dyn_obj[o->n_dyn++] = obj;
+        rigid_cm(o, obj, o->rest_cm[obj]);
+    }
+}
+/* Rotation of the polar decomposition A = R S as Taichi's polar_decompose3d gives it: U, sig, V = svd(A) with U and V
+ * PROPER rotations (the sign goes into the last singular value), R = U V^T.  Here: Jacobi eigen-decomposition of A^T A
+ * for V, u_k = A v_k / sigma_k, missing columns completed by cross products.  (Third-party arithmetic of the reference,
+ * any converged SVD agrees to ~1e-15.) */
+static void polar_rotation(const double A[9], double R[9]) {
+    double B[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) { double t = 0; for (int k = 0; k < 3; k++) t += A[3 * k + a] * A[3 * k + b]; B[3 * a + b] = t; }
+    for (int sweep = 0; sweep < 30; sweep++) {
+        const double off = fabs(B[1]) + fabs(B[2]) + fabs(B[5]);
+        if (off < 1e-300 || off <= 1e-18 * (fabs(B[0]) + fabs(B[4]) + fabs(B[8]))) break;
+        for (int pq = 0; pq < 3; pq++) {
+            const int pi = pq == 2 ? 1 : 0, qi = pq == 0 ? 1 : 2;
+            const double apq = B[3 * pi + qi];
+            if (apq == 0.0) continue;
+            const double theta = (B[3 * qi + qi] - B[3 * pi + pi]) / (2.0 * apq);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+            for (int k = 0; k < 3; k++) {                    /* B <- J^T B J, V <- V J */
+                const double bkp = B[3 * k + pi], bkq = B[3 * k + qi];
+                B[3 * k + pi] = cs * bkp - sn * bkq; B[3 * k + qi] = sn * bkp + cs * bkq;
+            }
+            for (int k = 0; k < 3; k++) {
+                const double bpk = B[3 * pi + k], bqk = B[3 * qi + k];
+                B[3 * pi + k] = cs * bpk - sn * bqk; B[3 * qi + k] = sn * bpk + cs * bqk;
+            }
+            for (int k = 0; k < 3; k++) {
+                const double vkp = V[3 * k + pi], vkq = V[3 * k + qi];
+                V[3 * k + pi] = cs * vkp - sn * vkq; V[3 * k + qi] = sn * vkp + cs * vkq;
+            }
+        }
+    }
+    int ord[3] = {0, 1, 2};                              /* eigenvalues descending */
+    for (int a = 0; a < 2; a++)
+        for (int b = a + 1; b < 3; b++) if (B[4 * ord[b]] > B[4 * ord[a]]) { int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
+    double v[3][3], u[3][3], sig[3];
+    for (int k = 0; k < 3; k++) {
+        for (int a = 0; a < 3; a++) v[k][a] = V[3 * a + ord[k]];
+        sig[k] = sqrt(B[4 * ord[k]] > 0.0 ? B[4 * ord[k]] : 0.0);
+    }
+    /* V proper: v2 = v0 x v1 */
+    v[2][0] = v[0][1] * v[1][2] - v[0][2] * v[1][1]; v[2][1] = v[0][2] * v[1][0] - v[0][0] * v[1][2]; v[2][2] = v[0][0] * v[1][1] - v[0][1] * v[1][0];
+    const double tol = 1e-12 * (sig[0] > 0 ? sig[0] : 1.0);
+    int rank = 0;
+    for (int k = 0; k < 2; k++) {
+        if (sig[k] <= tol) break;
+        for (int a = 0; a < 3; a++) { double t = 0; for (int b = 0; b < 3; b++) t += A[3 * a + b] * v[k][b]; u[k][a] = t / sig[k]; }
+        rank++;
+    }
+    if (rank == 0) { for (int a = 0; a < 9; a++) R[a] = (a % 4 == 0) ? 1.0 : 0.0; return; }   /* A == 0: identity (base:491-492) */
+    if (rank == 1) {                                     /* a line of particles: any unit vector normal to u0 */
+        const int m = fabs(u[0][0]) < fabs(u[0][1]) ? (fabs(u[0][0]) < fabs(u[0][2]) ? 0 : 2) : (fabs(u[0][1]) < fabs(u[0][2]) ? 1 : 2);
+        double e[3] = {0, 0, 0}; e[m] = 1.0;
+        double w[3] = {u[0][1] * e[2] - u[0][2] * e[1], u[0][2] * e[0] - u[0][0] * e[2], u[0][0] * e[1] - u[0][1] * e[0]};
+        const double nw = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        for (int a = 0; a < 3; a++) u[1][a] = w[a] / nw;
+    }
+    u[2][0] = u[0][1] * u[1][2] - u[0][2] * u[1][1]; u[2][1] = u[0][2] * u[1][0] - u[0][0] * u[1][2]; u[2][2] = u[0][0] * u[1][1] - u[0][1] * u[1][0];
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) R[3 * a + b] = u[0][a] * v[0][b] + u[1][a] * v[1][b] + u[2][a] * v[2][b];
+}
+void orc_polar_rotation(const double *A, double *R) { polar_rotation(A, R); }      /* (exported for its unit test) */
+/* solve_rigid_body / solve_constraints (base:472-499): shape matching of every dynamic rigid object */
+void orc_solve_rigid_body(Orc *o) {
+    for (int q = 0; q < o->n_dyn; q++) {
+        const int obj = o->dyn_obj[q];
+        double cm[3], A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, R[9];
+        rigid_cm(o, obj, cm);
+        for (int64_t i = 0; i < o->n; i++)
+            if (RIGID_DYN(o, i) && o->ia[I_OBJ_ID][i] == obj) {
+                const double w = o->f[F_M_V][i] * o->f[F_DENSITY][i];
+                for (int a = 0; a < 3; a++)
+                    for (int b = 0; b < 3; b++)
+                        A[3 * a + b] += w * (X(o, i)[a] - cm[a]) * (o->f[F_X0][3 * i + b] - o->rest_cm[obj][b]);
+            }
+        polar_rotation(A, R);
+        for (int64_t i = 0; i < o->n; i++)
+            if (RIGID_DYN(o, i) && o->ia[I_OBJ_ID][i] == obj)
+                for (int a = 0; a < 3; a++) {
+                    double g = cm[a];
+                    for (int b = 0; b < 3; b++) g += R[3 * a + b] * (o->f[F_X0][3 * i + b] - o->rest_cm[obj][b]);
+                    X(o, i)[a] += (g - X(o, i)[a]) * 1.0;
+                }
+    }
+}
+
+/* enforce_boundary (base:525-601): dynamic rigid particles, and with boundary == 1 flow particles too, are put back
+ * inside the domain box (no lid) and lose (1 + c_f) of their normal velocity. */
 void orc_enforce_boundary(Orc *o) {
     const OrcParams *p = &o->p;
-    if (p->boundary != 1) return;
+    if (p->boundary != 1 && o->n_dyn == 0) return;
     const double rr = p->radius - p->eps;
     for (int64_t i = 0; i < o->n; i++) {
-        if (!is_flow(TYPE(o, i))) continue;
+        if (!(RIGID_DYN(o, i) || (p->boundary == 1 && is_flow(TYPE(o, i))))) continue;
         double *x = X(o, i), *v = &o->f[F_V][3 * i], nrm[3] = {0, 0, 0};
         const double pos[3] = {x[0], x[1], x[2]};
         if (pos[0] > p->dend[0] - rr) { nrm[0] += 1.0; x[0] = p->dend[0] - rr; }
@@ -803,6 +923,7 @@ int64_t orc_step(Orc *o) {
     }
     orc_advect_pos(o);
     orc_post_step(o);
+    orc_solve_rigid_body(o);
     orc_enforce_boundary(o);
     return bad;
 }

@@ -401,7 +401,23 @@ def _mod(a, b):
 
 
 def polar_decompose(A):
-    raise NotImplementedError("rigid bodies are outside the emulated path")
+    """ti.polar_decompose for 3x3 (Taichi 1.2.2: python/taichi/_funcs.py polar_decompose3d): U, sig, V = svd(A) with U
+    and V PROPER rotations (McAdams et al. 3x3 SVD: the sign goes into the last singular value), R = U V^T,
+    S = V sig V^T.  Restated with numpy's SVD and the same sign convention; Taichi's float32-tuned iteration counts are
+    not emulated (third-party arithmetic, agreed to ~1e-12 by any converged SVD)."""
+    import numpy as _np
+    a = _np.array(A.d if hasattr(A, "d") else A, dtype=_np.float64).reshape(3, 3)
+    U, sv, Vt = _np.linalg.svd(a)
+    sig = _np.diag(sv)
+    if _np.linalg.det(U) < 0:
+        U[:, 2] *= -1
+        sig[2, 2] *= -1
+    if _np.linalg.det(Vt) < 0:
+        Vt[2, :] *= -1
+        sig[2, 2] *= -1
+    R = U @ Vt
+    S = Vt.T @ sig @ Vt
+    return Matrix(R.tolist()), Matrix(S.tolist())
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -28,6 +28,7 @@ pytestmark = pytest.mark.gpu
 # (max-norm tolerance, element-wise tolerance) per field; about 10x what the B200 run measured (profiles/r2_horizon_parity.log)
 F64_WC = {"x": (1e-12, 1e-10), "v": (1e-11, 1e-8), "density": (1e-13, 1e-13), "pressure": (1e-10, 1e-7), "d_vel": (1e-10, 1e-7),
           "d_density": (1e-10, 1e-7)}
+MIXED_WC3D_20 = {"x": (1e-8, 1e-6), "density": (5e-6, 5e-6), "v": (2e-4, 5e-2), "pressure": (2e-4, 5e-2)}
 MIXED_WC_100 = {"x": (1e-9, 1e-6), "density": (1e-8, 1e-8), "v": (1e-5, 1e-2), "pressure": (1e-5, 1e-2)}
 # DP + CSPM + RK4 with XSPH: the float64 figures are the in-place vs snapshot XSPH of the reference (module docstring)
 F64_DP_30 = {"x": (1e-9, 1e-6), "v": (1e-7, 1e-5), "density": (1e-12, 1e-12), "stress": (1e-7, 1e-6), "d_vel": (1e-7, 1e-5),
@@ -115,6 +116,13 @@ def test_c2_100_steps_f64():
 
 def test_c2_100_steps_mixed():
     _run_horizon("c2_test2_mui_lf_h100", "f32", MIXED_MUI_100)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_wc3d_20k_20_steps(prec):
+    """3D WCSPH dambreak with the C4 parameter set at 20 772 particles against the reference run, snapshots 1, 10, 20
+    (the reference's 3D scheme diverges after ~35 steps)."""
+    _run_horizon("wc3d_20k_lf", prec, F64_WC if prec == "f64" else MIXED_WC3D_20, ok_mask=prec != "f64")
 
 
 def test_dump_matches_reference_keys():

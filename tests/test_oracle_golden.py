@@ -12,10 +12,14 @@ CASES = ["wc2d_small_lf", "wc2d_small_se_cubic", "wc2d_small_rk4_cspm", "mui2d_s
          "dp2d_indenter_lf", "wc2d_indenter_lf",
          # shipped test5 shrunken: four soil blocks + a static rigid plate pushed sideways
          "dp2d_plate_lf",
+         # DYNAMIC rigid body: reaction of the momentum sums, shape matching, collision clamp
+         "mui2d_dynrigid_lf", "dp2d_dynrigid_wall_lf", "dp2d_dynrigid_lf",
          # boundary modes 3 (repulsive particles), 4 (dummy + repulsive), 1 (enforced collision)
          "wc2d_rep_lf", "wc2d_dummyrep_lf", "wc2d_collision_lf", "mui2d_dummyrep_lf",
          # round 2: the BASELINE configs over their full horizons (C1, C2: 100 steps, C3: 30 steps; ~1 h of emulator each)
-         "c1_test1_wc_lf_h100", "c2_test2_mui_lf_h100", "c3_test2_dp_rk4_cspm_h30"]
+         "c1_test1_wc_lf_h100", "c2_test2_mui_lf_h100", "c3_test2_dp_rk4_cspm_h30",
+         # 3D dambreak with the C4 parameter set, 20 772 particles, steps 1 / 10 / 20 (2.6 h of emulator)
+         "wc3d_20k_lf"]
 
 # float64 restatement of the same serial algorithm: only summation-order / libm noise is allowed
 TOL = 1e-9
@@ -33,7 +37,7 @@ def test_oracle_matches_reference_run(name):
     assert o.n == g.meta["n"]
     assert o.P.dt == g.meta["dt"]
     assert [int(v) for v in o.D["grid_num"]] == g.meta["grid_num"]
-    last = max(g.steps) if name.endswith("small_lf") or "tiny" in name or "indenter" in name or "plate" in name or "_h" in name or "rep" in name or "collision" in name else min(max(g.steps), 10)
+    last = max(g.steps) if name.endswith("small_lf") or "tiny" in name or "indenter" in name or "plate" in name or "_h" in name or "rep" in name or "collision" in name or "dynrigid" in name or "20k" in name else min(max(g.steps), 10)
     for s in range(1, last + 1):
         if s in g.steps:
             # state right after the grid build + kernel correction of step s
@@ -42,7 +46,11 @@ def test_oracle_matches_reference_run(name):
             assert np.array_equal(o.grid_ids, g.grid(s, "grid_ids")), f"cell ids differ at step {s}"
             assert np.array_equal(o.id0, g.grid(s, "id0")), f"sorted order differs at step {s}"
             assert np.array_equal(o.cell_end, g.grid(s, "grid_particle_num")), f"cell offsets differ at step {s}"
-            assert np.array_equal(o.neighbor_count(), g.grid(s, "neighbor_count")), f"neighbour counts differ at step {s}"
+            # a shape-matched rigid body is its rest lattice rotated by a third-party SVD (ti.polar_decompose): its
+            # lattice pairs sit exactly ON the support sphere, so from the second step on their count (never
+            # their contribution, W = 0 there) depends on the last bit of that SVD -- checked for the first step only
+            if "dynrigid" not in name or s == 1:
+                assert np.array_equal(o.neighbor_count(), g.grid(s, "neighbor_count")), f"neighbour counts differ at step {s}"
             assert relmax(o.CSPM_f, g.grid(s, "CSPM_f")) < TOL
             assert relmax(o.CSPM_L, g.grid(s, "CSPM_L")) < TOL
         bad = o.step()          # (re-runs the idempotent grid build)

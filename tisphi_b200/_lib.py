@@ -22,7 +22,7 @@ SYMBOLS = ["sph_arena_bytes", "sph_create", "sph_destroy", "sph_last_error", "sp
            "sph_add_particles", "sph_num_particles", "sph_clear_particles", "sph_read_state", "sph_read_state_async",
            "sph_synchronize", "sph_grid_build",
            "sph_calc_kernel_corr", "sph_calc_kernel_corr_deferred", "sph_init_real2tmp", "sph_one_step", "sph_advect", "sph_advect_pos", "sph_post_step",
-           "sph_init_stress", "sph_init_stress_ymax", "sph_enforce_boundary", "sph_step", "sph_neighbor_count", "sph_neighbor_count_masks", "sph_density_sum", "sph_density_sweep", "sph_read_bad_cells", "sph_read_flagged_cells",
+           "sph_init_stress", "sph_init_stress_ymax", "sph_enforce_boundary", "sph_set_rigid_bodies", "sph_init_rigid_body", "sph_solve_rigid_body", "sph_rigid_rest_cm", "sph_step", "sph_neighbor_count", "sph_neighbor_count_masks", "sph_density_sum", "sph_density_sweep", "sph_read_bad_cells", "sph_read_flagged_cells",
            "sph_launch_count", "sph_num_phases", "sph_one_step_phase", "sph_set_owned_columns",
            "sph_column_starts", "sph_state_fields", "sph_message_bytes", "sph_pack_fields", "sph_unpack_fields",
            "sph_replace_particles", "sph_select_columns", "sph_select_counts", "sph_pack_selected", "sph_profile_enable", "sph_profile_num_kernels",
@@ -72,9 +72,11 @@ def load():
     L.sph_read_state_async.restype, L.sph_read_state_async.argtypes = C.c_int, [vp, vp, vp, vp, vp, vp]
     L.sph_synchronize.restype, L.sph_synchronize.argtypes = C.c_int, [vp]
     for fn in ("sph_grid_build", "sph_calc_kernel_corr", "sph_calc_kernel_corr_deferred", "sph_init_real2tmp", "sph_one_step", "sph_advect_pos",
-               "sph_post_step", "sph_init_stress", "sph_enforce_boundary"):
+               "sph_post_step", "sph_init_stress", "sph_enforce_boundary", "sph_init_rigid_body", "sph_solve_rigid_body"):
         getattr(L, fn).restype, getattr(L, fn).argtypes = C.c_int, [vp]
     L.sph_advect.restype, L.sph_advect.argtypes = C.c_int, [vp, C.c_int, C.c_int]
+    L.sph_set_rigid_bodies.restype, L.sph_set_rigid_bodies.argtypes = C.c_int, [vp, i64, vp, vp, i32]
+    L.sph_rigid_rest_cm.restype, L.sph_rigid_rest_cm.argtypes = C.c_int, [vp, vp]
     L.sph_init_stress_ymax.restype, L.sph_init_stress_ymax.argtypes = C.c_int, [vp, C.c_double]
     L.sph_step.restype, L.sph_step.argtypes = C.c_int, [vp, C.c_int]
     L.sph_neighbor_count.restype, L.sph_neighbor_count.argtypes = C.c_int, [vp, vp]

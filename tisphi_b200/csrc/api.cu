@@ -90,6 +90,7 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
     // Per-step neighbour lists of the generic sweeps (every solver / precision that does not run the cell-tile WCSPH
     // path).  2D: ~28 neighbours among 81 candidates, 64 entries cover compressed states; 3D would need ~160 entries
     // (640 B per particle), so there the sweeps keep walking the cells.  Particles that do not fit walk, too.
+    int64_t o_rig = off; off += align_up((int64_t)RIG_MAX * RIG_STRIDE * 8);
     int64_t o_sor = 0;
     if (soil) { o_sor = off; off += align_up(n_max * 6 * (int64_t)rb); }
     const int nl_cap = (p->fast && !fast && p->dim == 2 && n_max < (1ll << 27)) ? 64 : 0;
@@ -128,7 +129,7 @@ int64_t layout(const SphParams *p, int64_t n_max, SphCtx *c) {
         c->off_nlist = o_nlist; c->off_lrounds = o_lrounds; c->use_list = lists; c->list_valid = false;
         c->off_gid_unsorted = o_gid; c->off_slot = o_slot; c->off_perm = o_perm; c->off_tmpidx = o_tmp;
         c->off_bad = o_bad; c->off_scan_tiles = o_tiles; c->off_slabctl = o_ctl;
-        c->off_sor = o_sor; c->off_gnl = o_nl; c->off_gnl_count = o_nc; c->gnl_cap = nl_cap; c->gnl_valid = false;
+        c->off_rigid = o_rig; c->off_sor = o_sor; c->off_gnl = o_nl; c->off_gnl_count = o_nc; c->gnl_cap = nl_cap; c->gnl_valid = false;
         c->real_bytes = rb; c->soil = soil; c->rk = rk; c->has_L = hasL; c->C = (int)C;
     }
     return off;
@@ -248,6 +249,8 @@ template <typename T> Dev<T> make_dev(SphCtx *c, int which) {
     d.stress = (T *)ptr(SPH_F_STRESS, alt);
     d.stress_t = (T *)ptr(SPH_F_STRESS_TMP, false);
     d.sor = c->off_sor ? (T *)(c->arena + c->off_sor) : nullptr;
+    d.rig_obj = c->rig_n > 0 ? c->rig_obj : nullptr; d.rig_x0 = c->rig_x0; d.rig_n = c->rig_n;
+    d.rig_buf = (double *)(c->arena + c->off_rigid);
     d.strain = (T *)ptr(SPH_F_STRAIN_EQU, alt);
     d.strain_p = (T *)ptr(SPH_F_STRAIN_EQU_P, alt);
     d.cspm_f = (T *)ptr(SPH_F_CSPM_F, false);
@@ -332,7 +335,8 @@ template <typename T> int step_once(SphCtx *c) {
         r = post_step<T>(c);
     }
     if (r) return r;
-    return enforce_boundary<T>(c);                             // (solve_rigid_body: no dynamic rigid bodies)
+    if ((r = solve_rigid_body<T>(c))) return r;
+    return enforce_boundary<T>(c);
 }
 template <typename T> int dispatch_step(SphCtx *c, int nsteps) {
     for (int s = 0; s < nsteps; s++) {
@@ -479,6 +483,25 @@ int sph_advect(SphCtx *c, int kind, int m) { return DISPATCH(c, advect, c, kind,
 int sph_advect_pos(SphCtx *c) { return DISPATCH(c, advect_pos, c); }
 int sph_post_step(SphCtx *c) { return DISPATCH(c, post_step, c); }
 int sph_enforce_boundary(SphCtx *c) { return DISPATCH(c, enforce_boundary, c); }
+int sph_set_rigid_bodies(SphCtx *c, int64_t n_ids, const int32_t *body_of_id0_dev, const double *x0_of_id0_dev, int32_t n_bodies) {
+    if (n_bodies < 0 || n_bodies > RIG_MAX || (n_bodies > 0 && (!body_of_id0_dev || !x0_of_id0_dev || n_ids <= 0))) {
+        snprintf(c->err, sizeof(c->err), "sph_set_rigid_bodies: at most %d dynamic rigid bodies, tables indexed by id0", RIG_MAX); return -2;
+    }
+    if (n_bodies > 0 && c->p.solver == SPH_SOLVER_WC) {
+        snprintf(c->err, sizeof(c->err), "dynamic rigid bodies under WCSPH do not run in the reference either (wc:129-132 calls a kernel from kernel scope)"); return -2;
+    }
+    if (n_bodies > 0 && c->slab) { snprintf(c->err, sizeof(c->err), "dynamic rigid bodies are not supported on slabs (a body would span ranks)"); return -2; }
+    c->rig_obj = body_of_id0_dev; c->rig_x0 = x0_of_id0_dev; c->rig_n = n_bodies;
+    return 0;
+}
+int sph_init_rigid_body(SphCtx *c) { return DISPATCH(c, init_rigid_body, c); }
+int sph_solve_rigid_body(SphCtx *c) { return DISPATCH(c, solve_rigid_body, c); }
+int sph_rigid_rest_cm(SphCtx *c, double *out_host) {
+    for (int b = 0; b < c->rig_n; b++)
+        SPH_CHECK(c, cudaMemcpyAsync(out_host + 3 * b, c->arena + c->off_rigid + (size_t)b * RIG_STRIDE * 8, 24, cudaMemcpyDeviceToHost, c->stream));
+    SPH_CHECK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
 int sph_init_stress(SphCtx *c) { return DISPATCH(c, init_stress, c, nullptr); }
 int sph_init_stress_ymax(SphCtx *c, double ymax) { return DISPATCH(c, init_stress, c, &ymax); }
 int sph_step(SphCtx *c, int nsteps) { return DISPATCH(c, dispatch_step, c, nsteps); }

@@ -21,6 +21,7 @@ __host__ __device__ __forceinline__ bool is_rigid(int t) { return t == 11; }
 __host__ __device__ __forceinline__ bool is_wall(int t) { return is_bdy(t) || is_rigid(t); }
 
 __host__ __device__ __forceinline__ bool is_rep(int t) { return t == -2; }
+constexpr int RIG_STRIDE = 32, RIG_MAX = 64;      // doubles per dynamic rigid body in Dev::rig_buf; bodies per scene
 
 // rounding-exact helpers: the neighbour predicate must not be FMA-contracted
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
@@ -103,6 +104,12 @@ template <typename T> struct Dev {
     int *lrounds;
     int flagged_only;         // generic kernels: process only particles of flagged cells
     double *xnew;             // XSPH: the alternate position buffer the advected positions go to
+    // dynamic rigid bodies: per CREATION index (id0) the body a particle belongs to (-1: none / static) and
+    // its rest position x0; per body 32 doubles: rest_cm[3], cm[3], mass, A[9], R[9]  (null: the scene has none)
+    const int *rig_obj;
+    const double *rig_x0;
+    double *rig_buf;
+    int rig_n;
     // per-step neighbour lists of the generic sweeps (sweeps.cu::k_build_nlist): positions are frozen between the grid build
     // and advect_pos, so the candidate walk is done ONCE per step and every sweep in between replays its result.
     // Entry k of particle i: gnl[k * gnl_stride + i] = (stencil cell << 27) | j; gnl_count[i] < 0: did not fit (walk again).
@@ -110,6 +117,15 @@ template <typename T> struct Dev {
     const int *gnl_count;
     int gnl_stride, gnl_cap;
 };
+
+// ps:356-362: is_rigid_dynamic / the body index of a dynamic rigid particle (-1 otherwise); pt.is_dynamic is 1 for every
+// other kind of particle (ps:150-174)
+template <typename T> __device__ __forceinline__ int rigid_body_of(const Dev<T> &c, int i) {
+    return (c.rig_obj && c.type[i] == 11) ? c.rig_obj[c.id0[i]] : -1;
+}
+template <typename T> __device__ __forceinline__ bool is_dynamic(const Dev<T> &c, int i) {
+    return c.type[i] != 11 || rigid_body_of(c, i) >= 0;
+}
 
 // ------------------------------------------------------------------------------------------------ cells
 template <typename T>

@@ -84,6 +84,8 @@ struct SphCtx {
     int own0, own1;      // owned x-columns [own0, own1) (multi-GPU slabs); the whole grid on one GPU
     int64_t off_slabctl; // device-resident control block of the native slab step (slab.cu)
     sph::SlabState *slab;   // native multi-GPU slab step (sph_slab_init); null on one GPU
+    int64_t off_rigid;   // per dynamic rigid body: rest_cm, cm, mass, A, R (RIG_STRIDE doubles each)
+    const int *rig_obj; const double *rig_x0; int rig_n;     // caller-owned device tables (sph_set_rigid_bodies)
     int64_t off_sor;     // soil: stress_tmp / density_tmp^2 of every particle, written right before a momentum sweep
     int64_t off_gnl, off_gnl_count;  // per-step neighbour lists of the generic sweeps (0: not allocated)
     int gnl_cap;
@@ -140,6 +142,8 @@ template <typename T> int one_step_phase(SphCtx *c, int phase);
 template <typename T> int advect_pos(SphCtx *c);
 template <typename T> int post_step(SphCtx *c);
 template <typename T> int enforce_boundary(SphCtx *c);
+template <typename T> int init_rigid_body(SphCtx *c);
+template <typename T> int solve_rigid_body(SphCtx *c);
 template <typename T> int finish_step(SphCtx *c);      // advect_SE/LF + advect_pos + advect_something of WCSPH in one kernel
 template <typename T> int neighbor_count(SphCtx *c, int32_t *out);
 template <typename T> int density_sum(SphCtx *c, void *out);

@@ -11,6 +11,8 @@
 
 namespace sph {
 
+template <typename T> static int rigid_reaction(SphCtx *c);     // dynamic rigid bodies: defined with their kernels below
+
 // --------------------------------------------------------------------------------------------- kernel correction
 // flagged-only mode: the cell-tile kernels handled every particle except those of flagged cells
 template <typename T> __device__ __forceinline__ bool not_owned(const Dev<T> &c, int i) {
@@ -204,9 +206,12 @@ template <typename T> __global__ void __launch_bounds__(256) k_wc_eos(Dev<T> c) 
 // and keep d_vel = 0 (wc:125-126, muI:131-132, dp:273-274) and the d_density = 0 they were created with; the
 // integrators treat them as real particles (base:79-170), so both are written here -- the derivative arrays are
 // scratch that does not travel through the sort.
+// (a DYNAMIC rigid particle starts every one_step from d_vel = g instead -- wc:105-106, muI:111-112, dp:233-234 -- and
+// k_rigid_reaction subtracts the momentum terms it takes part in)
 template <typename T> __device__ __forceinline__ void zero_rigid_derivatives(const Dev<T> &c, int i) {
     c.d_rho[i] = 0;
     Vec4<T> z; z.x = z.y = z.z = z.w = 0;
+    if (rigid_body_of(c, i) >= 0) { z.x = c.g[0]; z.y = c.g[1]; z.z = c.g[2]; }
     c.d_vel[i] = z;
 }
 template <typename T> __device__ __forceinline__ void body_wc_wall(const Dev<T> &c, int i) {
@@ -617,6 +622,8 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
             SPH_LAUNCH_CHECK(c);
             SPH_PROF(c, K_MUI_SOIL3);
             k_mui_soil3<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+            SPH_LAUNCH_CHECK(c);
+            return rigid_reaction<T>(c);
         }
         SPH_LAUNCH_CHECK(c);
     } else if (solver == SPH_SOLVER_DP) {
@@ -633,6 +640,8 @@ template <typename T> int one_step_phase(SphCtx *c, int phase) {
             SPH_LAUNCH_CHECK(c);
             SPH_PROF(c, K_DP_SOIL);
             k_dp_soil<T><<<blocks_for(n, 128), 128, 0, st>>>(d);
+            SPH_LAUNCH_CHECK(c);
+            return rigid_reaction<T>(c);
         }
         SPH_LAUNCH_CHECK(c);
     } else {
@@ -670,7 +679,7 @@ template <typename T> __device__ __forceinline__ void body_advect_pos_xsph(const
     if (is_real(ti)) {
         const Vec4<T> vi = c.v4[i];
         T s0 = 0, s1 = 0, s2 = 0;
-        if (!is_rigid(ti))                                           // base:234: XSPH only for dynamic particles (rigid here = static)
+        if (is_dynamic(c, i))                                        // base:234: XSPH only moves dynamic particles
             for_neighbors(c, i, [&](int j, T dx, T dy, T dz, T r, T Vj) {
                 if (c.type[j] == ti) {
                     const T w = kernel_W(c, r);
@@ -718,6 +727,175 @@ template <typename T> int advect_pos(SphCtx *c) {
         SPH_LAUNCH_CHECK(c);
         flip(c, SPH_F_X);
     }
+    return 0;
+}
+
+// --------------------------------------------------------------------------- dynamic rigid bodies
+// Reaction on a dynamic rigid particle j (muI:45-46, dp:164-165): the reference lets every soil particle i subtract its
+// momentum term  V_j rho~_j (sigma~_j / rho~_j^2 + sigma~_i / rho~_i^2) . gradW^c_i(x_i - x_j)  from d_vel_j while it
+// forms its own sum (a scatter, serial in index order).  Here j GATHERS the same terms from its soil neighbours in
+// ascending index order -- the order the serial scatter reaches it -- starting from the d_vel = g of the wall loop.
+template <typename T> __global__ void __launch_bounds__(128) k_rigid_reaction(Dev<T> c) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c.N()) return;
+    if (rigid_body_of(c, j) < 0 || not_owned(c, j)) return;
+    const T cf = c.xs4[j].w * c.vt4[j].w;
+    const T *qj = c.sor + 6 * (size_t)j;
+    Vec4<T> acc = c.d_vel[j];
+    for_neighbors(c, j, [&](int i, T dx, T dy, T dz, T r, T Vi) {
+        if (!is_soil(c.type[i])) return;
+        T L[9], g[3], gc[3];
+        load_L(c, i, L);
+        grad_corr(c, L, kernel_dW_over_r(c, r), -dx, -dy, -dz, g, gc);      // d = x_i - x_j as the soil particle sees it
+        const T *qi = c.sor + 6 * (size_t)i;
+        const T mxx = cf * (qj[0] + qi[0]), myy = cf * (qj[1] + qi[1]), mzz = cf * (qj[2] + qi[2]);
+        const T mxy = cf * (qj[3] + qi[3]), myz = cf * (qj[4] + qi[4]), mzx = cf * (qj[5] + qi[5]);
+        T t0 = 0, t1 = 0, t2 = 0;
+        t0 += mxx * gc[0]; t0 += mxy * gc[1]; t0 += mzx * gc[2];
+        t1 += mxy * gc[0]; t1 += myy * gc[1]; t1 += myz * gc[2];
+        t2 += mzx * gc[0]; t2 += myz * gc[1]; t2 += mzz * gc[2];
+        acc.x -= t0; acc.y -= t1; acc.z -= t2;
+    });
+    c.d_vel[j] = acc;
+}
+template <typename T> static int rigid_reaction(SphCtx *c) {
+    if (c->rig_n == 0 || c->n == 0) return 0;
+    SPH_PROF(c, K_OTHER);
+    k_rigid_reaction<T><<<blocks_for(c->n, 128), 128, 0, c->stream>>>(make_dev<T>(c));
+    SPH_LAUNCH_CHECK(c);
+    return 0;
+}
+
+// Per body one block: deterministic sums over the body's particles (strided partial sums in index order, then a tree).
+// what = 0: mass-weighted centre cm (calc_cm, base:501-510; also written to rest_cm when `rest`);
+// what = 1: A = sum m_V rho (x - cm)(x0 - rest_cm)^T (base:483-488), then R of its polar decomposition.
+__device__ void rigid_polar_rotation(const double A[9], double R[9]);
+template <typename T> __global__ void __launch_bounds__(256) k_rigid_reduce(Dev<T> c, int what, int rest) {
+    __shared__ double sh[256][10];
+    const int body = blockIdx.x, tid = threadIdx.x;
+    double *buf = c.rig_buf + (size_t)body * RIG_STRIDE;
+    double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const int n = c.N();
+    for (int i = tid; i < n; i += 256) {
+        if (rigid_body_of(c, i) != body) continue;
+        const double *x = c.x + 3 * (size_t)i;
+        if (what == 0) {
+            const double m = (double)c.v4[i].w;
+            acc[0] += m * x[0]; acc[1] += m * x[1]; acc[2] += m * x[2]; acc[3] += m;
+        } else {
+            const double w = (double)c.xs4[i].w * c.rho[i];
+            const double *x0 = c.rig_x0 + 3 * (size_t)c.id0[i];
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) acc[3 * a + b] += w * (x[a] - buf[3 + a]) * (x0[b] - buf[b]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 10; k++) sh[tid][k] = acc[k];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (tid < s)
+#pragma unroll
+            for (int k = 0; k < 10; k++) sh[tid][k] += sh[tid + s][k];
+        __syncthreads();
+    }
+    if (tid != 0) return;
+    if (what == 0) {
+        for (int a = 0; a < 3; a++) { buf[3 + a] = sh[0][a] / sh[0][3]; if (rest) buf[a] = buf[3 + a]; }
+        buf[6] = sh[0][3];
+    } else {
+        double A[9], R[9];
+        for (int k = 0; k < 9; k++) { A[k] = sh[0][k]; buf[7 + k] = A[k]; }
+        rigid_polar_rotation(A, R);
+        for (int k = 0; k < 9; k++) buf[16 + k] = R[k];
+    }
+}
+// goal position of every particle of a dynamic rigid body: x := cm + R (x0 - rest_cm)   (base:494-498)
+template <typename T> __global__ void __launch_bounds__(256) k_rigid_apply(Dev<T> c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N()) return;
+    const int body = rigid_body_of(c, i);
+    if (body < 0) return;
+    const double *buf = c.rig_buf + (size_t)body * RIG_STRIDE, *R = buf + 16;
+    const double *x0 = c.rig_x0 + 3 * (size_t)c.id0[i];
+    double *x = c.x + 3 * (size_t)i;
+    const double q[3] = {x0[0] - buf[0], x0[1] - buf[1], x0[2] - buf[2]};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const double goal = buf[3 + a] + (R[3 * a] * q[0] + R[3 * a + 1] * q[1] + R[3 * a + 2] * q[2]);
+        x[a] += (goal - x[a]) * 1.0;
+    }
+}
+// Rotation of the polar decomposition as Taichi's polar_decompose3d defines it (U, V proper rotations of the SVD,
+// R = U V^T): Jacobi eigen-decomposition of A^T A for V, u_k = A v_k / sigma_k, missing columns by cross products.
+__device__ void rigid_polar_rotation(const double A[9], double R[9]) {
+    double B[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) { double t = 0; for (int k = 0; k < 3; k++) t += A[3 * k + a] * A[3 * k + b]; B[3 * a + b] = t; }
+    for (int sweep = 0; sweep < 30; sweep++) {
+        const double off = fabs(B[1]) + fabs(B[2]) + fabs(B[5]);
+        if (off < 1e-300 || off <= 1e-18 * (fabs(B[0]) + fabs(B[4]) + fabs(B[8]))) break;
+        for (int pq = 0; pq < 3; pq++) {
+            const int pi = pq == 2 ? 1 : 0, qi = pq == 0 ? 1 : 2;
+            const double apq = B[3 * pi + qi];
+            if (apq == 0.0) continue;
+            const double theta = (B[3 * qi + qi] - B[3 * pi + pi]) / (2.0 * apq);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+            for (int k = 0; k < 3; k++) { const double bp = B[3 * k + pi], bq = B[3 * k + qi]; B[3 * k + pi] = cs * bp - sn * bq; B[3 * k + qi] = sn * bp + cs * bq; }
+            for (int k = 0; k < 3; k++) { const double bp = B[3 * pi + k], bq = B[3 * qi + k]; B[3 * pi + k] = cs * bp - sn * bq; B[3 * qi + k] = sn * bp + cs * bq; }
+            for (int k = 0; k < 3; k++) { const double vp = V[3 * k + pi], vq = V[3 * k + qi]; V[3 * k + pi] = cs * vp - sn * vq; V[3 * k + qi] = sn * vp + cs * vq; }
+        }
+    }
+    int ord[3] = {0, 1, 2};
+    for (int a = 0; a < 2; a++)
+        for (int b = a + 1; b < 3; b++) if (B[4 * ord[b]] > B[4 * ord[a]]) { const int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
+    double v[3][3], u[3][3], sig[3];
+    for (int k = 0; k < 3; k++) {
+        for (int a = 0; a < 3; a++) v[k][a] = V[3 * a + ord[k]];
+        sig[k] = sqrt(B[4 * ord[k]] > 0.0 ? B[4 * ord[k]] : 0.0);
+    }
+    v[2][0] = v[0][1] * v[1][2] - v[0][2] * v[1][1]; v[2][1] = v[0][2] * v[1][0] - v[0][0] * v[1][2]; v[2][2] = v[0][0] * v[1][1] - v[0][1] * v[1][0];
+    const double tol = 1e-12 * (sig[0] > 0 ? sig[0] : 1.0);
+    int rank = 0;
+    for (int k = 0; k < 2; k++) {
+        if (sig[k] <= tol) break;
+        for (int a = 0; a < 3; a++) { double t = 0; for (int b = 0; b < 3; b++) t += A[3 * a + b] * v[k][b]; u[k][a] = t / sig[k]; }
+        rank++;
+    }
+    if (rank == 0) { for (int a = 0; a < 9; a++) R[a] = (a % 4 == 0) ? 1.0 : 0.0; return; }   // A == 0: identity (base:491-492)
+    if (rank == 1) {
+        const int m = fabs(u[0][0]) < fabs(u[0][1]) ? (fabs(u[0][0]) < fabs(u[0][2]) ? 0 : 2) : (fabs(u[0][1]) < fabs(u[0][2]) ? 1 : 2);
+        double e[3] = {0, 0, 0}; e[m] = 1.0;
+        const double w[3] = {u[0][1] * e[2] - u[0][2] * e[1], u[0][2] * e[0] - u[0][0] * e[2], u[0][0] * e[1] - u[0][1] * e[0]};
+        const double nw = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        for (int a = 0; a < 3; a++) u[1][a] = w[a] / nw;
+    }
+    u[2][0] = u[0][1] * u[1][2] - u[0][2] * u[1][1]; u[2][1] = u[0][2] * u[1][0] - u[0][0] * u[1][2]; u[2][2] = u[0][0] * u[1][1] - u[0][1] * u[1][0];
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) R[3 * a + b] = u[0][a] * v[0][b] + u[1][a] * v[1][b] + u[2][a] * v[2][b];
+}
+template <typename T> int init_rigid_body(SphCtx *c) {
+    if (c->rig_n == 0 || c->n == 0) return 0;
+    SPH_PROF(c, K_OTHER);
+    k_rigid_reduce<T><<<c->rig_n, 256, 0, c->stream>>>(make_dev<T>(c), 0, 1);
+    SPH_LAUNCH_CHECK(c);
+    return 0;
+}
+template <typename T> int solve_rigid_body(SphCtx *c) {
+    if (c->rig_n == 0 || c->n == 0) return 0;
+    Dev<T> d = make_dev<T>(c);
+    c->gnl_valid = false; c->masks_valid = false;                   // positions move
+    SPH_PROF(c, K_OTHER);
+    k_rigid_reduce<T><<<c->rig_n, 256, 0, c->stream>>>(d, 0, 0);
+    SPH_LAUNCH_CHECK(c);
+    SPH_PROF(c, K_OTHER);
+    k_rigid_reduce<T><<<c->rig_n, 256, 0, c->stream>>>(d, 1, 0);
+    SPH_LAUNCH_CHECK(c);
+    SPH_PROF(c, K_OTHER);
+    k_rigid_apply<T><<<blocks_for(c->n, 256), 256, 0, c->stream>>>(d);
+    SPH_LAUNCH_CHECK(c);
     return 0;
 }
 
@@ -809,7 +987,7 @@ template <typename T> int post_step(SphCtx *c) {
 template <typename T> __global__ void __launch_bounds__(256) k_enforce_boundary(Dev<T> c) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.N()) return;
-    if (!is_flow(c.type[i])) return;
+    if (!(rigid_body_of(c, i) >= 0 || (c.boundary == 1 && is_flow(c.type[i])))) return;      // judge_enforce_bdy (base:531-538)
     double *x = c.x + 3 * (size_t)i;
     const double rr = c.radius_d - 1e-8;
     const double p0 = x[0], p1 = x[1], p2 = x[2];
@@ -831,7 +1009,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_enforce_boundary(
     }
 }
 template <typename T> int enforce_boundary(SphCtx *c) {
-    if (c->n == 0 || c->p.boundary != 1) return 0;
+    if (c->n == 0 || (c->p.boundary != 1 && c->rig_n == 0)) return 0;
     SPH_PROF(c, K_OTHER);
     k_enforce_boundary<T><<<blocks_for(c->n, 256), 256, 0, c->stream>>>(make_dev<T>(c));
     SPH_LAUNCH_CHECK(c);
@@ -935,6 +1113,8 @@ template <typename T> int density_sum(SphCtx *c, void *out) {
     template int advect_pos<T>(SphCtx *);                  \
     template int post_step<T>(SphCtx *);                   \
     template int enforce_boundary<T>(SphCtx *);            \
+    template int init_rigid_body<T>(SphCtx *);             \
+    template int solve_rigid_body<T>(SphCtx *);            \
     template int finish_step<T>(SphCtx *);                   \
     template int neighbor_count<T>(SphCtx *, int32_t *);   \
     template int density_sum<T>(SphCtx *, void *);           \

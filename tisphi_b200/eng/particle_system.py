@@ -225,6 +225,7 @@ class ParticleSystem:
             self.initialize_particles()
             self._upload_slab()
         self.set_id0()
+        self._upload_rigid_bodies()
         print("Particle system construction complete!")
 
     # ------------------------------------------------------------------------------------------ construction
@@ -243,9 +244,12 @@ class ParticleSystem:
         if mat_type > 10:                                   # ps:160-162
             self.object_id_rigid.add(block["objectId"])
             is_dynamic = bool(block["isDynamic"])
-            if is_dynamic:
-                raise NotImplementedError("dynamic rigid bodies (shape matching, base:467-518) are not built yet "
-                                          "(SURVEY 8 f2); static rigid blocks with a prescribed velocity are")
+            if is_dynamic and self.params.solver == _lib.SOLVER_WC:
+                raise NotImplementedError("a dynamic rigid body under WCSPH does not run in the reference either: "
+                                          "WCSPHSolver.advect_something_func calls init_rigid_body, i.e. a kernel, from "
+                                          "kernel scope (eng/solver_sph_wc.py:129-132); use the mu(I) or DP solver")
+            if is_dynamic and self._slab is not None:
+                raise NotImplementedError("dynamic rigid bodies are not supported on multi-GPU slabs (a body would span ranks)")
         add_cube(self, object_id=block["objectId"], lower_corner=np.array(block["translation"]),
                  cube_size=np.array(block["size"]), velocity=block["velocity"], density=mat["density0"],
                  is_dynamic=is_dynamic, color=np.array([ic / 255 for ic in mat["color"]], dtype=np.float32),
@@ -309,6 +313,24 @@ class ParticleSystem:
             self.engine.field("ID0").copy_(self._torch.from_numpy(mine.astype(np.int32)).to(self.engine.device))
         self.particle_num[None] = self.engine.n
         print(f"slab rank {slab['rank']}/{slab['world']}: columns [{a}, {b}) of {n_cols}, {len(mine)} particles, capacity {cap}")
+
+    def _upload_rigid_bodies(self):
+        """Dynamic rigid bodies: per creation index the body a particle belongs to and its rest position."""
+        self.rigid_dynamic_ids = sorted(o for o in self.object_id_rigid if bool(self.object_collection[o].get("isDynamic", 0)))
+        self._rigid_tables = None
+        if not self.rigid_dynamic_ids:
+            return
+        torch = self._torch
+        obj = np.concatenate(self._const["obj_id"])
+        dyn = np.concatenate(self._const["is_dynamic"])
+        body = np.full(len(obj), -1, dtype=np.int32)
+        for k, oid in enumerate(self.rigid_dynamic_ids):
+            body[(obj == oid) & (dyn != 0)] = k
+        x0 = np.ascontiguousarray(np.concatenate(self._const["x0"]), dtype=np.float64)
+        dev = self.engine.device
+        self._rigid_tables = (torch.from_numpy(body).to(dev), torch.from_numpy(x0).to(dev))       # kept alive: the engine reads them
+        self.engine.call("sph_set_rigid_bodies", len(body), self._rigid_tables[0].data_ptr(), self._rigid_tables[1].data_ptr(),
+                         len(self.rigid_dynamic_ids))
 
     def _const_dev(self, name):
         if name not in self._const_cache:

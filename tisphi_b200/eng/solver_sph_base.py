@@ -27,6 +27,7 @@ class SPHBase:
         self.epsilon = 1e-8
         self.alert_ratio = 0.01
         self._eng = self.ps.engine
+        self.init_rigid_body()                                                       # base:28
 
     # -------------------------------------------------------------------------------------- parameters
     def _push_dt(self, value):
@@ -147,8 +148,19 @@ class SPHBase:
     def calc_CSPM_L(self):
         self._eng.call("sph_calc_kernel_corr")
 
+    def init_rigid_body(self):
+        """base:467-470: the rest centre of mass of every dynamic rigid body (-> ps.rigid_rest_cm[object id])."""
+        ids = getattr(self.ps, "rigid_dynamic_ids", [])
+        if not ids:
+            return
+        self._eng.call("sph_init_rigid_body")
+        out = np.zeros((len(ids), 3), dtype=np.float64)
+        self._eng.call("sph_rigid_rest_cm", out.ctypes.data)
+        self.ps.rigid_rest_cm = {oid: out[k].copy() for k, oid in enumerate(ids)}
+
     def solve_rigid_body(self):
-        return None
+        """base:472-499: shape matching of every dynamic rigid body (a no-op without one)."""
+        self._eng.call("sph_solve_rigid_body")
 
     def enforce_boundary(self):
         """base:525-601: with ``boundary == 1`` flow particles are clamped into the domain box and reflected."""
