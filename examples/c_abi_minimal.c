@@ -3,7 +3,8 @@
  * plain cudaMalloc.  This is what a non-Python host (or the cgo / JNI stub of another front end) would do.
  *
  *   nvcc -o c_abi_minimal examples/c_abi_minimal.c -Iinclude -Ltisphi_b200 -ltisphi_b200 -Xlinker -rpath=$PWD/tisphi_b200
- *   ./c_abi_minimal
+ *   ./c_abi_minimal [state.bin]     (state.bin: n, then id0[n], x[3n], v[4n] float, density[n] -- what tests/ compare
+ *                                    with the CPU oracle on the same particles)
  */
 #include <math.h>
 #include <stdio.h>
@@ -14,7 +15,7 @@
 
 #define CHECK(call) do { int rc_ = (call); if (rc_) { fprintf(stderr, "%s -> %d: %s\n", #call, rc_, sph_last_error(ctx)); return 1; } } while (0)
 
-int main(void) {
+int main(int argc, char **argv) {
     /* scene constants exactly as ParticleSystem.__init__ derives them (eng/particle_system.py:32-59) */
     const double d = 0.02, h = 1.5 * d, support = 2.0 * h, gs = ceil(2.0 * 1.5) * d;
     const int nx = 20, ny = 15, nz = 10, layers = 3;              /* fluid block and wall thickness in particles */
@@ -27,6 +28,8 @@ int main(void) {
     for (int a = 0; a < 3; a++) { p.vstart[a] = -gs; p.gn[a] = (int)ceil((size[a] + 2 * gs) / gs); }
     p.h = h; p.support = support; p.grid_size = gs; p.m_V0 = d * d * d; p.eps = 1e-8;
     p.g[1] = -9.81; p.rho0 = 1000.0; p.visc = 0.01; p.stiff = 5e5; p.gamma_ = 7.0; p.vsound = 60.0;
+    p.boundary = 2; p.radius = d / 2;                             /* dummy-particle walls (ps:18) */
+    for (int a = 0; a < 3; a++) { p.dstart[a] = 0.0; p.dend[a] = size[a]; }
     p.dt = 0.2 * h / p.vsound;                                    /* calc_dt_CFL, base:209-212 (before the dt_min rounding) */
 
     /* particles: fluid lattice + a floor of dummy particles (three layers below y = 0) */
@@ -54,12 +57,19 @@ int main(void) {
     float *vout = malloc(n * 16);                                 /* MIXED engine: v comes back as n x 4 float (xyz, mass) */
     double *rout = malloc(n * 8);
     int32_t *id0 = malloc(n * 4);
-    CHECK(sph_read_state(ctx, x, (double *)vout, rout, NULL, id0));
+    if (sph_real_bytes(ctx) != 4) { fprintf(stderr, "expected a float32 engine\n"); return 1; }
+    CHECK(sph_read_state(ctx, x, vout, rout, NULL, id0));
     double vy = 0.0, rmax = 0.0;
     for (int64_t i = 0; i < n; i++) if (id0[i] < n_fluid) { vy += vout[4 * i + 1]; if (rout[i] > rmax) rmax = rout[i]; }
     printf("n = %lld, arena = %.1f MB, launches = %lld, mean v_y of the fluid after 10 steps = %.6f m/s, max density = %.3f, "
            "particles outside the grid = %lld\n", (long long)n, bytes / 1e6, (long long)sph_launch_count(ctx), vy / n_fluid, rmax,
            (long long)sph_read_bad_cells(ctx));
+    if (argc > 1) {
+        FILE *f = fopen(argv[1], "wb");
+        if (!f) { fprintf(stderr, "cannot write %s\n", argv[1]); return 1; }
+        fwrite(&n, 8, 1, f); fwrite(id0, 4, n, f); fwrite(x, 8, 3 * n, f); fwrite(vout, 4, 4 * n, f); fwrite(rout, 8, n, f);
+        fclose(f);
+    }
     sph_destroy(ctx);
     cudaFree(arena);
     return 0;

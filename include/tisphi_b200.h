@@ -113,11 +113,18 @@ int sph_add_particles(SphCtx *ctx, int64_t n, const double *x, const double *v, 
 int64_t sph_num_particles(SphCtx *ctx);
 int sph_clear_particles(SphCtx *ctx);
 /* device -> host copies of the dump() state (ps:459-545) in current (sorted) order; any pointer may be NULL.
- * Synchronises the stream. */
-int sph_read_state(SphCtx *ctx, double *x, double *v, double *density, double *pressure, int32_t *id0);
+ * Layout of the host buffers, n = sph_num_particles(ctx), R = sph_real_bytes(ctx) (8 in SPH_PREC_F64, 4 in MIXED):
+ *   x         n x 3 float64                                   (24 n bytes)
+ *   v         n x 4 engine reals: vx, vy, vz, mass            (4 R n bytes -- NOT n x 3 float64 like sph_add_particles)
+ *   density   n float64                                       ( 8 n bytes)
+ *   pressure  n engine reals                                  ( R n bytes)
+ *   id0       n int32                                         ( 4 n bytes)
+ * The arrays are copied as they are stored (no conversion pass).  Synchronises the stream. */
+int32_t sph_real_bytes(SphCtx *ctx);
+int sph_read_state(SphCtx *ctx, double *x, void *v, double *density, void *pressure, int32_t *id0);
 /* the same copies enqueued on the ctx's stream without waiting (pinned host buffers); sph_synchronize waits for
  * everything enqueued on the ctx.  Several ctxs on different streams pipeline upload / step / download. */
-int sph_read_state_async(SphCtx *ctx, double *x, double *v, double *density, double *pressure, int32_t *id0);
+int sph_read_state_async(SphCtx *ctx, double *x, void *v, double *density, void *pressure, int32_t *id0);
 int sph_synchronize(SphCtx *ctx);
 
 /* ParticleSystem.initialize_particle_system (ps:254-257): cell ids, histogram, inclusive scan, stable counting

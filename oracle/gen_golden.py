@@ -129,6 +129,12 @@ CASES = {
     "dp2d_plate_lf": (lambda: _plate(), [1, 2, 10]),
     # tiny 3D dambreak with the C4 parameter set
     "wc3d_tiny_lf": (lambda: _scene("test1_db_water.json", dict(WATER3D), dict(size=[0.16, 0.12, 0.12])), [1, 2, 3]),
+    # ---- round 2, SURVEY 8 f4: the cubic-spline kernel through the soil sweeps (kernel = 0)
+    "dp2d_small_lf_cubic": (lambda: _scene("test2_cc_sand.json", dict(domainEnd=[0.2, 0.08, 0.05], kernel=0),
+                                           dict(size=[0.08, 0.05, 0.05])), [1, 2, 10]),
+    "mui2d_small_lf_cubic": (lambda: _scene("test2_cc_sand.json",
+                                            dict(domainEnd=[0.2, 0.08, 0.05], simulationMethod=2, kernel=0),
+                                            dict(size=[0.08, 0.05, 0.05])), [1, 2, 10]),
     # ---- round 2, SURVEY 8 f2: DYNAMIC rigid body (shape matching + collision clamp) under the two soil solvers
     "dp2d_dynrigid_lf": (lambda: _dynrigid(3), [1, 2, 10, 30]),
     "mui2d_dynrigid_lf": (lambda: _dynrigid(2), [1, 2, 10]),

@@ -104,3 +104,29 @@ def test_viewer_members_and_host_neighbour_helper():
     y = pt.x[:, 1]
     want = 1000.0 * 9.81 * (y[flow].max() - y[flow])
     assert torch.allclose(pt.pressure[flow].double(), want.double(), rtol=1e-12, atol=1e-9)
+
+
+def test_mesh_body_points_become_particles(monkeypatch):
+    """Bodies (ps:83-91, 176-199): the voxelised points of a mesh enter the particle set after the blocks and before the
+    walls, with the body's material.  The voxeliser itself is trimesh (absent in this image), so load_body is replaced by
+    a fake that returns a small lattice -- everything downstream of it is the real path."""
+    import copy
+    import torch
+    from tisphi_b200.eng import particle_system as PS
+    from tisphi_b200.eng.simulation import Simulation, SimConfiger
+    g = Golden("wc2d_small_lf")
+    scene = copy.deepcopy(g.scene)
+    d = 2 * scene["Configuration"]["particleRadius"]
+    pts = np.array([[0.6 + (i + 0.5) * d, 0.1 + (j + 0.5) * d, 0.0] for i in range(4) for j in range(5)])
+    scene["Bodies"] = [dict(objectId=7, materialId=0, geometryFile="unused.obj", translation=[0, 0, 0], scale=[1, 1, 1],
+                            rotationAxis=[0, 0, 1], rotationAngle=0.0, velocity=[0.0, -1.0, 0.0], isDynamic=1)]
+    monkeypatch.setattr(PS, "load_body", lambda body, vox_len: pts.copy())
+    sim = Simulation(SimConfiger(config=scene))
+    n0 = g.meta["n"]
+    assert sim.ps.particle_num[None] == n0 + len(pts)
+    obj = sim.ps.pt.obj_id.cpu().numpy()
+    idx = np.nonzero(obj == 7)[0]
+    assert len(idx) == len(pts)
+    assert np.allclose(sim.ps.pt.x.cpu().numpy()[idx], pts) and np.allclose(sim.ps.pt.v.cpu().numpy()[idx, 1], -1.0)
+    sim.solver.run_steps(5)
+    assert bool(torch.isfinite(sim.ps.pt.v).all())

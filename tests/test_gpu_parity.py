@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 WC_CASES = ["wc2d_small_lf", "wc2d_small_se_cubic", "wc2d_small_rk4_cspm", "wc3d_tiny_lf", "c1_test1_wc_lf", "wc2d_indenter_lf",
             "wc2d_rep_lf", "wc2d_dummyrep_lf", "wc2d_collision_lf"]
 SOIL_CASES = ["mui2d_small_lf", "dp2d_small_rk4_cspm", "dp2d_small_lf", "c2_test2_mui_lf", "c3_test2_dp_rk4_cspm",
-              "dp2d_indenter_lf", "mui2d_dummyrep_lf",
+              "dp2d_indenter_lf", "mui2d_dummyrep_lf", "dp2d_small_lf_cubic", "mui2d_small_lf_cubic",
               # DYNAMIC rigid body: reaction terms, shape matching, collision clamp
               "mui2d_dynrigid_lf", "dp2d_dynrigid_wall_lf", "dp2d_dynrigid_lf"]
 ALL_CASES = WC_CASES + SOIL_CASES

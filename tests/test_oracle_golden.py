@@ -12,6 +12,8 @@ CASES = ["wc2d_small_lf", "wc2d_small_se_cubic", "wc2d_small_rk4_cspm", "mui2d_s
          "dp2d_indenter_lf", "wc2d_indenter_lf",
          # shipped test5 shrunken: four soil blocks + a static rigid plate pushed sideways
          "dp2d_plate_lf",
+         # the cubic-spline kernel through the soil sweeps
+         "dp2d_small_lf_cubic", "mui2d_small_lf_cubic",
          # DYNAMIC rigid body: reaction of the momentum sums, shape matching, collision clamp
          "mui2d_dynrigid_lf", "dp2d_dynrigid_wall_lf", "dp2d_dynrigid_lf",
          # boundary modes 3 (repulsive particles), 4 (dummy + repulsive), 1 (enforced collision)
@@ -37,7 +39,7 @@ def test_oracle_matches_reference_run(name):
     assert o.n == g.meta["n"]
     assert o.P.dt == g.meta["dt"]
     assert [int(v) for v in o.D["grid_num"]] == g.meta["grid_num"]
-    last = max(g.steps) if name.endswith("small_lf") or "tiny" in name or "indenter" in name or "plate" in name or "_h" in name or "rep" in name or "collision" in name or "dynrigid" in name or "20k" in name else min(max(g.steps), 10)
+    last = max(g.steps) if name.endswith("small_lf") or name.endswith("_cubic") or "tiny" in name or "indenter" in name or "plate" in name or "_h" in name or "rep" in name or "collision" in name or "dynrigid" in name or "20k" in name else min(max(g.steps), 10)
     for s in range(1, last + 1):
         if s in g.steps:
             # state right after the grid build + kernel correction of step s

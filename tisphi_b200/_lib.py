@@ -19,7 +19,7 @@ FIELD_ID = {name: k for k, name in enumerate(FIELDS)}
 
 # every symbol include/tisphi_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ["sph_arena_bytes", "sph_create", "sph_destroy", "sph_last_error", "sph_set_params", "sph_field_info",
-           "sph_add_particles", "sph_num_particles", "sph_clear_particles", "sph_read_state", "sph_read_state_async",
+           "sph_add_particles", "sph_num_particles", "sph_clear_particles", "sph_real_bytes", "sph_read_state", "sph_read_state_async",
            "sph_synchronize", "sph_grid_build",
            "sph_calc_kernel_corr", "sph_calc_kernel_corr_deferred", "sph_init_real2tmp", "sph_one_step", "sph_advect", "sph_advect_pos", "sph_post_step",
            "sph_init_stress", "sph_init_stress_ymax", "sph_enforce_boundary", "sph_set_rigid_bodies", "sph_init_rigid_body", "sph_solve_rigid_body", "sph_rigid_rest_cm", "sph_step", "sph_neighbor_count", "sph_neighbor_count_masks", "sph_density_sum", "sph_density_sweep", "sph_read_bad_cells", "sph_read_flagged_cells",
@@ -68,6 +68,7 @@ def load():
     L.sph_add_particles.restype, L.sph_add_particles.argtypes = C.c_int, [vp, i64, vp, vp, vp, vp]
     L.sph_num_particles.restype, L.sph_num_particles.argtypes = i64, [vp]
     L.sph_clear_particles.restype, L.sph_clear_particles.argtypes = C.c_int, [vp]
+    L.sph_real_bytes.restype, L.sph_real_bytes.argtypes = i32, [vp]
     L.sph_read_state.restype, L.sph_read_state.argtypes = C.c_int, [vp, vp, vp, vp, vp, vp]
     L.sph_read_state_async.restype, L.sph_read_state_async.argtypes = C.c_int, [vp, vp, vp, vp, vp, vp]
     L.sph_synchronize.restype, L.sph_synchronize.argtypes = C.c_int, [vp]

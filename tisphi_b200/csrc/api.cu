@@ -453,7 +453,8 @@ int sph_clear_particles(SphCtx *c) {
     return 0;
 }
 
-int sph_read_state_async(SphCtx *c, double *x, double *v, double *density, double *pressure, int32_t *id0) {
+int32_t sph_real_bytes(SphCtx *c) { return c->real_bytes; }
+int sph_read_state_async(SphCtx *c, double *x, void *v, double *density, void *pressure, int32_t *id0) {
     const int64_t n = slab_exact_n(c);
     if (x) SPH_CHECK(c, cudaMemcpyAsync(x, c->arena + c->f[SPH_F_X].off[c->f[SPH_F_X].cur], (size_t)n * 24, cudaMemcpyDefault, c->stream));
     if (density) SPH_CHECK(c, cudaMemcpyAsync(density, c->arena + c->f[SPH_F_DENSITY].off[c->f[SPH_F_DENSITY].cur], (size_t)n * 8, cudaMemcpyDefault, c->stream));
@@ -468,7 +469,7 @@ int sph_synchronize(SphCtx *c) {
     SPH_CHECK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
-int sph_read_state(SphCtx *c, double *x, double *v, double *density, double *pressure, int32_t *id0) {
+int sph_read_state(SphCtx *c, double *x, void *v, double *density, void *pressure, int32_t *id0) {
     int r = sph_read_state_async(c, x, v, density, pressure, id0);
     return r ? r : sph_synchronize(c);
 }

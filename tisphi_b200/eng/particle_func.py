@@ -5,7 +5,7 @@ Mirror of the scene builders of the reference's eng/particle_func.py (function n
   set_material / get_material pf:218-244, chk_block_in_domain pf:246-251, count_boundary / add_boundary pf:302-313,
   calc_dummy_boundary pf:316-343.
 The particle SET (positions, creation order) must be bit-identical to the reference's: it is the precondition of
-every parity test.  calc_rep_boundary pf:346-374.  Mesh bodies are out of scope (they need trimesh).
+every parity test.  calc_rep_boundary pf:346-374, load_body pf:265-294 (needs trimesh, like the reference).
 """
 import numpy as np
 
@@ -131,4 +131,20 @@ def calc_rep_boundary(dim, domain_start, domain_end, pt_radius):
 
 
 def load_body(body, vox_len):
-    raise NotImplementedError("mesh bodies need trimesh and are out of scope of this engine (SURVEY 2.1)")
+    """Voxelised points of a mesh body (pf:265-294).  Like the reference this is ``trimesh`` from start to end -- load,
+    scale, rotation about ``rotationAxis`` through the reference's pivot, filled voxelisation at one particle diameter --
+    so it needs that package at run time (it is not part of this image; no scene of the reference ships a mesh)."""
+    try:
+        import trimesh as tm
+    except ImportError as e:                             # the reference fails at the same line (pf:266)
+        raise ImportError("mesh Bodies need the 'trimesh' package, as in the reference (eng/particle_func.py:266)") from e
+    mesh = tm.load(body["geometryFile"])
+    mesh.apply_scale(body["scale"])
+    offset = np.array(body["translation"])
+    angle = body["rotationAngle"] / 180 * np.pi
+    mesh.apply_transform(tm.transformations.rotation_matrix(angle, body["rotationAxis"], mesh.vertices.mean(axis=-1)))
+    if body["isDynamic"]:                                # kept for exporters (pf:279-285)
+        backup = mesh.copy()
+        backup.vertices += offset
+        body["mesh"], body["restPosition"], body["restCenterOfMass"] = backup, backup.vertices, backup.vertices.mean(axis=-1)
+    return mesh.voxelized(pitch=vox_len).fill().points + offset

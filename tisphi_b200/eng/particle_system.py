@@ -12,7 +12,7 @@ import numpy as np
 from .. import _lib
 from .configer_builder import SimConfiger
 from .particle_func import (add_boundary, add_cube, calc_cube_particle_num, calc_dummy_boundary, calc_rep_boundary, chk_block_in_domain,
-                            count_boundary, get_material, set_material)
+                            count_boundary, get_material, load_body, set_material)
 
 
 class _Scalar:
@@ -166,9 +166,14 @@ class ParticleSystem:
             self.object_collection[block["objectId"]] = block
             block_particle_num += particle_num
             print("Block %d particle number: %d" % (block["objectId"], particle_num))
-        self.bodies = self.cfg.get_bodies()
-        if self.bodies:
-            raise NotImplementedError("mesh Bodies are out of scope of this engine (SURVEY 2.1)")
+        self.bodies = self.cfg.get_bodies()                                          # ps:83-91
+        body_particle_num = 0
+        for body in self.bodies:
+            points = load_body(body, self.particle_diameter)
+            body["particleNum"], body["voxelizedPoints"] = points.shape[0], points
+            self.object_collection[body["objectId"]] = body
+            body_particle_num += points.shape[0]
+            print("Body %d particle number: %d" % (body["objectId"], points.shape[0]))
         dummy_particle_num = 0
         if self.flag_boundary in (self.bdy_dummy, self.bdy_dummy_rep):
             self.dummy_boundary = calc_dummy_boundary(self.dim, self.domain_start, self.domain_end, self.vdomain_start,
@@ -180,7 +185,7 @@ class ParticleSystem:
             self.rep_boundary = calc_rep_boundary(self.dim, self.domain_start, self.domain_end, self.particle_radius)
             rep_particle_num = count_boundary(self.rep_boundary, self.dim, self.particle_radius)
             print("Repulsive particle number: %d" % rep_particle_num)
-        self.particle_max_num = block_particle_num + dummy_particle_num + rep_particle_num
+        self.particle_max_num = block_particle_num + body_particle_num + dummy_particle_num + rep_particle_num
         print(f"Particle total num: {self.particle_max_num}")
 
         # engine (replaces the Taichi struct fields pt / pt_buf, the grid counters and the prefix-sum executor)
@@ -232,6 +237,8 @@ class ParticleSystem:
     def initialize_particles(self):
         for block in self.blocks:
             self.init_block(block)
+        for body in self.bodies:
+            self.init_body(body)
         if self.flag_boundary in (self.bdy_dummy, self.bdy_dummy_rep):
             add_boundary(self, self.dummy_boundary, self.mat_dummy_type, color=[153, 153, 255])
         if self.flag_boundary in (self.bdy_rep, self.bdy_dummy_rep):                 # ps:147-148
@@ -256,7 +263,21 @@ class ParticleSystem:
                  mat_id=block["materialId"], mat_type=mat_type)
 
     def init_body(self, body):
-        raise NotImplementedError("mesh Bodies are out of scope of this engine (SURVEY 2.1)")
+        """ps:176-199: the voxelised points of a mesh body as particles of its material."""
+        mat = get_material(self, body["materialId"])
+        mat_type, n = mat["matType"], body["particleNum"]
+        is_dynamic = True
+        if mat_type > 10:
+            self.object_id_rigid.add(body["objectId"])
+            is_dynamic = bool(body["isDynamic"])
+            if is_dynamic and self.params.solver == _lib.SOLVER_WC:
+                raise NotImplementedError("a dynamic rigid body under WCSPH does not run in the reference either (wc:129-132)")
+        self._add_particles(body["objectId"], n, np.array(body["voxelizedPoints"], dtype=np.float64),
+                            np.tile(np.array(body["velocity"], dtype=np.float64), (n, 1)),
+                            np.full(n, mat["density0"], dtype=np.float64), np.zeros(n, dtype=np.float64),
+                            np.full(n, body["materialId"], dtype=np.int32), np.full(n, mat_type, dtype=np.int32),
+                            np.full(n, int(is_dynamic), dtype=np.int32),
+                            np.tile(np.array([ic / 255 for ic in mat["color"]], dtype=np.float32), (n, 1)))
 
     def _add_particles(self, object_id, new_particles_num, new_particles_positions, new_particles_velocity,
                        new_particle_density, new_particle_pressure, new_particles_material_id,
