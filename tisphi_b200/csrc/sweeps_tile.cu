@@ -668,12 +668,22 @@ template <int KERNEL, class FT> __global__ void __launch_bounds__(FT::BT) k_tile
 // ------------------------------------------------------------------------------------------------ count + density sweep
 // BASELINE config C5: the bare for_all_neighbors iteration (ps:259-269) with the density task (wc:30-31) -- per FLOW
 // particle of an unflagged cell the neighbour count (popcount of its mask words: exact) and sum_j mass_j W_ij over the
-// set bits, in ONE walk of the masks.  Payloads: ps4 (coordinates) and v4 (.w = mass).  Everything else (wall particles,
-// whose masks hold flow neighbours only, and flagged cells) is left to the generic kernel.
+// set bits, in ONE walk of the masks.  Payload: ONE float4 per neighbour (coordinates, mass), written by k_density_payload
+// into the pk4 array right before -- a second shared-memory gather for the mass alone made the kernel 1.5x slower (the
+// pass is bound by shared-memory gather wavefronts, profiles/r2_ncu_evidence.json).  Everything else (wall particles, whose
+// masks hold flow neighbours only, and flagged cells) is left to the generic kernel.
+__global__ void __launch_bounds__(256) k_density_payload(DevF c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N()) return;
+    F4 p = c.xs4[i];
+    p.w = c.v4[i].w;
+    c.pk4[i] = p;
+}
 template <int KERNEL, class FT>
-__device__ __forceinline__ bool density_body(const DevF &c, const TileGeom &g, TileShared<FT, 2> &sh, int blk, unsigned parity,
+__device__ __forceinline__ bool density_body(const DevF &c, const TileGeom &g, TileShared<FT, 1> &sh1, int blk, unsigned parity,
                                              int *__restrict__ count_out, float *__restrict__ rho_out) {
     WarpCell w = warp_cell<FT>(c, g, blk);
+    TileShared<FT, 1> &sh = sh1;
     const int lane = threadIdx.x & 31;
     if (w.nc > 0 && c.cellflag[w.gcell]) w.nc = 0;
     const int i = w.is + lane;
@@ -681,10 +691,10 @@ __device__ __forceinline__ bool density_body(const DevF &c, const TileGeom &g, T
     const unsigned nz = work ? c.nzw[i] : 0u;
     if (!__syncthreads_or(work)) return false;
     cursor_prefetch(mask_row(c.mask, w.is, FT::NW, work ? lane : 0), (unsigned)w.nc, nz);
-    if (!tile_setup<FT, 2>(c, g, sh, w, parity, c.ps4, c.v4)) return true;
-    build_ctab<FT, 2>(c, sh, w, lane);
+    if (!tile_setup<FT, 1>(c, g, sh, w, parity, c.pk4)) return true;
+    build_ctab<FT, 1>(c, sh, w, lane);
     if (!__any_sync(0xffffffffu, work)) return true;
-    const F4 *A = sh.P[0], *B = sh.P[1];
+    const F4 *A = sh.P[0];
     const F4 *ct = sh.ctab + (threadIdx.x >> 5) * FT::NW;
     const F4 pi = A[sh.cb[stencil_cb<FT>(w, 0, 0, 0)] + (work ? lane : 0)];
     const KernConst kc = kern_const(c);
@@ -706,12 +716,11 @@ __device__ __forceinline__ bool density_body(const DevF &c, const TileGeom &g, T
         cursor_jump(k, mrow, n, ct, pi);
         if (before2 != k.nz) cnt += __popc(k.m);
         cursor_take2<FT::SENT>(k, i2, i3);
-        const F4 p0 = A[i0], p1 = A[i1], p2 = A[i2], p3 = A[i3];
-        const float m0 = B[i0].w, m1 = B[i1].w, m2 = B[i2].w, m3 = B[i3].w;     // sentinel: mass 0
-        s0 = fmaf(m0, fastW<KERNEL>(kc, dist2(e0x - p0.x, e0y - p0.y, e0z - p0.z)), s0);
-        s1 = fmaf(m1, fastW<KERNEL>(kc, dist2(e0x - p1.x, e0y - p1.y, e0z - p1.z)), s1);
-        s0 = fmaf(m2, fastW<KERNEL>(kc, dist2(k.ex - p2.x, k.ey - p2.y, k.ez - p2.z)), s0);
-        s1 = fmaf(m3, fastW<KERNEL>(kc, dist2(k.ex - p3.x, k.ey - p3.y, k.ez - p3.z)), s1);
+        const F4 p0 = A[i0], p1 = A[i1], p2 = A[i2], p3 = A[i3];                // .w = mass; sentinel: 0
+        s0 = fmaf(p0.w, fastW<KERNEL>(kc, dist2(e0x - p0.x, e0y - p0.y, e0z - p0.z)), s0);
+        s1 = fmaf(p1.w, fastW<KERNEL>(kc, dist2(e0x - p1.x, e0y - p1.y, e0z - p1.z)), s1);
+        s0 = fmaf(p2.w, fastW<KERNEL>(kc, dist2(k.ex - p2.x, k.ey - p2.y, k.ez - p2.z)), s0);
+        s1 = fmaf(p3.w, fastW<KERNEL>(kc, dist2(k.ex - p3.x, k.ey - p3.y, k.ez - p3.z)), s1);
     }
     if (work) { count_out[i] = cnt; rho_out[i] = s0 + s1; }
     return true;
@@ -719,8 +728,8 @@ __device__ __forceinline__ bool density_body(const DevF &c, const TileGeom &g, T
 template <int KERNEL, class FT>
 __global__ void __launch_bounds__(FT::BT, 2) k_tile_density(DevF c, TileGeom g, int *__restrict__ count_out, float *__restrict__ rho_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileShared<FT, 2> &sh = *reinterpret_cast<TileShared<FT, 2> *>(smem_raw);
-    tile_init<FT, 2>(sh);
+    TileShared<FT, 1> &sh = *reinterpret_cast<TileShared<FT, 1> *>(smem_raw);
+    tile_init<FT, 1>(sh);
     TILE_PERSISTENT_LOOP(sh, c.worklist[1], c.wcount + 1, c.wcount + 6, (density_body<KERNEL, FT>(c, g, sh, blk, parity, count_out, rho_out)))
 }
 
@@ -808,9 +817,9 @@ __device__ __forceinline__ void wall_pair(const KernConst &kc, float ex, float e
 // particles take part in this pass and each has few (flow-only) neighbours, so staging 54 cells x 3 payloads per four
 // cells left the SMs idle behind TMA latency and block barriers (ncu: 12 % issue slots used, 9.6 warp-cycles of
 // barrier stall per issue).  Warps are independent here: no block barrier, 32 warps per SM.
-template <bool D3> __global__ void __launch_bounds__(256) k_wall_cells(DevF c) {
-    const int gcell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gcell >= c.C) return;
+template <bool D3> __global__ void __launch_bounds__(256) k_wall_cells(DevF c, int cell0, int cell1) {
+    const int gcell = cell0 + blockIdx.x * blockDim.x + threadIdx.x;      // (a slab only looks at the cells of its own columns)
+    if (gcell >= cell1) return;
     if (!(c.cellinfo[gcell] & 4) || c.cellflag[gcell]) return;
     const int nF = D3 ? c.gn[2] : c.gn[1], n1 = D3 ? c.gn[1] : 1;
     const int cx = gcell / (nF * n1);
@@ -1108,7 +1117,7 @@ template <int KERNEL, class FT> static int set_fluid_attrs(SphCtx *c) {
     if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 1>, smem_of<FT, 2>());
     if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, true, 1>, smem_of<FT, 2>());
     if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 2>, smem_of<FT, 2>());
-    if (!r) r = set_smem(c, k_tile_density<KERNEL, FT>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_density<KERNEL, FT>, smem_of<FT, 1>());
     return r;
 }
 template <int KERNEL> static int set_attrs(SphCtx *c) {
@@ -1177,8 +1186,9 @@ int tile_mask(SphCtx *c, bool shepard) {
     if ((r = d3 ? build_worklist<F3M>(c, d, 1) : build_worklist<F2M>(c, d, 1))) return r;
     SPH_CHECK(c, cudaMemsetAsync(d.wcount + 2, 0, 4, c->stream));           // wall CELLS with flow particles in reach
     SPH_PROF(c, K_OTHER);
-    if (d3) k_wall_cells<true><<<blocks_for(c->C, 256), 256, 0, c->stream>>>(d);
-    else k_wall_cells<false><<<blocks_for(c->C, 256), 256, 0, c->stream>>>(d);
+    const int nyz_ = c->p.gn[1] * (d3 ? c->p.gn[2] : 1), wc0 = c->own0 * nyz_, wc1 = c->own1 * nyz_;
+    if (d3) k_wall_cells<true><<<blocks_for(wc1 - wc0, 256), 256, 0, c->stream>>>(d, wc0, wc1);
+    else k_wall_cells<false><<<blocks_for(wc1 - wc0, 256), 256, 0, c->stream>>>(d, wc0, wc1);
     SPH_LAUNCH_CHECK(c);
     c->shep_pending = c->shep_wall_pending = !shepard;
     c->list_valid = false;
@@ -1258,11 +1268,14 @@ int tile_wc_fluid(SphCtx *c) {
 template <int KERNEL, class FT> static void launch_density(SphCtx *c, const DevF &d, int *count_out, float *rho_out) {
     const TileGeom g_ = make_geom<FT>(d.gn);
     cudaMemsetAsync(d.wcount + 6, 0, 4, c->stream);
-    k_tile_density<KERNEL, FT><<<pgrid(k_tile_density<KERNEL, FT>, FT::BT, smem_of<FT, 2>(), nblocks<FT>(g_)), FT::BT, smem_of<FT, 2>(), c->stream>>>(d, g_, count_out, rho_out);
+    k_tile_density<KERNEL, FT><<<pgrid(k_tile_density<KERNEL, FT>, FT::BT, smem_of<FT, 1>(), nblocks<FT>(g_)), FT::BT, smem_of<FT, 1>(), c->stream>>>(d, g_, count_out, rho_out);
 }
 int tile_density_sweep(SphCtx *c, int32_t *count_out, float *rho_out) {
     if (need_masks(c)) return -3;
     DevF d = make_dev<float>(c);
+    SPH_PROF(c, K_OTHER);
+    k_density_payload<<<blocks_for(c->n, 256), 256, 0, c->stream>>>(d);
+    SPH_LAUNCH_CHECK(c);
     SPH_PROF(c, K_C5);
     if (c->p.dim == 3) {
         if (c->p.kernel == 0) launch_density<0, F3M>(c, d, count_out, rho_out); else launch_density<1, F3M>(c, d, count_out, rho_out);

@@ -1,12 +1,17 @@
 #!/usr/bin/env python
-"""profiles/r1_ncu_evidence.json from `ncu --set full` captures: per kernel class the DRAM bytes of one launch and
-the utilisation of the units that bound it.  usage: ncu_evidence.py class=report.ncu-rep[:kernel substring] ..."""
+"""profiles/<round>_ncu_evidence.json from `ncu --set full` captures: per kernel class the DRAM bytes of one launch and
+the utilisation of the units that bound it.
+usage: ncu_evidence.py [--out profiles/r2_ncu_evidence.json] class=report.ncu-rep[:kernel substring] ..."""
 import csv, io, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_path = os.path.join(ROOT, "profiles", "r1_ncu_evidence.json")
+args = sys.argv[1:]
+if args and args[0] == "--out":
+    out_path = os.path.join(ROOT, args[1]) if not os.path.isabs(args[1]) else args[1]
+    args = args[2:]
 out = json.load(open(out_path)) if os.path.exists(out_path) else {}
-for arg in sys.argv[1:]:
+for arg in args:
     cls, rep = arg.split("=", 1)
     sub = None
     if ":" in rep:
