@@ -474,6 +474,11 @@ def run_ours_multi(args, rank, local, world):
     from tisphi_b200.eng.simulation import SimConfiger
     from tisphi_b200.parallel import SlabSimulation
 
+    if args.workload == "c5":
+        from tisphi_b200 import bench_c5
+        bench_c5.run_multi(args, rank, local, world, log, ClockSampler, measured_peaks)
+        dist.destroy_process_group()
+        return
     parity = slab_parity_check(rank, local, world, log) if not args.no_parity else None
     scene = scenes.dambreak3d(scale=args.scale, precision=args.precision, **scene_options(args))
     t0 = time.time()

@@ -11,7 +11,7 @@ STATE = list(orc.FIELDS) + list(orc.IFIELDS)
 
 
 class OracleSlabEngine:
-    def __init__(self, params, x, v, density, mat_type, id0, stress=None):
+    def __init__(self, params, x, v, density, mat_type, id0, stress=None, obj_id=None, is_dynamic=None):
         self.P = params
         self.ti, self.xsph, self.solver = params.ti, params.xsph, params.solver
         self.o = self._alloc(len(x))
@@ -19,6 +19,9 @@ class OracleSlabEngine:
         o.x[:], o.v[:], o.density[:], o.mat_type[:], o.id0[:] = x, v, density, mat_type, id0
         o.m_V[:] = params.m_V0
         o.mass[:] = params.m_V0 * np.asarray(density)
+        o.obj_id[:] = 0 if obj_id is None else obj_id            # Oracle.__init__ defaults; static rigid blocks carry is_dynamic = 0
+        o.is_dynamic[:] = 1 if is_dynamic is None else is_dynamic
+        o.x0[:] = x
         if stress is not None:
             o.stress[:] = stress
         self.state_fields = STATE

@@ -40,6 +40,7 @@ def _worker(rank, world, port, name, nsteps, serial):
         g = Golden(name)
         P, D = orc.make_params(g.scene, serial=serial)
         _, x, v, rho, typ = orc.build_particles(g.scene)
+        obj, dyn = orc.build_particles.last_obj_dyn
         ref = orc.Oracle.from_scene(g.scene, serial=serial) if rank == 0 else None
         n_cols = int(D["grid_num"][0])
         w, cx = column_weights(x[:, 0], typ, float(D["vstart"][0]), D["grid_size"], n_cols)
@@ -50,7 +51,7 @@ def _worker(rank, world, port, name, nsteps, serial):
         if P.solver == 3:                      # init_stress needs the global column top (base:249-260)
             full = orc.Oracle.from_scene(g.scene, serial=serial)
             stress = full.stress[mine].copy()
-        eng = OracleSlabEngine(P, x[mine], v[mine], rho[mine], typ[mine], mine.astype(np.int32), stress)
+        eng = OracleSlabEngine(P, x[mine], v[mine], rho[mine], typ[mine], mine.astype(np.int32), stress, obj[mine], dyn[mine])
         drv = SlabDriver(eng, (a, b), rank, world, n_cols, check=True)
         fields = CHECK[P.solver] + ["id0", "grid_ids", "mat_type"]
         for s in range(nsteps):

@@ -121,3 +121,82 @@ def run(args, local, log, ClockSampler, measured_peaks, host_threads=None):
                     "ms_per_step": e2e_s / k * 1e3},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
+
+
+def run_multi(args, rank, local, world, log, ClockSampler, measured_peaks):
+    """The same box slab-partitioned along x over `world` GPUs (strong scaling): every sweep = sph_grid_build on the slab
+    (selection of the face columns, push into the neighbours' inboxes, ONE sort of the virtual concatenation) +
+    sph_density_sweep on the owned columns.  One process per GPU, csrc/slab.cu."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    from .c5 import box_positions, box_params
+    from .parallel import partition_columns, connect_p2p
+    n_target = int(args.size or 1e7)
+    x, n_side = box_positions(n_target)
+    n = len(x)
+    P = box_params(n_side)
+    gs, ncol = P.grid_size, int(P.gn[0])
+    cx = np.clip(((x[:, 0] - P.vstart[0]) / gs).astype(np.int64), 0, ncol - 1)
+    counts = np.bincount(cx, minlength=ncol)
+    cols = partition_columns(counts.astype(np.float64), world)
+    a, b = cols[rank]
+    mine = np.nonzero((cx >= a) & (cx < b))[0]
+    cap = int(1.3 * (len(mine) + counts[max(a - 1, 0):a].sum() + counts[b:b + 1].sum())) + 4 * int(counts.max()) + 1024
+    eng = _lib.Engine(P, cap, device=f"cuda:{local}")
+    eng.add_particles(x[mine], np.zeros((len(mine), 3)), np.ones(len(mine)), np.ones(len(mine), dtype=np.int32))
+    eng.field("ID0").copy_(torch.from_numpy(mine.astype(np.int32)).to(eng.device))
+    del x
+    face_cap = 2 * int(counts.max()) + 4096
+    drv, inbox, ipc = connect_p2p(eng, rank, world, (a, b), face_cap)
+    count = torch.empty(cap, dtype=torch.int32, device=eng.device)
+    rho = torch.empty(cap, dtype=eng.real, device=eng.device)
+
+    def sweep():
+        eng.call("sph_grid_build")
+        eng.call("sph_density_sweep", count.data_ptr(), rho.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        sweep()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record(eng.stream)
+        for _ in range(args.steps):
+            sweep()
+        e1.record(eng.stream)
+        barrier()
+    ms_t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=eng.device)
+    dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms = float(ms_t)
+    drv.sync()
+    own = slice(drv.own_first, drv.own_first + drv.own_count)
+    tot = torch.tensor([drv.own_count, int(count[own].long().sum()), int(count[own].max())], dtype=torch.int64, device=eng.device)
+    allv = [torch.zeros_like(tot) for _ in range(world)]
+    dist.all_gather(allv, tot)
+    assert sum(int(v[0]) for v in allv) == n, "particles lost or duplicated by the slab exchange"
+    pairs = sum(int(v[1]) for v in allv)
+    assert pairs % 2 == 0, "the neighbour relation across the slab faces is not symmetric"
+    if rank == 0:
+        cells = int(P.gn[0]) * int(P.gn[1]) * int(P.gn[2])
+        line = {"metric": METRIC, "value": n * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"C5 synthetic 3D uniform box: N={n} ({n_side}^3 jittered lattice, seed 1234), cells={cells}; "
+                                       "one step = grid build + neighbour count + density sum",
+                           "partition": f"slab-partitioned over {world} GPUs along x; every step starts with the face exchange of csrc/slab.cu",
+                           "columns": [list(c) for c in cols], "owned_particles": [int(v[0]) for v in allv],
+                           "mean_neighbours": pairs / n, "max_neighbours": max(int(v[2]) for v in allv),
+                           "l2": "state larger than L2, no flush needed"},
+                "clocks": clocks.summary(), "e2e": None, "gpu_launches": int(eng.L.sph_launch_count(eng.h)), "roofline": None,
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    barrier()
+    for p in ipc:
+        eng.L.sph_ipc_close(p)
+    eng.L.sph_ipc_free(inbox)

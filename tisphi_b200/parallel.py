@@ -408,6 +408,47 @@ class NativeSlab:
         return int(self.L.sph_slab_epoch(self.e.h))
 
 
+def connect_p2p(eng, rank, world, columns, face_cap, group=None):
+    """Allocate this rank's inbox, exchange CUDA IPC handles, map the neighbours' inboxes, arm the native slab step.
+    Every rank takes part in every collective whatever happens locally, then all ranks raise together if any of them
+    failed.  Returns (NativeSlab, inbox pointer, [mapped neighbour pointers])."""
+    import torch.distributed as dist
+    L = eng.L
+    nbytes = NativeSlab.inbox_bytes(eng, face_cap)
+    problem, drv, handle, ipc = None, None, (C.c_ubyte * 64)(), []
+    with eng.torch.cuda.device(eng.device):
+        inbox = L.sph_ipc_alloc(nbytes)
+        if not inbox:
+            problem = f"cudaMalloc of the {nbytes}-byte slab inbox failed"
+        elif L.sph_ipc_get_handle(inbox, handle) != 0:
+            problem = "cudaIpcGetMemHandle failed for the slab inbox"
+        else:
+            drv = NativeSlab(eng, rank, world, columns, face_cap, inbox, nbytes)
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle) if problem is None else None, group=group)
+        ptrs = [None, None]
+        if problem is None:
+            for side, nb in ((0, rank - 1), (1, rank + 1)):
+                if 0 <= nb < world and handles[nb] is not None:
+                    p = L.sph_ipc_open((C.c_ubyte * 64).from_buffer_copy(handles[nb]))
+                    if not p:
+                        problem = f"cudaIpcOpenMemHandle failed for the inbox of rank {nb} (no peer access between the GPUs?)"
+                        break
+                    ipc.append(p)
+                    ptrs[side] = p
+        problems = [None] * world
+        dist.all_gather_object(problems, problem, group=group)
+        if any(problems):
+            for p in ipc:
+                L.sph_ipc_close(p)
+            if inbox:
+                L.sph_ipc_free(inbox)
+            raise RuntimeError("slab p2p transport unavailable: " + "; ".join(f"rank {r}: {p}" for r, p in enumerate(problems) if p))
+        drv.connect(ptrs[0], ptrs[1])
+    dist.barrier(group=group)
+    return drv, inbox, ipc
+
+
 class SlabSimulation:
     """``Simulation`` for one rank of a slab-partitioned run (same scene JSON; torch.distributed must be initialised).
 
@@ -435,40 +476,7 @@ class SlabSimulation:
             self.driver = SlabDriver(self.engine, self.columns, rank, world, int(self.ps.grid_num[0]), group=group, check=check)
 
     def _connect_p2p(self, group):
-        """Allocate the inbox, exchange CUDA IPC handles, map the neighbours' inboxes.  Every rank takes part in every
-        collective whatever happens locally, then all ranks raise together if any of them failed."""
-        import torch.distributed as dist
-        eng = self.ps.engine
-        L = eng.L
-        nbytes = NativeSlab.inbox_bytes(eng, self.ps.slab_face_cap)
-        problem, drv, handle = None, None, (C.c_ubyte * 64)()
-        with eng.torch.cuda.device(eng.device):
-            self._inbox = L.sph_ipc_alloc(nbytes)
-            if not self._inbox:
-                problem = f"cudaMalloc of the {nbytes}-byte slab inbox failed"
-            elif L.sph_ipc_get_handle(self._inbox, handle) != 0:
-                problem = "cudaIpcGetMemHandle failed for the slab inbox"
-            else:
-                drv = NativeSlab(eng, self.rank, self.world, self.columns, self.ps.slab_face_cap, self._inbox, nbytes)
-            handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle) if problem is None else None, group=group)
-            ptrs = [None, None]
-            if problem is None:
-                for side, nb in ((0, self.rank - 1), (1, self.rank + 1)):
-                    if 0 <= nb < self.world and handles[nb] is not None:
-                        p = L.sph_ipc_open((C.c_ubyte * 64).from_buffer_copy(handles[nb]))
-                        if not p:
-                            problem = f"cudaIpcOpenMemHandle failed for the inbox of rank {nb} (no peer access between the GPUs?)"
-                            break
-                        self._ipc.append(p)
-                        ptrs[side] = p
-            problems = [None] * self.world
-            dist.all_gather_object(problems, problem, group=group)
-            if any(problems):
-                self.close()
-                raise RuntimeError("slab p2p transport unavailable: " + "; ".join(f"rank {r}: {p}" for r, p in enumerate(problems) if p))
-            drv.connect(ptrs[0], ptrs[1])
-        dist.barrier(group=group)
+        drv, self._inbox, self._ipc = connect_p2p(self.ps.engine, self.rank, self.world, self.columns, self.ps.slab_face_cap, group)
         return drv
 
     def close(self):
