@@ -414,3 +414,45 @@ def test_tile_path_partially_flagged_cells():
         keys = ("x", "v", "density", "pressure", "d_vel", "d_density", "CSPM_f") if s == 0 else ("x", "v", "density", "pressure")
         errs = {k: relmax(fa[k][ia][ok], fb[k][ib][ok]) for k in keys}
         assert all(e < tol for e in errs.values()), (s, errs)
+
+
+@pytest.mark.parametrize("name", ["c1_test1_wc_lf_h100", "wc3d_20k_lf", "c2_test2_mui_lf_h100"])
+def test_mixed_neighbor_counts_bracketed_by_reference_positions(name):
+    """Pins the float32 (cell-local) neighbour predicate to the REFERENCE run, not to the oracle's restatement of it:
+    the fixture's float64 positions of every snapshot are injected, the MIXED engine sorts and counts, and every count
+    must lie between #{r < support (1 - tol)} and #{r < support (1 + tol)} evaluated in float64 on those positions (KD
+    tree), tol = 1e-6 -- i.e. the MIXED neighbour set differs from the reference's only by pairs within 1e-6 (relative)
+    of the support sphere, of which a rest lattice has many.  The reference's own counts satisfy the same
+    bracket, and wherever the bracket is tight (no borderline pair) the MIXED count equals the reference's exactly."""
+    import torch
+    from scipy.spatial import cKDTree
+    g = Golden(name)
+    tol = 1e-6
+    for s in g.steps:
+        sim = make_sim(g.scene, precision="f32")
+        ps = sim.ps
+        sup = float(ps.support_radius)
+        xs, id0 = g.grid(s, "x"), g.grid(s, "id0")
+        x_creation = np.empty_like(xs)
+        x_creation[id0] = xs
+        ps.pt.x.copy_(torch.from_numpy(x_creation).to(ps.pt.x.device))          # before the first sort: creation order
+        ps.initialize_particle_system()
+        mine_sorted = ps.neighbor_count().cpu().numpy()
+        mine = np.empty_like(mine_sorted)
+        mine[ps.pt.id0.cpu().numpy()] = mine_sorted                              # by creation index
+        ref = np.empty_like(mine)
+        ref[id0] = g.grid(s, "neighbor_count")
+        tree = cKDTree(x_creation)
+        lo = tree.query_ball_point(x_creation, sup * (1 - tol), return_length=True) - 1
+        hi = tree.query_ball_point(x_creation, sup * (1 + tol), return_length=True) - 1
+        assert np.all((lo <= ref) & (ref <= hi)), (name, s, "the reference's own counts leave the bracket")
+        assert np.all((lo <= mine) & (mine <= hi)), (name, s, int(((mine < lo) | (mine > hi)).sum()))
+        tight = lo == hi
+        assert np.array_equal(mine[tight], ref[tight]), (name, s)
+        if sim.solver_type == 1:                                                 # the cell-tile path's bit masks (flow particles)
+            out = torch.empty(ps.engine.n, dtype=torch.int32, device=ps.engine.device)
+            sim.solver.calc_kernel_corr()                                        # builds the masks
+            ps.engine.call("sph_neighbor_count_masks", out.data_ptr())
+            m_sorted = out.cpu().numpy()
+            assert np.array_equal(m_sorted[m_sorted >= 0], mine_sorted[m_sorted >= 0]), (name, s, "mask counts differ from the walk")
+            assert (m_sorted >= 0).sum() > 0
