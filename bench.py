@@ -423,6 +423,7 @@ def slab_parity_check(rank, local, world, log):
     c1["Configuration"]["precision"] = "f32"
     cases = {"c1_2d": c1, "c4_coarse_3d": scenes.dambreak3d(scale=0.2, precision="f32")}
     fields = ["x", "v", "density", "pressure", "d_vel", "id0", "grid_ids"]
+    out["c4_full_hash"] = slab_parity_hash(rank, local, world, log, scenes.dambreak3d(scale=1.0, precision="f32"), fields)
     for name, scene in cases.items():
         ok, mine, slab, ref = True, None, None, None
         try:                                         # whatever fails locally, every rank reaches every collective
@@ -462,6 +463,72 @@ def slab_parity_check(rank, local, world, log):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         out[name] = bool(int(flag))
     return out
+
+
+def state_hash(torch, cols, id0):
+    """Order-independent 64-bit hash of per-particle state: every word of every field folded per particle (LCG steps,
+    wrap-around int64), weighted by the particle's creation index, summed.  Equal sums <=> bit-identical state (w.h.p.)."""
+    n = id0.numel()
+    acc = torch.zeros(n, dtype=torch.int64, device=id0.device)
+    for t in cols:
+        t = t.contiguous()
+        w = (t.view(torch.int64) if t.element_size() == 8 else t.view(torch.int32).to(torch.int64)).reshape(n, -1)
+        for j in range(w.shape[1]):
+            acc = acc * 6364136223846793005 + w[:, j] + 1442695040888963407
+    acc = (acc ^ (acc >> 31)) * (2 * id0.to(torch.int64) + 1)
+    return acc.sum()
+
+
+def slab_parity_hash(rank, local, world, log, scene, fields, steps=3):
+    """The benchmarked scene itself at FULL size: `steps` steps on the slabs and (rank 0) on one GPU, compared through
+    state_hash of the owned particles (the arrays are too large to gather through the host)."""
+    import copy
+    import torch
+    import torch.distributed as dist
+    from tisphi_b200.eng.simulation import Simulation, SimConfiger
+    from tisphi_b200.parallel import SlabSimulation
+    ok, slab, h = True, None, torch.zeros(2, dtype=torch.int64, device=f"cuda:{local}")
+    try:
+        slab = SlabSimulation(SimConfiger(config=copy.deepcopy(scene)), f"cuda:{local}", rank, world, transport="p2p")
+    except Exception as e:
+        ok = False
+        log(f"[rank {rank}] slab parity (full): {type(e).__name__}: {e}")
+    flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if not int(flag):
+        return False
+    try:
+        slab.run_steps(steps)
+        slab.sync()
+        cols = [slab.owned(f) for f in fields if f != "id0"]
+        h[0] = state_hash(torch, cols, slab.owned("id0"))
+        h[1] = slab.owned("id0").numel()
+    except Exception as e:
+        ok = False
+        log(f"[rank {rank}] slab parity (full): {type(e).__name__}: {e}")
+    dist.all_reduce(h)                                   # int64 sums wrap around
+    torch.cuda.synchronize()
+    dist.barrier()
+    slab.close()
+    del slab
+    torch.cuda.empty_cache()
+    if rank == 0 and ok:
+        try:
+            ref = Simulation(SimConfiger(config=copy.deepcopy(scene)), device=f"cuda:{local}")
+            ref.solver.run_steps(steps)
+            torch.cuda.synchronize()
+            want = state_hash(torch, [getattr(ref.ps.pt, f) for f in fields if f != "id0"], ref.ps.pt.id0)
+            ok = int(h[1]) == ref.ps.pt.id0.numel() and int(want) == int(h[0])
+            if not ok:
+                log(f"slab parity (full): hash {int(h[0])} over {int(h[1])} particles != single-GPU {int(want)} over {ref.ps.pt.id0.numel()}")
+            del ref
+            torch.cuda.empty_cache()
+        except Exception as e:
+            ok = False
+            log(f"slab parity (full) reference: {type(e).__name__}: {e}")
+    flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(int(flag))
 
 
 def run_ours_multi(args, rank, local, world):
@@ -591,6 +658,19 @@ def run_ours_multi(args, rank, local, world):
         eng.call("sph_read_state", out_x.data_ptr(), out_v.data_ptr(), out_rho.data_ptr(), out_p.data_ptr(), out_id.data_ptr())
 
     e2e_step()
+    # where an end-to-end step spends its time (one extra, untimed step with a synchronize between the parts)
+    barrier()
+    tb = [time.perf_counter()]
+    eng.call("sph_clear_particles")
+    eng.call("sph_add_particles", n0, h_x.data_ptr(), h_v.data_ptr(), h_rho.data_ptr(), h_typ.data_ptr())
+    eng.field("ID0", count=n0).copy_(h_id, non_blocking=True)
+    torch.cuda.synchronize(); tb.append(time.perf_counter())
+    drv.reset()
+    sim.run_steps(1)
+    sim.sync(); tb.append(time.perf_counter())
+    eng.call("sph_read_state", out_x.data_ptr(), out_v.data_ptr(), out_rho.data_ptr(), out_p.data_ptr(), out_id.data_ptr())
+    tb.append(time.perf_counter())
+    e2e_parts = {"upload_ms": round((tb[1] - tb[0]) * 1e3, 3), "step_ms": round((tb[2] - tb[1]) * 1e3, 3), "readback_ms": round((tb[3] - tb[2]) * 1e3, 3)}
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -647,7 +727,8 @@ def run_ours_multi(args, rank, local, world):
                            "legs": "legs of <= 20 steps from the restored initial state" if replay else "one run from rest"},
                 "clocks": clocks.summary(),
                 "e2e": {"value": n_global * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(io[0]),
-                        "d2h_bytes_per_step": int(io[1]), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
+                        "d2h_bytes_per_step": int(io[1]), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                        "rank0_parts_ms": e2e_parts},
                 "gpu_launches": int(sum(v["launches"] for v in allv)), "roofline": roofline, "cpu_baseline": None}
         print(json.dumps(line), flush=True)
     if transport == "p2p":

@@ -15,7 +15,7 @@ SOURCES = ["api.cu", "grid.cu", "integrate.cu", "sweeps.cu", "sweeps_tile.cu", "
 HEADERS = ["sph_dev.cuh", "sph_host.h", os.path.join("..", "..", "include", "tisphi_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--extended-lambda", "-Xptxas", "-v"]
+         "--extended-lambda", "-Xptxas", "-v"] + os.environ.get("TISPHI_NVCC_EXTRA", "").split()    # e.g. -DTILE_TIMING
 
 
 def _stale(target, deps):

@@ -54,6 +54,11 @@ template <class FT, int NP> struct TileShared {
     int gdelta[FT::NR];               // global index = tile index + gdelta[run]
     int total, overflow, item;
     F4 ctab[FT::NWARP * FT::NW];      // per (warp, stencil cell): shift xyz, tile index of the cell's first particle | flags
+    // pipelined loop (tile_stage / tile_issue): spans of the NEXT work item, computed while the current tile is in flight
+    int ncb[FT::NR * FT::CBW], ngdelta[FT::NR], nS[FT::NR], nlen[FT::NR], nroff[FT::NR], ntotal;
+    int blkq[3];                      // work items of iterations k, k+1, k+2 (ring; -1 = the list is exhausted)
+    int claim;                        // 0 until a warp has taken the staging duty of this iteration
+    unsigned flagbits, nflagbits;     // flagged own cells (bit = warp of the footprint): active / staged
 };
 constexpr unsigned CT_BEFORE = 1u << 30, CT_SAME = 1u << 29, CT_IDX = (1u << 24) - 1, CT_CC = 0x1fu << 24;   // CT_CC: the stencil cell
 
@@ -195,13 +200,195 @@ __device__ __forceinline__ bool tile_setup(const DevF &c, const TileGeom &g, Til
     mbar_wait(&sh.bar, parity);
     return true;
 }
+// ---- pipelined variant: the global-memory latency of a work item's set-up is taken off the critical path ----
+// Measured with clock64 on C4 before this existed: of the 82 k cycles a block spent per work item, 14 k were set-up
+// (atomic cursor -> list -> cell_end -> spans -> TMA, plus every warp's own cell_end / flag / nzw look-ups) and 9 k the
+// wait for the slowest warp at the end.  Now:
+//   tile_stage  (the FIRST warp that finishes its cell; it would idle at the end barrier anyway): fetches the work item
+//               of iteration k+2 (atomic cursor + list), computes the spans, cell boundaries and flagged-cell bits of
+//               item k+1 into the staging members -- all the dependent global reads happen here;
+//   tile_issue  (warp 0, right after the barrier that frees the tile): staging -> active members and the TMA copies;
+//               shared-memory work only;
+//   tile_begin  (all): barrier; a warp reads its cell's first particle / count from the active boundaries (no global
+//               read), issues its nzw load, then waits for the copies (mbarrier, one phase per work item).
+template <class FT, int NP>
+__device__ __forceinline__ void tile_stage(const DevF &c, const TileGeom &g, TileShared<FT, NP> &sh, int blk) {
+    const int lane = threadIdx.x & 31;
+    const int seg = blk % g.nseg, tq = blk / g.nseg, b1 = tq % g.nb1, b0 = tq / g.nb1;
+    const int f0 = seg * ZB, f_lo = max(f0 - 1, 0), f_hi = min(f0 + ZB, g.nF - 1);
+    int len = 0, S = 0;
+    int e[FT::CBW];                                               // cell_end of cells f0-2 .. f0+ZB (clamped), one round trip
+    bool valid = false;
+    if (lane < FT::NR) {
+        const int n0 = b0 * FT::BX + lane / FT::NRY - 1;
+        const int n1 = FT::d3 ? b1 * FT::BY + lane % FT::NRY - 1 : 0;
+        valid = n0 >= 0 && n0 < g.n0 && n1 >= 0 && n1 < g.n1;
+        const int gb = valid ? (n0 * g.n1 + n1) * g.nF : 0;
+#pragma unroll
+        for (int k = 0; k < FT::CBW; k++) {                       // e[k] = start of cell f0 - 1 + k = cell_end of the cell before
+            const int f = min(max(f0 - 1 + k, f_lo), f_hi + 1);   // clamped: below f_lo -> start of f_lo, above -> end of f_hi
+            const int gi = gb + f - 1;
+            e[k] = (valid && gi >= 0) ? c.cell_end[gi] : 0;
+        }
+        if (valid) { S = e[f_lo - (f0 - 1)]; len = e[min(f_hi + 1, f0 + ZB + 1) - (f0 - 1)] - S; }
+    }
+    int inc = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const int roff = inc - len;
+    if (lane < FT::NR) {
+        sh.ngdelta[lane] = S - roff;
+        sh.nS[lane] = S; sh.nlen[lane] = len; sh.nroff[lane] = roff;
+#pragma unroll
+        for (int k = 0; k < FT::CBW; k++) sh.ncb[lane * FT::CBW + k] = valid ? roff + e[k] - S : roff;
+    }
+    // flagged own cells (handled by the generic kernels): one bit per warp of the footprint
+    bool fl = false;
+    if (lane < FT::NWARP) {
+        const int wz = lane % ZB, wy = (lane / ZB) % FT::BY, wx = lane / (ZB * FT::BY);
+        const int cx = b0 * FT::BX + wx, cy = b1 * FT::BY + wy, f = f0 + wz;
+        if (cx < g.n0 && cy < g.n1 && f < g.nF) fl = c.cellflag[(cx * g.n1 + cy) * g.nF + f] != 0;
+    }
+    const unsigned flb = __ballot_sync(0xffffffffu, fl);
+    const int total = __shfl_sync(0xffffffffu, inc, FT::NR - 1);
+    if (lane == 0) { sh.ntotal = total; sh.nflagbits = flb; }
+    __syncwarp();
+}
+template <class FT, int NP>
+__device__ __forceinline__ void tile_issue(TileShared<FT, NP> &sh, const F4 *src0, const F4 *src1 = nullptr, const F4 *src2 = nullptr) {
+    const int tid = threadIdx.x;                                  // < 32
+    for (int k = tid; k < FT::NR * FT::CBW; k += 32) sh.cb[k] = sh.ncb[k];
+    const int total = sh.ntotal;
+    int S = 0, len = 0, roff = 0;
+    if (tid < FT::NR) { sh.gdelta[tid] = sh.ngdelta[tid]; S = sh.nS[tid]; len = sh.nlen[tid]; roff = sh.nroff[tid]; }
+    if (tid == 0) { sh.total = total; sh.overflow = total > FT::CAP; sh.flagbits = sh.nflagbits; sh.claim = 0; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the block's reads of the old tile precede the bulk copies
+    __syncwarp();
+    if (total > FT::CAP) {
+        if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sh.bar)) : "memory");
+    } else {
+        if (tid == 0) mbar_expect_tx(&sh.bar, (unsigned)(total * 16 * NP));
+        __syncwarp();
+        if (tid < FT::NR && len > 0) {
+            tma_load_1d(&sh.P[0][roff], src0 + S, (unsigned)(len * 16), &sh.bar);
+            if (NP > 1) tma_load_1d(&sh.P[1][roff], src1 + S, (unsigned)(len * 16), &sh.bar);
+            if (NP > 2) tma_load_1d(&sh.P[NP - 1][roff], src2 + S, (unsigned)(len * 16), &sh.bar);
+        }
+    }
+}
+// the warp's cell from the work item number alone (arithmetic), then -- after the barrier -- first particle and count
+// from the active cell boundaries.  Cells outside the grid, in ghost columns of a slab or flagged get nc = 0.
+template <class FT, int NP>
+__device__ __forceinline__ WarpCell tile_begin(const DevF &c, const TileGeom &g, TileShared<FT, NP> &sh, int blk) {
+    WarpCell w;
+    const int seg = blk % g.nseg, t = blk / g.nseg;
+    w.b1 = t % g.nb1; w.b0 = t / g.nb1; w.f0 = seg * ZB;
+    const int wi = threadIdx.x >> 5;
+    w.wz = wi % ZB; w.wy = (wi / ZB) % FT::BY; w.wx = wi / (ZB * FT::BY);
+    w.cx = w.b0 * FT::BX + w.wx; w.cy = w.b1 * FT::BY + w.wy; w.f = w.f0 + w.wz;
+    w.gcell = 0; w.is = 0; w.nc = 0;
+    const bool inside = w.cx < g.n0 && w.cy < g.n1 && w.f < g.nF && w.cx >= c.own0 && w.cx < c.own1;
+    if (inside) w.gcell = (w.cx * g.n1 + w.cy) * g.nF + w.f;
+    __syncthreads();                                               // the active members of this work item are visible
+    if (inside && !((sh.flagbits >> wi) & 1u)) {
+        const int q = stencil_cb<FT>(w, 0, 0, 0);
+        const int a = sh.cb[q];
+        w.is = a + sh.gdelta[q / FT::CBW];
+        w.nc = sh.cb[q + 1] - a;
+    }
+    return w;
+}
+template <class FT, int NP> __device__ __forceinline__ bool tile_wait(TileShared<FT, NP> &sh, unsigned parity) {
+    if (sh.overflow) return false;
+    mbar_wait(&sh.bar, parity);
+    return true;
+}
+// end of a warp's work on the item: the first warp to get here prepares the next ones
+template <class FT, int NP>
+__device__ __forceinline__ void tile_finish(const DevF &c, const TileGeom &g, TileShared<FT, NP> &sh, const int *list, int items,
+                                            int *cursor, unsigned k, int next_blk) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    int mine = 0;
+    if (lane == 0) mine = atomicExch(&sh.claim, 1) == 0;
+    mine = __shfl_sync(0xffffffffu, mine, 0);
+    if (!mine) return;
+    int nb2 = -1;
+    if (lane == 0) {
+        const int a = atomicAdd(cursor, 1);
+        nb2 = a < items ? list[a] : -1;
+    }
+    if (next_blk >= 0) tile_stage<FT, NP>(c, g, sh, next_blk);    // the cursor round trip overlaps the cell_end reads
+    if (lane == 0) sh.blkq[(k + 2u) % 3u] = nb2;
+}
+// The loop.  BODY(blk, parity, next_blk, k_) must call tile_begin once and tile_finish once on every path.
+#define TILE_PIPELINED_LOOP(FT_, NP_, SH, LIST, COUNT, CURSOR, SRC0, SRC1, CALL)                       \
+    {                                                                                                     \
+        const int items_ = *(COUNT);                                                                      \
+        const int *list_ = (LIST);                                                                        \
+        int *cursor_ = (CURSOR);                                                                          \
+        if (threadIdx.x == 0) {                                                                           \
+            const int a0_ = atomicAdd(cursor_, 1), a1_ = atomicAdd(cursor_, 1);                           \
+            (SH).blkq[0] = a0_ < items_ ? list_[a0_] : -1;                                                \
+            (SH).blkq[1] = a1_ < items_ ? list_[a1_] : -1;                                                \
+        }                                                                                                 \
+        __syncthreads();                                                                                  \
+        if (threadIdx.x < 32 && (SH).blkq[0] >= 0) tile_stage<FT_, NP_>(c, g, (SH), (SH).blkq[0]);        \
+        TT_DECL                                                                                           \
+        for (unsigned k_ = 0;; k_++) {                                                                    \
+            TT_A                                                                                          \
+            const int blk = (SH).blkq[k_ % 3u];                                                           \
+            if (blk < 0) break;                                                                           \
+            const int next_blk = (SH).blkq[(k_ + 1u) % 3u];                                               \
+            if (threadIdx.x < 32) tile_issue<FT_, NP_>((SH), (SRC0), (SRC1));                             \
+            const unsigned parity = k_ & 1u;                                                              \
+            CALL;                                                                                         \
+            TT_END                                                                                        \
+            __syncthreads();                                                                              \
+            TT_D                                                                                          \
+        }                                                                                                 \
+        TT_PRINT                                                                                          \
+    }
+
 // Persistent blocks walk a work list of footprint segments.  BODY(blk, parity) returns true when it used the tile
 // (block-uniform), which flips the mbarrier parity for the next item.
+#ifdef TILE_TIMING
+__device__ unsigned long long g_tt[8];
+#define TT_DECL long long tt_a_ = 0, tt_setup_ = 0, tt_end_ = 0;
+#define TT_A tt_a_ = clock64();
+#define TT_END tt_end_ = clock64();
+#define TT_D                                                                                              \
+    if ((threadIdx.x == 0 || threadIdx.x == blockDim.x - 32) && tt_setup_ != 0) {                         \
+        const long long td_ = clock64();                                                                  \
+        const int o_ = threadIdx.x == 0 ? 0 : 3;                                                          \
+        atomicAdd(&g_tt[o_], (unsigned long long)(tt_setup_ - tt_a_));                                    \
+        atomicAdd(&g_tt[o_ + 1], (unsigned long long)(tt_end_ - tt_setup_));                              \
+        atomicAdd(&g_tt[o_ + 2], (unsigned long long)(td_ - tt_end_));                                    \
+        if (threadIdx.x == 0) atomicAdd(&g_tt[6], 1ull);                                                  \
+    }                                                                                                     \
+    tt_setup_ = 0;
+#define TT_PRINT                                                                                          \
+    if (blockIdx.x == 0 && threadIdx.x == 0)                                                              \
+        printf("TT items %llu  w0: pro %llu cmp %llu bar %llu   w15: pro %llu cmp %llu bar %llu\n", g_tt[6], g_tt[0], g_tt[1], g_tt[2], g_tt[3], g_tt[4], g_tt[5]);
+#define TT_ARG , &tt_setup_
+#else
+#define TT_DECL
+#define TT_A
+#define TT_END
+#define TT_D
+#define TT_PRINT
+#define TT_ARG
+#endif
 #define TILE_PERSISTENT_LOOP(SH, LIST, COUNT, CURSOR, CALL)                           \
     {                                                                                 \
         unsigned uses_ = 0;                                                           \
         const int items_ = *(COUNT);                                                  \
+        TT_DECL                                                                       \
         while (true) {                                                                \
+            TT_A                                                                      \
             if (threadIdx.x == 0) (SH).item = atomicAdd((CURSOR), 1);                 \
             __syncthreads();                                                          \
             const int it_ = (SH).item;                                                \
@@ -209,8 +396,11 @@ __device__ __forceinline__ bool tile_setup(const DevF &c, const TileGeom &g, Til
             const int blk = (LIST)[it_];                                              \
             const unsigned parity = uses_ & 1u;                                       \
             if (CALL) uses_++;                                                        \
+            TT_END                                                                    \
             __syncthreads();                                                          \
+            TT_D                                                                      \
         }                                                                             \
+        TT_PRINT                                                                      \
     }
 
 // per-warp table of the stencil cells, so that advancing to the next cell costs one shared load
@@ -993,19 +1183,10 @@ __device__ __forceinline__ void fluid_pair(const KernConst &kc, const FluidI &I,
 // every round (the first fluid pass after the masks were built); 2 this pass REPLAYS the recorded rounds -- same
 // neighbours, same order, same arithmetic, without the bit cursor (cells whose list overflowed walk the bits again).
 template <int KERNEL, class FT, bool SHEP, int LIST>
-__device__ __forceinline__ bool fluid_body(const DevF &c, const TileGeom &g, TileShared<FT, 2> &sh, int blk, unsigned parity) {
-    WarpCell w = warp_cell<FT>(c, g, blk);
-    const int lane = threadIdx.x & 31;
-    if (w.nc > 0 && c.cellflag[w.gcell]) w.nc = 0;
-    const int i = w.is + lane;
-    const bool work = lane < w.nc && c.ps4[i].w > 0.f;              // flow particle (fluid: the only flow type of WCSPH)
-    const unsigned nz = work ? c.nzw[i] : 0u;
-    if (!__syncthreads_or(work)) return false;
+__device__ __forceinline__ void fluid_work(const DevF &c, const TileGeom &g, TileShared<FT, 2> &sh, const WarpCell &w, int lane, int i, bool work, unsigned nz) {
     const int rounds = (LIST == 2 && w.nc > 0) ? c.lrounds[w.gcell] : -1;     // warp-uniform
     if (rounds < 0) cursor_prefetch(mask_row(c.mask, w.is, FT::NW, work ? lane : 0), (unsigned)w.nc, nz);
-    if (!tile_setup<FT, 2>(c, g, sh, w, parity, c.ps4, c.pk4)) return true;
     build_ctab<FT, 2>(c, sh, w, lane);
-    if (!__any_sync(0xffffffffu, work)) return true;
     const F4 *A = sh.P[0], *B = sh.P[1];
     const F4 *ct = sh.ctab + (threadIdx.x >> 5) * FT::NW;
     const int ci = sh.cb[stencil_cb<FT>(w, 0, 0, 0)] + (work ? lane : 0);
@@ -1070,18 +1251,37 @@ __device__ __forceinline__ bool fluid_body(const DevF &c, const TileGeom &g, Til
         }
         if (LIST == 1 && lane == 0) c.lrounds[w.gcell] = r <= LIST_ROUNDS ? r : -1;
     }
-    if (!work) return true;
+    if (!work) return;
     c.d_rho[i] = dd * rhoi;
     F4 dv; dv.x = a0 + c.g[0]; dv.y = a1 + c.g[1]; dv.z = a2 + c.g[2]; dv.w = 0.f;
     c.d_vel[i] = dv;
     if (SHEP) c.cspm_f[i] = (ssum != 0.f) ? 1.f / ssum : 1.f;
-    return true;
+}
+// One work item of the pipelined loop: cell from the active boundaries, nzw in flight during the wait for the copies,
+// the flow flag from the tile itself; the first warp to finish stages the next item (tile_finish).
+template <int KERNEL, class FT, bool SHEP, int LIST>
+__device__ __forceinline__ void fluid_body(const DevF &c, const TileGeom &g, TileShared<FT, 2> &sh, int blk, unsigned parity, int next_blk,
+                                           unsigned k, const int *list, int items, int *cursor, long long *tt = nullptr) {
+    const int lane = threadIdx.x & 31;
+    const WarpCell w = tile_begin<FT, 2>(c, g, sh, blk);
+    const int i = w.is + lane;
+    unsigned nz = lane < w.nc ? c.nzw[i] : 0u;
+    if (tile_wait<FT, 2>(sh, parity)) {
+#ifdef TILE_TIMING
+        if (tt) *tt = clock64();
+#endif
+        const int ci = sh.cb[stencil_cb<FT>(w, 0, 0, 0)] + (lane < w.nc ? lane : 0);
+        const bool work = lane < w.nc && sh.P[0][ci].w > 0.f;          // flow particle (fluid: the only flow type of WCSPH)
+        if (!work) nz = 0u;
+        if (__any_sync(0xffffffffu, work)) fluid_work<KERNEL, FT, SHEP, LIST>(c, g, sh, w, lane, i, work, nz);
+    }
+    tile_finish<FT, 2>(c, g, sh, list, items, cursor, k, next_blk);
 }
 template <int KERNEL, class FT, bool SHEP, int LIST> __global__ void __launch_bounds__(FT::BT, 2) k_tile_fluid(DevF c, TileGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileShared<FT, 2> &sh = *reinterpret_cast<TileShared<FT, 2> *>(smem_raw);
     tile_init<FT, 2>(sh);
-    TILE_PERSISTENT_LOOP(sh, c.worklist[1], c.wcount + 1, c.wcount + 7, (fluid_body<KERNEL, FT, SHEP, LIST>(c, g, sh, blk, parity)))
+    TILE_PIPELINED_LOOP(FT, 2, sh, c.worklist[1], c.wcount + 1, c.wcount + 7, c.ps4, c.pk4, (fluid_body<KERNEL, FT, SHEP, LIST>(c, g, sh, blk, parity, next_blk, k_, list_, items_, cursor_ TT_ARG)))
 }
 
 // ------------------------------------------------------------------------------------------------ mask-based count

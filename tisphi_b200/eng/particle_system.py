@@ -479,13 +479,14 @@ class ParticleSystem:
     # ------------------------------------------------------------------------------------------ viewer members (ps:380-407)
     def _vis_store(self, name, values):
         """Viewer members are kept keyed by id0, so that they follow their particle through the sorts."""
-        n = self.engine.n
+        n = max(self.engine.n, int(getattr(self, "global_particle_num", 0)))     # a slab rank holds GLOBAL creation indices
         shape = (n,) + tuple(values.shape[1:])
         buf = self._vis.get(name)
         if buf is None or tuple(buf.shape) != shape or buf.dtype != values.dtype:
             buf = self._torch.zeros(shape, dtype=values.dtype, device=self.engine.device)
             if name == "color":
-                buf.copy_(self._const_dev("color").to(values.dtype))
+                base = self._const_dev("color").to(values.dtype)
+                buf[:len(base)].copy_(base[:len(buf)])
         buf[self.pt.id0.long()] = values
         self._vis[name] = buf
 
