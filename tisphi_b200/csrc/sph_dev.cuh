@@ -245,6 +245,8 @@ __device__ __forceinline__ int for_neighbors_walk(const Dev<T> &c, int i, unsign
     }
     return cnt;
 }
+// (Tried and measured slower on dp_soil, 0.35 ms: an L1 prefetch instruction per gathered member of the next neighbour, 0.40 ms;
+// holding the next neighbour's v~ in registers, 92 registers -> one block less per SM, 0.40 ms.)
 template <typename T, typename F> __device__ __forceinline__ void for_neighbors(const Dev<T> &c, int i, F &&body) {
     const int cnt = c.gnl ? c.gnl_count[i] : -1;
     if (cnt < 0) {
@@ -256,18 +258,29 @@ template <typename T, typename F> __device__ __forceinline__ void for_neighbors(
     const int gi = sizeof(T) == 4 ? c.gid[i] : 0;
     if (sizeof(T) == 4) unflatten(c, gi, sc);
     const Vec4<T> pi = c.xs4[i];
+    // Software pipeline: the list word of neighbour k+2 and the position of neighbour k+1 are in flight while the task
+    // of neighbour k runs.  Without it every neighbour costs three dependent memory round trips (list word -> position
+    // -> the task's own gathers) and the soil sweeps sat at 53 % issue with 57 % of the stalls on the long scoreboard
+    // (profiles/r2_ncu_soil.csv); the order of the neighbours and the arithmetic are unchanged.
     const unsigned *e = c.gnl + i;
-    for (int k = 0; k < cnt; k++, e += c.gnl_stride) {
-        const unsigned w = *e;
-        const int j = (int)(w & NB_IDX_MASK), code = (int)(w >> NB_IDX_BITS);
+    const size_t st = (size_t)c.gnl_stride;
+    unsigned w0 = cnt > 0 ? e[0] : 0u;
+    unsigned w1 = cnt > 1 ? e[st] : 0u;
+    Vec4<T> p0 = c.xs4[cnt > 0 ? (int)(w0 & NB_IDX_MASK) : i];
+    for (int k = 0; k < cnt; k++) {
+        const unsigned w2 = k + 2 < cnt ? e[(size_t)(k + 2) * st] : 0u;
+        const int jn = k + 1 < cnt ? (int)(w1 & NB_IDX_MASK) : i;
+        const Vec4<T> p1 = c.xs4[jn];
+        const int j = (int)(w0 & NB_IDX_MASK), code = (int)(w0 >> NB_IDX_BITS);
         const int ox = code / 9 - 1, oy = (code / 3) % 3 - 1, oz = code % 3 - 1;     // neighbour cell - stored cell, per axis
         const T sx = (T)ox * c.gsT, sy = (T)oy * c.gsT, sz = (T)oz * c.gsT;
         const bool rev = sizeof(T) == 4 && (ox < 0 || (ox == 0 && (oy < 0 || (oy == 0 && oz < 0))));
-        const Vec4<T> pj = c.xs4[j];
+        const Vec4<T> pj = p0;
         T dx, dy, dz;
         if (!rev) { dx = (pi.x - sx) - pj.x; dy = (pi.y - sy) - pj.y; dz = (pi.z - sz) - pj.z; }
         else { dx = -((pj.x + sx) - pi.x); dy = -((pj.y + sy) - pi.y); dz = -((pj.z + sz) - pi.z); }
         body(j, dx, dy, dz, sqrt_rn(dist2(dx, dy, dz)), pj.w);
+        w0 = w1; w1 = w2; p0 = p1;
     }
 }
 

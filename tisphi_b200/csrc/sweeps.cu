@@ -559,7 +559,7 @@ template <typename T> __device__ __forceinline__ void body_dp_soil(const Dev<T> 
     dv.x = mom[0] + c.g[0] + dc * vi.x; dv.y = mom[1] + c.g[1] + dc * vi.y; dv.z = mom[2] + c.g[2] + dc * vi.z; dv.w = 0;
     c.d_vel[i] = dv;
 }
-template <typename T> __global__ void __launch_bounds__(128) k_dp_soil(Dev<T> c) {
+template <typename T> __global__ void __launch_bounds__(128, sizeof(T) == 4 ? 7 : 4) k_dp_soil(Dev<T> c) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < c.N()) body_dp_soil(c, i);
 }
