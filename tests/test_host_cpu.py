@@ -135,3 +135,32 @@ def test_reference_module_paths_resolve_to_the_engine():
         real = importlib.import_module("tisphi_b200.eng." + mod)
         for n in names:
             assert getattr(shim, n) is getattr(real, n), (mod, n)
+
+
+def test_bench_state_hash_is_order_independent_and_bit_sensitive():
+    """bench.py::state_hash (the full-size slab parity check): permutations and splits of the particle set leave the
+    sum unchanged, one flipped mantissa bit changes it."""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    g = torch.Generator().manual_seed(7)
+    n = 4096
+    x = torch.randn(n, 3, dtype=torch.float64, generator=g)
+    v = torch.randn(n, 4, generator=g)
+    p = torch.randn(n, generator=g)
+    gid = torch.randint(0, 1000, (n,), dtype=torch.int32, generator=g)
+    id0 = torch.arange(n, dtype=torch.int32)
+    h = int(bench.state_hash(torch, [x, v, p, gid], id0))
+    perm = torch.randperm(n, generator=g)
+    assert int(bench.state_hash(torch, [x[perm], v[perm], p[perm], gid[perm]], id0[perm])) == h
+    parts = [slice(0, 1000), slice(1000, 1001), slice(1001, n)]
+    total = sum(bench.state_hash(torch, [x[s], v[s], p[s], gid[s]], id0[s]) for s in parts)
+    assert int(total) == h
+    v2 = v.clone()
+    v2[17, 1] = torch.nextafter(v2[17, 1], torch.tensor(10.0))
+    assert int(bench.state_hash(torch, [x, v2, p, gid], id0)) != h
+    x2 = x.clone()
+    x2[[3, 4]] = x2[[4, 3]]                                     # two particles swap their positions: ids matter
+    assert int(bench.state_hash(torch, [x2, v, p, gid], id0)) != h

@@ -1017,7 +1017,7 @@ template <bool D3> __global__ void __launch_bounds__(256) k_wall_cells(DevF c, i
     c.worklist[2][atomicAdd(c.wcount + 2, 1)] = gcell;
 }
 constexpr int WG_WARPS = 8;
-template <int KERNEL, bool D3, bool SHEP> __global__ void __launch_bounds__(WG_WARPS * 32) k_wall_gather(DevF c) {
+template <int KERNEL, bool D3, bool SHEP> __global__ void __launch_bounds__(WG_WARPS * 32, 4) k_wall_gather(DevF c) {
     constexpr int NW = D3 ? 27 : 9, CENTRE = NW / 2;
     __shared__ F4 s_ct[WG_WARPS][NW];        // per warp and stencil cell: shift xyz, CT_BEFORE / CT_SAME
     __shared__ int s_start[WG_WARPS][NW];    // global index of the stencil cell's first particle
@@ -1030,7 +1030,11 @@ template <int KERNEL, bool D3, bool SHEP> __global__ void __launch_bounds__(WG_W
     // (the stride between a particle's mask words is its cell's particle count)
     const F4 *ct = s_ct[wi];
     const int *cs = s_start[wi];
-    for (int it = blockIdx.x * WG_WARPS + wi; it < items; it += gridDim.x * WG_WARPS) {
+    while (true) {                                                 // wall cells differ a lot in cost: warps pull them from a cursor
+        int it = 0;
+        if (lane == 0) it = atomicAdd(c.wcount + 8, 1);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= items) break;
         const int gcell = c.worklist[2][it];
         const int f = gcell % nF, t = gcell / nF, cy = t % n1, cx = t / n1;
         const int is = cell_start(c.cell_end, gcell), nc = c.cell_end[gcell] - is;
@@ -1406,7 +1410,8 @@ int tile_mask(SphCtx *c, bool shepard) {
 }
 
 template <int KERNEL, bool D3> static void launch_wall_gather(SphCtx *c, const DevF &d, bool shep) {
-    const int grid = 148 * 4;                                       // 4 blocks of 8 independent warps per SM, grid-stride over the cell list
+    const int grid = 148 * 4;                                       // 4 blocks of 8 independent warps per SM (64 registers: all resident)
+    cudaMemsetAsync(d.wcount + 8, 0, 4, c->stream);                 // the cursor the warps pull wall cells from
     if (shep) k_wall_gather<KERNEL, D3, true><<<grid, WG_WARPS * 32, 0, c->stream>>>(d);
     else k_wall_gather<KERNEL, D3, false><<<grid, WG_WARPS * 32, 0, c->stream>>>(d);
 }
