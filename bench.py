@@ -747,7 +747,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="lattice refinement of the C4 scene (1 = 12.96 M particles)")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-depth", type=int, default=3, help="contexts the end-to-end jobs are pipelined over (1 = serial)")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="contexts the end-to-end jobs are pipelined over (1 = serial)")
     ap.add_argument("--cpu-scale", type=float, default=1.0, help="coarsening of the CPU arm's scene (1 = the benchmarked scene itself)")
     ap.add_argument("--cpu-steps", type=int, default=2, help="timed steps of the cpu_baseline leg (about 10 s each on 32 threads)")
     ap.add_argument("--no-cpu", action="store_true")
