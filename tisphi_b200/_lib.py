@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtisphi_b200.so")
+LIB_PATH = os.environ.get("TISPHI_B200_LIB") or os.path.join(HERE, "libtisphi_b200.so")   # override: A/B runs of two builds
 
 PREC_F64, PREC_MIXED = 0, 1
 SOLVER_WC, SOLVER_MUI, SOLVER_DP = 1, 2, 3

@@ -56,7 +56,7 @@ template <class FT, int NP> struct TileShared {
     F4 ctab[FT::NWARP * FT::NW];      // per (warp, stencil cell): shift xyz, tile index of the cell's first particle | flags
     // pipelined loop (tile_stage / tile_issue): spans of the NEXT work item, computed while the current tile is in flight
     int ncb[FT::NR * FT::CBW], ngdelta[FT::NR], nS[FT::NR], nlen[FT::NR], nroff[FT::NR], ntotal;
-    int blkq[3];                      // work items of iterations k, k+1, k+2 (ring; -1 = the list is exhausted)
+    int blkq[2];                      // work items of iterations k and k+1 (by parity; -1 = the list is exhausted)
     int claim;                        // 0 until a warp has taken the staging duty of this iteration
     unsigned flagbits, nflagbits;     // flagged own cells (bit = warp of the footprint): active / staged
 };
@@ -204,9 +204,9 @@ __device__ __forceinline__ bool tile_setup(const DevF &c, const TileGeom &g, Til
 // Measured with clock64 on C4 before this existed: of the 82 k cycles a block spent per work item, 14 k were set-up
 // (atomic cursor -> list -> cell_end -> spans -> TMA, plus every warp's own cell_end / flag / nzw look-ups) and 9 k the
 // wait for the slowest warp at the end.  Now:
-//   tile_stage  (the FIRST warp that finishes its cell; it would idle at the end barrier anyway): fetches the work item
-//               of iteration k+2 (atomic cursor + list), computes the spans, cell boundaries and flagged-cell bits of
-//               item k+1 into the staging members -- all the dependent global reads happen here;
+//   tile_stage  (the FIRST warp that finishes its cell; it would idle at the end barrier anyway): fetches the next work
+//               item (atomic cursor + list) and computes its spans, cell boundaries and flagged-cell bits into the
+//               staging members -- all the dependent global reads happen here;
 //   tile_issue  (warp 0, right after the barrier that frees the tile): staging -> active members and the TMA copies;
 //               shared-memory work only;
 //   tile_begin  (all): barrier; a warp reads its cell's first particle / count from the active boundaries (no global
@@ -306,43 +306,44 @@ template <class FT, int NP> __device__ __forceinline__ bool tile_wait(TileShared
     mbar_wait(&sh.bar, parity);
     return true;
 }
-// end of a warp's work on the item: the first warp to get here prepares the next ones
+// end of a warp's work on the item: the first warp to get here fetches the next work item and stages it.  A block
+// thus holds ONE item beyond the one it is working on -- fetching two ahead (one more round trip hidden) cost 2-4 % of
+// the pass on an 8-GPU slab, where a block sees only ~10 items and reserved items lengthen the tail.
 template <class FT, int NP>
 __device__ __forceinline__ void tile_finish(const DevF &c, const TileGeom &g, TileShared<FT, NP> &sh, const int *list, int items,
-                                            int *cursor, unsigned k, int next_blk) {
+                                            int *cursor, unsigned k) {
     const int lane = threadIdx.x & 31;
     __syncwarp();
     int mine = 0;
     if (lane == 0) mine = atomicExch(&sh.claim, 1) == 0;
     mine = __shfl_sync(0xffffffffu, mine, 0);
     if (!mine) return;
-    int nb2 = -1;
+    int nb = -1;
     if (lane == 0) {
         const int a = atomicAdd(cursor, 1);
-        nb2 = a < items ? list[a] : -1;
+        nb = a < items ? list[a] : -1;
     }
-    if (next_blk >= 0) tile_stage<FT, NP>(c, g, sh, next_blk);    // the cursor round trip overlaps the cell_end reads
-    if (lane == 0) sh.blkq[(k + 2u) % 3u] = nb2;
+    nb = __shfl_sync(0xffffffffu, nb, 0);
+    if (nb >= 0) tile_stage<FT, NP>(c, g, sh, nb);
+    if (lane == 0) sh.blkq[(k + 1u) & 1u] = nb;
 }
-// The loop.  BODY(blk, parity, next_blk, k_) must call tile_begin once and tile_finish once on every path.
+// The loop.  BODY(blk, parity, k_) must call tile_begin once and tile_finish once on every path.
 #define TILE_PIPELINED_LOOP(FT_, NP_, SH, LIST, COUNT, CURSOR, SRC0, SRC1, CALL)                       \
     {                                                                                                     \
         const int items_ = *(COUNT);                                                                      \
         const int *list_ = (LIST);                                                                        \
         int *cursor_ = (CURSOR);                                                                          \
         if (threadIdx.x == 0) {                                                                           \
-            const int a0_ = atomicAdd(cursor_, 1), a1_ = atomicAdd(cursor_, 1);                           \
+            const int a0_ = atomicAdd(cursor_, 1);                                                        \
             (SH).blkq[0] = a0_ < items_ ? list_[a0_] : -1;                                                \
-            (SH).blkq[1] = a1_ < items_ ? list_[a1_] : -1;                                                \
         }                                                                                                 \
         __syncthreads();                                                                                  \
         if (threadIdx.x < 32 && (SH).blkq[0] >= 0) tile_stage<FT_, NP_>(c, g, (SH), (SH).blkq[0]);        \
         TT_DECL                                                                                           \
         for (unsigned k_ = 0;; k_++) {                                                                    \
             TT_A                                                                                          \
-            const int blk = (SH).blkq[k_ % 3u];                                                           \
+            const int blk = (SH).blkq[k_ & 1u];                                                           \
             if (blk < 0) break;                                                                           \
-            const int next_blk = (SH).blkq[(k_ + 1u) % 3u];                                               \
             if (threadIdx.x < 32) tile_issue<FT_, NP_>((SH), (SRC0), (SRC1));                             \
             const unsigned parity = k_ & 1u;                                                              \
             CALL;                                                                                         \
@@ -1017,7 +1018,7 @@ template <bool D3> __global__ void __launch_bounds__(256) k_wall_cells(DevF c, i
     c.worklist[2][atomicAdd(c.wcount + 2, 1)] = gcell;
 }
 constexpr int WG_WARPS = 8;
-template <int KERNEL, bool D3, bool SHEP> __global__ void __launch_bounds__(WG_WARPS * 32, 4) k_wall_gather(DevF c) {
+template <int KERNEL, bool D3, bool SHEP, bool DYN> __global__ void __launch_bounds__(WG_WARPS * 32, 4) k_wall_gather(DevF c) {
     constexpr int NW = D3 ? 27 : 9, CENTRE = NW / 2;
     __shared__ F4 s_ct[WG_WARPS][NW];        // per warp and stencil cell: shift xyz, CT_BEFORE / CT_SAME
     __shared__ int s_start[WG_WARPS][NW];    // global index of the stencil cell's first particle
@@ -1030,10 +1031,11 @@ template <int KERNEL, bool D3, bool SHEP> __global__ void __launch_bounds__(WG_W
     // (the stride between a particle's mask words is its cell's particle count)
     const F4 *ct = s_ct[wi];
     const int *cs = s_start[wi];
-    while (true) {                                                 // wall cells differ a lot in cost: warps pull them from a cursor
-        int it = 0;
-        if (lane == 0) it = atomicAdd(c.wcount + 8, 1);
-        it = __shfl_sync(0xffffffffu, it, 0);
+    for (int it = blockIdx.x * WG_WARPS + wi;; it += gridDim.x * WG_WARPS) {
+        if (DYN) {                                                 // wall cells differ a lot in cost: warps pull them from a cursor
+            if (lane == 0) it = atomicAdd(c.wcount + 8, 1);
+            it = __shfl_sync(0xffffffffu, it, 0);
+        }
         if (it >= items) break;
         const int gcell = c.worklist[2][it];
         const int f = gcell % nF, t = gcell / nF, cy = t % n1, cx = t / n1;
@@ -1264,7 +1266,7 @@ __device__ __forceinline__ void fluid_work(const DevF &c, const TileGeom &g, Til
 // One work item of the pipelined loop: cell from the active boundaries, nzw in flight during the wait for the copies,
 // the flow flag from the tile itself; the first warp to finish stages the next item (tile_finish).
 template <int KERNEL, class FT, bool SHEP, int LIST>
-__device__ __forceinline__ void fluid_body(const DevF &c, const TileGeom &g, TileShared<FT, 2> &sh, int blk, unsigned parity, int next_blk,
+__device__ __forceinline__ void fluid_body(const DevF &c, const TileGeom &g, TileShared<FT, 2> &sh, int blk, unsigned parity,
                                            unsigned k, const int *list, int items, int *cursor, long long *tt = nullptr) {
     const int lane = threadIdx.x & 31;
     const WarpCell w = tile_begin<FT, 2>(c, g, sh, blk);
@@ -1279,13 +1281,32 @@ __device__ __forceinline__ void fluid_body(const DevF &c, const TileGeom &g, Til
         if (!work) nz = 0u;
         if (__any_sync(0xffffffffu, work)) fluid_work<KERNEL, FT, SHEP, LIST>(c, g, sh, w, lane, i, work, nz);
     }
-    tile_finish<FT, 2>(c, g, sh, list, items, cursor, k, next_blk);
+    tile_finish<FT, 2>(c, g, sh, list, items, cursor, k);
 }
-template <int KERNEL, class FT, bool SHEP, int LIST> __global__ void __launch_bounds__(FT::BT, 2) k_tile_fluid(DevF c, TileGeom g) {
+// The same work item in the classic loop (cursor -> barrier -> look-ups -> spans -> TMA -> barrier -> wait): a block
+// holds no item beyond the one it works on, which matters when it sees only a handful of them (slabs of a multi-GPU run).
+template <int KERNEL, class FT, bool SHEP, int LIST>
+__device__ __forceinline__ bool fluid_body_classic(const DevF &c, const TileGeom &g, TileShared<FT, 2> &sh, int blk, unsigned parity) {
+    WarpCell w = warp_cell<FT>(c, g, blk);
+    const int lane = threadIdx.x & 31;
+    if (w.nc > 0 && c.cellflag[w.gcell]) w.nc = 0;
+    const int i = w.is + lane;
+    const bool work = lane < w.nc && c.ps4[i].w > 0.f;
+    const unsigned nz = work ? c.nzw[i] : 0u;
+    if (!__syncthreads_or(work)) return false;
+    if (!tile_setup<FT, 2>(c, g, sh, w, parity, c.ps4, c.pk4)) return true;
+    if (__any_sync(0xffffffffu, work)) fluid_work<KERNEL, FT, SHEP, LIST>(c, g, sh, w, lane, i, work, nz);
+    return true;
+}
+template <int KERNEL, class FT, bool SHEP, int LIST, bool PIPE> __global__ void __launch_bounds__(FT::BT, 2) k_tile_fluid(DevF c, TileGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileShared<FT, 2> &sh = *reinterpret_cast<TileShared<FT, 2> *>(smem_raw);
     tile_init<FT, 2>(sh);
-    TILE_PIPELINED_LOOP(FT, 2, sh, c.worklist[1], c.wcount + 1, c.wcount + 7, c.ps4, c.pk4, (fluid_body<KERNEL, FT, SHEP, LIST>(c, g, sh, blk, parity, next_blk, k_, list_, items_, cursor_ TT_ARG)))
+    if (PIPE) {
+        TILE_PIPELINED_LOOP(FT, 2, sh, c.worklist[1], c.wcount + 1, c.wcount + 7, c.ps4, c.pk4, (fluid_body<KERNEL, FT, SHEP, LIST>(c, g, sh, blk, parity, k_, list_, items_, cursor_ TT_ARG)))
+    } else {
+        TILE_PERSISTENT_LOOP(sh, c.worklist[1], c.wcount + 1, c.wcount + 7, (fluid_body_classic<KERNEL, FT, SHEP, LIST>(c, g, sh, blk, parity)))
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ mask-based count
@@ -1316,11 +1337,16 @@ template <typename K> static int set_smem(SphCtx *c, K kern, size_t bytes) {
 }
 template <int KERNEL, class FT> static int set_fluid_attrs(SphCtx *c) {
     int r = 0;
-    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 0>, smem_of<FT, 2>());
-    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, true, 0>, smem_of<FT, 2>());
-    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 1>, smem_of<FT, 2>());
-    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, true, 1>, smem_of<FT, 2>());
-    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 2>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 0, true>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, true, 0, true>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 1, true>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, true, 1, true>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 2, true>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 0, false>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, true, 0, false>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 1, false>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, true, 1, false>, smem_of<FT, 2>());
+    if (!r) r = set_smem(c, k_tile_fluid<KERNEL, FT, false, 2, false>, smem_of<FT, 2>());
     if (!r) r = set_smem(c, k_tile_density<KERNEL, FT>, smem_of<FT, 1>());
     return r;
 }
@@ -1409,11 +1435,22 @@ int tile_mask(SphCtx *c, bool shepard) {
     return 0;
 }
 
+static int tune_env(const char *name, int dflt) {                      // A/B switches of the tile path (tools/gpu_ab.sh)
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
 template <int KERNEL, bool D3> static void launch_wall_gather(SphCtx *c, const DevF &d, bool shep) {
     const int grid = 148 * 4;                                       // 4 blocks of 8 independent warps per SM (64 registers: all resident)
-    cudaMemsetAsync(d.wcount + 8, 0, 4, c->stream);                 // the cursor the warps pull wall cells from
-    if (shep) k_wall_gather<KERNEL, D3, true><<<grid, WG_WARPS * 32, 0, c->stream>>>(d);
-    else k_wall_gather<KERNEL, D3, false><<<grid, WG_WARPS * 32, 0, c->stream>>>(d);
+    static const int dyn_env = tune_env("TISPHI_WALL_DYN", -1);     // -1: cursor on one GPU, static stride on slabs
+    const bool dyn = dyn_env < 0 ? c->slab == nullptr : dyn_env != 0;
+    if (dyn) {
+        cudaMemsetAsync(d.wcount + 8, 0, 4, c->stream);             // the cursor the warps pull wall cells from
+        if (shep) k_wall_gather<KERNEL, D3, true, true><<<grid, WG_WARPS * 32, 0, c->stream>>>(d);
+        else k_wall_gather<KERNEL, D3, false, true><<<grid, WG_WARPS * 32, 0, c->stream>>>(d);
+    } else {
+        if (shep) k_wall_gather<KERNEL, D3, true, false><<<grid, WG_WARPS * 32, 0, c->stream>>>(d);
+        else k_wall_gather<KERNEL, D3, false, false><<<grid, WG_WARPS * 32, 0, c->stream>>>(d);
+    }
 }
 // WCSPH one_step (wc:82-126) on the tile path; flagged cells are completed by the generic kernels (flagged_only).
 static int need_masks(SphCtx *c) {
@@ -1443,15 +1480,20 @@ int tile_wc_prep_and_wall(SphCtx *c) {
     return 0;
 }
 // list: 0 no lists, 1 record, 2 replay (never together with the Shepard sums: those belong to the first pass)
-template <int KERNEL, class FT> static void launch_fluid(SphCtx *c, const DevF &d, bool shep, int list) {
-    if (list == 2) TILE_LAUNCH((k_tile_fluid<KERNEL, FT, false, 2>), FT, 2, 7);
+template <int KERNEL, class FT, bool PIPE> static void launch_fluid_p(SphCtx *c, const DevF &d, bool shep, int list) {
+    if (list == 2) TILE_LAUNCH((k_tile_fluid<KERNEL, FT, false, 2, PIPE>), FT, 2, 7);
     else if (list == 1) {
-        if (shep) TILE_LAUNCH((k_tile_fluid<KERNEL, FT, true, 1>), FT, 2, 7);
-        else TILE_LAUNCH((k_tile_fluid<KERNEL, FT, false, 1>), FT, 2, 7);
+        if (shep) TILE_LAUNCH((k_tile_fluid<KERNEL, FT, true, 1, PIPE>), FT, 2, 7);
+        else TILE_LAUNCH((k_tile_fluid<KERNEL, FT, false, 1, PIPE>), FT, 2, 7);
     } else {
-        if (shep) TILE_LAUNCH((k_tile_fluid<KERNEL, FT, true, 0>), FT, 2, 7);
-        else TILE_LAUNCH((k_tile_fluid<KERNEL, FT, false, 0>), FT, 2, 7);
+        if (shep) TILE_LAUNCH((k_tile_fluid<KERNEL, FT, true, 0, PIPE>), FT, 2, 7);
+        else TILE_LAUNCH((k_tile_fluid<KERNEL, FT, false, 0, PIPE>), FT, 2, 7);
     }
+}
+template <int KERNEL, class FT> static void launch_fluid(SphCtx *c, const DevF &d, bool shep, int list) {
+    static const int pipe_env = tune_env("TISPHI_FLUID_PIPE", -1);     // -1: pipelined loop on one GPU, classic loop on slabs
+    const bool pipe = pipe_env < 0 ? c->slab == nullptr : pipe_env != 0;
+    if (pipe) launch_fluid_p<KERNEL, FT, true>(c, d, shep, list); else launch_fluid_p<KERNEL, FT, false>(c, d, shep, list);
 }
 int tile_wc_fluid(SphCtx *c) {
     if (need_masks(c)) return -3;
