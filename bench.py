@@ -232,10 +232,10 @@ def run_ours(args):
         return run_ours_multi(args, rank, local, world)
     torch.cuda.set_device(local)
     if args.workload == "c5":
-        from tisphi_b200 import bench_c5
+        from bench_workloads import c5 as bench_c5
         return bench_c5.run(args, local, log, ClockSampler, measured_peaks)
     if args.workload == "c3":
-        from tisphi_b200 import bench_soil
+        from bench_workloads import soil as bench_soil
         return bench_soil.run(args, local, log, ClockSampler, measured_peaks, host_threads)
     from tisphi_b200 import scenes
     from tisphi_b200.eng.simulation import Simulation, SimConfiger
@@ -542,7 +542,7 @@ def run_ours_multi(args, rank, local, world):
     from tisphi_b200.parallel import SlabSimulation
 
     if args.workload == "c5":
-        from tisphi_b200 import bench_c5
+        from bench_workloads import c5 as bench_c5
         bench_c5.run_multi(args, rank, local, world, log, ClockSampler, measured_peaks)
         dist.destroy_process_group()
         return

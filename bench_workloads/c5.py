@@ -17,7 +17,7 @@ METRIC, UNIT = "particle-updates/s", "particle-updates/s"
 def _cpu_baseline(n_target, threads, log):
     """oracle (float64, OpenMP): grid build + neighbour count + density sum on a bounded box."""
     from oracle import oracle as orc
-    from .c5 import box_positions, box_params
+    from tisphi_b200.c5 import box_positions, box_params
     L = orc.lib()
     L.orc_set_threads(threads)
     x, n_side = box_positions(n_target)
@@ -41,7 +41,7 @@ def _cpu_baseline(n_target, threads, log):
 
 def run(args, local, log, ClockSampler, measured_peaks, host_threads=None):
     import torch
-    from .c5 import UniformBox
+    from tisphi_b200.c5 import UniformBox
     n_target = int(args.size or 1e7)
     t0 = time.time()
     box = UniformBox(n_target, device=f"cuda:{local}")
@@ -129,9 +129,9 @@ def run_multi(args, rank, local, world, log, ClockSampler, measured_peaks):
     sph_density_sweep on the owned columns.  One process per GPU, csrc/slab.cu."""
     import torch
     import torch.distributed as dist
-    from . import _lib
-    from .c5 import box_positions, box_params
-    from .parallel import partition_columns, connect_p2p
+    from tisphi_b200 import _lib
+    from tisphi_b200.c5 import box_positions, box_params
+    from tisphi_b200.parallel import partition_columns, connect_p2p
     n_target = int(args.size or 1e7)
     x, n_side = box_positions(n_target)
     n = len(x)

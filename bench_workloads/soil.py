@@ -41,8 +41,8 @@ def _cpu_baseline(refine, soil, steps, threads):
 
 def run(args, local, log, ClockSampler, measured_peaks, host_threads):
     import torch
-    from .eng.simulation import Simulation, SimConfiger
-    from . import _lib as L_
+    from tisphi_b200.eng.simulation import Simulation, SimConfiger
+    from tisphi_b200 import _lib as L_
     refine = float(args.size or 18)
     soil = getattr(args, "soil", "dp")
     scene = soil_scene(refine, soil, args.precision)
