@@ -164,3 +164,25 @@ def test_bench_state_hash_is_order_independent_and_bit_sensitive():
     x2 = x.clone()
     x2[[3, 4]] = x2[[4, 3]]                                     # two particles swap their positions: ids matter
     assert int(bench.state_hash(torch, [x2, v, p, gid], id0)) != h
+
+
+def test_product_code_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke(), bench.py's CPU legs and bench_workloads/
+    (their cpu_baseline legs) may import it -- never the package, the eng shim or the run script."""
+    import ast
+    offenders = []
+    files = [os.path.join(ROOT, "run_simulation.py")]
+    for top in ("tisphi_b200", "eng"):
+        for d, _, names in os.walk(os.path.join(ROOT, top)):
+            files += [os.path.join(d, n) for n in names if n.endswith(".py")]
+    for f in files:
+        for node in ast.walk(ast.parse(open(f).read())):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom) and node.module:
+                mods = [node.module]
+            if any(m == "oracle" or m.startswith("oracle.") for m in mods):
+                offenders.append(os.path.relpath(f, ROOT))
+    assert not offenders, offenders
+    assert len(files) > 15
