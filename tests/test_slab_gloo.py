@@ -83,6 +83,8 @@ def _worker(rank, world, port, name, nsteps, serial):
     ("c1_test1_wc_lf", 4, 2, 0),              # four slabs of the full test1 scene (92 columns)
     ("c1_test1_wc_lf", 8, 2, 0),              # eight slabs: the width the driver's scaling run goes to
     ("dp2d_indenter_lf", 2, 3, 0),            # a static rigid indenter inside one slab, next to the face
+    ("wc2d_collision_lf", 2, 4, 0),           # boundary mode 1: enforced collision, no wall particles
+    ("mui2d_dummyrep_lf", 3, 3, 0),           # boundary mode 4: dummy + repulsive wall particles
 ])
 def test_slab_protocol_equals_single_process(name, world, nsteps, serial):
     mp.start_processes(_worker, args=(world, _free_port(), name, nsteps, serial), nprocs=world, join=True,
